@@ -1,0 +1,179 @@
+/* zipvoice_b200 — C ABI of the B200-native ZipVoice sampler hot path.
+ *
+ * The reference (ayutaz/ZipVoice) has no C/FFI plugin API; its operator seam is attribute
+ * replacement on the model object as done by `load_trt`
+ * (reference: zipvoice/utils/tensorrt.py:128-143).  These entry points are what a binding for
+ * that seam calls:
+ *   seam 1  model.fm_decoder(x, t, padding_mask, guidance_scale)   -> zvb_decoder_forward_f32
+ *           (reference: zipvoice/models/zipvoice.py:180-184, modules/zipformer.py:242-293,
+ *            zipvoice/utils/tensorrt.py:69-126)
+ *   seam 2  model.solver.sample(x, text_condition, speech_condition, padding_mask, num_step,
+ *           guidance_scale, t_start, t_end, t_shift)                -> zvb_sample
+ *           (reference: modules/solver.py:182-240, 40-110, 113-165)
+ *   text    model.text_encoder(x, t=None, padding_mask)             -> zvb_decoder_forward_f32
+ *           on a plan built from the text-encoder description (reference: zipvoice.py:209-211)
+ *
+ * Conventions: plain pointers and sizes only; every device buffer (weights, workspace,
+ * inputs, outputs) is allocated and owned by the caller (PyTorch); the library never
+ * allocates device memory and never synchronises, so every call is CUDA-graph capturable on
+ * the given stream.  All functions return 0 on success, a negative zvb_status otherwise
+ * (no exceptions cross the ABI); zvb_last_error() describes the last failure of the calling
+ * thread.  One host thread drives one plan at a time; distinct plans may run concurrently
+ * on distinct streams (cf. the TensorRT context pool, reference: tensorrt.py:44-52).
+ */
+#ifndef ZIPVOICE_B200_H_
+#define ZIPVOICE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZVB_ABI_VERSION 1
+#define ZVB_MAX_STACKS 8
+#define ZVB_MAX_LAYERS 64
+
+typedef enum {
+    ZVB_OK = 0,
+    ZVB_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+    ZVB_ERR_WORKSPACE = -2,   /* workspace too small */
+    ZVB_ERR_CUDA = -3,        /* CUDA runtime / driver error */
+    ZVB_ERR_NO_DEVICE = -4    /* no sm_100 device: there is no CPU fallback */
+} zvb_status;
+
+/* One nn.Linear: W is bf16 row-major (out_features, k_pitch) with k_pitch a multiple of 8,
+ * zero padded; bias is fp32 (nullable).  "Gated" projections are re-ordered per 256-row tile
+ * as [128 rows of the first operand | 128 rows of the second] and zero padded to a multiple
+ * of 256 rows (bias likewise), see zipvoice_b200/weights.py. */
+typedef struct {
+    const void* w;
+    const float* b;
+    int32_t out_features;
+    int32_t in_features;
+    int32_t k_pitch;
+    int32_t rows;             /* rows physically present in w (>= out_features for gated) */
+} zvb_linear;
+
+/* Zipformer2EncoderLayer (reference: modules/zipformer.py:370-404) */
+typedef struct {
+    zvb_linear attn_in;       /* self_attn_weights.in_proj : D -> H*(2*32+4)               */
+    const float* pos_table;   /* E = linear_pos(pos_emb): fp32 [H][2L-1][4] for this plan's L */
+    zvb_linear ff_in[3], ff_out[3];
+    zvb_linear na_sx;         /* nonlin_attention.in_proj rows (s,x), gated-packed          */
+    zvb_linear na_y;          /* nonlin_attention.in_proj rows y                            */
+    zvb_linear na_out;
+    zvb_linear sa_in[2], sa_out[2];
+    zvb_linear conv_in[2];    /* conv_module{1,2}.in_proj rows (x,s), gated-packed          */
+    const float* dw_w[2];     /* depthwise weight transposed to fp32 [K][D]                 */
+    const float* dw_b[2];
+    zvb_linear conv_out[2];
+    const float* norm_bias;   /* BiasNorm.bias [D]                                          */
+    const float* norm_log_scale; /* BiasNorm.log_scale, device scalar                       */
+    const float* bypass_scale;
+    const float* bypass_mid_scale;
+} zvb_layer;
+
+typedef struct {
+    int32_t downsample;       /* 1, 2 or 4                                                   */
+    int32_t num_layers;
+    int32_t conv_kernel;      /* 7, 9, 15 or 31                                              */
+    int32_t first_layer;      /* index into zvb_model.layers                                 */
+    float ds_weights[4];      /* softmax(downsample.bias) (reference: zipformer.py:906)      */
+    const float* out_combiner_scale;  /* [D], null when downsample == 1                      */
+    const float* time_w;      /* encoders.i.time_emb.1.weight fp32 [D][time_dim] (nullable)  */
+    const float* time_b;
+} zvb_stack;
+
+/* TTSZipformer (reference: modules/zipformer.py:109-240; two-stream: the caller passes the
+ * in/out projection pair selected by input width, zipformer_two_stream.py:236-262) */
+typedef struct {
+    int32_t abi_version;
+    int32_t dim;              /* D                                                           */
+    int32_t num_heads;        /* H (query_head_dim 32, pos_head_dim 4 are fixed)             */
+    int32_t value_head_dim;   /* 12                                                          */
+    int32_t in_dim;           /* 300 / 500 / 192                                             */
+    int32_t out_dim;          /* 100 / 200                                                   */
+    int32_t ff_dims[3];
+    int32_t na_hidden;
+    int32_t time_dim;         /* 192, or 0 when the network takes no time embedding          */
+    int32_t use_guidance_embed;
+    int32_t num_stacks;
+    int32_t num_layers;
+    zvb_linear in_proj, out_proj;
+    const float* time0_w; const float* time0_b;   /* time_embed.0 fp32 [2*time_dim][time_dim] */
+    const float* time2_w; const float* time2_b;   /* time_embed.2 fp32 [time_dim][2*time_dim] */
+    const float* guidance_w;                      /* guidance_scale_embed.weight (nullable)   */
+    zvb_stack stacks[ZVB_MAX_STACKS];
+    const zvb_layer* layers;  /* host array of num_layers entries                            */
+} zvb_model;
+
+/* Device buffers inside the workspace a plan reads its inputs from / writes its output to. */
+typedef struct {
+    void* xin;                /* bf16 [N][T][xin_pitch] = [x | text | speech | 0-pad]        */
+    float* t;                 /* [N]                                                         */
+    float* g;                 /* [N] guidance scale (distill only)                           */
+    uint8_t* mask;            /* [N][T] non-zero = padded frame                              */
+    float* out;               /* fp32 [N][T][out_dim]                                        */
+    int32_t xin_pitch;
+} zvb_io;
+
+typedef struct zvb_plan zvb_plan;
+
+const char* zvb_last_error(void);
+int zvb_abi_version(void);
+/* number of kernels of this library launched by the calling thread since process start */
+long long zvb_launch_count(void);
+
+/* Workspace size (bytes) for a plan over N rows of T frames.  The workspace must be zero
+ * filled once by the caller before zvb_plan_create. */
+int zvb_plan_workspace_bytes(const zvb_model* model, int N, int T, size_t* bytes);
+int zvb_plan_create(const zvb_model* model, int N, int T, void* workspace, size_t workspace_bytes,
+                    zvb_plan** plan);
+void zvb_plan_destroy(zvb_plan* plan);
+int zvb_plan_io(const zvb_plan* plan, zvb_io* io);
+
+/* Forward over the resident io buffers: out = fm_decoder(xin, t, mask[, g]). */
+int zvb_decoder_forward(zvb_plan* plan, void* stream);
+
+/* Seam 1: x fp32 [N][T][in_dim], t fp32 [N] (null for the text encoder), mask u8 [N][T],
+ * g fp32 [N] or null, out fp32 [N][T][out_dim]. */
+int zvb_decoder_forward_f32(zvb_plan* plan, const float* x, const float* t, const uint8_t* mask,
+                            const float* g, float* out, void* stream);
+
+/* Seam 2: Euler ODE with classifier-free guidance.
+ *   x        fp32 [B][T][F]   state, updated in place (x0 in, x(t_end) out)
+ *   text     fp32 [B][T][Ft]  ; speech fp32 [B][T][F] ; mask u8 [B][T]
+ *   guidance fp32 [B] per-utterance scale (device)
+ *   ts       fp32 [num_step+1] time grid (device), ts_host the same values on the host
+ *   mode     0: single pass, no guidance input (all scales zero)
+ *            1: CFG, batch doubled [uncond ; cond] (plan N == 2B), scale doubled and speech
+ *               kept for the uncond half while t <= 0.5 (reference: solver.py:83-110)
+ *            2: distilled model: single pass, guidance fed to the network (plan N == B)
+ *   vrec     optional fp32 [num_step][B][T][F]: every step's (blended) velocity */
+int zvb_sample(zvb_plan* plan, float* x, const float* text, const float* speech, const uint8_t* mask,
+               const float* guidance, const float* ts, const float* ts_host, int num_step, int mode,
+               int B, int F, int Ft, float* vrec, void* stream);
+
+/* ---- single-kernel entry points used by the parity tests -------------------------------- */
+/* C = epilogue(A·Wᵀ): A bf16 [M][lda], W bf16 [n_out][k_pitch]; act 0 none/1 SwooshL/2 SwooshR;
+ * resid bf16 [M][ldc] nullable; out bf16 [M][ldc] (or fp32 when out_f32). */
+int zvb_test_linear(const void* A, int M, int K, int lda, const void* W, const float* bias, int n_out,
+                    int k_pitch, int block_n, int act, const void* resid, void* out, int ldc, int out_f32,
+                    void* stream);
+int zvb_test_attn_weights(const void* qkp, int ld, const float* pos_table, const uint8_t* mask, void* P,
+                          int N, int H, int L, int Lk, void* stream);
+int zvb_test_pv(const void* P, const void* Vt, void* out, int N, int H, int L, int Lk, int hd, int hp,
+                int per_head, void* stream);
+int zvb_test_biasnorm_bypass(const void* src, const void* orig, void* out, const float* nbias,
+                             const float* log_scale, const float* bscale, long long rows, int C, void* stream);
+int zvb_test_dwconv(const void* x, void* out, const float* wt, const float* bias, int N, int L, int C, int K,
+                    void* stream);
+int zvb_test_cfg_euler(float* x, const float* v, const float* guidance, float gscale, const float* ts,
+                       int step, int B, long long per_utt, int cfg, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZIPVOICE_B200_H_ */

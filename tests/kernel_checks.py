@@ -1,0 +1,228 @@
+"""Single-kernel parity checks through the C ABI test entry points, shared by
+tests/test_kernels_gpu.py (pytest, -m gpu) and tools/gpu_check.py (one process per check).
+Each check compares a CUDA kernel with a plain PyTorch fp32 computation of the same op on the
+same (bf16-rounded) inputs and returns a dict of error metrics; `assert_ok` applies the
+tolerances written next to each check."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from zipvoice_b200 import _lib
+
+DEV = "cuda"
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _swoosh_l(x):
+    return torch.logaddexp(torch.zeros((), device=x.device), x - 4.0) - 0.08 * x - 0.035
+
+
+def _swoosh_r(x):
+    return torch.logaddexp(torch.zeros((), device=x.device), x - 1.0) - 0.08 * x - 0.313261687
+
+
+def check_linear(M=300, K=512, N=272, block_n=0, act=0, resid=False, out_f32=False, seed=0):
+    """tolerance: rel-L2 <= 6e-3 (bf16 output rounding 2^-9 + fp32 accumulation order)"""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    kp = (K + 7) // 8 * 8
+    A = torch.zeros(M, kp, dtype=torch.bfloat16)
+    A[:, :K] = (torch.randn(M, K, generator=g) * 1.0).to(torch.bfloat16)
+    W = torch.zeros(N, kp, dtype=torch.bfloat16)
+    W[:, :K] = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    b = torch.randn(N, generator=g)
+    R = torch.randn(M, N, generator=g).to(torch.bfloat16) if resid else None
+    A, W, b = A.to(DEV), W.to(DEV), b.to(DEV)
+    R = R.to(DEV) if resid else None
+    out = torch.full((M, N), float("nan"), dtype=torch.float32 if out_f32 else torch.bfloat16, device=DEV)
+    _lib.check(lib.zvb_test_linear(A.data_ptr(), M, K, kp, W.data_ptr(), b.data_ptr(), N, kp, block_n, act,
+                                   R.data_ptr() if resid else None, out.data_ptr(), N, 1 if out_f32 else 0, _s()))
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + b
+    if act == 1:
+        ref = _swoosh_l(ref)
+    elif act == 2:
+        ref = _swoosh_r(ref)
+    if resid:
+        ref = ref + R.float()
+    err = (out.float() - ref).abs().nan_to_num(1e9)
+    am = int(err.argmax())
+    return dict(rel=_rel(out.float().nan_to_num(0.0), ref), nan=int(torch.isnan(out.float()).sum()), tol=6e-3,
+                worst=[am // N, am % N, float(out.float().flatten()[am]), float(ref.flatten()[am])],
+                bad_frac=float((err > 0.1).float().mean()),
+                bad_rows=int((err.max(dim=1).values > 0.1).sum()), bad_cols=int((err.max(dim=0).values > 0.1).sum()))
+
+
+def _attn_inputs(N, H, L, seed, masked):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    ld = H * 68
+    qkp = torch.randn(N, L, ld, generator=g)
+    qkp[..., : 2 * H * 32] *= 0.45          # q.k std ~ 1.1 ... a few units of score range
+    qkp = qkp.to(torch.bfloat16)
+    E = torch.randn(H, 2 * L - 1, 4, generator=g) * 0.5
+    mask = torch.zeros(N, L, dtype=torch.bool)
+    if masked:
+        lens = torch.randint(max(1, L // 2), L + 1, (N,), generator=g)
+        lens[0] = L
+        mask = torch.arange(L)[None, :] >= lens[:, None]
+    return qkp.to(DEV), E.to(DEV), mask.to(DEV)
+
+
+def _attn_ref(qkp, E, mask, H):
+    N, L, _ = qkp.shape
+    x = qkp.float()
+    q = x[..., : H * 32].reshape(N, L, H, 32).permute(0, 2, 1, 3)
+    k = x[..., H * 32: 2 * H * 32].reshape(N, L, H, 32).permute(0, 2, 1, 3)
+    p = x[..., 2 * H * 32:].reshape(N, L, H, 4).permute(0, 2, 1, 3)
+    s = q @ k.transpose(-1, -2)
+    idx = (L - 1) - torch.arange(L, device=x.device)[:, None] + torch.arange(L, device=x.device)[None, :]
+    pos = torch.einsum("nhic,hrc->nhir", p, E)                 # (N,H,L,2L-1)
+    s = s + torch.gather(pos, 3, idx.expand(N, H, L, L))
+    s = s.masked_fill(mask[:, None, None, :], -1000.0)
+    return s.softmax(-1)
+
+
+def check_attn(N=2, H=4, L=200, masked=True, seed=0):
+    """tolerance: max-abs <= 4e-3 on probabilities (bf16 storage of P: 2^-9 relative)"""
+    lib = _lib.load()
+    qkp, E, mask = _attn_inputs(N, H, L, seed, masked)
+    Lk = (L + 7) // 8 * 8
+    P = torch.full((N, H, L, Lk), float("nan"), dtype=torch.bfloat16, device=DEV)
+    m8 = mask.to(torch.uint8).contiguous()
+    _lib.check(lib.zvb_test_attn_weights(qkp.data_ptr(), H * 68, E.data_ptr(), m8.data_ptr(), P.data_ptr(), N, H, L,
+                                         Lk, _s()))
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkp, E, mask, H)
+    got = P.float()
+    pad = got[..., L:]
+    return dict(maxabs=float((got[..., :L] - ref).abs().max()), rel=_rel(got[..., :L], ref),
+                nan=int(torch.isnan(got).sum()), pad_nonzero=int((pad != 0).sum()),
+                rowsum_err=float((got[..., :L].sum(-1) - 1).abs().max()), tol=4e-3)
+
+
+def check_pv(N=2, H=4, L=200, hd=12, hp=16, per_head=True, seed=0):
+    """tolerance: rel-L2 <= 6e-3"""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    Lk = (L + 7) // 8 * 8
+    P = torch.zeros(N, H, L, Lk)
+    P[..., :L] = torch.rand(N, H, L, L, generator=g).pow(4)
+    P = (P / P.sum(-1, keepdim=True)).to(torch.bfloat16).to(DEV)
+    if per_head:
+        V = torch.randn(N, H, hd, L, generator=g).to(torch.bfloat16)
+        Vt = torch.zeros(N, H, hp, Lk, dtype=torch.bfloat16)
+        Vt[:, :, :hd, :L] = V
+        out = torch.full((N, L, H * hd), float("nan"), dtype=torch.bfloat16, device=DEV)
+        ref = torch.einsum("nhij,nhdj->nihd", P.float()[..., :L], V.float().to(DEV)).reshape(N, L, H * hd)
+    else:
+        V = torch.randn(N, hd, L, generator=g).to(torch.bfloat16)
+        Vt = torch.zeros(N, hd, Lk, dtype=torch.bfloat16)
+        Vt[:, :, :L] = V
+        out = torch.full((N, L, hd), float("nan"), dtype=torch.bfloat16, device=DEV)
+        ref = torch.einsum("nij,ndj->nid", P.float()[:, 0, :, :L], V.float().to(DEV))
+    Vt = Vt.to(DEV)
+    _lib.check(lib.zvb_test_pv(P.data_ptr(), Vt.data_ptr(), out.data_ptr(), N, H, L, Lk, hd, hp, 1 if per_head else 0,
+                               _s()))
+    torch.cuda.synchronize()
+    return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=6e-3)
+
+
+def check_biasnorm(rows=1000, C=512, seed=0):
+    """tolerance: rel-L2 <= 5e-3 (bf16 output)"""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    src = torch.randn(rows, C, generator=g).mul(2).to(torch.bfloat16).to(DEV)
+    orig = torch.randn(rows, C, generator=g).to(torch.bfloat16).to(DEV)
+    nb = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    ls = torch.tensor([0.4], device=DEV)
+    bs = (torch.rand(C, generator=g) * 0.6 + 0.3).to(DEV)
+    out = torch.full((rows, C), float("nan"), dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.zvb_test_biasnorm_bypass(src.data_ptr(), orig.data_ptr(), out.data_ptr(), nb.data_ptr(),
+                                            ls.data_ptr(), bs.data_ptr(), rows, C, _s()))
+    torch.cuda.synchronize()
+    x = src.float()
+    y = x * (((x - nb) ** 2).mean(-1, keepdim=True) ** -0.5) * ls.exp()
+    ref = orig.float() + (y - orig.float()) * bs
+    return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=5e-3)
+
+
+def check_dwconv(N=2, L=150, C=512, K=31, seed=0):
+    """tolerance: rel-L2 <= 5e-3 (bf16 output)"""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(N, L, C, generator=g).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(C, 1, K, generator=g) / math.sqrt(K)).to(DEV)
+    b = (torch.randn(C, generator=g) * 0.2).to(DEV)
+    wt = w.reshape(C, K).t().contiguous()
+    out = torch.full((N, L, C), float("nan"), dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.zvb_test_dwconv(x.data_ptr(), out.data_ptr(), wt.data_ptr(), b.data_ptr(), N, L, C, K, _s()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv1d(x.float().permute(0, 2, 1), w, b, padding=K // 2, groups=C).permute(0, 2, 1)
+    ref = _swoosh_r(ref)
+    return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=5e-3)
+
+
+def check_cfg_euler(B=3, T=50, F=100, cfg=1, seed=0):
+    """tolerance: exact to fp32 rounding (rel-L2 <= 1e-6)"""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(B, T, F, generator=g).to(DEV)
+    v = torch.randn(2 * B if cfg else B, T, F, generator=g).to(DEV)
+    gd = torch.tensor([0.0, 0.7, 2.0])[:B].to(DEV)
+    ts = torch.tensor([0.1, 0.35, 0.8], device=DEV)
+    x0 = x.clone()
+    _lib.check(lib.zvb_test_cfg_euler(x.data_ptr(), v.data_ptr(), gd.data_ptr(), 2.0, ts.data_ptr(), 0, B, T * F, cfg,
+                                      _s()))
+    torch.cuda.synchronize()
+    if cfg:
+        gg = (2.0 * gd)[:, None, None]
+        vel = (1 + gg) * v[B:] - gg * v[:B]
+    else:
+        vel = v
+    ref = x0 + vel * (ts[1] - ts[0])
+    return dict(rel=_rel(x, ref), tol=1e-6)
+
+
+def assert_ok(name, r):
+    assert r.get("nan", 0) == 0, (name, r)
+    if "maxabs" in r:
+        assert r["maxabs"] <= r["tol"], (name, r)
+        assert r.get("pad_nonzero", 0) == 0, (name, r)
+    else:
+        assert r["rel"] <= r["tol"], (name, r)
+
+
+ALL = {
+    "linear_basic": lambda: check_linear(M=300, K=512, N=272),
+    "linear_k48": lambda: check_linear(M=257, K=48, N=512, resid=True),
+    "linear_k300": lambda: check_linear(M=130, K=300, N=512),
+    "linear_swoosh": lambda: check_linear(M=1000, K=512, N=1152, act=1),
+    "linear_big": lambda: check_linear(M=20000, K=1536, N=512, resid=True),
+    "linear_f32_n100": lambda: check_linear(M=333, K=512, N=100, out_f32=True),
+    "linear_bn64": lambda: check_linear(M=128, K=64, N=64, block_n=64),
+    "linear_tail": lambda: check_linear(M=77, K=192, N=640, act=2),
+    "attn_small": lambda: check_attn(N=2, H=4, L=100, masked=False),
+    "attn_masked": lambda: check_attn(N=3, H=4, L=333, masked=True),
+    "attn_long": lambda: check_attn(N=1, H=4, L=1219, masked=True),
+    "pv_heads": lambda: check_pv(N=2, H=4, L=333, per_head=True),
+    "pv_wide": lambda: check_pv(N=2, H=4, L=333, hd=384, hp=384, per_head=False),
+    "pv_wide96": lambda: check_pv(N=2, H=4, L=81, hd=96, hp=96, per_head=False),
+    "biasnorm": lambda: check_biasnorm(),
+    "biasnorm_c192": lambda: check_biasnorm(rows=77, C=192),
+    "dwconv31": lambda: check_dwconv(K=31),
+    "dwconv15": lambda: check_dwconv(K=15, L=77),
+    "dwconv7": lambda: check_dwconv(K=7, L=64, C=128),
+    "dwconv9": lambda: check_dwconv(K=9, L=20, C=192),
+    "cfg_euler": lambda: check_cfg_euler(cfg=1),
+    "euler_nocfg": lambda: check_cfg_euler(cfg=0),
+}

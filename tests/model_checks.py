@@ -1,0 +1,54 @@
+"""End-to-end parity of the CUDA path against the golden fixtures (which the reference itself
+produced, tools/make_golden.py).  bf16 tolerances are the ones published in BASELINE.md §5:
+per-step velocity rel-L2 <= 1.5e-2 / max-abs <= 0.15, final state rel-L2 <= 2e-2 / max-abs <= 0.25."""
+from __future__ import annotations
+
+import torch
+
+from zipvoice_b200.model import build_model
+from zipvoice_b200.synth import synth_state_dict, synth_utterances
+from util import CASE_CFG, load_golden, max_abs, rel_l2
+
+TOL_V_REL, TOL_V_ABS, TOL_X_REL, TOL_X_ABS = 1.5e-2, 0.15, 2e-2, 0.25
+TOL_TEXT_REL = 1.5e-2
+
+
+def run_case(name: str, use_cuda_graph: bool = False):
+    cfg = CASE_CFG[name]()
+    gold = load_golden(name)
+    u = synth_utterances(cfg, **gold["ukw"])
+    model = build_model(cfg, synth_state_dict(cfg, 0), "cuda", use_cuda_graph=use_cuda_graph)
+    dev = model.device
+    res = {}
+    # text prelude (text encoder on the GPU) -- reference: zipvoice.py:270-288
+    tc, pm = model.forward_text_inference_gt_duration(
+        tokens=u["tokens"], features_lens=u["target_lens"], prompt_tokens=u["prompt_tokens"],
+        prompt_features_lens=u["prompt_features_lens"].to(dev))
+    res["mask_equal"] = bool(torch.equal(pm.cpu(), gold["padding_mask"]))
+    res["text_rel"] = rel_l2(tc, gold["text_condition"])
+    # seam 1 with the golden conditions
+    xin = torch.cat([u["x0"], gold["text_condition"], gold["speech_condition"]], dim=2).to(dev)
+    g = torch.full((xin.shape[0],), 2.0, device=dev) if cfg.is_distill else None
+    out = model.fm_decoder(x=xin, t=gold["fm_in_t"].to(dev), padding_mask=gold["padding_mask"].to(dev),
+                           guidance_scale=g)
+    res["fm_rel"], res["fm_abs"] = rel_l2(out, gold["fm_out"]), max_abs(out, gold["fm_out"])
+    # seam 2
+    model.solver.record_velocities = True
+    x1 = model.solver.sample(x=u["x0"].to(dev), text_condition=gold["text_condition"].to(dev),
+                             speech_condition=gold["speech_condition"].to(dev),
+                             padding_mask=gold["padding_mask"].to(dev), **gold["skw"])
+    v = model.solver.last_velocities
+    res["v_rel"] = [rel_l2(v[i], gold["velocities"][i]) for i in range(v.shape[0])]
+    res["v_abs"] = [max_abs(v[i], gold["velocities"][i]) for i in range(v.shape[0])]
+    res["x_rel"], res["x_abs"] = rel_l2(x1, gold["x1"]), max_abs(x1, gold["x1"])
+    res["finite"] = bool(torch.isfinite(x1).all())
+    return res
+
+
+def assert_case(name, res):
+    assert res["finite"], (name, res)
+    assert res["mask_equal"], (name, res)
+    assert res["text_rel"] <= TOL_TEXT_REL, (name, res)
+    assert res["fm_rel"] <= TOL_V_REL and res["fm_abs"] <= TOL_V_ABS, (name, res)
+    assert max(res["v_rel"]) <= TOL_V_REL and max(res["v_abs"]) <= TOL_V_ABS, (name, res)
+    assert res["x_rel"] <= TOL_X_REL and res["x_abs"] <= TOL_X_ABS, (name, res)

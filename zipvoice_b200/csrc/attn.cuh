@@ -1,0 +1,230 @@
+// Attention-weights kernel (reference: modules/zipformer.py:1149-1306
+// RelPositionMultiheadAttentionWeights.forward, eval path):
+//   P[n,h,i,:] = softmax_j( q_i·k_j + p_i·E_h[j-i] , key-padding mask -> -1000 )   (fp32 softmax)
+// q·kᵀ runs on tcgen05 (K = 32: two UMMA_K steps per 128x128 score tile, accumulators in
+// TMEM, double buffered); the rel-pos bias is a 4-term dot product per score with the
+// per-layer table E = linear_pos(pos_emb) staged in shared memory as the (i-tile, j-tile)
+// window of 255 relative offsets; softmax is two-pass (row max / sum, then normalise) with
+// the cheap q·kᵀ recomputed in the second pass; P is written once as bf16 for the three
+// consumers of the layer (NonlinAttention, SelfAttention x2).
+#pragma once
+#include "ptx.cuh"
+
+namespace zvb {
+
+constexpr int ATT_BM = 128;          // queries per CTA
+constexpr int ATT_BN = 128;          // keys per score tile
+constexpr int ATT_KSTAGES = 3;
+constexpr int ATT_TILE_BYTES = 128 * 64 * 2;      // one 128-row x 64-col bf16 box (only 32 cols used)
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TMEM_COLS = 256;
+constexpr int ATT_EWIN = 256;        // 255 offsets used
+constexpr int ATT_SMEM_BYTES = (1 + ATT_KSTAGES) * ATT_TILE_BYTES + 2 * ATT_EWIN * 16 + 2 * ATT_BN +
+                               1024 + 256;
+
+struct AttnParams {
+    int L, Lk, H, N;
+    int qd;                          // H * 32: column of head-0 keys inside a qkp row
+    const __nv_bfloat16* qkp;        // [N*L, ld] = [q | k | p]
+    int ld;
+    const float* E;                  // [H][2L-1][4]
+    const uint8_t* mask;             // [N][L], non-zero = padded key
+    __nv_bfloat16* P;                // [N][H][L][Lk]
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint8_t* q_tile = smem;
+    uint8_t* k_tiles = smem + ATT_TILE_BYTES;
+    float4* ewin = reinterpret_cast<float4*>(smem + (1 + ATT_KSTAGES) * ATT_TILE_BYTES);   // [2][256]
+    uint8_t* mwin = reinterpret_cast<uint8_t*>(ewin + 2 * ATT_EWIN);                        // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(mwin + 2 * ATT_BN);
+    uint64_t* q_full = bars;
+    uint64_t* k_full = bars + 1;                      // [KSTAGES]
+    uint64_t* k_empty = k_full + ATT_KSTAGES;         // [KSTAGES]
+    uint64_t* s_full = k_empty + ATT_KSTAGES;         // [2]
+    uint64_t* s_empty = s_full + 2;                   // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(s_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int i0 = blockIdx.x * ATT_BM;
+    const int h = blockIdx.y;
+    const int n = blockIdx.z;
+    const int num_jt = (p.L + ATT_BN - 1) / ATT_BN;
+    const int total_it = 2 * num_jt;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_qk);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < ATT_KSTAGES; ++s) {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_holder, ATT_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+            tma_load_3d(q_tile, &tma_qk, q_full, h * 32, i0, n);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < total_it; ++it) {
+                const int jt = it >= num_jt ? it - num_jt : it;
+                mbar_wait(&k_empty[stage], phase ^ 1u);
+                mbar_arrive_expect_tx(&k_full[stage], ATT_TILE_BYTES);
+                tma_load_3d(k_tiles + stage * ATT_TILE_BYTES, &tma_qk, &k_full[stage], p.qd + h * 32,
+                            jt * ATT_BN, n);
+                if (++stage == ATT_KSTAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(ATT_BN);
+            mbar_wait(q_full, 0);
+            tc_fence_after();
+            const uint64_t dq = umma_desc_k_sw128(smem_u32(q_tile));
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < total_it; ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = static_cast<uint32_t>(it >> 1) & 1u;
+                mbar_wait(&s_empty[acc], acc_phase ^ 1u);
+                mbar_wait(&k_full[stage], phase);
+                tc_fence_after();
+                const uint64_t dk = umma_desc_k_sw128(smem_u32(k_tiles + stage * ATT_TILE_BYTES));
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc) * ATT_BN;
+                umma_bf16(tmem_d, dq, dk, idesc, 0u);            // head-dim columns  0..15
+                umma_bf16(tmem_d, dq + 2, dk + 2, idesc, 1u);    // head-dim columns 16..31
+                umma_commit(&k_empty[stage]);
+                umma_commit(&s_full[acc]);
+                if (++stage == ATT_KSTAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax warps
+        const int quarter = warp & 3;
+        const int tid = threadIdx.x - 64;                 // 0..127 (not row order; only for staging)
+        const int r = quarter * 32 + lane;                // row inside the query tile
+        const int i = i0 + r;
+        const bool row_ok = i < p.L;
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+        if (row_ok) {
+            const __nv_bfloat16* pp = p.qkp + (static_cast<long long>(n) * p.L + i) * p.ld + 2 * p.qd + h * 4;
+            const uint2 w = *reinterpret_cast<const uint2*>(pp);
+            p0 = bf16_lo(w.x); p1 = bf16_hi(w.x); p2 = bf16_lo(w.y); p3 = bf16_hi(w.y);
+        }
+        const float4* Eh = reinterpret_cast<const float4*>(p.E) + static_cast<long long>(h) * (2 * p.L - 1);
+        const uint8_t* mrow = p.mask + static_cast<long long>(n) * p.L;
+        __nv_bfloat16* prow = p.P + ((static_cast<long long>(n) * p.H + h) * p.L + i) * p.Lk;
+        constexpr float LOG2E = 1.4426950408889634f;
+        float m_run = -INFINITY, l_run = 0.f, inv_l = 0.f, m_l2 = 0.f;
+
+        for (int it = 0; it < total_it; ++it) {
+            const int pass = it >= num_jt ? 1 : 0;
+            const int jt = pass ? it - num_jt : it;
+            const int j0 = jt * ATT_BN;
+            const int acc = it & 1;
+            const uint32_t acc_phase = static_cast<uint32_t>(it >> 1) & 1u;
+            if (it == num_jt) {                           // between the passes
+                inv_l = 1.0f / l_run;
+                m_l2 = m_run * LOG2E;
+            }
+            // stage the rel-pos window and the key mask of this tile (double buffered)
+            float4* ew = ewin + acc * ATT_EWIN;
+            uint8_t* mw = mwin + acc * ATT_BN;
+            for (int w = tid; w < 255; w += 128) {
+                const int rel = (j0 - i0) - 127 + w + (p.L - 1);
+                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rel >= 0 && rel <= 2 * p.L - 2) e = __ldg(Eh + rel);
+                ew[w] = e;
+            }
+            {
+                const int j = j0 + tid;
+                mw[tid] = j < p.L ? (mrow[j] != 0 ? 1 : 0) : 2;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&s_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * ATT_BN +
+                                   (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
+                uint32_t sr[32];
+                tmem_ld32(taddr + c0, sr);
+                tmem_ld_wait();
+                float s[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float4 e = ew[c0 + c - r + 127];
+                    float v = __uint_as_float(sr[c]);
+                    v = fmaf(p0, e.x, v);
+                    v = fmaf(p1, e.y, v);
+                    v = fmaf(p2, e.z, v);
+                    v = fmaf(p3, e.w, v);
+                    const uint8_t mk = mw[c0 + c];
+                    v = mk == 0 ? v : (mk == 1 ? -1000.0f : -INFINITY);
+                    s[c] = v;
+                }
+                if (pass == 0) {
+                    float cm = s[0];
+#pragma unroll
+                    for (int c = 1; c < 32; ++c) cm = fmaxf(cm, s[c]);
+                    const float m_new = fmaxf(m_run, cm);
+                    if (m_new != -INFINITY) {
+                        const float ml2 = m_new * LOG2E;
+                        float acc_sum = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) acc_sum += fast_exp2(fmaf(s[c], LOG2E, -ml2));
+                        l_run = l_run * fast_exp2(fmaf(m_run, LOG2E, -ml2)) + acc_sum;
+                        m_run = m_new;
+                    }
+                } else if (row_ok) {
+                    const int j = j0 + c0;
+                    if (j < p.Lk) {
+                        uint32_t w[16];
+#pragma unroll
+                        for (int c = 0; c < 32; c += 2) {
+                            const float a = fast_exp2(fmaf(s[c], LOG2E, -m_l2)) * inv_l;
+                            const float b = fast_exp2(fmaf(s[c + 1], LOG2E, -m_l2)) * inv_l;
+                            w[c >> 1] = pack_bf16(a, b);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(prow + j);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            if (j + g * 8 < p.Lk) dst[g] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+    }
+}
+
+}  // namespace zvb

@@ -1,0 +1,741 @@
+// Host side of the C ABI (include/zipvoice_b200.h): builds a static launch plan for one
+// TTSZipformer over (N rows, T frames) -- TMA tensor maps, tile shapes, workspace carving --
+// and replays it on a stream.  No allocation, no synchronisation, graph capturable.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/zipvoice_b200.h"
+#include "attn.cuh"
+#include "gemm.cuh"
+namespace zvb { constexpr int ACT_SWOOSH_R_ = 2; }
+#include "elementwise.cuh"
+
+using namespace zvb;
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static thread_local long long g_launches = 0;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) return fail(ZVB_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+#define TRY(expr)                 \
+    do {                          \
+        int r_ = (expr);          \
+        if (r_ != 0) return r_;   \
+    } while (0)
+
+static int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ZVB_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
+    ++g_launches;
+    return 0;
+}
+
+static int g_num_sms = 0;
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static int init_device() {
+    if (g_encode != nullptr) return 0;
+    int dev = 0, count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(ZVB_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(ZVB_ERR_NO_DEVICE, "device sm_%d%d is not sm_100 (B200)", prop.major, prop.minor);
+    g_num_sms = prop.multiProcessorCount;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (fn == nullptr || q != cudaDriverEntryPointSuccess)
+        return fail(ZVB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(attn_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    return 0;
+}
+
+// bf16 tensor (dim0 fastest) viewed as 3-D, box = (64, box1, 1), 128B swizzle, zero OOB fill.
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
+                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box1) {
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (stride1_bytes & 15) != 0 || (stride2_bytes & 15) != 0)
+        return fail(ZVB_ERR_INVALID, "tensor map: pointer/strides must be 16-byte aligned");
+    if (box1 == 0 || box1 > 256 || d0 == 0 || d1 == 0 || d2 == 0)
+        return fail(ZVB_ERR_INVALID, "tensor map: bad box/dims (%u, %llu, %llu, %llu)", box1,
+                    (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {64, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ZVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ ops
+enum OpType { OP_GEMM, OP_ATTN, OP_BIASNORM, OP_ADDROW, OP_DOWN, OP_UP, OP_DWCONV, OP_MASK, OP_TSEMB, OP_SMALL };
+
+struct Op {
+    OpType type;
+    // GEMM / ATTN
+    CUtensorMap ma, mb;
+    GemmParams gp;
+    int kind = 0, grid = 0;
+    AttnParams ap;
+    // elementwise
+    const void *p0 = nullptr, *p1 = nullptr;
+    void *o0 = nullptr, *o1 = nullptr;
+    const float *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *f3 = nullptr;
+    long long rows = 0;
+    int i0 = 0, i1 = 0, i2 = 0, i3 = 0, i4 = 0, i5 = 0;
+    float w[4] = {0, 0, 0, 0};
+};
+
+static int pick_block_n(int n_out, long long m_tiles) {
+    int tiles = (n_out + 255) / 256;
+    int bn = (((n_out + tiles - 1) / tiles) + 15) / 16 * 16;
+    // small problems: prefer more, narrower tiles until the grid covers the SMs
+    while (m_tiles * tiles < g_num_sms && bn > 64) {
+        ++tiles;
+        bn = (((n_out + tiles - 1) / tiles) + 15) / 16 * 16;
+    }
+    return bn;
+}
+
+static void gp_defaults(GemmParams& p) { memset(&p, 0, sizeof p); p.rows_per_group = 1; }
+
+struct LinearEpi {
+    int act = ACT_NONE;
+    const bf16* resid = nullptr;
+    const float* rowbias = nullptr;
+    int rows_per_group = 1;
+    const bf16* orig = nullptr;
+    const float* bypass_scale = nullptr;
+    int out_f32 = 0;
+    // transposed store
+    int transposed = 0, t_L = 0, t_pitch = 0, t_batch_rows = 0, t_hd = 1, t_hp = 1;
+    int block_n = 0;   // 0 = choose
+};
+
+// out[M, n_out] = epi(A[M, K] · W[n_out, K]ᵀ + b)
+static int build_linear(Op& op, const bf16* A, long long M, int lda, const zvb_linear& lin, void* out, int ldc,
+                        const LinearEpi& e) {
+    op.type = OP_GEMM;
+    op.kind = EPI_LINEAR;
+    if (lin.k_pitch % 8 != 0 || lda % 8 != 0) return fail(ZVB_ERR_INVALID, "linear: pitches must be multiples of 8");
+    const int K = lin.k_pitch < lda ? lin.k_pitch : lda;    // both zero padded beyond in_features
+    const long long m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+    const int bn = e.block_n ? e.block_n : pick_block_n(lin.out_features, m_tiles);
+    GemmParams& p = op.gp;
+    gp_defaults(p);
+    p.M = static_cast<int>(M);
+    p.n_out = lin.out_features;
+    p.num_k_blocks = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+    p.block_n = bn;
+    p.num_m_tiles = static_cast<int>(m_tiles);
+    p.num_n_tiles = (lin.out_features + bn - 1) / bn;
+    p.batches = 1;
+    p.out = out; p.ldc = ldc; p.out_f32 = e.out_f32;
+    p.out_col_stride = bn; p.n_valid = bn;
+    p.bias = lin.b;
+    p.rowbias = e.rowbias; p.rows_per_group = e.rows_per_group; p.ld_rowbias = lin.out_features;
+    p.resid = e.resid; p.ldr = ldc;
+    p.orig = e.orig; p.bypass_scale = e.bypass_scale;
+    p.act = e.act;
+    p.transposed = e.transposed; p.t_L = e.t_L; p.t_pitch = e.t_pitch; p.t_batch_rows = e.t_batch_rows;
+    p.t_hd = e.t_hd; p.t_hp = e.t_hp;
+    TRY(make_tmap(&op.ma, A, K, M, 1, (uint64_t)lda * 2, (uint64_t)lda * 2 * M, GEMM_BLOCK_M));
+    TRY(make_tmap(&op.mb, lin.w, K, lin.rows, 1, (uint64_t)lin.k_pitch * 2, (uint64_t)lin.k_pitch * 2 * lin.rows, bn));
+    const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
+    op.grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+    return 0;
+}
+
+// gated projection (weights packed per 256-row tile as [128 | 128]); n_out = gated outputs
+static int build_gated(Op& op, const bf16* A, long long M, int lda, const zvb_linear& lin, int n_out, int gate_mode,
+                       void* out, int ldc, const uint8_t* row_mask, const LinearEpi& e) {
+    op.type = OP_GEMM;
+    op.kind = EPI_GATED;
+    const int K = lin.k_pitch < lda ? lin.k_pitch : lda;
+    GemmParams& p = op.gp;
+    gp_defaults(p);
+    p.M = static_cast<int>(M);
+    p.n_out = n_out;
+    p.num_k_blocks = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+    p.block_n = 256;
+    p.num_m_tiles = static_cast<int>((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
+    p.num_n_tiles = (n_out + 127) / 128;
+    if (lin.rows != p.num_n_tiles * 256) return fail(ZVB_ERR_INVALID, "gated linear: expected %d packed rows, got %d", p.num_n_tiles * 256, lin.rows);
+    p.batches = 1;
+    p.out = out; p.ldc = ldc;
+    p.out_col_stride = 128; p.n_valid = 256;
+    p.bias = lin.b;
+    p.gate_mode = gate_mode;
+    p.row_mask = row_mask;
+    p.transposed = e.transposed; p.t_L = e.t_L; p.t_pitch = e.t_pitch; p.t_batch_rows = e.t_batch_rows;
+    p.t_hd = e.t_hd; p.t_hp = e.t_hp;
+    TRY(make_tmap(&op.ma, A, K, M, 1, (uint64_t)lda * 2, (uint64_t)lda * 2 * M, GEMM_BLOCK_M));
+    TRY(make_tmap(&op.mb, lin.w, K, lin.rows, 1, (uint64_t)lin.k_pitch * 2, (uint64_t)lin.k_pitch * 2 * lin.rows, 256));
+    const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
+    op.grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+    return 0;
+}
+
+// out[n*L+i, :] = P[n,h] · V  with V given transposed: Vt[n][rows][Lk].
+//   per_head != 0 (SelfAttention): head h uses Vt rows [h*hp, h*hp+hd) -> out cols [h*hd, (h+1)*hd)
+//   per_head == 0 (NonlinAttention): head 0 weights, all `hd` value columns, out *= mul
+static int build_pv(Op& op, const bf16* P, const bf16* Vt, void* out, int ldc, int N, int H, int L, int Lk, int hd,
+                    int hp, int per_head, const bf16* mul, int ldm) {
+    op.type = OP_GEMM;
+    op.kind = per_head ? EPI_LINEAR : EPI_MUL;
+    GemmParams& p = op.gp;
+    gp_defaults(p);
+    p.M = L;
+    p.num_k_blocks = (Lk + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+    p.num_m_tiles = (L + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+    p.batches = N;
+    p.b_zb = 1;
+    p.a_zb = H;
+    p.out = out; p.ldc = ldc;
+    int vt_rows;
+    if (per_head) {
+        if (hp % 16 != 0 || hd > hp) return fail(ZVB_ERR_INVALID, "pv: head pad must be a multiple of 16");
+        p.block_n = hp; p.num_n_tiles = H; p.a_zn = 1;
+        p.n_out = H * hd; p.out_col_stride = hd; p.n_valid = hd;
+        vt_rows = H * hp;
+    } else {
+        const int tiles = (hd + 255) / 256;
+        p.block_n = (((hd + tiles - 1) / tiles) + 15) / 16 * 16;
+        p.num_n_tiles = (hd + p.block_n - 1) / p.block_n; p.a_zn = 0;
+        p.n_out = hd; p.out_col_stride = p.block_n; p.n_valid = p.block_n;
+        p.mul = mul; p.ldm = ldm;
+        vt_rows = hd;
+    }
+    TRY(make_tmap(&op.ma, P, Lk, L, (uint64_t)N * H, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * L, GEMM_BLOCK_M));
+    TRY(make_tmap(&op.mb, Vt, Lk, vt_rows, N, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * vt_rows, p.block_n));
+    const long long tiles = (long long)p.batches * p.num_m_tiles * p.num_n_tiles;
+    op.grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+    return 0;
+}
+
+static int build_attn(Op& op, const bf16* qkp, int ld, const float* E, const uint8_t* mask, bf16* P, int N, int H,
+                      int L, int Lk) {
+    op.type = OP_ATTN;
+    AttnParams& a = op.ap;
+    a.L = L; a.Lk = Lk; a.H = H; a.N = N; a.qd = H * 32;
+    a.qkp = qkp; a.ld = ld; a.E = E; a.mask = mask; a.P = P;
+    if (ld % 8 != 0 || Lk % 8 != 0) return fail(ZVB_ERR_INVALID, "attn: pitches must be multiples of 8");
+    TRY(make_tmap(&op.ma, qkp, ld, L, N, (uint64_t)ld * 2, (uint64_t)ld * 2 * L, ATT_BM));
+    return 0;
+}
+
+static int launch_op(const Op& op, cudaStream_t st) {
+    switch (op.type) {
+        case OP_GEMM: {
+            if (op.grid <= 0) return 0;
+            if (op.kind == EPI_LINEAR)
+                gemm_kernel<EPI_LINEAR><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, op.gp);
+            else if (op.kind == EPI_GATED)
+                gemm_kernel<EPI_GATED><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, op.gp);
+            else
+                gemm_kernel<EPI_MUL><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, op.gp);
+            return check_launch("gemm");
+        }
+        case OP_ATTN: {
+            dim3 grid((op.ap.L + ATT_BM - 1) / ATT_BM, op.ap.H, op.ap.N);
+            attn_weights_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(op.ma, op.ap);
+            return check_launch("attn_weights");
+        }
+        case OP_BIASNORM: {
+            const int blocks = static_cast<int>((op.rows + 7) / 8);
+            biasnorm_bypass_kernel<<<blocks, 256, 0, st>>>(
+                (const bf16*)op.p0, (const bf16*)op.p1, (bf16*)op.o0, (bf16*)op.o1, op.f3, op.i1, op.f0, op.f1, op.f2,
+                op.rows, op.i0);
+            return check_launch("biasnorm_bypass");
+        }
+        case OP_ADDROW: {
+            const long long n = op.rows * (op.i0 / 8);
+            add_rowbias_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)op.p0, (bf16*)op.o0, op.f0,
+                                                                           op.i1, op.rows, op.i0);
+            return check_launch("add_rowbias");
+        }
+        case OP_DOWN: {
+            const long long n = (long long)op.i0 * op.i2 * (op.i4 / 8);
+            downsample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+                (const bf16*)op.p0, (bf16*)op.o0, op.i0, op.i1, op.i2, op.i3, op.w[0], op.w[1], op.w[2], op.w[3], op.i4);
+            return check_launch("downsample");
+        }
+        case OP_UP: {
+            const long long n = (long long)op.i0 * op.i1 * (op.i4 / 8);
+            upsample_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+                (const bf16*)op.p0, (const bf16*)op.p1, (bf16*)op.o0, op.f0, op.i0, op.i1, op.i2, op.i3, op.i4);
+            return check_launch("upsample_combine");
+        }
+        case OP_DWCONV: {
+            const int N = op.i0, L = op.i1, C = op.i2, K = op.i3;
+            dim3 grid((C + 63) / 64, (L + 63) / 64, N);
+            const bf16* x = (const bf16*)op.p0;
+            bf16* o = (bf16*)op.o0;
+            if (K == 7) dwconv_swooshr_kernel<7><<<grid, 256, 0, st>>>(x, o, op.f0, op.f1, L, C);
+            else if (K == 9) dwconv_swooshr_kernel<9><<<grid, 256, 0, st>>>(x, o, op.f0, op.f1, L, C);
+            else if (K == 15) dwconv_swooshr_kernel<15><<<grid, 256, 0, st>>>(x, o, op.f0, op.f1, L, C);
+            else if (K == 31) dwconv_swooshr_kernel<31><<<grid, 256, 0, st>>>(x, o, op.f0, op.f1, L, C);
+            else return fail(ZVB_ERR_INVALID, "depthwise kernel size %d not built (7, 9, 15, 31)", K);
+            return check_launch("dwconv");
+        }
+        case OP_MASK: {
+            const int n = op.i0 * op.i2;
+            stride_mask_kernel<<<(n + 255) / 256, 256, 0, st>>>((const uint8_t*)op.p0, (uint8_t*)op.o0, op.i0, op.i1,
+                                                                 op.i2, op.i3);
+            return check_launch("stride_mask");
+        }
+        case OP_TSEMB: {
+            const int n = op.i0 * (op.i1 / 2);
+            timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, st>>>(op.f0, (float*)op.o0, op.i0, op.i1);
+            return check_launch("timestep_embedding");
+        }
+        case OP_SMALL: {
+            const long long warps = (long long)op.i0 * op.i2;
+            small_linear_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+                op.f0, op.f1, op.f2, op.f3, (float*)op.o0, op.i0, op.i1, op.i2, op.i3, op.i4);
+            return check_launch("small_linear");
+        }
+    }
+    return fail(ZVB_ERR_INVALID, "unknown op");
+}
+
+// ------------------------------------------------------------------------------------------ plan
+struct zvb_plan {
+    int N = 0, T = 0;
+    int D = 0, in_dim = 0, out_dim = 0, xin_pitch = 0, has_time = 0, has_g = 0;
+    zvb_io io{};
+    std::vector<Op> ops;
+};
+
+struct Carver {
+    uint8_t* base;
+    size_t off = 0;
+    explicit Carver(void* b) : base(static_cast<uint8_t*>(b)) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 255) & ~static_cast<size_t>(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+static inline int round8(int x) { return (x + 7) / 8 * 8; }
+
+static Op small_op(const float* in, const float* W, const float* b, const float* addend, float* out, int N, int K,
+                   int O, int act_in, int act_out) {
+    Op op; op.type = OP_SMALL;
+    op.f0 = in; op.f1 = W; op.f2 = b; op.f3 = addend; op.o0 = out;
+    op.i0 = N; op.i1 = K; op.i2 = O; op.i3 = act_in; op.i4 = act_out;
+    return op;
+}
+
+// Builds the plan; with ws == nullptr only measures the workspace.
+static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_out, zvb_plan* plan) {
+    if (m == nullptr || m->abi_version != ZVB_ABI_VERSION) return fail(ZVB_ERR_INVALID, "model description: ABI version mismatch");
+    if (N <= 0 || T <= 0) return fail(ZVB_ERR_INVALID, "N and T must be positive");
+    const int D = m->dim, H = m->num_heads, dv = m->value_head_dim;
+    if (D % 64 != 0 || D > 1024) return fail(ZVB_ERR_INVALID, "dim %d unsupported (multiple of 64, <= 1024)", D);
+    if (m->num_stacks <= 0 || m->num_stacks > ZVB_MAX_STACKS) return fail(ZVB_ERR_INVALID, "bad stack count");
+    const bool building = ws != nullptr;
+    const int hp = (dv + 15) / 16 * 16;
+    const int attn_w = H * (2 * 32 + 4);
+    const int nah = m->na_hidden;
+    const int ffmax = std::max(m->ff_dims[0], std::max(m->ff_dims[1], m->ff_dims[2]));
+    const int xin_pitch = round8(m->in_dim);
+    const long long M = (long long)N * T;
+
+    Carver c(ws);
+    bf16* xin = c.take<bf16>(M * xin_pitch);
+    float* tbuf = c.take<float>(N);
+    float* gbuf = c.take<float>(N);
+    uint8_t* mask = c.take<uint8_t>(M);
+    float* out = c.take<float>(M * m->out_dim);
+    // time embedding chain
+    const int td = m->time_dim;
+    float *te0 = nullptr, *teg = nullptr, *te1 = nullptr, *te2 = nullptr, *te3 = nullptr;
+    float* temb[ZVB_MAX_STACKS] = {};
+    if (td > 0) {
+        te0 = c.take<float>((size_t)N * td);
+        teg = c.take<float>((size_t)N * td);
+        te1 = c.take<float>((size_t)N * 2 * td);
+        te2 = c.take<float>((size_t)N * td);
+        te3 = c.take<float>((size_t)N * td);
+        for (int s = 0; s < m->num_stacks; ++s) temb[s] = c.take<float>((size_t)N * D);
+    }
+    bf16* cur0 = c.take<bf16>(M * D);
+    bf16* cur1 = c.take<bf16>(M * D);
+    bf16* S[2] = {c.take<bf16>(M * D), c.take<bf16>(M * D)};
+    bf16* St[2] = {c.take<bf16>(M * D), c.take<bf16>(M * D)};
+    bf16* R[2] = {c.take<bf16>(M * D), c.take<bf16>(M * D)};
+    bf16* qkp = c.take<bf16>(M * attn_w);
+    bf16* hid = c.take<bf16>(M * ffmax);
+    bf16* nay = c.take<bf16>(M * nah);
+    bf16* pvna = c.take<bf16>(M * nah);
+    bf16* pvsa = c.take<bf16>(M * H * dv);
+    bf16* glu = c.take<bf16>(M * D);
+    bf16* cv = c.take<bf16>(M * D);
+    const int Lk0 = round8(T);
+    bf16* P = c.take<bf16>((size_t)N * H * T * Lk0);
+    // per-resolution buffers (pads of the transposed V stay zero for the lifetime of the plan)
+    bf16 *vtna[5] = {}, *vtsa[5] = {};
+    uint8_t* mask_ds[5] = {};
+    for (int ds = 1; ds <= 4; ds *= 2) {
+        bool used = false;
+        for (int s = 0; s < m->num_stacks; ++s) used |= m->stacks[s].downsample == ds;
+        if (!used) continue;
+        const int L = (T + ds - 1) / ds, Lk = round8(L);
+        vtna[ds] = c.take<bf16>((size_t)N * nah * Lk);
+        vtsa[ds] = c.take<bf16>((size_t)N * H * hp * Lk);
+        mask_ds[ds] = ds == 1 ? mask : c.take<uint8_t>((size_t)N * L);
+    }
+    if (bytes_out) *bytes_out = (c.off + 255) & ~static_cast<size_t>(255);
+    if (!building) return 0;
+
+    plan->N = N; plan->T = T; plan->D = D; plan->in_dim = m->in_dim; plan->out_dim = m->out_dim;
+    plan->xin_pitch = xin_pitch; plan->has_time = td > 0; plan->has_g = m->use_guidance_embed;
+    plan->io.xin = xin; plan->io.t = tbuf; plan->io.g = gbuf; plan->io.mask = mask; plan->io.out = out;
+    plan->io.xin_pitch = xin_pitch;
+    std::vector<Op>& ops = plan->ops;
+
+    // strided masks
+    for (int ds = 2; ds <= 4; ds *= 2) {
+        if (mask_ds[ds] == nullptr) continue;
+        Op op; op.type = OP_MASK; op.p0 = mask; op.o0 = mask_ds[ds];
+        op.i0 = N; op.i1 = T; op.i2 = (T + ds - 1) / ds; op.i3 = ds;
+        ops.push_back(op);
+    }
+    // time embedding chain (reference: modules/zipformer.py:267-278, 676-680, 727-729)
+    if (td > 0) {
+        Op e; e.type = OP_TSEMB; e.f0 = tbuf; e.o0 = te0; e.i0 = N; e.i1 = td;
+        ops.push_back(e);
+        const float* t_in = te0;
+        if (m->use_guidance_embed) {
+            Op eg; eg.type = OP_TSEMB; eg.f0 = gbuf; eg.o0 = teg; eg.i0 = N; eg.i1 = td;
+            ops.push_back(eg);
+            ops.push_back(small_op(teg, m->guidance_w, nullptr, te0, te2, N, td, td, 0, 0));   // te2 = te0 + Wg*emb(g)
+            t_in = te2;
+        }
+        ops.push_back(small_op(t_in, m->time0_w, m->time0_b, nullptr, te1, N, td, 2 * td, 0, ACT_SWOOSH_R_));
+        ops.push_back(small_op(te1, m->time2_w, m->time2_b, nullptr, te3, N, 2 * td, td, 0, 0));
+        for (int s = 0; s < m->num_stacks; ++s)
+            ops.push_back(small_op(te3, m->stacks[s].time_w, m->stacks[s].time_b, nullptr, temb[s], N, td, D,
+                                   ACT_SWOOSH_R_, 0));
+    }
+    // in_proj (reference: modules/zipformer.py:264-265)
+    {
+        Op op; LinearEpi e;
+        TRY(build_linear(op, xin, M, xin_pitch, m->in_proj, cur0, D, e));
+        ops.push_back(op);
+    }
+    bf16* cur = cur0;
+    bf16* cur_alt = cur1;
+
+    for (int s = 0; s < m->num_stacks; ++s) {
+        const zvb_stack& stk = m->stacks[s];
+        const int ds = stk.downsample;
+        if (ds != 1 && ds != 2 && ds != 4) return fail(ZVB_ERR_INVALID, "downsample %d unsupported", ds);
+        const int L = (T + ds - 1) / ds, Lk = round8(L);
+        const long long Ms = (long long)N * L;
+        const float* tb = td > 0 ? temb[s] : nullptr;
+        int si = 0;
+        // stack input -> S[0]
+        if (ds != 1) {   // ds == 1 runs the layers directly on `cur` as the first layer's src
+            Op op; op.type = OP_DOWN; op.p0 = cur; op.o0 = S[0];
+            op.i0 = N; op.i1 = T; op.i2 = L; op.i3 = ds; op.i4 = D;
+            for (int k = 0; k < 4; ++k) op.w[k] = stk.ds_weights[k];
+            ops.push_back(op);
+        }
+        const bf16* src = ds == 1 ? cur : S[0];
+        const bf16* srct = src;
+        if (tb != nullptr) {
+            Op op; op.type = OP_ADDROW; op.p0 = src; op.o0 = St[0]; op.f0 = tb; op.i0 = D; op.i1 = L; op.rows = Ms;
+            ops.push_back(op);
+            srct = St[0];
+        }
+        for (int j = 0; j < stk.num_layers; ++j) {
+            const zvb_layer& ly = m->layers[stk.first_layer + j];
+            const bool last = j == stk.num_layers - 1;
+            Op op;
+            LinearEpi e;
+            // 1. attention projections + weights
+            e = LinearEpi();
+            TRY(build_linear(op, src, Ms, D, ly.attn_in, qkp, attn_w, e)); ops.push_back(op);
+            TRY(build_attn(op, qkp, attn_w, ly.pos_table, mask_ds[ds], P, N, H, L, Lk)); ops.push_back(op);
+            // 2. feed_forward1 on src + temb
+            e = LinearEpi(); e.act = ACT_SWOOSH_L;
+            TRY(build_linear(op, srct, Ms, D, ly.ff_in[0], hid, m->ff_dims[0], e)); ops.push_back(op);
+            e = LinearEpi(); e.resid = srct;
+            TRY(build_linear(op, hid, Ms, m->ff_dims[0], ly.ff_out[0], R[0], D, e)); ops.push_back(op);
+            // 3. nonlin attention
+            e = LinearEpi(); e.transposed = 1; e.t_L = L; e.t_pitch = Lk; e.t_batch_rows = nah; e.t_hd = 1; e.t_hp = 1;
+            TRY(build_gated(op, R[0], Ms, D, ly.na_sx, nah, GATE_TANH_SX, vtna[ds], 0, nullptr, e)); ops.push_back(op);
+            e = LinearEpi();
+            TRY(build_linear(op, R[0], Ms, D, ly.na_y, nay, nah, e)); ops.push_back(op);
+            TRY(build_pv(op, P, vtna[ds], pvna, nah, N, H, L, Lk, nah, nah, 0, nay, nah)); ops.push_back(op);
+            e = LinearEpi(); e.resid = R[0];
+            TRY(build_linear(op, pvna, Ms, nah, ly.na_out, R[1], D, e)); ops.push_back(op);
+            // 4. self_attn1 (+ temb for the conv module that follows)
+            e = LinearEpi(); e.transposed = 1; e.t_L = L; e.t_pitch = Lk; e.t_batch_rows = H * hp; e.t_hd = dv; e.t_hp = hp;
+            TRY(build_linear(op, R[1], Ms, D, ly.sa_in[0], vtsa[ds], 0, e)); ops.push_back(op);
+            TRY(build_pv(op, P, vtsa[ds], pvsa, H * dv, N, H, L, Lk, dv, hp, 1, nullptr, 0)); ops.push_back(op);
+            e = LinearEpi(); e.resid = R[1]; e.rowbias = tb; e.rows_per_group = L;
+            TRY(build_linear(op, pvsa, Ms, H * dv, ly.sa_out[0], R[0], D, e)); ops.push_back(op);
+            // 5. conv_module1
+            e = LinearEpi();
+            TRY(build_gated(op, R[0], Ms, D, ly.conv_in[0], D, GATE_GLU_XS, glu, D, mask_ds[ds], e)); ops.push_back(op);
+            { Op d; d.type = OP_DWCONV; d.p0 = glu; d.o0 = cv; d.f0 = ly.dw_w[0]; d.f1 = ly.dw_b[0];
+              d.i0 = N; d.i1 = L; d.i2 = D; d.i3 = stk.conv_kernel; ops.push_back(d); }
+            e = LinearEpi(); e.resid = R[0];
+            TRY(build_linear(op, cv, Ms, D, ly.conv_out[0], R[1], D, e)); ops.push_back(op);
+            // 6. feed_forward2 + bypass_mid
+            e = LinearEpi(); e.act = ACT_SWOOSH_L;
+            TRY(build_linear(op, R[1], Ms, D, ly.ff_in[1], hid, m->ff_dims[1], e)); ops.push_back(op);
+            e = LinearEpi(); e.resid = R[1]; e.orig = src; e.bypass_scale = ly.bypass_mid_scale;
+            TRY(build_linear(op, hid, Ms, m->ff_dims[1], ly.ff_out[1], R[0], D, e)); ops.push_back(op);
+            // 7. self_attn2 (+ temb)
+            e = LinearEpi(); e.transposed = 1; e.t_L = L; e.t_pitch = Lk; e.t_batch_rows = H * hp; e.t_hd = dv; e.t_hp = hp;
+            TRY(build_linear(op, R[0], Ms, D, ly.sa_in[1], vtsa[ds], 0, e)); ops.push_back(op);
+            TRY(build_pv(op, P, vtsa[ds], pvsa, H * dv, N, H, L, Lk, dv, hp, 1, nullptr, 0)); ops.push_back(op);
+            e = LinearEpi(); e.resid = R[0]; e.rowbias = tb; e.rows_per_group = L;
+            TRY(build_linear(op, pvsa, Ms, H * dv, ly.sa_out[1], R[1], D, e)); ops.push_back(op);
+            // 8. conv_module2
+            e = LinearEpi();
+            TRY(build_gated(op, R[1], Ms, D, ly.conv_in[1], D, GATE_GLU_XS, glu, D, mask_ds[ds], e)); ops.push_back(op);
+            { Op d; d.type = OP_DWCONV; d.p0 = glu; d.o0 = cv; d.f0 = ly.dw_w[1]; d.f1 = ly.dw_b[1];
+              d.i0 = N; d.i1 = L; d.i2 = D; d.i3 = stk.conv_kernel; ops.push_back(d); }
+            e = LinearEpi(); e.resid = R[1];
+            TRY(build_linear(op, cv, Ms, D, ly.conv_out[1], R[0], D, e)); ops.push_back(op);
+            // 9. feed_forward3
+            e = LinearEpi(); e.act = ACT_SWOOSH_L;
+            TRY(build_linear(op, R[0], Ms, D, ly.ff_in[2], hid, m->ff_dims[2], e)); ops.push_back(op);
+            e = LinearEpi(); e.resid = R[0];
+            TRY(build_linear(op, hid, Ms, m->ff_dims[2], ly.ff_out[2], R[1], D, e)); ops.push_back(op);
+            // 10. BiasNorm + bypass -> next layer input (and its time-embedded copy)
+            bf16* nsrc;
+            if (last && ds == 1) nsrc = cur_alt;
+            else nsrc = S[si ^ 1];
+            // S[si ^ 1] never aliases `src`: src is `cur` (ds == 1, first layer) or S[si]
+            bf16* nsrct = (!last && tb != nullptr) ? St[si ^ 1] : nullptr;
+            { Op b; b.type = OP_BIASNORM; b.p0 = R[1]; b.p1 = src; b.o0 = nsrc; b.o1 = nsrct;
+              b.f0 = ly.norm_bias; b.f1 = ly.norm_log_scale; b.f2 = ly.bypass_scale; b.f3 = tb;
+              b.i0 = D; b.i1 = L; b.rows = Ms; ops.push_back(b); }
+            src = nsrc;
+            srct = nsrct != nullptr ? nsrct : nsrc;
+            si ^= 1;
+        }
+        if (ds == 1) {
+            std::swap(cur, cur_alt);        // the last layer wrote into cur_alt
+        } else {
+            Op op; op.type = OP_UP; op.p0 = cur; op.p1 = src; op.o0 = cur_alt; op.f0 = stk.out_combiner_scale;
+            op.i0 = N; op.i1 = T; op.i2 = L; op.i3 = ds; op.i4 = D;
+            ops.push_back(op);
+            std::swap(cur, cur_alt);
+        }
+    }
+    // out_proj (reference: modules/zipformer.py:291)
+    {
+        Op op; LinearEpi e; e.out_f32 = 1;
+        TRY(build_linear(op, cur, M, D, m->out_proj, out, m->out_dim, e));
+        ops.push_back(op);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* zvb_last_error(void) { return g_err.c_str(); }
+int zvb_abi_version(void) { return ZVB_ABI_VERSION; }
+long long zvb_launch_count(void) { return g_launches; }
+
+int zvb_plan_workspace_bytes(const zvb_model* model, int N, int T, size_t* bytes) {
+    if (bytes == nullptr) return fail(ZVB_ERR_INVALID, "bytes is null");
+    return build_plan(model, N, T, nullptr, bytes, nullptr);
+}
+
+int zvb_plan_create(const zvb_model* model, int N, int T, void* workspace, size_t workspace_bytes, zvb_plan** plan) {
+    if (plan == nullptr || workspace == nullptr) return fail(ZVB_ERR_INVALID, "null argument");
+    TRY(init_device());
+    size_t need = 0;
+    TRY(build_plan(model, N, T, nullptr, &need, nullptr));
+    if (workspace_bytes < need) return fail(ZVB_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+    zvb_plan* p = new zvb_plan();
+    int r = build_plan(model, N, T, workspace, nullptr, p);
+    if (r != 0) { delete p; return r; }
+    *plan = p;
+    return 0;
+}
+
+void zvb_plan_destroy(zvb_plan* plan) { delete plan; }
+
+int zvb_plan_io(const zvb_plan* plan, zvb_io* io) {
+    if (plan == nullptr || io == nullptr) return fail(ZVB_ERR_INVALID, "null argument");
+    *io = plan->io;
+    return 0;
+}
+
+int zvb_decoder_forward(zvb_plan* plan, void* stream) {
+    if (plan == nullptr) return fail(ZVB_ERR_INVALID, "null plan");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (const Op& op : plan->ops) TRY(launch_op(op, st));
+    return 0;
+}
+
+int zvb_decoder_forward_f32(zvb_plan* plan, const float* x, const float* t, const uint8_t* mask, const float* g,
+                            float* out, void* stream) {
+    if (plan == nullptr || x == nullptr || mask == nullptr || out == nullptr) return fail(ZVB_ERR_INVALID, "null argument");
+    if (plan->has_time && t == nullptr) return fail(ZVB_ERR_INVALID, "this network needs t");
+    if (plan->has_g && g == nullptr) return fail(ZVB_ERR_INVALID, "this network needs guidance_scale");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long M = (long long)plan->N * plan->T;
+    const long long n = M * plan->xin_pitch;
+    cast_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, (bf16*)plan->io.xin, M, plan->in_dim, plan->xin_pitch);
+    TRY(check_launch("cast_pad"));
+    if (plan->has_time) CUDA_TRY(cudaMemcpyAsync(plan->io.t, t, sizeof(float) * plan->N, cudaMemcpyDeviceToDevice, st));
+    if (plan->has_g) CUDA_TRY(cudaMemcpyAsync(plan->io.g, g, sizeof(float) * plan->N, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(plan->io.mask, mask, (size_t)M, cudaMemcpyDeviceToDevice, st));
+    TRY(zvb_decoder_forward(plan, stream));
+    CUDA_TRY(cudaMemcpyAsync(out, plan->io.out, sizeof(float) * M * plan->out_dim, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// fills a device float array with one value (captured as a kernel so graphs stay replayable)
+__global__ void fill_kernel(float* p, const float* src, int idx, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = src[idx];
+}
+__global__ void copy_scaled_kernel(float* dst, const float* src, float scale, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] * scale;
+}
+
+int zvb_sample(zvb_plan* plan, float* x, const float* text, const float* speech, const uint8_t* mask,
+               const float* guidance, const float* ts, const float* ts_host, int num_step, int mode, int B, int F,
+               int Ft, float* vrec, void* stream) {
+    if (plan == nullptr || x == nullptr || text == nullptr || speech == nullptr || mask == nullptr || ts == nullptr ||
+        ts_host == nullptr)
+        return fail(ZVB_ERR_INVALID, "null argument");
+    if (mode < 0 || mode > 2) return fail(ZVB_ERR_INVALID, "mode must be 0, 1 or 2");
+    const int N = mode == 1 ? 2 * B : B;
+    if (N != plan->N) return fail(ZVB_ERR_INVALID, "plan was built for N=%d rows, call needs %d", plan->N, N);
+    if (2 * F + Ft != plan->in_dim || F != plan->out_dim)
+        return fail(ZVB_ERR_INVALID, "feature dims (%d,%d) do not match the plan (%d,%d)", F, Ft, plan->in_dim, plan->out_dim);
+    if (mode != 0 && guidance == nullptr) return fail(ZVB_ERR_INVALID, "guidance is null");
+    if ((mode == 2) != (plan->has_g != 0)) return fail(ZVB_ERR_INVALID, "mode %d does not match the network (guidance embed %d)", mode, plan->has_g);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int T = plan->T;
+    const long long per_utt = (long long)T * F;
+    const size_t mbytes = (size_t)B * T;
+    CUDA_TRY(cudaMemcpyAsync(plan->io.mask, mask, mbytes, cudaMemcpyDeviceToDevice, st));
+    if (mode == 1) CUDA_TRY(cudaMemcpyAsync(plan->io.mask + mbytes, mask, mbytes, cudaMemcpyDeviceToDevice, st));
+    if (mode == 2) {
+        copy_scaled_kernel<<<(N + 127) / 128, 128, 0, st>>>(plan->io.g, guidance, 1.0f, N);
+        TRY(check_launch("copy_guidance"));
+    }
+    const long long n_in = (long long)N * T * plan->xin_pitch;
+    const long long n_x = (long long)B * per_utt;
+    for (int step = 0; step < num_step; ++step) {
+        const float t = ts_host[step];
+        const int drop_speech = t > 0.5f ? 1 : 0;                 // reference: solver.py:90-98
+        assemble_input_kernel<<<(unsigned)((n_in + 255) / 256), 256, 0, st>>>(
+            x, text, speech, (bf16*)plan->io.xin, B, T, F, Ft, plan->xin_pitch, mode == 1, drop_speech);
+        TRY(check_launch("assemble_input"));
+        fill_kernel<<<(N + 127) / 128, 128, 0, st>>>(plan->io.t, ts, step, N);
+        TRY(check_launch("fill_t"));
+        TRY(zvb_decoder_forward(plan, stream));
+        const float gscale = (mode == 1 && !drop_speech) ? 2.0f : 1.0f;
+        cfg_euler_kernel<<<(unsigned)((n_x + 255) / 256), 256, 0, st>>>(
+            x, plan->io.out, guidance, gscale, ts, step, vrec ? vrec + (long long)step * n_x : nullptr, B, per_utt,
+            mode == 1);
+        TRY(check_launch("cfg_euler"));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ test entry points
+int zvb_test_linear(const void* A, int M, int K, int lda, const void* W, const float* bias, int n_out, int k_pitch,
+                    int block_n, int act, const void* resid, void* out, int ldc, int out_f32, void* stream) {
+    TRY(init_device());
+    zvb_linear lin{W, bias, n_out, K, k_pitch, n_out};
+    Op op; LinearEpi e; e.act = act; e.resid = (const bf16*)resid; e.out_f32 = out_f32; e.block_n = block_n;
+    TRY(build_linear(op, (const bf16*)A, M, lda, lin, out, ldc, e));
+    return launch_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_attn_weights(const void* qkp, int ld, const float* pos_table, const uint8_t* mask, void* P, int N, int H,
+                          int L, int Lk, void* stream) {
+    TRY(init_device());
+    Op op;
+    TRY(build_attn(op, (const bf16*)qkp, ld, pos_table, mask, (bf16*)P, N, H, L, Lk));
+    return launch_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_pv(const void* P, const void* Vt, void* out, int N, int H, int L, int Lk, int hd, int hp, int per_head,
+                void* stream) {
+    TRY(init_device());
+    Op op;
+    const int ldc = per_head ? H * hd : hd;
+    if (per_head) {
+        TRY(build_pv(op, (const bf16*)P, (const bf16*)Vt, out, ldc, N, H, L, Lk, hd, hp, 1, nullptr, 0));
+    } else {
+        // NonlinAttention form without the y gate: reuse the LINEAR epilogue on head-0 weights
+        TRY(build_pv(op, (const bf16*)P, (const bf16*)Vt, out, ldc, N, H, L, Lk, hd, hp, 0, nullptr, 0));
+        op.kind = EPI_LINEAR;
+    }
+    return launch_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_biasnorm_bypass(const void* src, const void* orig, void* out, const float* nbias, const float* log_scale,
+                             const float* bscale, long long rows, int C, void* stream) {
+    Op b; b.type = OP_BIASNORM; b.p0 = src; b.p1 = orig; b.o0 = out; b.o1 = nullptr;
+    b.f0 = nbias; b.f1 = log_scale; b.f2 = bscale; b.f3 = nullptr; b.i0 = C; b.i1 = 1; b.rows = rows;
+    return launch_op(b, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_dwconv(const void* x, void* out, const float* wt, const float* bias, int N, int L, int C, int K,
+                    void* stream) {
+    Op d; d.type = OP_DWCONV; d.p0 = x; d.o0 = out; d.f0 = wt; d.f1 = bias; d.i0 = N; d.i1 = L; d.i2 = C; d.i3 = K;
+    return launch_op(d, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_cfg_euler(float* x, const float* v, const float* guidance, float gscale, const float* ts, int step, int B,
+                       long long per_utt, int cfg, void* stream) {
+    const long long n = (long long)B * per_utt;
+    cfg_euler_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, v, guidance, gscale, ts, step, nullptr, B, per_utt, cfg);
+    return check_launch("cfg_euler");
+}
+
+}  // extern "C"

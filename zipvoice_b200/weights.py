@@ -1,0 +1,233 @@
+"""Weight packer: reference-format fp32 `state_dict` -> device buffers laid out for the kernels.
+
+* every nn.Linear weight becomes bf16 row-major (out, k_pitch) with k_pitch = ceil8(in), zero
+  padded (TMA needs 16-byte row pitches; out-of-range rows/cols are zero-filled by TMA);
+* projections followed by a gate are re-ordered per 256-row tile as [128 | 128] so that both
+  gate operands of an output column land in one accumulator tile:
+    NonlinAttention.in_proj rows (s | x)  (reference: modules/zipformer.py:1516-1525),
+    ConvolutionModule.in_proj rows (x | s) (reference: modules/zipformer.py:1657-1661);
+* the depthwise kernel (D,1,K) is transposed to fp32 [K][D]; softmax(downsample.bias) and the
+  per-layer rel-pos table E = linear_pos(pos_emb) (reference: modules/zipformer.py:995-1056,
+  1215-1219) are folded on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from .config import ZipformerConfig
+
+
+def _ceil8(x: int) -> int:
+    return (x + 7) // 8 * 8
+
+
+def rel_pos_embedding(L: int, pos_dim: int, device) -> torch.Tensor:
+    """CompactRelPositionalEncoding rows for offsets -(L-1)..(L-1) (reference:
+    modules/zipformer.py:995-1056), shape (2L-1, pos_dim) fp32."""
+    x = torch.arange(-(L - 1), L, device=device, dtype=torch.float32).unsqueeze(1)
+    freqs = 1 + torch.arange(pos_dim // 2, device=device)
+    cl = pos_dim ** 0.5
+    xc = cl * x.sign() * ((x.abs() + cl).log() - math.log(cl))
+    xa = (xc / (pos_dim / (2.0 * math.pi))).atan()
+    pe = torch.zeros(x.shape[0], pos_dim, device=device)
+    pe[:, 0::2] = (xa * freqs).cos()
+    pe[:, 1::2] = (xa * freqs).sin()
+    pe[:, -1] = 1.0
+    return pe
+
+
+class PackedZipformer:
+    """Device-resident weights of one TTSZipformer plus builders for the `zvb_model` struct."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, cfg: ZipformerConfig, device,
+                 stream_index: int = 0):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.prefix = prefix
+        self._keep: List[torch.Tensor] = []
+        self._sd = sd
+        c = cfg
+        if len(c.in_dims) == 1:
+            pin, pout = prefix + "in_proj", prefix + "out_proj"
+        else:
+            pin, pout = prefix + f"in_proj.{stream_index}", prefix + f"out_proj.{stream_index}"
+        self.in_dim = c.in_dims[stream_index]
+        self.out_dim = c.out_dims[stream_index]
+        self.in_proj = self._linear(pin)
+        self.out_proj = self._linear(pout)
+        self.time = None
+        if c.time_embed_dim != -1:
+            self.time = dict(w0=self._f32(prefix + "time_embed.0.weight"), b0=self._f32(prefix + "time_embed.0.bias"),
+                             w2=self._f32(prefix + "time_embed.2.weight"), b2=self._f32(prefix + "time_embed.2.bias"),
+                             g=self._f32(prefix + "guidance_scale_embed.weight") if c.use_guidance_scale_embed else None)
+        self.stacks = []
+        self.layers = []
+        self.linear_pos = []            # per layer (H*4, pos_dim) fp32 on device
+        for s, (ds, nl, k) in enumerate(zip(c.downsampling_factor, c.num_layers, c.cnn_kernel)):
+            sp = prefix + f"encoders.{s}."
+            st = dict(ds=ds, nl=nl, k=k, first=len(self.layers), dsw=[1.0, 0.0, 0.0, 0.0], comb=None,
+                      tw=None, tb=None)
+            if ds != 1:
+                w = torch.softmax(sd[sp + "downsample.bias"].float().cpu(), dim=0).tolist()
+                st["dsw"] = (w + [0.0] * 4)[:4]
+                st["comb"] = self._f32(sp + "out_combiner.bypass_scale")
+                sp = sp + "encoder."
+            if c.time_embed_dim != -1:
+                st["tw"] = self._f32(sp + "time_emb.1.weight")
+                st["tb"] = self._f32(sp + "time_emb.1.bias")
+            for j in range(nl):
+                self.layers.append(self._layer(sp + f"layers.{j}.", k))
+            self.stacks.append(st)
+        self._sd = None
+        self._pos_cache: Dict[int, List[torch.Tensor]] = {}
+
+    # ------------------------------------------------------------------ tensor helpers
+    def _dev(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.contiguous().to(self.device)
+        self._keep.append(t)
+        return t
+
+    def _f32(self, key: str) -> torch.Tensor:
+        return self._dev(self._sd[key].detach().float())
+
+    def _pack_w(self, w: torch.Tensor) -> torch.Tensor:
+        out_f, in_f = w.shape
+        kp = _ceil8(in_f)
+        buf = torch.zeros(out_f, kp, dtype=torch.bfloat16)
+        buf[:, :in_f] = w.to(torch.bfloat16)
+        return self._dev(buf)
+
+    def _mk(self, w_dev: torch.Tensor, b_dev: Optional[torch.Tensor], out_f: int, in_f: int):
+        return dict(w=w_dev, b=b_dev, out=out_f, inf=in_f, kp=w_dev.shape[1], rows=w_dev.shape[0])
+
+    def _linear(self, p: str, rows: Optional[slice] = None):
+        w = self._sd[p + ".weight"].detach().float().cpu()
+        b = self._sd.get(p + ".bias")
+        if rows is not None:
+            w = w[rows]
+            b = b[rows] if b is not None else None
+        bd = self._dev(b.detach().float()) if b is not None else None
+        return self._mk(self._pack_w(w), bd, w.shape[0], w.shape[1])
+
+    def _gated(self, p: str, a: slice, b: slice):
+        w = self._sd[p + ".weight"].detach().float().cpu()
+        bias = self._sd[p + ".bias"].detach().float().cpu()
+        wa, wb, ba, bb = w[a], w[b], bias[a], bias[b]
+        n, in_f = wa.shape
+        tiles = (n + 127) // 128
+        W = torch.zeros(tiles * 256, in_f)
+        Bv = torch.zeros(tiles * 256)
+        for t in range(tiles):
+            r = min(128, n - t * 128)
+            W[t * 256: t * 256 + r] = wa[t * 128: t * 128 + r]
+            W[t * 256 + 128: t * 256 + 128 + r] = wb[t * 128: t * 128 + r]
+            Bv[t * 256: t * 256 + r] = ba[t * 128: t * 128 + r]
+            Bv[t * 256 + 128: t * 256 + 128 + r] = bb[t * 128: t * 128 + r]
+        return self._mk(self._pack_w(W), self._dev(Bv), n, in_f)
+
+    def _layer(self, p: str, k: int):
+        c = self.cfg
+        D, nah = c.dim, c.na_hidden
+        ly = dict(
+            attn_in=self._linear(p + "self_attn_weights.in_proj"),
+            ff_in=[self._linear(p + f"feed_forward{i}.in_proj") for i in (1, 2, 3)],
+            ff_out=[self._linear(p + f"feed_forward{i}.out_proj") for i in (1, 2, 3)],
+            na_sx=self._gated(p + "nonlin_attention.in_proj", slice(0, nah), slice(nah, 2 * nah)),
+            na_y=self._linear(p + "nonlin_attention.in_proj", slice(2 * nah, 3 * nah)),
+            na_out=self._linear(p + "nonlin_attention.out_proj"),
+            sa_in=[self._linear(p + f"self_attn{i}.in_proj") for i in (1, 2)],
+            sa_out=[self._linear(p + f"self_attn{i}.out_proj") for i in (1, 2)],
+            conv_in=[self._gated(p + f"conv_module{i}.in_proj", slice(0, D), slice(D, 2 * D)) for i in (1, 2)],
+            dw_w=[self._dev(self._sd[p + f"conv_module{i}.depthwise_conv.weight"].detach().float()
+                            .reshape(D, k).t()) for i in (1, 2)],
+            dw_b=[self._f32(p + f"conv_module{i}.depthwise_conv.bias") for i in (1, 2)],
+            conv_out=[self._linear(p + f"conv_module{i}.out_proj") for i in (1, 2)],
+            norm_bias=self._f32(p + "norm.bias"),
+            norm_log_scale=self._dev(self._sd[p + "norm.log_scale"].detach().float().reshape(1)),
+            bypass=self._f32(p + "bypass.bypass_scale"),
+            bypass_mid=self._f32(p + "bypass_mid.bypass_scale"),
+        )
+        self.linear_pos.append(self._f32(p + "self_attn_weights.linear_pos.weight"))
+        return ly
+
+    # ------------------------------------------------------------------ struct builders
+    def pos_tables(self, L: int) -> List[torch.Tensor]:
+        """Per-layer E[h][r][c] = sum_d W_pos[h*4+c][d] * pe[r][d], fp32 (H, 2L-1, 4)."""
+        if L not in self._pos_cache:
+            c = self.cfg
+            pe = rel_pos_embedding(L, c.pos_dim, self.device)
+            tabs = []
+            for wp in self.linear_pos:
+                e = (pe @ wp.t()).reshape(2 * L - 1, c.num_heads, c.pos_head_dim).permute(1, 0, 2)
+                tabs.append(e.contiguous())
+            self._pos_cache[L] = tabs
+        return self._pos_cache[L]
+
+    @staticmethod
+    def _lin_struct(d) -> _lib.zvb_linear:
+        return _lib.zvb_linear(d["w"].data_ptr(), d["b"].data_ptr() if d["b"] is not None else None,
+                               d["out"], d["inf"], d["kp"], d["rows"])
+
+    def model_struct(self, T: int):
+        """Returns (zvb_model, keepalive) for a plan over T frames."""
+        c = self.cfg
+        assert c.query_head_dim == 32 and c.pos_head_dim == 4, "kernels are built for q/k dim 32, pos dim 4"
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        nl = len(self.layers)
+        arr = (_lib.zvb_layer * nl)()
+        keep = [arr]
+        li = 0
+        m = _lib.zvb_model()
+        for s, st in enumerate(self.stacks):
+            L = (T + st["ds"] - 1) // st["ds"]
+            tabs = self.pos_tables(L)
+            keep.append(tabs)
+            for j in range(st["nl"]):
+                ly, z = self.layers[li], arr[li]
+                z.attn_in = self._lin_struct(ly["attn_in"])
+                z.pos_table = tabs[li].data_ptr()
+                for i in range(3):
+                    z.ff_in[i] = self._lin_struct(ly["ff_in"][i])
+                    z.ff_out[i] = self._lin_struct(ly["ff_out"][i])
+                z.na_sx = self._lin_struct(ly["na_sx"])
+                z.na_y = self._lin_struct(ly["na_y"])
+                z.na_out = self._lin_struct(ly["na_out"])
+                for i in range(2):
+                    z.sa_in[i] = self._lin_struct(ly["sa_in"][i])
+                    z.sa_out[i] = self._lin_struct(ly["sa_out"][i])
+                    z.conv_in[i] = self._lin_struct(ly["conv_in"][i])
+                    z.dw_w[i] = ly["dw_w"][i].data_ptr()
+                    z.dw_b[i] = ly["dw_b"][i].data_ptr()
+                    z.conv_out[i] = self._lin_struct(ly["conv_out"][i])
+                z.norm_bias = ly["norm_bias"].data_ptr()
+                z.norm_log_scale = ly["norm_log_scale"].data_ptr()
+                z.bypass_scale = ly["bypass"].data_ptr()
+                z.bypass_mid_scale = ly["bypass_mid"].data_ptr()
+                li += 1
+            zs = m.stacks[s]
+            zs.downsample, zs.num_layers, zs.conv_kernel, zs.first_layer = st["ds"], st["nl"], st["k"], st["first"]
+            for i in range(4):
+                zs.ds_weights[i] = st["dsw"][i]
+            zs.out_combiner_scale = ptr(st["comb"])
+            zs.time_w, zs.time_b = ptr(st["tw"]), ptr(st["tb"])
+        m.abi_version = _lib.ZVB_ABI_VERSION
+        m.dim, m.num_heads, m.value_head_dim = c.dim, c.num_heads, c.value_head_dim
+        m.in_dim, m.out_dim = self.in_dim, self.out_dim
+        for i in range(3):
+            m.ff_dims[i] = c.ff_dims[i]
+        m.na_hidden = c.na_hidden
+        m.time_dim = c.time_embed_dim if c.time_embed_dim != -1 else 0
+        m.use_guidance_embed = 1 if c.use_guidance_scale_embed else 0
+        m.num_stacks, m.num_layers = len(self.stacks), nl
+        m.in_proj, m.out_proj = self._lin_struct(self.in_proj), self._lin_struct(self.out_proj)
+        if self.time is not None:
+            m.time0_w, m.time0_b = self.time["w0"].data_ptr(), self.time["b0"].data_ptr()
+            m.time2_w, m.time2_b = self.time["w2"].data_ptr(), self.time["b2"].data_ptr()
+            m.guidance_w = ptr(self.time["g"])
+        m.layers = C.cast(arr, C.POINTER(_lib.zvb_layer))
+        return m, keep
