@@ -137,6 +137,18 @@ int zvb_plan_io(const zvb_plan* plan, zvb_io* io);
 /* Forward over the resident io buffers: out = fm_decoder(xin, t, mask[, g]). */
 int zvb_decoder_forward(zvb_plan* plan, void* stream);
 
+/* Profiling aid (NOT graph capturable: records one CUDA event per kernel and synchronises the
+ * stream): runs one forward over the resident io buffers and returns, per launched kernel, its
+ * duration in ms, its zvb_op_category and its algorithmic work (FLOPs for the tensor-core
+ * kernels, bytes for the memory-bound ones). */
+typedef enum {
+    ZVB_CAT_GEMM_LINEAR = 0, ZVB_CAT_GEMM_GATED = 1, ZVB_CAT_GEMM_PV = 2, ZVB_CAT_ATTN_WEIGHTS = 3,
+    ZVB_CAT_BIASNORM = 4, ZVB_CAT_ELEMENTWISE = 5, ZVB_CAT_RESAMPLE = 6, ZVB_CAT_DWCONV = 7,
+    ZVB_CAT_OTHER = 8
+} zvb_op_category;
+int zvb_decoder_profile(zvb_plan* plan, void* stream, int max_ops, float* ms, int* category, double* work,
+                        int* num_ops);
+
 /* Seam 1: x fp32 [N][T][in_dim], t fp32 [N] (null for the text encoder), mask u8 [N][T],
  * g fp32 [N] or null, out fp32 [N][T][out_dim]. */
 int zvb_decoder_forward_f32(zvb_plan* plan, const float* x, const float* t, const uint8_t* mask,

@@ -115,6 +115,10 @@ struct Op {
     long long rows = 0;
     int i0 = 0, i1 = 0, i2 = 0, i3 = 0, i4 = 0, i5 = 0;
     float w[4] = {0, 0, 0, 0};
+    // profiling metadata: category (zvb_op_category) and algorithmic work (FLOPs for the tensor-core
+    // kernels, bytes for the memory-bound ones)
+    int cat = ZVB_CAT_OTHER;
+    double work = 0.0;
 };
 
 static int pick_block_n(int n_out, long long m_tiles) {
@@ -174,6 +178,8 @@ static int build_linear(Op& op, const bf16* A, long long M, int lda, const zvb_l
     TRY(make_tmap(&op.mb, lin.w, K, lin.rows, 1, (uint64_t)lin.k_pitch * 2, (uint64_t)lin.k_pitch * 2 * lin.rows, bn));
     const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
     op.grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+    op.cat = ZVB_CAT_GEMM_LINEAR;
+    op.work = 2.0 * (double)M * lin.out_features * lin.in_features;
     return 0;
 }
 
@@ -204,6 +210,8 @@ static int build_gated(Op& op, const bf16* A, long long M, int lda, const zvb_li
     TRY(make_tmap(&op.mb, lin.w, K, lin.rows, 1, (uint64_t)lin.k_pitch * 2, (uint64_t)lin.k_pitch * 2 * lin.rows, 256));
     const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
     op.grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+    op.cat = ZVB_CAT_GEMM_GATED;
+    op.work = 2.0 * (double)M * (2.0 * n_out) * lin.in_features;
     return 0;
 }
 
@@ -241,6 +249,8 @@ static int build_pv(Op& op, const bf16* P, const bf16* Vt, void* out, int ldc, i
     TRY(make_tmap(&op.mb, Vt, Lk, vt_rows, N, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * vt_rows, p.block_n));
     const long long tiles = (long long)p.batches * p.num_m_tiles * p.num_n_tiles;
     op.grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+    op.cat = ZVB_CAT_GEMM_PV;
+    op.work = 2.0 * (double)N * (per_head ? H : 1) * (double)L * L * hd;
     return 0;
 }
 
@@ -252,6 +262,9 @@ static int build_attn(Op& op, const bf16* qkp, int ld, const float* E, const uin
     a.qkp = qkp; a.ld = ld; a.E = E; a.mask = mask; a.P = P;
     if (ld % 8 != 0 || Lk % 8 != 0) return fail(ZVB_ERR_INVALID, "attn: pitches must be multiples of 8");
     TRY(make_tmap(&op.ma, qkp, ld, L, N, (uint64_t)ld * 2, (uint64_t)ld * 2 * L, ATT_BM));
+    op.cat = ZVB_CAT_ATTN_WEIGHTS;
+    // q.k (K = 32) + rel-pos (4-dim dot against 2L-1 offsets), reference FLOP model SURVEY.md §8d
+    op.work = (double)N * H * (2.0 * L * L * 32 + 2.0 * L * (2.0 * L - 1) * 4);
     return 0;
 }
 
@@ -475,12 +488,14 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             Op op; op.type = OP_DOWN; op.p0 = cur; op.o0 = S[0];
             op.i0 = N; op.i1 = T; op.i2 = L; op.i3 = ds; op.i4 = D;
             for (int k = 0; k < 4; ++k) op.w[k] = stk.ds_weights[k];
+            op.cat = ZVB_CAT_RESAMPLE; op.work = 2.0 * ((double)M + (double)Ms) * D;
             ops.push_back(op);
         }
         const bf16* src = ds == 1 ? cur : S[0];
         const bf16* srct = src;
         if (tb != nullptr) {
             Op op; op.type = OP_ADDROW; op.p0 = src; op.o0 = St[0]; op.f0 = tb; op.i0 = D; op.i1 = L; op.rows = Ms;
+            op.cat = ZVB_CAT_ELEMENTWISE; op.work = 2.0 * 2.0 * (double)Ms * D;
             ops.push_back(op);
             srct = St[0];
         }
@@ -516,7 +531,8 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             e = LinearEpi();
             TRY(build_gated(op, R[0], Ms, D, ly.conv_in[0], D, GATE_GLU_XS, glu, D, mask_ds[ds], e)); ops.push_back(op);
             { Op d; d.type = OP_DWCONV; d.p0 = glu; d.o0 = cv; d.f0 = ly.dw_w[0]; d.f1 = ly.dw_b[0];
-              d.i0 = N; d.i1 = L; d.i2 = D; d.i3 = stk.conv_kernel; ops.push_back(d); }
+              d.i0 = N; d.i1 = L; d.i2 = D; d.i3 = stk.conv_kernel;
+              d.cat = ZVB_CAT_DWCONV; d.work = 2.0 * 2.0 * (double)Ms * D; ops.push_back(d); }
             e = LinearEpi(); e.resid = R[0];
             TRY(build_linear(op, cv, Ms, D, ly.conv_out[0], R[1], D, e)); ops.push_back(op);
             // 6. feed_forward2 + bypass_mid
@@ -534,7 +550,8 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             e = LinearEpi();
             TRY(build_gated(op, R[1], Ms, D, ly.conv_in[1], D, GATE_GLU_XS, glu, D, mask_ds[ds], e)); ops.push_back(op);
             { Op d; d.type = OP_DWCONV; d.p0 = glu; d.o0 = cv; d.f0 = ly.dw_w[1]; d.f1 = ly.dw_b[1];
-              d.i0 = N; d.i1 = L; d.i2 = D; d.i3 = stk.conv_kernel; ops.push_back(d); }
+              d.i0 = N; d.i1 = L; d.i2 = D; d.i3 = stk.conv_kernel;
+              d.cat = ZVB_CAT_DWCONV; d.work = 2.0 * 2.0 * (double)Ms * D; ops.push_back(d); }
             e = LinearEpi(); e.resid = R[1];
             TRY(build_linear(op, cv, Ms, D, ly.conv_out[1], R[0], D, e)); ops.push_back(op);
             // 9. feed_forward3
@@ -550,7 +567,8 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             bf16* nsrct = (!last && tb != nullptr) ? St[si ^ 1] : nullptr;
             { Op b; b.type = OP_BIASNORM; b.p0 = R[1]; b.p1 = src; b.o0 = nsrc; b.o1 = nsrct;
               b.f0 = ly.norm_bias; b.f1 = ly.norm_log_scale; b.f2 = ly.bypass_scale; b.f3 = tb;
-              b.i0 = D; b.i1 = L; b.rows = Ms; ops.push_back(b); }
+              b.i0 = D; b.i1 = L; b.rows = Ms;
+              b.cat = ZVB_CAT_BIASNORM; b.work = 2.0 * (double)Ms * D * (nsrct != nullptr ? 4 : 3); ops.push_back(b); }
             src = nsrc;
             srct = nsrct != nullptr ? nsrct : nsrc;
             si ^= 1;
@@ -560,6 +578,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
         } else {
             Op op; op.type = OP_UP; op.p0 = cur; op.p1 = src; op.o0 = cur_alt; op.f0 = stk.out_combiner_scale;
             op.i0 = N; op.i1 = T; op.i2 = L; op.i3 = ds; op.i4 = D;
+            op.cat = ZVB_CAT_RESAMPLE; op.work = 2.0 * (2.0 * (double)M + (double)Ms) * D;
             ops.push_back(op);
             std::swap(cur, cur_alt);
         }
@@ -611,6 +630,32 @@ int zvb_decoder_forward(zvb_plan* plan, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     for (const Op& op : plan->ops) TRY(launch_op(op, st));
     return 0;
+}
+
+int zvb_decoder_profile(zvb_plan* plan, void* stream, int max_ops, float* ms, int* category, double* work,
+                        int* num_ops) {
+    if (plan == nullptr || ms == nullptr || category == nullptr || work == nullptr || num_ops == nullptr)
+        return fail(ZVB_ERR_INVALID, "null argument");
+    const int n = static_cast<int>(plan->ops.size());
+    *num_ops = n;
+    if (n > max_ops) return fail(ZVB_ERR_INVALID, "profile buffers too small: %d ops", n);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaEventRecord(ev[0], st));
+    int rc = 0;
+    for (int i = 0; i < n && rc == 0; ++i) {
+        rc = launch_op(plan->ops[i], st);
+        if (rc == 0 && cudaEventRecord(ev[i + 1], st) != cudaSuccess) rc = fail(ZVB_ERR_CUDA, "event record");
+    }
+    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(ZVB_ERR_CUDA, "profile: stream sync failed");
+    for (int i = 0; i < n && rc == 0; ++i) {
+        cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+        category[i] = plan->ops[i].cat;
+        work[i] = plan->ops[i].work;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
 }
 
 int zvb_decoder_forward_f32(zvb_plan* plan, const float* x, const float* t, const uint8_t* mask, const float* g,

@@ -69,6 +69,20 @@ class DecoderPlan:
                 g32.data_ptr() if g32 is not None else None, out.data_ptr(), _stream_ptr()))
         return out
 
+    def profile(self):
+        """One forward over the resident buffers with a CUDA event per kernel (synchronises).
+        Returns a list of (category name, milliseconds, algorithmic work)."""
+        import numpy as np
+        cap = 4096
+        ms = np.zeros(cap, dtype=np.float32)
+        cat = np.zeros(cap, dtype=np.int32)
+        work = np.zeros(cap, dtype=np.float64)
+        n = C.c_int(0)
+        with torch.cuda.device(self.packed.device):
+            _lib.check(self.lib.zvb_decoder_profile(self.handle, _stream_ptr(), cap, ms.ctypes.data, cat.ctypes.data,
+                                                    work.ctypes.data, C.byref(n)))
+        return [(_lib.CATEGORIES[int(cat[i])], float(ms[i]), float(work[i])) for i in range(n.value)]
+
     def sample(self, x: torch.Tensor, text: torch.Tensor, speech: torch.Tensor, mask8: torch.Tensor,
                guidance: Optional[torch.Tensor], ts_dev: torch.Tensor, ts_host: torch.Tensor, num_step: int,
                mode: int, vrec: Optional[torch.Tensor] = None) -> None:

@@ -21,6 +21,14 @@ import torch
 from .config import ZipVoiceConfig, ZipformerConfig
 
 
+# Gains over the reference initialisers (see module docstring): chosen so that attention scores
+# have a spread of a few units (peaky but not arg-max) while the reference's own bf16-autocast
+# deviation from fp32 on these weights stays below 1e-2 rel-L2 per velocity (tools/make_golden.py
+# prints it), i.e. the synthetic network is as well conditioned as a trained one.
+GAINS = dict(attn=2.0, pos=6.0, sa_out=3.0, ff_in=1.0, ff_out=2.0, na_in=1.0, na_out=3.0, conv_in=1.0,
+             conv_out=3.0)
+
+
 class _Gen:
     def __init__(self, seed: int):
         self.g = torch.Generator(device="cpu")
@@ -47,27 +55,29 @@ def _layer(sd, g: _Gen, p: str, c: ZipformerConfig, kernel: int):
     sd[p + "bypass.bypass_scale"] = g.uniform((D,), 0.3) + 0.6
     sd[p + "bypass_mid.bypass_scale"] = g.uniform((D,), 0.3) + 0.6
     # attention: initial_scale = query_head_dim**-0.25 (reference: zipformer.py:1108-1113);
-    # gain 6 gives score std of a few units instead of ~0.05.
+    # the gain gives a score spread of a few units instead of ~0.05 at a fresh init.
     _linear(sd, g, p + "self_attn_weights.in_proj", c.attn_in_dim, D,
-            scale=c.query_head_dim ** -0.25, scaled=True, gain=6.0)
+            scale=c.query_head_dim ** -0.25, scaled=True, gain=GAINS["attn"])
     _linear(sd, g, p + "self_attn_weights.linear_pos", H * c.pos_head_dim, c.pos_dim,
-            scale=0.05, bias=False, gain=20.0)
+            scale=0.05, bias=False, gain=GAINS["pos"])
     for i in (1, 2):
         _linear(sd, g, p + f"self_attn{i}.in_proj", H * c.value_head_dim, D)
         _linear(sd, g, p + f"self_attn{i}.out_proj", D, H * c.value_head_dim, scale=0.05,
-                scaled=True, gain=8.0)
+                scaled=True, gain=GAINS["sa_out"])
     for i, f in zip((1, 2, 3), c.ff_dims):
-        _linear(sd, g, p + f"feed_forward{i}.in_proj", f, D, gain=2.0)
-        _linear(sd, g, p + f"feed_forward{i}.out_proj", D, f, scale=0.1, scaled=True, gain=4.0)
-    _linear(sd, g, p + "nonlin_attention.in_proj", 3 * c.na_hidden, D, gain=2.0)
+        _linear(sd, g, p + f"feed_forward{i}.in_proj", f, D, gain=GAINS["ff_in"])
+        _linear(sd, g, p + f"feed_forward{i}.out_proj", D, f, scale=0.1, scaled=True,
+                gain=GAINS["ff_out"])
+    _linear(sd, g, p + "nonlin_attention.in_proj", 3 * c.na_hidden, D, gain=GAINS["na_in"])
     _linear(sd, g, p + "nonlin_attention.out_proj", D, c.na_hidden, scale=0.05, scaled=True,
-            gain=8.0)
+            gain=GAINS["na_out"])
     for i in (1, 2):
-        _linear(sd, g, p + f"conv_module{i}.in_proj", 2 * D, D, gain=2.0)
+        _linear(sd, g, p + f"conv_module{i}.in_proj", 2 * D, D, gain=GAINS["conv_in"])
         kb = 1.0 / math.sqrt(kernel)
         sd[p + f"conv_module{i}.depthwise_conv.weight"] = g.uniform((D, 1, kernel), kb)
         sd[p + f"conv_module{i}.depthwise_conv.bias"] = g.uniform((D,), kb)
-        _linear(sd, g, p + f"conv_module{i}.out_proj", D, D, scale=0.05, scaled=True, gain=8.0)
+        _linear(sd, g, p + f"conv_module{i}.out_proj", D, D, scale=0.05, scaled=True,
+                gain=GAINS["conv_out"])
     sd[p + "norm.log_scale"] = g.normal((), 0.2, 0.5)
     sd[p + "norm.bias"] = g.normal((D,), 0.1)
 
