@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library builds for sm_100a without a GPU, loads, and exports every symbol that
+include/zipvoice_b200.h declares; host-only entry points work; compute entry points fail loudly."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+import __graft_entry__ as entry
+from zipvoice_b200 import _lib
+from zipvoice_b200.config import ZipVoiceConfig, tiny_config
+from zipvoice_b200.synth import synth_state_dict
+from zipvoice_b200.weights import PackedZipformer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    entry.build()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    header = open(os.path.join(ROOT, "include", "zipvoice_b200.h")).read()
+    declared = set(re.findall(r"\b(zvb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    raw = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert lib.zvb_abi_version() == _lib.ZVB_ABI_VERSION
+
+
+def test_library_is_sm100a_tcgen05_tma():
+    sass = os.popen(f"cuobjdump -sass {_lib.LIB_PATH} 2>/dev/null").read()
+    if not sass:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):     # tcgen05.mma / TMA load / tcgen05.ld
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16816" not in sass                      # no legacy mma.sync path
+
+
+def test_workspace_sizing_is_host_only(lib):
+    cfg = ZipVoiceConfig()
+    pk = PackedZipformer(synth_state_dict(tiny_config()), "fm_decoder.", tiny_config().fm_decoder(), "cpu")
+    m, keep = pk.model_struct(200)
+    n = C.c_size_t()
+    assert lib.zvb_plan_workspace_bytes(C.byref(m), 4, 200, C.byref(n)) == 0
+    small = n.value
+    assert lib.zvb_plan_workspace_bytes(C.byref(m), 8, 200, C.byref(n)) == 0
+    assert n.value > small > 0
+    assert lib.zvb_plan_workspace_bytes(C.byref(m), 0, 200, C.byref(n)) == _lib.ZVB_ABI_VERSION * -1  # ZVB_ERR_INVALID
+    assert b"positive" in lib.zvb_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(lib):
+    from zipvoice_b200.model import build_model
+    cfg = tiny_config()
+    pk = PackedZipformer(synth_state_dict(cfg), "fm_decoder.", cfg.fm_decoder(), "cpu")
+    m, keep = pk.model_struct(64)
+    ws = torch.zeros(1 << 20, dtype=torch.uint8)
+    h = C.c_void_p()
+    rc = lib.zvb_plan_create(C.byref(m), 2, 64, ws.data_ptr(), ws.numel(), C.byref(h))
+    assert rc in (-4, -2), rc                           # no device (or workspace) -- never a silent CPU path
+    model = build_model(cfg, synth_state_dict(cfg), "cpu")
+    with pytest.raises(_lib.ZvbError):
+        model.sample([[1, 2]], [[3]], torch.zeros(1, 4, 100), torch.tensor([4]), num_step=1)

@@ -1,0 +1,57 @@
+"""CPU, world_size 2 over gloo: the multi-GPU path's host logic -- deterministic utterance
+partition, per-rank work on its own shard, one all_gather of mels+lengths, original order restored."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from zipvoice_b200.sharding import gather_mels, partition_utterances
+
+
+def _fake_mel(uid: int, length: int, F: int) -> torch.Tensor:
+    return (torch.arange(length * F, dtype=torch.float32).reshape(length, F) % 17) + 100.0 * uid
+
+
+def _worker(rank: int, world: int, port: int, lens, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    F, U, maxf = 8, len(lens), max(lens)
+    shard = partition_utterances(lens, world)[rank]
+    Tr = max(lens[i] for i in shard)
+    mel = torch.zeros(len(shard), Tr, F)
+    for k, uid in enumerate(shard):
+        mel[k, : lens[uid]] = _fake_mel(uid, lens[uid], F)
+    out, out_lens = gather_mels(mel, torch.tensor([lens[i] for i in shard]), shard, U, maxf)
+    ok = out_lens.tolist() == list(lens)
+    for uid in range(U):
+        ok &= bool(torch.equal(out[uid, : lens[uid]], _fake_mel(uid, lens[uid], F)))
+        ok &= float(out[uid, lens[uid]:].abs().sum()) == 0.0
+    out_q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_partition_and_gather_world2():
+    lens = [37, 12, 50, 44, 9, 28, 31]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, lens, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == {0: True, 1: True}
+
+
+def test_gather_single_process():
+    lens = [5, 3]
+    mel = torch.zeros(2, 5, 4)
+    mel[0, :5] = 1.0
+    mel[1, :3] = 2.0
+    out, ol = gather_mels(mel, torch.tensor(lens), [0, 1], 2, 5)
+    assert ol.tolist() == lens and torch.equal(out, mel)
