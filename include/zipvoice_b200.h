@@ -170,16 +170,21 @@ int zvb_sample(zvb_plan* plan, float* x, const float* text, const float* speech,
 
 /* ---- single-kernel entry points used by the parity tests -------------------------------- */
 /* C = epilogue(A·Wᵀ): A bf16 [M][lda], W bf16 [n_out][k_pitch]; act 0 none/1 SwooshL/2 SwooshR;
- * resid bf16 [M][ldc] nullable; out bf16 [M][ldc] (or fp32 when out_f32). */
+ * resid fp32 [M][ldc] nullable; out_mode 0: out bf16 / 1: out fp32 / 2: out fp32 + out_bf16 shadow. */
 int zvb_test_linear(const void* A, int M, int K, int lda, const void* W, const float* bias, int n_out,
-                    int k_pitch, int block_n, int act, const void* resid, void* out, int ldc, int out_f32,
-                    void* stream);
+                    int k_pitch, int block_n, int act, const float* resid, void* out, void* out_bf16, int ldc,
+                    int out_mode, void* stream);
 int zvb_test_attn_weights(const void* qkp, int ld, const float* pos_table, const uint8_t* mask, void* P,
                           int N, int H, int L, int Lk, void* stream);
+/* mul: bf16 [N*L][hd] gate of NonlinAttention (per_head == 0 only, nullable) */
 int zvb_test_pv(const void* P, const void* Vt, void* out, int N, int H, int L, int Lk, int hd, int hp,
-                int per_head, void* stream);
-int zvb_test_biasnorm_bypass(const void* src, const void* orig, void* out, const float* nbias,
-                             const float* log_scale, const float* bscale, long long rows, int C, void* stream);
+                int per_head, const void* mul, void* stream);
+/* gated projection on tile-packed weights (rows = tiles*256); gate_mode 1: x*tanh(s), 2: GLU */
+int zvb_test_gated(const void* A, int M, int K, int lda, const void* W, const float* bias, int rows, int n_out,
+                   int k_pitch, int gate_mode, const uint8_t* row_mask, void* out, int ldc, void* stream);
+int zvb_test_biasnorm_bypass(const float* src, const float* orig, float* out, void* out_b, void* out_t,
+                             const float* temb, int rows_per_group, const float* nbias, const float* log_scale,
+                             const float* bscale, long long rows, int C, void* stream);
 int zvb_test_dwconv(const void* x, void* out, const float* wt, const float* bias, int N, int L, int C, int K,
                     void* stream);
 int zvb_test_cfg_euler(float* x, const float* v, const float* guidance, float gscale, const float* ts,

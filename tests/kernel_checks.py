@@ -31,8 +31,9 @@ def _swoosh_r(x):
     return torch.logaddexp(torch.zeros((), device=x.device), x - 1.0) - 0.08 * x - 0.313261687
 
 
-def check_linear(M=300, K=512, N=272, block_n=0, act=0, resid=False, out_f32=False, seed=0):
-    """tolerance: rel-L2 <= 6e-3 (bf16 output rounding 2^-9 + fp32 accumulation order)"""
+def check_linear(M=300, K=512, N=272, block_n=0, act=0, resid=False, out_mode=0, seed=0):
+    """tolerance: rel-L2 <= 6e-3 for bf16 outputs (rounding 2^-9), <= 1e-5 for fp32 outputs.
+    out_mode 0: bf16, 1: fp32, 2: fp32 stream + bf16 shadow; resid: fp32 residual tile (TMA aux ring)."""
     lib = _lib.load()
     g = torch.Generator(device="cpu").manual_seed(seed)
     kp = (K + 7) // 8 * 8
@@ -41,12 +42,14 @@ def check_linear(M=300, K=512, N=272, block_n=0, act=0, resid=False, out_f32=Fal
     W = torch.zeros(N, kp, dtype=torch.bfloat16)
     W[:, :K] = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
     b = torch.randn(N, generator=g)
-    R = torch.randn(M, N, generator=g).to(torch.bfloat16) if resid else None
+    R = torch.randn(M, N, generator=g) if resid else None
     A, W, b = A.to(DEV), W.to(DEV), b.to(DEV)
     R = R.to(DEV) if resid else None
-    out = torch.full((M, N), float("nan"), dtype=torch.float32 if out_f32 else torch.bfloat16, device=DEV)
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16 if out_mode == 0 else torch.float32, device=DEV)
+    shadow = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV) if out_mode == 2 else None
     _lib.check(lib.zvb_test_linear(A.data_ptr(), M, K, kp, W.data_ptr(), b.data_ptr(), N, kp, block_n, act,
-                                   R.data_ptr() if resid else None, out.data_ptr(), N, 1 if out_f32 else 0, _s()))
+                                   R.data_ptr() if resid else None, out.data_ptr(),
+                                   shadow.data_ptr() if shadow is not None else None, N, out_mode, _s()))
     torch.cuda.synchronize()
     ref = A.float() @ W.float().t() + b
     if act == 1:
@@ -54,13 +57,51 @@ def check_linear(M=300, K=512, N=272, block_n=0, act=0, resid=False, out_f32=Fal
     elif act == 2:
         ref = _swoosh_r(ref)
     if resid:
-        ref = ref + R.float()
+        ref = ref + R
     err = (out.float() - ref).abs().nan_to_num(1e9)
     am = int(err.argmax())
-    return dict(rel=_rel(out.float().nan_to_num(0.0), ref), nan=int(torch.isnan(out.float()).sum()), tol=6e-3,
-                worst=[am // N, am % N, float(out.float().flatten()[am]), float(ref.flatten()[am])],
-                bad_frac=float((err > 0.1).float().mean()),
-                bad_rows=int((err.max(dim=1).values > 0.1).sum()), bad_cols=int((err.max(dim=0).values > 0.1).sum()))
+    res = dict(rel=_rel(out.float().nan_to_num(0.0), ref), nan=int(torch.isnan(out.float()).sum()),
+               tol=6e-3 if out_mode == 0 else 2e-5,
+               worst=[am // N, am % N, float(out.float().flatten()[am]), float(ref.flatten()[am])],
+               bad_frac=float((err > 0.1).float().mean()),
+               bad_rows=int((err.max(dim=1).values > 0.1).sum()), bad_cols=int((err.max(dim=0).values > 0.1).sum()))
+    if shadow is not None:
+        res["shadow_rel"] = _rel(shadow.float().nan_to_num(0.0), ref)
+        res["nan"] += int(torch.isnan(shadow.float()).sum())
+    return res
+
+
+def check_gated(M=300, K=512, n_out=384, mode=1, masked=False, seed=0):
+    """Gated projection on tile-packed weights: mode 1 x*tanh(s) (rows [s|x]), mode 2 GLU x*sigmoid(s)
+    (rows [x|s]) with optional zeroed rows.  tolerance: rel-L2 <= 8e-3 (tanh.approx / fast sigmoid + bf16)."""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    Wa = (torch.randn(n_out, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    Wb = (torch.randn(n_out, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    ba, bb = torch.randn(n_out, generator=g) * 0.3, torch.randn(n_out, generator=g) * 0.3
+    tiles = (n_out + 127) // 128
+    W = torch.zeros(tiles * 256, K, dtype=torch.bfloat16)
+    Bv = torch.zeros(tiles * 256)
+    for t in range(tiles):
+        r = min(128, n_out - t * 128)
+        W[t * 256: t * 256 + r] = Wa[t * 128: t * 128 + r]
+        W[t * 256 + 128: t * 256 + 128 + r] = Wb[t * 128: t * 128 + r]
+        Bv[t * 256: t * 256 + r] = ba[t * 128: t * 128 + r]
+        Bv[t * 256 + 128: t * 256 + 128 + r] = bb[t * 128: t * 128 + r]
+    rm = (torch.rand(M, generator=g) < 0.3) if masked else None
+    A, W, Bv = A.to(DEV), W.to(DEV), Bv.to(DEV)
+    rm8 = rm.to(torch.uint8).to(DEV) if masked else None
+    out = torch.full((M, n_out), float("nan"), dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.zvb_test_gated(A.data_ptr(), M, K, K, W.data_ptr(), Bv.data_ptr(), tiles * 256, n_out, K, mode,
+                                  rm8.data_ptr() if masked else None, out.data_ptr(), n_out, _s()))
+    torch.cuda.synchronize()
+    a = A.float() @ Wa.float().to(DEV).t() + ba.to(DEV)
+    b = A.float() @ Wb.float().to(DEV).t() + bb.to(DEV)
+    ref = b * torch.tanh(a) if mode == 1 else a * torch.sigmoid(b)
+    if masked:
+        ref = ref * (~rm).to(DEV).unsqueeze(-1)
+    return dict(rel=_rel(out.float().nan_to_num(0.0), ref), nan=int(torch.isnan(out.float()).sum()), tol=8e-3)
 
 
 def _attn_inputs(N, H, L, seed, masked):
@@ -110,7 +151,7 @@ def check_attn(N=2, H=4, L=200, masked=True, seed=0):
                 rowsum_err=float((got[..., :L].sum(-1) - 1).abs().max()), tol=4e-3)
 
 
-def check_pv(N=2, H=4, L=200, hd=12, hp=16, per_head=True, seed=0):
+def check_pv(N=2, H=4, L=200, hd=12, hp=16, per_head=True, mul=False, seed=0):
     """tolerance: rel-L2 <= 6e-3"""
     lib = _lib.load()
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -130,30 +171,43 @@ def check_pv(N=2, H=4, L=200, hd=12, hp=16, per_head=True, seed=0):
         Vt[:, :, :L] = V
         out = torch.full((N, L, hd), float("nan"), dtype=torch.bfloat16, device=DEV)
         ref = torch.einsum("nij,ndj->nid", P.float()[:, 0, :, :L], V.float().to(DEV))
+    Y = None
+    if mul:
+        Y = torch.randn(N, L, hd, generator=g).to(torch.bfloat16).to(DEV)
+        ref = ref * Y.float()
     Vt = Vt.to(DEV)
     _lib.check(lib.zvb_test_pv(P.data_ptr(), Vt.data_ptr(), out.data_ptr(), N, H, L, Lk, hd, hp, 1 if per_head else 0,
-                               _s()))
+                               Y.data_ptr() if mul else None, _s()))
     torch.cuda.synchronize()
     return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=6e-3)
 
 
 def check_biasnorm(rows=1000, C=512, seed=0):
-    """tolerance: rel-L2 <= 5e-3 (bf16 output)"""
+    """fp32 stream in/out + bf16 shadow + bf16 time-embedded shadow.
+    tolerance: rel-L2 <= 1e-5 (fp32 out), <= 5e-3 (bf16 shadows)"""
     lib = _lib.load()
     g = torch.Generator(device="cpu").manual_seed(seed)
-    src = torch.randn(rows, C, generator=g).mul(2).to(torch.bfloat16).to(DEV)
-    orig = torch.randn(rows, C, generator=g).to(torch.bfloat16).to(DEV)
+    L = 37
+    src = torch.randn(rows, C, generator=g).mul(2).to(DEV)
+    orig = torch.randn(rows, C, generator=g).to(DEV)
     nb = (torch.randn(C, generator=g) * 0.1).to(DEV)
     ls = torch.tensor([0.4], device=DEV)
     bs = (torch.rand(C, generator=g) * 0.6 + 0.3).to(DEV)
-    out = torch.full((rows, C), float("nan"), dtype=torch.bfloat16, device=DEV)
-    _lib.check(lib.zvb_test_biasnorm_bypass(src.data_ptr(), orig.data_ptr(), out.data_ptr(), nb.data_ptr(),
-                                            ls.data_ptr(), bs.data_ptr(), rows, C, _s()))
+    temb = torch.randn((rows + L - 1) // L, C, generator=g).to(DEV)
+    out = torch.full((rows, C), float("nan"), dtype=torch.float32, device=DEV)
+    ob = torch.full((rows, C), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ot = torch.full((rows, C), float("nan"), dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.zvb_test_biasnorm_bypass(src.data_ptr(), orig.data_ptr(), out.data_ptr(), ob.data_ptr(),
+                                            ot.data_ptr(), temb.data_ptr(), L, nb.data_ptr(), ls.data_ptr(),
+                                            bs.data_ptr(), rows, C, _s()))
     torch.cuda.synchronize()
-    x = src.float()
-    y = x * (((x - nb) ** 2).mean(-1, keepdim=True) ** -0.5) * ls.exp()
-    ref = orig.float() + (y - orig.float()) * bs
-    return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=5e-3)
+    y = src * (((src - nb) ** 2).mean(-1, keepdim=True) ** -0.5) * ls.exp()
+    ref = orig + (y - orig) * bs
+    ref_t = ref + temb[torch.arange(rows, device=DEV) // L]
+    rel32 = _rel(out, ref)
+    relb = max(_rel(ob.float(), ref), _rel(ot.float(), ref_t))
+    return dict(rel=relb, rel_f32=rel32, nan=int(torch.isnan(out).sum() + torch.isnan(ob.float()).sum()),
+                tol=5e-3 if rel32 <= 1e-5 else 0.0)
 
 
 def check_dwconv(N=2, L=150, C=512, K=31, seed=0):
@@ -204,11 +258,16 @@ def assert_ok(name, r):
 
 ALL = {
     "linear_basic": lambda: check_linear(M=300, K=512, N=272),
-    "linear_k48": lambda: check_linear(M=257, K=48, N=512, resid=True),
+    "linear_k48": lambda: check_linear(M=257, K=48, N=512, resid=True, out_mode=2),
     "linear_k300": lambda: check_linear(M=130, K=300, N=512),
     "linear_swoosh": lambda: check_linear(M=1000, K=512, N=1152, act=1),
-    "linear_big": lambda: check_linear(M=20000, K=1536, N=512, resid=True),
-    "linear_f32_n100": lambda: check_linear(M=333, K=512, N=100, out_f32=True),
+    "linear_big": lambda: check_linear(M=20000, K=1536, N=512, resid=True, out_mode=2),
+    "linear_resid_f32only": lambda: check_linear(M=777, K=384, N=512, resid=True, out_mode=1),
+    "linear_f32_n100": lambda: check_linear(M=333, K=512, N=100, out_mode=1),
+    "linear_n1920_swoosh": lambda: check_linear(M=5000, K=512, N=1920, act=1),
+    "gated_tanh": lambda: check_gated(M=300, n_out=384, mode=1),
+    "gated_tanh96": lambda: check_gated(M=81, K=128, n_out=96, mode=1),
+    "gated_glu_masked": lambda: check_gated(M=1000, n_out=512, mode=2, masked=True),
     "linear_bn64": lambda: check_linear(M=128, K=64, N=64, block_n=64),
     "linear_tail": lambda: check_linear(M=77, K=192, N=640, act=2),
     "attn_small": lambda: check_attn(N=2, H=4, L=100, masked=False),
@@ -217,6 +276,8 @@ ALL = {
     "pv_heads": lambda: check_pv(N=2, H=4, L=333, per_head=True),
     "pv_wide": lambda: check_pv(N=2, H=4, L=333, hd=384, hp=384, per_head=False),
     "pv_wide96": lambda: check_pv(N=2, H=4, L=81, hd=96, hp=96, per_head=False),
+    "pv_wide_mul": lambda: check_pv(N=3, H=4, L=333, hd=384, hp=384, per_head=False, mul=True),
+    "pv_wide144_mul": lambda: check_pv(N=2, H=4, L=130, hd=144, hp=144, per_head=False, mul=True),
     "biasnorm": lambda: check_biasnorm(),
     "biasnorm_c192": lambda: check_biasnorm(rows=77, C=192),
     "dwconv31": lambda: check_dwconv(K=31),

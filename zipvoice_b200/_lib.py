@@ -71,12 +71,15 @@ EXPORTS = {
     "zvb_decoder_forward_f32": (C.c_int, [C.c_void_p] * 7),
     "zvb_sample": (C.c_int, [C.c_void_p] * 8 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "zvb_test_linear": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
-                                  C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_void_p]),
     "zvb_test_attn_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "zvb_test_pv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]),
-    "zvb_test_biasnorm_bypass": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_void_p]),
+    "zvb_test_pv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),
+    "zvb_test_gated": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "zvb_test_biasnorm_bypass": (C.c_int, [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3 +
+                                 [C.c_longlong, C.c_int, C.c_void_p]),
     "zvb_test_dwconv": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]),
     "zvb_test_cfg_euler": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
                                      C.c_int, C.c_longlong, C.c_int, C.c_void_p]),

@@ -16,14 +16,27 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 }
 
 // ---------------------------------------------------------------------------------------
+// The residual stream is fp32 (N, L, C); kernels that end a module also emit the bf16 shadow copy
+// the next tensor-core kernel consumes (and the copy with the time embedding added, reference:
+// modules/zipformer.py:532-534).
+__device__ __forceinline__ void load8f(const float* p, float* v) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8f(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 // BiasNorm + bypass (reference: modules/scaling.py:358-363, modules/zipformer.py:634-637,
 // 803-804):  y = x * rsqrt(mean((x-b)^2)) * exp(log_scale);  out = orig + (y-orig)*scale.
-// One warp per row, C <= 1024, C % 8 == 0.  Optionally also writes out + temb[row/L]
-// (the next layer's time-embedded input, reference: modules/zipformer.py:532-534).
+// One warp per row, C <= 1024, C % 8 == 0.  Outputs (each nullable): fp32 stream `out`, bf16
+// shadow `out_b`, bf16 `out_t` = out + temb[row / rows_per_group].
 __global__ void __launch_bounds__(256)
-biasnorm_bypass_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ orig,
-                       __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out2,
-                       const float* __restrict__ temb, int rows_per_group,
+biasnorm_bypass_kernel(const float* __restrict__ src, const float* __restrict__ orig,
+                       float* __restrict__ out, __nv_bfloat16* __restrict__ out_b,
+                       __nv_bfloat16* __restrict__ out_t, const float* __restrict__ temb, int rows_per_group,
                        const float* __restrict__ nbias, const float* __restrict__ log_scale,
                        const float* __restrict__ bscale, long long rows, int C) {
     const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -35,7 +48,7 @@ biasnorm_bypass_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat1
     for (int k = 0; k < 4; ++k) {
         const int c = (k * 32 + lane) * 8;
         if (c < C) {
-            unpack8(*reinterpret_cast<const uint4*>(src + row * C + c), x[k]);
+            load8f(src + row * C + c, x[k]);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float d = x[k][i] - __ldg(nbias + c + i);
@@ -46,46 +59,51 @@ biasnorm_bypass_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat1
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float scale = rsqrtf(ss / static_cast<float>(C)) * __expf(__ldg(log_scale));
-    const long long grp = temb != nullptr ? row / rows_per_group : 0;
+    const long long grp = out_t != nullptr ? row / rows_per_group : 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int c = (k * 32 + lane) * 8;
         if (c < C) {
             float o[8], y[8];
-            unpack8(*reinterpret_cast<const uint4*>(orig + row * C + c), o);
+            load8f(orig + row * C + c, o);
 #pragma unroll
             for (int i = 0; i < 8; ++i) y[i] = o[i] + (x[k][i] * scale - o[i]) * __ldg(bscale + c + i);
-            *reinterpret_cast<uint4*>(out + row * C + c) = pack8(y);
-            if (out2 != nullptr) {
+            if (out != nullptr) store8f(out + row * C + c, y);
+            if (out_b != nullptr) *reinterpret_cast<uint4*>(out_b + row * C + c) = pack8(y);
+            if (out_t != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) y[i] += __ldg(temb + grp * C + c + i);
-                *reinterpret_cast<uint4*>(out2 + row * C + c) = pack8(y);
+                *reinterpret_cast<uint4*>(out_t + row * C + c) = pack8(y);
             }
         }
     }
 }
 
-// out = x + temb[row / L]   (reference: modules/zipformer.py:532-534)
+// Stack entry: bf16 shadow of the fp32 stream and its time-embedded copy (each nullable):
+// xb = bf16(x), xt = bf16(x + temb[row / L])   (reference: modules/zipformer.py:532-534)
 __global__ void __launch_bounds__(256)
-add_rowbias_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+stream_prep_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, __nv_bfloat16* __restrict__ xt,
                    const float* __restrict__ temb, int rows_per_group, long long rows, int C) {
     const int cv = C >> 3;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= rows * cv) return;
     const long long row = idx / cv;
     const int c = static_cast<int>(idx - row * cv) * 8;
-    const long long grp = row / rows_per_group;
     float v[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + row * C + c), v);
+    load8f(x + row * C + c, v);
+    if (xb != nullptr) *reinterpret_cast<uint4*>(xb + row * C + c) = pack8(v);
+    if (xt != nullptr) {
+        const long long grp = row / rows_per_group;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += __ldg(temb + grp * C + c + i);
-    *reinterpret_cast<uint4*>(out + row * C + c) = pack8(v);
+        for (int i = 0; i < 8; ++i) v[i] += __ldg(temb + grp * C + c + i);
+        *reinterpret_cast<uint4*>(xt + row * C + c) = pack8(v);
+    }
 }
 
 // SimpleDownsample (reference: modules/zipformer.py:887-913): weighted sum over groups of ds
 // frames, right-padded by repeating frame L-1.  w = softmax(bias) precomputed on the host.
 __global__ void __launch_bounds__(256)
-downsample_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ out, int N, int L,
+downsample_kernel(const float* __restrict__ src, float* __restrict__ out, int N, int L,
                   int Ld, int ds, float w0, float w1, float w2, float w3, int C) {
     const int cv = C >> 3;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -100,19 +118,19 @@ downsample_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restri
         int l = ld * ds + k;
         l = l < L ? l : L - 1;
         float v[8];
-        unpack8(*reinterpret_cast<const uint4*>(src + (static_cast<long long>(n) * L + l) * C + c), v);
+        load8f(src + (static_cast<long long>(n) * L + l) * C + c, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i], w[k], acc[i]);
     }
-    *reinterpret_cast<uint4*>(out + (static_cast<long long>(n) * Ld + ld) * C + c) = pack8(acc);
+    store8f(out + (static_cast<long long>(n) * Ld + ld) * C + c, acc);
 }
 
 // SimpleUpsample + truncate + out_combiner bypass (reference: modules/zipformer.py:866-870,
-// 925-935):  out[n,l] = orig[n,l] + (y[n, l/ds] - orig[n,l]) * scale
+// 925-935):  out[n,l] = orig[n,l] + (y[n, l/ds] - orig[n,l]) * scale   (+ optional bf16 shadow)
 __global__ void __launch_bounds__(256)
-upsample_combine_kernel(const __nv_bfloat16* __restrict__ orig, const __nv_bfloat16* __restrict__ y,
-                        __nv_bfloat16* __restrict__ out, const float* __restrict__ scale, int N, int L,
-                        int Ld, int ds, int C) {
+upsample_combine_kernel(const float* __restrict__ orig, const float* __restrict__ y,
+                        float* __restrict__ out, __nv_bfloat16* __restrict__ out_b,
+                        const float* __restrict__ scale, int N, int L, int Ld, int ds, int C) {
     const int cv = C >> 3;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= static_cast<long long>(N) * L * cv) return;
@@ -121,11 +139,12 @@ upsample_combine_kernel(const __nv_bfloat16* __restrict__ orig, const __nv_bfloa
     const int l = static_cast<int>(rl % L);
     const int n = static_cast<int>(rl / L);
     float o[8], v[8];
-    unpack8(*reinterpret_cast<const uint4*>(orig + rl * C + c), o);
-    unpack8(*reinterpret_cast<const uint4*>(y + (static_cast<long long>(n) * Ld + l / ds) * C + c), v);
+    load8f(orig + rl * C + c, o);
+    load8f(y + (static_cast<long long>(n) * Ld + l / ds) * C + c, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = o[i] + (v[i] - o[i]) * __ldg(scale + c + i);
-    *reinterpret_cast<uint4*>(out + rl * C + c) = pack8(v);
+    store8f(out + rl * C + c, v);
+    if (out_b != nullptr) *reinterpret_cast<uint4*>(out_b + rl * C + c) = pack8(v);
 }
 
 // Depthwise Conv1d over time (cross-correlation, zero padding K/2) + bias + SwooshR

@@ -74,14 +74,13 @@ static int init_device() {
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(attn_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     return 0;
 }
 
-// bf16 tensor (dim0 fastest) viewed as 3-D, box = (64, box1, 1), 128B swizzle, zero OOB fill.
+// Tensor (dim0 fastest) viewed as 3-D, box = (128 bytes, box1, 1), 128B swizzle, zero OOB fill.
 static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
-                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box1) {
+                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box1, bool f32 = false) {
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (stride1_bytes & 15) != 0 || (stride2_bytes & 15) != 0)
         return fail(ZVB_ERR_INVALID, "tensor map: pointer/strides must be 16-byte aligned");
     if (box1 == 0 || box1 > 256 || d0 == 0 || d1 == 0 || d2 == 0)
@@ -89,28 +88,30 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
                     (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
     cuuint64_t dims[3] = {d0, d1, d2};
     cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
-    cuuint32_t box[3] = {64, box1, 1};
+    cuuint32_t box[3] = {f32 ? 32u : 64u, box1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box,
-                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                          const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ZVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------ ops
-enum OpType { OP_GEMM, OP_ATTN, OP_BIASNORM, OP_ADDROW, OP_DOWN, OP_UP, OP_DWCONV, OP_MASK, OP_TSEMB, OP_SMALL };
+enum OpType { OP_GEMM, OP_ATTN, OP_BIASNORM, OP_PREP, OP_DOWN, OP_UP, OP_DWCONV, OP_MASK, OP_TSEMB, OP_SMALL };
 
 struct Op {
     OpType type;
     // GEMM / ATTN
-    CUtensorMap ma, mb;
+    CUtensorMap ma, mb, mx;
+    bool has_mx = false;
     GemmParams gp;
     int kind = 0, grid = 0;
     AttnParams ap;
     // elementwise
     const void *p0 = nullptr, *p1 = nullptr;
-    void *o0 = nullptr, *o1 = nullptr;
+    void *o0 = nullptr, *o1 = nullptr, *o2 = nullptr;
     const float *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *f3 = nullptr;
     long long rows = 0;
     int i0 = 0, i1 = 0, i2 = 0, i3 = 0, i4 = 0, i5 = 0;
@@ -136,16 +137,22 @@ static void gp_defaults(GemmParams& p) { memset(&p, 0, sizeof p); p.rows_per_gro
 
 struct LinearEpi {
     int act = ACT_NONE;
-    const bf16* resid = nullptr;
+    const float* resid = nullptr;        // fp32 residual stream tile (TMA aux ring), pitch = ldc
     const float* rowbias = nullptr;
     int rows_per_group = 1;
-    const bf16* orig = nullptr;
+    const float* orig = nullptr;         // fp32, pitch = ldc
     const float* bypass_scale = nullptr;
-    int out_f32 = 0;
-    // transposed store
-    int transposed = 0, t_L = 0, t_pitch = 0, t_batch_rows = 0, t_hd = 1, t_hp = 1;
-    int block_n = 0;   // 0 = choose
+    int out_mode = OUT_BF16;
+    bf16* out_bf16 = nullptr;            // OUT_F32_BF16 shadow
+    int t_L = 0, t_pitch = 0, t_batch_rows = 0, t_hd = 1, t_hp = 1;   // OUT_T_BF16
+    int block_n = 0;                     // 0 = choose
 };
+
+static void set_grid(Op& op) {
+    const GemmParams& p = op.gp;
+    const long long tiles = (long long)p.batches * p.num_m_tiles * p.num_n_tiles;
+    op.grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+}
 
 // out[M, n_out] = epi(A[M, K] · W[n_out, K]ᵀ + b)
 static int build_linear(Op& op, const bf16* A, long long M, int lda, const zvb_linear& lin, void* out, int ldc,
@@ -165,19 +172,22 @@ static int build_linear(Op& op, const bf16* A, long long M, int lda, const zvb_l
     p.num_m_tiles = static_cast<int>(m_tiles);
     p.num_n_tiles = (lin.out_features + bn - 1) / bn;
     p.batches = 1;
-    p.out = out; p.ldc = ldc; p.out_f32 = e.out_f32;
+    p.out_mode = e.out_mode; p.out = out; p.out_bf16 = e.out_bf16; p.ldc = ldc;
     p.out_col_stride = bn; p.n_valid = bn;
     p.bias = lin.b;
     p.rowbias = e.rowbias; p.rows_per_group = e.rows_per_group; p.ld_rowbias = lin.out_features;
-    p.resid = e.resid; p.ldr = ldc;
     p.orig = e.orig; p.bypass_scale = e.bypass_scale;
     p.act = e.act;
-    p.transposed = e.transposed; p.t_L = e.t_L; p.t_pitch = e.t_pitch; p.t_batch_rows = e.t_batch_rows;
-    p.t_hd = e.t_hd; p.t_hp = e.t_hp;
+    p.t_L = e.t_L; p.t_pitch = e.t_pitch; p.t_batch_rows = e.t_batch_rows; p.t_hd = e.t_hd; p.t_hp = e.t_hp;
     TRY(make_tmap(&op.ma, A, K, M, 1, (uint64_t)lda * 2, (uint64_t)lda * 2 * M, GEMM_BLOCK_M));
     TRY(make_tmap(&op.mb, lin.w, K, lin.rows, 1, (uint64_t)lin.k_pitch * 2, (uint64_t)lin.k_pitch * 2 * lin.rows, bn));
-    const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
-    op.grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+    if (e.resid != nullptr) {
+        if (ldc % 4 != 0) return fail(ZVB_ERR_INVALID, "linear: fp32 residual pitch must be a multiple of 4");
+        p.aux_mode = AUX_RESID_F32; p.aux_zb = 0;
+        TRY(make_tmap(&op.mx, e.resid, ldc, M, 1, (uint64_t)ldc * 4, (uint64_t)ldc * 4 * M, GEMM_BLOCK_M, true));
+        op.has_mx = true;
+    }
+    set_grid(op);
     op.cat = ZVB_CAT_GEMM_LINEAR;
     op.work = 2.0 * (double)M * lin.out_features * lin.in_features;
     return 0;
@@ -199,17 +209,15 @@ static int build_gated(Op& op, const bf16* A, long long M, int lda, const zvb_li
     p.num_n_tiles = (n_out + 127) / 128;
     if (lin.rows != p.num_n_tiles * 256) return fail(ZVB_ERR_INVALID, "gated linear: expected %d packed rows, got %d", p.num_n_tiles * 256, lin.rows);
     p.batches = 1;
-    p.out = out; p.ldc = ldc;
+    p.out_mode = e.out_mode; p.out = out; p.ldc = ldc;
     p.out_col_stride = 128; p.n_valid = 256;
     p.bias = lin.b;
     p.gate_mode = gate_mode;
     p.row_mask = row_mask;
-    p.transposed = e.transposed; p.t_L = e.t_L; p.t_pitch = e.t_pitch; p.t_batch_rows = e.t_batch_rows;
-    p.t_hd = e.t_hd; p.t_hp = e.t_hp;
+    p.t_L = e.t_L; p.t_pitch = e.t_pitch; p.t_batch_rows = e.t_batch_rows; p.t_hd = e.t_hd; p.t_hp = e.t_hp;
     TRY(make_tmap(&op.ma, A, K, M, 1, (uint64_t)lda * 2, (uint64_t)lda * 2 * M, GEMM_BLOCK_M));
     TRY(make_tmap(&op.mb, lin.w, K, lin.rows, 1, (uint64_t)lin.k_pitch * 2, (uint64_t)lin.k_pitch * 2 * lin.rows, 256));
-    const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
-    op.grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+    set_grid(op);
     op.cat = ZVB_CAT_GEMM_GATED;
     op.work = 2.0 * (double)M * (2.0 * n_out) * lin.in_features;
     return 0;
@@ -217,11 +225,11 @@ static int build_gated(Op& op, const bf16* A, long long M, int lda, const zvb_li
 
 // out[n*L+i, :] = P[n,h] · V  with V given transposed: Vt[n][rows][Lk].
 //   per_head != 0 (SelfAttention): head h uses Vt rows [h*hp, h*hp+hd) -> out cols [h*hd, (h+1)*hd)
-//   per_head == 0 (NonlinAttention): head 0 weights, all `hd` value columns, out *= mul
+//   per_head == 0 (NonlinAttention): head 0 weights, all `hd` value columns, out *= mul (bf16 [N*L, ldm])
 static int build_pv(Op& op, const bf16* P, const bf16* Vt, void* out, int ldc, int N, int H, int L, int Lk, int hd,
                     int hp, int per_head, const bf16* mul, int ldm) {
     op.type = OP_GEMM;
-    op.kind = per_head ? EPI_LINEAR : EPI_MUL;
+    op.kind = EPI_LINEAR;
     GemmParams& p = op.gp;
     gp_defaults(p);
     p.M = L;
@@ -230,7 +238,7 @@ static int build_pv(Op& op, const bf16* P, const bf16* Vt, void* out, int ldc, i
     p.batches = N;
     p.b_zb = 1;
     p.a_zb = H;
-    p.out = out; p.ldc = ldc;
+    p.out_mode = OUT_BF16; p.out = out; p.ldc = ldc;
     int vt_rows;
     if (per_head) {
         if (hp % 16 != 0 || hd > hp) return fail(ZVB_ERR_INVALID, "pv: head pad must be a multiple of 16");
@@ -242,13 +250,17 @@ static int build_pv(Op& op, const bf16* P, const bf16* Vt, void* out, int ldc, i
         p.block_n = (((hd + tiles - 1) / tiles) + 15) / 16 * 16;
         p.num_n_tiles = (hd + p.block_n - 1) / p.block_n; p.a_zn = 0;
         p.n_out = hd; p.out_col_stride = p.block_n; p.n_valid = p.block_n;
-        p.mul = mul; p.ldm = ldm;
         vt_rows = hd;
+        if (mul != nullptr) {
+            if (ldm % 8 != 0) return fail(ZVB_ERR_INVALID, "pv: multiplier pitch must be a multiple of 8");
+            p.aux_mode = AUX_MUL_BF16; p.aux_zb = 1;
+            TRY(make_tmap(&op.mx, mul, ldm, L, N, (uint64_t)ldm * 2, (uint64_t)ldm * 2 * L, GEMM_BLOCK_M));
+            op.has_mx = true;
+        }
     }
     TRY(make_tmap(&op.ma, P, Lk, L, (uint64_t)N * H, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * L, GEMM_BLOCK_M));
     TRY(make_tmap(&op.mb, Vt, Lk, vt_rows, N, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * vt_rows, p.block_n));
-    const long long tiles = (long long)p.batches * p.num_m_tiles * p.num_n_tiles;
-    op.grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+    set_grid(op);
     op.cat = ZVB_CAT_GEMM_PV;
     op.work = 2.0 * (double)N * (per_head ? H : 1) * (double)L * L * hd;
     return 0;
@@ -272,12 +284,11 @@ static int launch_op(const Op& op, cudaStream_t st) {
     switch (op.type) {
         case OP_GEMM: {
             if (op.grid <= 0) return 0;
+            const CUtensorMap& mx = op.has_mx ? op.mx : op.ma;
             if (op.kind == EPI_LINEAR)
-                gemm_kernel<EPI_LINEAR><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, op.gp);
-            else if (op.kind == EPI_GATED)
-                gemm_kernel<EPI_GATED><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, op.gp);
+                gemm_kernel<EPI_LINEAR><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, mx, op.gp);
             else
-                gemm_kernel<EPI_MUL><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, op.gp);
+                gemm_kernel<EPI_GATED><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, mx, op.gp);
             return check_launch("gemm");
         }
         case OP_ATTN: {
@@ -288,26 +299,27 @@ static int launch_op(const Op& op, cudaStream_t st) {
         case OP_BIASNORM: {
             const int blocks = static_cast<int>((op.rows + 7) / 8);
             biasnorm_bypass_kernel<<<blocks, 256, 0, st>>>(
-                (const bf16*)op.p0, (const bf16*)op.p1, (bf16*)op.o0, (bf16*)op.o1, op.f3, op.i1, op.f0, op.f1, op.f2,
-                op.rows, op.i0);
+                (const float*)op.p0, (const float*)op.p1, (float*)op.o0, (bf16*)op.o1, (bf16*)op.o2, op.f3, op.i1, op.f0,
+                op.f1, op.f2, op.rows, op.i0);
             return check_launch("biasnorm_bypass");
         }
-        case OP_ADDROW: {
+        case OP_PREP: {
             const long long n = op.rows * (op.i0 / 8);
-            add_rowbias_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)op.p0, (bf16*)op.o0, op.f0,
-                                                                           op.i1, op.rows, op.i0);
-            return check_launch("add_rowbias");
+            stream_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)op.p0, (bf16*)op.o0, (bf16*)op.o1,
+                                                                           op.f0, op.i1, op.rows, op.i0);
+            return check_launch("stream_prep");
         }
         case OP_DOWN: {
             const long long n = (long long)op.i0 * op.i2 * (op.i4 / 8);
             downsample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-                (const bf16*)op.p0, (bf16*)op.o0, op.i0, op.i1, op.i2, op.i3, op.w[0], op.w[1], op.w[2], op.w[3], op.i4);
+                (const float*)op.p0, (float*)op.o0, op.i0, op.i1, op.i2, op.i3, op.w[0], op.w[1], op.w[2], op.w[3], op.i4);
             return check_launch("downsample");
         }
         case OP_UP: {
             const long long n = (long long)op.i0 * op.i1 * (op.i4 / 8);
             upsample_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-                (const bf16*)op.p0, (const bf16*)op.p1, (bf16*)op.o0, op.f0, op.i0, op.i1, op.i2, op.i3, op.i4);
+                (const float*)op.p0, (const float*)op.p1, (float*)op.o0, (bf16*)op.o1, op.f0, op.i0, op.i1, op.i2, op.i3,
+                op.i4);
             return check_launch("upsample_combine");
         }
         case OP_DWCONV: {
@@ -375,6 +387,10 @@ static Op small_op(const float* in, const float* W, const float* b, const float*
 }
 
 // Builds the plan; with ws == nullptr only measures the workspace.
+//
+// Residual stream: fp32 (as the reference under bf16 autocast effectively keeps it: BiasNorm and the
+// bypass return fp32).  Every kernel that updates the stream also writes the bf16 shadow that the
+// next tensor-core kernel reads as its A operand.
 static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_out, zvb_plan* plan) {
     if (m == nullptr || m->abi_version != ZVB_ABI_VERSION) return fail(ZVB_ERR_INVALID, "model description: ABI version mismatch");
     if (N <= 0 || T <= 0) return fail(ZVB_ERR_INVALID, "N and T must be positive");
@@ -407,11 +423,14 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
         te3 = c.take<float>((size_t)N * td);
         for (int s = 0; s < m->num_stacks; ++s) temb[s] = c.take<float>((size_t)N * D);
     }
-    bf16* cur0 = c.take<bf16>(M * D);
-    bf16* cur1 = c.take<bf16>(M * D);
-    bf16* S[2] = {c.take<bf16>(M * D), c.take<bf16>(M * D)};
-    bf16* St[2] = {c.take<bf16>(M * D), c.take<bf16>(M * D)};
-    bf16* R[2] = {c.take<bf16>(M * D), c.take<bf16>(M * D)};
+    float* cur0 = c.take<float>(M * D);           // full-rate fp32 stream (ping-pong)
+    float* cur1 = c.take<float>(M * D);
+    bf16* curb = c.take<bf16>(M * D);             // bf16 shadow of the final stream (out_proj operand)
+    float* S[2] = {c.take<float>(M * D), c.take<float>(M * D)};     // layer inputs inside a stack
+    bf16* Sb[2] = {c.take<bf16>(M * D), c.take<bf16>(M * D)};       // their bf16 shadows
+    bf16* St[2] = {c.take<bf16>(M * D), c.take<bf16>(M * D)};       // bf16(src + temb)
+    float* R[2] = {c.take<float>(M * D), c.take<float>(M * D)};     // stream inside a layer
+    bf16* Rb[2] = {c.take<bf16>(M * D), c.take<bf16>(M * D)};
     bf16* qkp = c.take<bf16>(M * attn_w);
     bf16* hid = c.take<bf16>(M * ffmax);
     bf16* nay = c.take<bf16>(M * nah);
@@ -466,127 +485,150 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             ops.push_back(small_op(te3, m->stacks[s].time_w, m->stacks[s].time_b, nullptr, temb[s], N, td, D,
                                    ACT_SWOOSH_R_, 0));
     }
-    // in_proj (reference: modules/zipformer.py:264-265)
+    // in_proj (reference: modules/zipformer.py:264-265) -> fp32 stream
     {
-        Op op; LinearEpi e;
+        Op op; LinearEpi e; e.out_mode = OUT_F32;
         TRY(build_linear(op, xin, M, xin_pitch, m->in_proj, cur0, D, e));
         ops.push_back(op);
     }
-    bf16* cur = cur0;
-    bf16* cur_alt = cur1;
+    float* cur = cur0;
+    float* cur_alt = cur1;
+    bool curb_valid = false;
 
     for (int s = 0; s < m->num_stacks; ++s) {
         const zvb_stack& stk = m->stacks[s];
         const int ds = stk.downsample;
+        const bool last_stack = s == m->num_stacks - 1;
         if (ds != 1 && ds != 2 && ds != 4) return fail(ZVB_ERR_INVALID, "downsample %d unsupported", ds);
+        if (stk.num_layers <= 0) return fail(ZVB_ERR_INVALID, "empty stack");
         const int L = (T + ds - 1) / ds, Lk = round8(L);
         const long long Ms = (long long)N * L;
         const float* tb = td > 0 ? temb[s] : nullptr;
         int si = 0;
-        // stack input -> S[0]
         if (ds != 1) {   // ds == 1 runs the layers directly on `cur` as the first layer's src
             Op op; op.type = OP_DOWN; op.p0 = cur; op.o0 = S[0];
             op.i0 = N; op.i1 = T; op.i2 = L; op.i3 = ds; op.i4 = D;
             for (int k = 0; k < 4; ++k) op.w[k] = stk.ds_weights[k];
-            op.cat = ZVB_CAT_RESAMPLE; op.work = 2.0 * ((double)M + (double)Ms) * D;
+            op.cat = ZVB_CAT_RESAMPLE; op.work = 4.0 * ((double)M + (double)Ms) * D;
             ops.push_back(op);
         }
-        const bf16* src = ds == 1 ? cur : S[0];
-        const bf16* srct = src;
-        if (tb != nullptr) {
-            Op op; op.type = OP_ADDROW; op.p0 = src; op.o0 = St[0]; op.f0 = tb; op.i0 = D; op.i1 = L; op.rows = Ms;
-            op.cat = ZVB_CAT_ELEMENTWISE; op.work = 2.0 * 2.0 * (double)Ms * D;
+        const float* src = ds == 1 ? cur : S[0];
+        {   // bf16 shadows of the stack input: Sb[0] = bf16(src), St[0] = bf16(src + temb)
+            Op op; op.type = OP_PREP; op.p0 = src; op.o0 = Sb[0]; op.o1 = tb != nullptr ? St[0] : nullptr;
+            op.f0 = tb; op.i0 = D; op.i1 = L; op.rows = Ms;
+            op.cat = ZVB_CAT_ELEMENTWISE; op.work = (double)Ms * D * (4.0 + 2.0 + (tb != nullptr ? 2.0 : 0.0));
             ops.push_back(op);
-            srct = St[0];
         }
+        const bf16* srcb = Sb[0];
+        const bf16* srct = tb != nullptr ? St[0] : Sb[0];
         for (int j = 0; j < stk.num_layers; ++j) {
             const zvb_layer& ly = m->layers[stk.first_layer + j];
             const bool last = j == stk.num_layers - 1;
             Op op;
             LinearEpi e;
-            // 1. attention projections + weights
+            auto stream_epi = [&](const float* resid, bf16* shadow) {
+                LinearEpi x; x.resid = resid; x.out_mode = shadow != nullptr ? OUT_F32_BF16 : OUT_F32; x.out_bf16 = shadow;
+                return x;
+            };
+            auto t_epi = [&](int batch_rows, int hd_, int hp_) {
+                LinearEpi x; x.out_mode = OUT_T_BF16; x.t_L = L; x.t_pitch = Lk; x.t_batch_rows = batch_rows;
+                x.t_hd = hd_; x.t_hp = hp_;
+                return x;
+            };
+            // 1. attention projections + weights (on the un-time-embedded input)
             e = LinearEpi();
-            TRY(build_linear(op, src, Ms, D, ly.attn_in, qkp, attn_w, e)); ops.push_back(op);
+            TRY(build_linear(op, srcb, Ms, D, ly.attn_in, qkp, attn_w, e)); ops.push_back(op);
             TRY(build_attn(op, qkp, attn_w, ly.pos_table, mask_ds[ds], P, N, H, L, Lk)); ops.push_back(op);
-            // 2. feed_forward1 on src + temb
+            // 2. feed_forward1 on src + temb:  R0 = src + temb + FF1(src + temb)
             e = LinearEpi(); e.act = ACT_SWOOSH_L;
             TRY(build_linear(op, srct, Ms, D, ly.ff_in[0], hid, m->ff_dims[0], e)); ops.push_back(op);
-            e = LinearEpi(); e.resid = srct;
+            e = stream_epi(src, Rb[0]); e.rowbias = tb; e.rows_per_group = L;
             TRY(build_linear(op, hid, Ms, m->ff_dims[0], ly.ff_out[0], R[0], D, e)); ops.push_back(op);
             // 3. nonlin attention
-            e = LinearEpi(); e.transposed = 1; e.t_L = L; e.t_pitch = Lk; e.t_batch_rows = nah; e.t_hd = 1; e.t_hp = 1;
-            TRY(build_gated(op, R[0], Ms, D, ly.na_sx, nah, GATE_TANH_SX, vtna[ds], 0, nullptr, e)); ops.push_back(op);
+            e = t_epi(nah, 1, 1);
+            TRY(build_gated(op, Rb[0], Ms, D, ly.na_sx, nah, GATE_TANH_SX, vtna[ds], 0, nullptr, e)); ops.push_back(op);
             e = LinearEpi();
-            TRY(build_linear(op, R[0], Ms, D, ly.na_y, nay, nah, e)); ops.push_back(op);
+            TRY(build_linear(op, Rb[0], Ms, D, ly.na_y, nay, nah, e)); ops.push_back(op);
             TRY(build_pv(op, P, vtna[ds], pvna, nah, N, H, L, Lk, nah, nah, 0, nay, nah)); ops.push_back(op);
-            e = LinearEpi(); e.resid = R[0];
+            e = stream_epi(R[0], Rb[1]);
             TRY(build_linear(op, pvna, Ms, nah, ly.na_out, R[1], D, e)); ops.push_back(op);
             // 4. self_attn1 (+ temb for the conv module that follows)
-            e = LinearEpi(); e.transposed = 1; e.t_L = L; e.t_pitch = Lk; e.t_batch_rows = H * hp; e.t_hd = dv; e.t_hp = hp;
-            TRY(build_linear(op, R[1], Ms, D, ly.sa_in[0], vtsa[ds], 0, e)); ops.push_back(op);
+            e = t_epi(H * hp, dv, hp);
+            TRY(build_linear(op, Rb[1], Ms, D, ly.sa_in[0], vtsa[ds], 0, e)); ops.push_back(op);
             TRY(build_pv(op, P, vtsa[ds], pvsa, H * dv, N, H, L, Lk, dv, hp, 1, nullptr, 0)); ops.push_back(op);
-            e = LinearEpi(); e.resid = R[1]; e.rowbias = tb; e.rows_per_group = L;
+            e = stream_epi(R[1], Rb[0]); e.rowbias = tb; e.rows_per_group = L;
             TRY(build_linear(op, pvsa, Ms, H * dv, ly.sa_out[0], R[0], D, e)); ops.push_back(op);
             // 5. conv_module1
             e = LinearEpi();
-            TRY(build_gated(op, R[0], Ms, D, ly.conv_in[0], D, GATE_GLU_XS, glu, D, mask_ds[ds], e)); ops.push_back(op);
+            TRY(build_gated(op, Rb[0], Ms, D, ly.conv_in[0], D, GATE_GLU_XS, glu, D, mask_ds[ds], e)); ops.push_back(op);
             { Op d; d.type = OP_DWCONV; d.p0 = glu; d.o0 = cv; d.f0 = ly.dw_w[0]; d.f1 = ly.dw_b[0];
               d.i0 = N; d.i1 = L; d.i2 = D; d.i3 = stk.conv_kernel;
               d.cat = ZVB_CAT_DWCONV; d.work = 2.0 * 2.0 * (double)Ms * D; ops.push_back(d); }
-            e = LinearEpi(); e.resid = R[0];
+            e = stream_epi(R[0], Rb[1]);
             TRY(build_linear(op, cv, Ms, D, ly.conv_out[0], R[1], D, e)); ops.push_back(op);
             // 6. feed_forward2 + bypass_mid
             e = LinearEpi(); e.act = ACT_SWOOSH_L;
-            TRY(build_linear(op, R[1], Ms, D, ly.ff_in[1], hid, m->ff_dims[1], e)); ops.push_back(op);
-            e = LinearEpi(); e.resid = R[1]; e.orig = src; e.bypass_scale = ly.bypass_mid_scale;
+            TRY(build_linear(op, Rb[1], Ms, D, ly.ff_in[1], hid, m->ff_dims[1], e)); ops.push_back(op);
+            e = stream_epi(R[1], Rb[0]); e.orig = src; e.bypass_scale = ly.bypass_mid_scale;
             TRY(build_linear(op, hid, Ms, m->ff_dims[1], ly.ff_out[1], R[0], D, e)); ops.push_back(op);
             // 7. self_attn2 (+ temb)
-            e = LinearEpi(); e.transposed = 1; e.t_L = L; e.t_pitch = Lk; e.t_batch_rows = H * hp; e.t_hd = dv; e.t_hp = hp;
-            TRY(build_linear(op, R[0], Ms, D, ly.sa_in[1], vtsa[ds], 0, e)); ops.push_back(op);
+            e = t_epi(H * hp, dv, hp);
+            TRY(build_linear(op, Rb[0], Ms, D, ly.sa_in[1], vtsa[ds], 0, e)); ops.push_back(op);
             TRY(build_pv(op, P, vtsa[ds], pvsa, H * dv, N, H, L, Lk, dv, hp, 1, nullptr, 0)); ops.push_back(op);
-            e = LinearEpi(); e.resid = R[0]; e.rowbias = tb; e.rows_per_group = L;
+            e = stream_epi(R[0], Rb[1]); e.rowbias = tb; e.rows_per_group = L;
             TRY(build_linear(op, pvsa, Ms, H * dv, ly.sa_out[1], R[1], D, e)); ops.push_back(op);
             // 8. conv_module2
             e = LinearEpi();
-            TRY(build_gated(op, R[1], Ms, D, ly.conv_in[1], D, GATE_GLU_XS, glu, D, mask_ds[ds], e)); ops.push_back(op);
+            TRY(build_gated(op, Rb[1], Ms, D, ly.conv_in[1], D, GATE_GLU_XS, glu, D, mask_ds[ds], e)); ops.push_back(op);
             { Op d; d.type = OP_DWCONV; d.p0 = glu; d.o0 = cv; d.f0 = ly.dw_w[1]; d.f1 = ly.dw_b[1];
               d.i0 = N; d.i1 = L; d.i2 = D; d.i3 = stk.conv_kernel;
               d.cat = ZVB_CAT_DWCONV; d.work = 2.0 * 2.0 * (double)Ms * D; ops.push_back(d); }
-            e = LinearEpi(); e.resid = R[1];
+            e = stream_epi(R[1], Rb[0]);
             TRY(build_linear(op, cv, Ms, D, ly.conv_out[1], R[0], D, e)); ops.push_back(op);
-            // 9. feed_forward3
+            // 9. feed_forward3 (only the fp32 stream is needed afterwards)
             e = LinearEpi(); e.act = ACT_SWOOSH_L;
-            TRY(build_linear(op, R[0], Ms, D, ly.ff_in[2], hid, m->ff_dims[2], e)); ops.push_back(op);
-            e = LinearEpi(); e.resid = R[0];
+            TRY(build_linear(op, Rb[0], Ms, D, ly.ff_in[2], hid, m->ff_dims[2], e)); ops.push_back(op);
+            e = stream_epi(R[0], nullptr);
             TRY(build_linear(op, hid, Ms, m->ff_dims[2], ly.ff_out[2], R[1], D, e)); ops.push_back(op);
-            // 10. BiasNorm + bypass -> next layer input (and its time-embedded copy)
-            bf16* nsrc;
-            if (last && ds == 1) nsrc = cur_alt;
-            else nsrc = S[si ^ 1];
-            // S[si ^ 1] never aliases `src`: src is `cur` (ds == 1, first layer) or S[si]
-            bf16* nsrct = (!last && tb != nullptr) ? St[si ^ 1] : nullptr;
-            { Op b; b.type = OP_BIASNORM; b.p0 = R[1]; b.p1 = src; b.o0 = nsrc; b.o1 = nsrct;
+            // 10. BiasNorm + bypass -> next layer input (fp32), its bf16 shadow, its time-embedded shadow
+            float* nsrc = (last && ds == 1) ? cur_alt : S[si ^ 1];   // never aliases `src`
+            bf16* nsrcb = nullptr;
+            bf16* nsrct = nullptr;
+            if (!last) {
+                nsrcb = Sb[si ^ 1];
+                nsrct = tb != nullptr ? St[si ^ 1] : nullptr;
+            } else if (ds == 1 && last_stack) {
+                nsrcb = curb;                                       // operand of out_proj
+                curb_valid = true;
+            }
+            { Op b; b.type = OP_BIASNORM; b.p0 = R[1]; b.p1 = src; b.o0 = nsrc; b.o1 = nsrcb; b.o2 = nsrct;
               b.f0 = ly.norm_bias; b.f1 = ly.norm_log_scale; b.f2 = ly.bypass_scale; b.f3 = tb;
               b.i0 = D; b.i1 = L; b.rows = Ms;
-              b.cat = ZVB_CAT_BIASNORM; b.work = 2.0 * (double)Ms * D * (nsrct != nullptr ? 4 : 3); ops.push_back(b); }
+              b.cat = ZVB_CAT_BIASNORM;
+              b.work = (double)Ms * D * (3 * 4.0 + (nsrcb != nullptr ? 2.0 : 0.0) + (nsrct != nullptr ? 2.0 : 0.0));
+              ops.push_back(b); }
             src = nsrc;
-            srct = nsrct != nullptr ? nsrct : nsrc;
+            srcb = nsrcb;
+            srct = nsrct != nullptr ? nsrct : nsrcb;
             si ^= 1;
         }
         if (ds == 1) {
             std::swap(cur, cur_alt);        // the last layer wrote into cur_alt
         } else {
-            Op op; op.type = OP_UP; op.p0 = cur; op.p1 = src; op.o0 = cur_alt; op.f0 = stk.out_combiner_scale;
+            Op op; op.type = OP_UP; op.p0 = cur; op.p1 = src; op.o0 = cur_alt; op.o1 = last_stack ? curb : nullptr;
+            op.f0 = stk.out_combiner_scale;
             op.i0 = N; op.i1 = T; op.i2 = L; op.i3 = ds; op.i4 = D;
-            op.cat = ZVB_CAT_RESAMPLE; op.work = 2.0 * (2.0 * (double)M + (double)Ms) * D;
+            op.cat = ZVB_CAT_RESAMPLE; op.work = 4.0 * (2.0 * (double)M + (double)Ms) * D;
             ops.push_back(op);
+            if (last_stack) curb_valid = true;
             std::swap(cur, cur_alt);
         }
     }
+    if (!curb_valid) return fail(ZVB_ERR_INVALID, "internal: final stream has no bf16 shadow");
     // out_proj (reference: modules/zipformer.py:291)
     {
-        Op op; LinearEpi e; e.out_f32 = 1;
-        TRY(build_linear(op, cur, M, D, m->out_proj, out, m->out_dim, e));
+        Op op; LinearEpi e; e.out_mode = OUT_F32;
+        TRY(build_linear(op, curb, M, D, m->out_proj, out, m->out_dim, e));
         ops.push_back(op);
     }
     return 0;
@@ -731,10 +773,12 @@ int zvb_sample(zvb_plan* plan, float* x, const float* text, const float* speech,
 
 // ------------------------------------------------------------------------------------------ test entry points
 int zvb_test_linear(const void* A, int M, int K, int lda, const void* W, const float* bias, int n_out, int k_pitch,
-                    int block_n, int act, const void* resid, void* out, int ldc, int out_f32, void* stream) {
+                    int block_n, int act, const float* resid, void* out, void* out_bf16, int ldc, int out_mode,
+                    void* stream) {
     TRY(init_device());
     zvb_linear lin{W, bias, n_out, K, k_pitch, n_out};
-    Op op; LinearEpi e; e.act = act; e.resid = (const bf16*)resid; e.out_f32 = out_f32; e.block_n = block_n;
+    Op op; LinearEpi e; e.act = act; e.resid = resid; e.out_mode = out_mode; e.out_bf16 = (bf16*)out_bf16;
+    e.block_n = block_n;
     TRY(build_linear(op, (const bf16*)A, M, lda, lin, out, ldc, e));
     return launch_op(op, static_cast<cudaStream_t>(stream));
 }
@@ -748,24 +792,28 @@ int zvb_test_attn_weights(const void* qkp, int ld, const float* pos_table, const
 }
 
 int zvb_test_pv(const void* P, const void* Vt, void* out, int N, int H, int L, int Lk, int hd, int hp, int per_head,
-                void* stream) {
+                const void* mul, void* stream) {
     TRY(init_device());
     Op op;
     const int ldc = per_head ? H * hd : hd;
-    if (per_head) {
-        TRY(build_pv(op, (const bf16*)P, (const bf16*)Vt, out, ldc, N, H, L, Lk, hd, hp, 1, nullptr, 0));
-    } else {
-        // NonlinAttention form without the y gate: reuse the LINEAR epilogue on head-0 weights
-        TRY(build_pv(op, (const bf16*)P, (const bf16*)Vt, out, ldc, N, H, L, Lk, hd, hp, 0, nullptr, 0));
-        op.kind = EPI_LINEAR;
-    }
+    TRY(build_pv(op, (const bf16*)P, (const bf16*)Vt, out, ldc, N, H, L, Lk, hd, hp, per_head, (const bf16*)mul, hd));
     return launch_op(op, static_cast<cudaStream_t>(stream));
 }
 
-int zvb_test_biasnorm_bypass(const void* src, const void* orig, void* out, const float* nbias, const float* log_scale,
+int zvb_test_gated(const void* A, int M, int K, int lda, const void* W, const float* bias, int rows, int n_out,
+                   int k_pitch, int gate_mode, const uint8_t* row_mask, void* out, int ldc, void* stream) {
+    TRY(init_device());
+    zvb_linear lin{W, bias, n_out, K, k_pitch, rows};
+    Op op; LinearEpi e;
+    TRY(build_gated(op, (const bf16*)A, M, lda, lin, n_out, gate_mode, out, ldc, row_mask, e));
+    return launch_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_biasnorm_bypass(const float* src, const float* orig, float* out, void* out_b, void* out_t,
+                             const float* temb, int rows_per_group, const float* nbias, const float* log_scale,
                              const float* bscale, long long rows, int C, void* stream) {
-    Op b; b.type = OP_BIASNORM; b.p0 = src; b.p1 = orig; b.o0 = out; b.o1 = nullptr;
-    b.f0 = nbias; b.f1 = log_scale; b.f2 = bscale; b.f3 = nullptr; b.i0 = C; b.i1 = 1; b.rows = rows;
+    Op b; b.type = OP_BIASNORM; b.p0 = src; b.p1 = orig; b.o0 = out; b.o1 = out_b; b.o2 = out_t;
+    b.f0 = nbias; b.f1 = log_scale; b.f2 = bscale; b.f3 = temb; b.i0 = C; b.i1 = rows_per_group; b.rows = rows;
     return launch_op(b, static_cast<cudaStream_t>(stream));
 }
 

@@ -1,8 +1,12 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C = epilogue(A · Bᵀ)
-//   A: (rows, K) bf16 K-major, B: (cols, K) bf16 K-major (an nn.Linear weight, or Vᵀ),
-//   both streamed by TMA (128B swizzle) through a 4-stage mbarrier ring; fp32 accumulators
-//   live in TMEM (2 stages x <=256 columns) so the epilogue of tile i overlaps the MMAs of
-//   tile i+1.  Warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
+//   A: (rows, K) bf16 K-major, B: (cols, K) bf16 K-major (an nn.Linear weight, or Vᵀ), both
+//   streamed by TMA (128B swizzle) through a 3-stage mbarrier ring; fp32 accumulators live in
+//   TMEM (2 stages x <=256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   The epilogue's tile-shaped operand (the fp32 residual stream, or the bf16 `y` gate of
+//   NonlinAttention) is streamed by a second TMA ring of 16 KB sub-tiles (128 rows x 128 bytes),
+//   so the epilogue threads never wait on a global load.
+//   Warp 0 = TMA producer (A/B), warp 1 = MMA issuer (+TMEM alloc), warp 2 = TMA producer (aux),
+//   warps 4..11 = epilogue (two warps per TMEM lane quarter, alternating 64-column sub-tiles).
 // Serves every dense contraction of the TTSZipformer forward (reference:
 // modules/zipformer.py:1172,1377,1393,1434-1437,1511,1534,1542,1655,1678, 265, 291).
 #pragma once
@@ -13,50 +17,55 @@ namespace zvb {
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_UMMA_K = 16;
-constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_STAGES = 3;
 constexpr int GEMM_A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB
 constexpr int GEMM_B_BYTES = 256 * GEMM_BLOCK_K * 2;            // 32 KB (block_n <= 256)
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_AUX_SLOTS = 4;
+constexpr int GEMM_AUX_BYTES = 128 * 128;                       // 128 rows x 128 B
+constexpr int GEMM_BIAS_BYTES = 2 * 256 * 4;
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_AUX_SLOTS * GEMM_AUX_BYTES +
+                                GEMM_BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_THREADS = 256;
 constexpr int GEMM_TMEM_COLS = 512;
 
-enum { EPI_LINEAR = 0, EPI_GATED = 1, EPI_MUL = 2 };
+enum { EPI_LINEAR = 0, EPI_GATED = 1 };
 enum { ACT_NONE = 0, ACT_SWOOSH_L = 1, ACT_SWOOSH_R = 2 };
 enum { GATE_TANH_SX = 1, GATE_GLU_XS = 2 };
+enum { AUX_NONE = 0, AUX_RESID_F32 = 1, AUX_MUL_BF16 = 2 };
+enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_BF16 = 2, OUT_T_BF16 = 3 };
 
 struct GemmParams {
     // problem / tiling
     int M;                 // valid rows per batch (A rows beyond M are TMA zero-fill, never stored)
     int n_out;             // valid output columns per batch
     int num_k_blocks;
-    int block_n;           // UMMA N: multiple of 16 (32 for EPI_GATED), <= 256
+    int block_n;           // UMMA N: multiple of 16, <= 256 (256 for EPI_GATED)
     int num_m_tiles, num_n_tiles, batches;
     int a_zb, a_zn;        // A tensor-map z = b*a_zb + n_tile*a_zn
     int b_zb;              // B tensor-map z = b*b_zb
-    // output
-    void* out;             // bf16 (or fp32 when out_f32), row = b*M + m
-    int ldc;
-    int out_f32;
+    // output: row = b*M + m
+    int out_mode;
+    void* out;             // bf16 (OUT_BF16, OUT_T_BF16) or fp32 (OUT_F32, OUT_F32_BF16)
+    __nv_bfloat16* out_bf16;   // OUT_F32_BF16: bf16 shadow copy (GEMM operand of the next kernel)
+    int ldc;               // pitch of `out` (and of out_bf16), in elements
     int out_col_stride;    // first output column of a tile = n_tile*out_col_stride
     int n_valid;           // valid accumulator columns inside one tile
     // epilogue operands (nullable)
-    const float* bias;     // [num_n_tiles*block_n], accumulator-column indexed
-    const float* rowbias;  // [(row / rows_per_group)*ld_rowbias + outcol]
+    const float* bias;     // accumulator-column indexed, at least n_out (LINEAR) / tiles*256 (GATED)
+    const float* rowbias;  // fp32 [(row / rows_per_group)*ld_rowbias + outcol]
     int rows_per_group;
     int ld_rowbias;
-    const __nv_bfloat16* resid;
-    int ldr;
-    const __nv_bfloat16* orig;      // bypass: orig + (v - orig)*scale[col]
+    int aux_mode;          // tile operand streamed by TMA: fp32 residual or bf16 multiplier
+    int aux_zb;            // aux tensor-map z = b*aux_zb
+    const float* orig;     // bypass: orig + (v - orig)*scale[col]; fp32, pitch ldc
     const float* bypass_scale;
     int act;
     int gate_mode;
     const uint8_t* row_mask;        // [rows] non-zero -> output row is zero
-    const __nv_bfloat16* mul;
-    int ldm;
-    // transposed store: dst[(row / t_L)*t_batch_rows + drow(col)][row % t_L], pitch t_pitch,
+    // OUT_T_BF16: dst[(row / t_L)*t_batch_rows + drow(col)][row % t_L], pitch t_pitch,
     // drow(col) = col + (col / t_hd)*(t_hp - t_hd)
-    int transposed;
     int t_L, t_pitch, t_batch_rows, t_hd, t_hp;
 };
 
@@ -66,100 +75,94 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
-// Stores 16 consecutive output columns [col0, col0+16) of one row.
-__device__ __forceinline__ void store_row16(const GemmParams& p, long long row, int col0, int ncols,
+// Stores 32 consecutive output columns [col0, col0+32) of one row (ncols valid).
+__device__ __forceinline__ void store_row32(const GemmParams& p, long long row, int col0, int ncols,
                                             const float* v) {
-    if (p.transposed) {
+    if (p.out_mode == OUT_T_BF16) {
         const int n = static_cast<int>(row / p.t_L);
         const int l = static_cast<int>(row - static_cast<long long>(n) * p.t_L);
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out);
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                             static_cast<long long>(n) * p.t_batch_rows * p.t_pitch + l;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 32; ++i) {
             if (i < ncols) {
                 const int c = col0 + i;
                 const int drow = c + (c / p.t_hd) * (p.t_hp - p.t_hd);
-                dst[(static_cast<long long>(n) * p.t_batch_rows + drow) * p.t_pitch + l] =
-                    __float2bfloat16(v[i]);
+                dst[static_cast<long long>(drow) * p.t_pitch] = __float2bfloat16(v[i]);
             }
         }
         return;
     }
-    if (p.out_f32) {
+    const bool full = ncols == 32 && (p.ldc & 7) == 0 && (col0 & 7) == 0;
+    if (p.out_mode == OUT_F32 || p.out_mode == OUT_F32_BF16) {
         float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + col0;
-        if (ncols == 16 && (p.ldc & 3) == 0) {
+        if (full) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4)
+            for (int i = 0; i < 32; i += 4)
                 *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
+            for (int i = 0; i < 32; ++i)
                 if (i < ncols) dst[i] = v[i];
         }
-        return;
+        if (p.out_mode == OUT_F32) return;
     }
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col0;
-    if (ncols == 16 && (p.ldc & 7) == 0 && (col0 & 7) == 0) {
-        uint4 a, b;
-        a.x = pack_bf16(v[0], v[1]);   a.y = pack_bf16(v[2], v[3]);
-        a.z = pack_bf16(v[4], v[5]);   a.w = pack_bf16(v[6], v[7]);
-        b.x = pack_bf16(v[8], v[9]);   b.y = pack_bf16(v[10], v[11]);
-        b.z = pack_bf16(v[12], v[13]); b.w = pack_bf16(v[14], v[15]);
-        *reinterpret_cast<uint4*>(dst) = a;
-        *reinterpret_cast<uint4*>(dst + 8) = b;
+    __nv_bfloat16* dst = (p.out_mode == OUT_F32_BF16 ? p.out_bf16 : reinterpret_cast<__nv_bfloat16*>(p.out)) +
+                         row * p.ldc + col0;
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+            *reinterpret_cast<uint4*>(dst + i) =
+                make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
+                           pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
     } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
+        for (int i = 0; i < 32; ++i)
             if (i < ncols) dst[i] = __float2bfloat16(v[i]);
-    }
-}
-
-// Loads 16 bf16 of one row as floats (vectorised when aligned, zero beyond ncols).
-__device__ __forceinline__ void load_row16(const __nv_bfloat16* base, long long row, int ld, int col0,
-                                           int ncols, float* v) {
-    const __nv_bfloat16* src = base + row * ld + col0;
-    if (ncols == 16 && (ld & 7) == 0 && (col0 & 7) == 0) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
-        const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + 8));
-        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            v[2 * i] = bf16_lo(w[i]);
-            v[2 * i + 1] = bf16_hi(w[i]);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = i < ncols ? __bfloat162float(src[i]) : 0.0f;
     }
 }
 
 template <int KIND>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const GemmParams p) {
+            const __grid_constant__ CUtensorMap tma_aux, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
-    uint64_t* full_bar = bars;                        // [STAGES] TMA -> MMA
-    uint64_t* empty_bar = bars + GEMM_STAGES;         // [STAGES] MMA -> TMA
-    uint64_t* tmem_full = bars + 2 * GEMM_STAGES;     // [2] MMA -> epilogue
-    uint64_t* tmem_empty = bars + 2 * GEMM_STAGES + 2;  // [2] epilogue -> MMA
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_STAGES + 4);
+    uint8_t* aux_smem = smem + GEMM_STAGES * GEMM_STAGE_BYTES;
+    float* bias_smem = reinterpret_cast<float*>(aux_smem + GEMM_AUX_SLOTS * GEMM_AUX_BYTES);   // [2][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_smem) + GEMM_BIAS_BYTES);
+    uint64_t* full_bar = bars;                                  // [STAGES] TMA -> MMA
+    uint64_t* empty_bar = full_bar + GEMM_STAGES;               // [STAGES] MMA -> TMA
+    uint64_t* tmem_full = empty_bar + GEMM_STAGES;              // [2] MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;                       // [2] epilogue -> MMA
+    uint64_t* aux_full = tmem_empty + 2;                        // [AUX_SLOTS] TMA -> epilogue
+    uint64_t* aux_empty = aux_full + GEMM_AUX_SLOTS;            // [AUX_SLOTS] epilogue -> TMA
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(aux_empty + GEMM_AUX_SLOTS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_tiles = p.batches * p.num_m_tiles * p.num_n_tiles;
+    // accumulator columns are consumed in units of 32; aux sub-tiles hold 32 (fp32) or 64 (bf16) columns
+    const int n_units = (p.block_n + 31) >> 5;
+    const int units_per_sub = p.aux_mode == AUX_RESID_F32 ? 1 : 2;
+    const int n_sub = (n_units + units_per_sub - 1) / units_per_sub;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
+        if (p.aux_mode != AUX_NONE) tma_prefetch_desc(&tma_aux);
         for (int s = 0; s < GEMM_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 4);
+            mbar_init(&tmem_empty[s], 8);
+        }
+        for (int s = 0; s < GEMM_AUX_SLOTS; ++s) {
+            mbar_init(&aux_full[s], 1);
+            mbar_init(&aux_empty[s], 4);
         }
         fence_barrier_init();
     }
@@ -173,7 +176,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const uint32_t tmem_base = *tmem_holder;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------------ TMA producer (A, B)
         if (lane == 0) {
             const uint32_t stage_bytes = GEMM_A_BYTES + static_cast<uint32_t>(p.block_n) * GEMM_BLOCK_K * 2;
             int stage = 0;
@@ -227,101 +230,151 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
-    } else {
-        // ------------------------------------------------------------------ epilogue (4 warps)
+    } else if (warp == 2) {
+        // ------------------------------------------------------------------ TMA producer (aux tiles)
+        if (lane == 0 && p.aux_mode != AUX_NONE) {
+            const int sub_cols = p.aux_mode == AUX_RESID_F32 ? 32 : 64;
+            uint32_t q = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.num_n_tiles;
+                const int rest = tile / p.num_n_tiles;
+                const int m_tile = rest % p.num_m_tiles;
+                const int b = rest / p.num_m_tiles;
+                for (int s = 0; s < n_sub; ++s, ++q) {
+                    const int slot = q % GEMM_AUX_SLOTS;
+                    const uint32_t par = (q / GEMM_AUX_SLOTS) & 1u;
+                    mbar_wait(&aux_empty[slot], par ^ 1u);
+                    mbar_arrive_expect_tx(&aux_full[slot], GEMM_AUX_BYTES);
+                    tma_load_3d(aux_smem + slot * GEMM_AUX_BYTES, &tma_aux, &aux_full[slot],
+                                n_tile * p.out_col_stride + s * sub_cols, m_tile * GEMM_BLOCK_M, b * p.aux_zb);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (8 warps)
         const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;                 // which of the two warps of the quarter
+        const int et = threadIdx.x - 128;                 // 0..255
+        const int r = quarter * 32 + lane;                // accumulator row inside the tile
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        uint32_t tile_iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
             const int n_tile = tile % p.num_n_tiles;
             const int rest = tile / p.num_n_tiles;
             const int m_tile = rest % p.num_m_tiles;
             const int b = rest / p.num_m_tiles;
-            const int m = m_tile * GEMM_BLOCK_M + quarter * 32 + lane;
+            const int m = m_tile * GEMM_BLOCK_M + r;
             const bool row_ok = m < p.M;
             const long long row = static_cast<long long>(b) * p.M + m;
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * 256u +
-                                   (static_cast<uint32_t>(quarter * 32) << 16);
             const int out_base = n_tile * p.out_col_stride;
             const int acc_base = n_tile * p.block_n;
+            // stage this tile's bias (double buffered by accumulator stage)
+            float* bs = bias_smem + acc * 256;
+            {
+                const int c = acc_base + et;
+                const int lim = KIND == EPI_GATED ? p.num_n_tiles * 256 : p.n_out;
+                bs[et] = (p.bias != nullptr && et < p.block_n && c < lim) ? __ldg(p.bias + c) : 0.0f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             bool masked = false;
             if (p.row_mask != nullptr && row_ok) masked = p.row_mask[row] != 0;
             long long grp = 0;
             if (p.rowbias != nullptr && row_ok) grp = row / p.rows_per_group;
 
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * 256u +
+                                   (static_cast<uint32_t>(quarter * 32) << 16);
+
             if (KIND == EPI_GATED) {
-                const int half = p.block_n >> 1;
-                for (int c0 = 0; c0 < half; c0 += 16) {
-                    uint32_t ra[16], rb[16];
-                    tmem_ld16(taddr + c0, ra);
-                    tmem_ld16(taddr + half + c0, rb);
+                const int hcols = p.block_n >> 1;                       // 128
+                for (int u = half; u * 32 < hcols; u += 2) {
+                    const int c0 = u * 32;
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32(taddr + c0, ra);
+                    tmem_ld32(taddr + hcols + c0, rb);
                     tmem_ld_wait();
                     const int oc = out_base + c0;
                     int ncols = p.n_out - oc;
-                    ncols = ncols > 16 ? 16 : ncols;
+                    ncols = ncols > 32 ? 32 : ncols;
                     if (row_ok && ncols > 0) {
-                        float v[16];
+                        float v[32];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float a = __uint_as_float(ra[i]) + __ldg(p.bias + acc_base + c0 + i);
-                            const float g = __uint_as_float(rb[i]) + __ldg(p.bias + acc_base + half + c0 + i);
-                            float r = p.gate_mode == GATE_TANH_SX ? g * fast_tanh(a) : a * fast_sigmoid(g);
-                            v[i] = masked ? 0.0f : r;
+                        for (int i = 0; i < 32; ++i) {
+                            const float a = __uint_as_float(ra[i]) + bs[c0 + i];
+                            const float g = __uint_as_float(rb[i]) + bs[hcols + c0 + i];
+                            const float o = p.gate_mode == GATE_TANH_SX ? g * fast_tanh(a) : a * fast_sigmoid(g);
+                            v[i] = masked ? 0.0f : o;
                         }
-                        store_row16(p, row, oc, ncols, v);
+                        store_row32(p, row, oc, ncols, v);
                     }
                 }
             } else {
-                for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(taddr + c0, r);
-                    tmem_ld_wait();
-                    const int oc = out_base + c0;
-                    int ncols = p.n_valid - c0;
-                    if (p.n_out - oc < ncols) ncols = p.n_out - oc;
-                    ncols = ncols > 16 ? 16 : ncols;
-                    if (row_ok && ncols > 0) {
-                        float v[16];
+                for (int s = half; s < n_sub; s += 2) {
+                    const uint8_t* aux_row = nullptr;
+                    int slot = 0;
+                    if (p.aux_mode != AUX_NONE) {
+                        const uint32_t q = tile_iter * static_cast<uint32_t>(n_sub) + static_cast<uint32_t>(s);
+                        slot = q % GEMM_AUX_SLOTS;
+                        mbar_wait(&aux_full[slot], (q / GEMM_AUX_SLOTS) & 1u);
+                        aux_row = aux_smem + slot * GEMM_AUX_BYTES + r * 128;
+                    }
+                    for (int uu = 0; uu < units_per_sub; ++uu) {
+                        const int c0 = (s * units_per_sub + uu) * 32;
+                        if (c0 >= p.block_n) break;
+                        uint32_t acc_r[32];
+                        tmem_ld32(taddr + c0, acc_r);
+                        tmem_ld_wait();
+                        const int oc = out_base + c0;
+                        int ncols = p.n_valid - c0;
+                        if (p.n_out - oc < ncols) ncols = p.n_out - oc;
+                        ncols = ncols > 32 ? 32 : ncols;
+                        if (row_ok && ncols > 0) {
+                            float v[32];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-                        if (KIND == EPI_MUL) {
-                            float y[16];
-                            load_row16(p.mul, row, p.ldm, oc, ncols, y);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] *= y[i];
-                        } else {
-                            if (p.bias != nullptr) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (i < ncols) v[i] += __ldg(p.bias + acc_base + c0 + i);
-                            }
+                            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc_r[i]) + bs[c0 + i];
                             if (p.rowbias != nullptr) {
                                 const float* rbp = p.rowbias + grp * p.ld_rowbias + oc;
 #pragma unroll
-                                for (int i = 0; i < 16; ++i)
+                                for (int i = 0; i < 32; ++i)
                                     if (i < ncols) v[i] += __ldg(rbp + i);
                             }
                             if (p.act != ACT_NONE) {
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.act);
+                                for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
                             }
-                            if (p.resid != nullptr) {
-                                float y[16];
-                                load_row16(p.resid, row, p.ldr, oc, ncols, y);
+                            if (p.aux_mode == AUX_RESID_F32) {
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) v[i] += y[i];
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 a = *reinterpret_cast<const float4*>(aux_row + ((j ^ (r & 7)) << 4));
+                                    v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+                                }
+                            } else if (p.aux_mode == AUX_MUL_BF16) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint4 a = *reinterpret_cast<const uint4*>(aux_row + (((4 * uu + j) ^ (r & 7)) << 4));
+                                    v[8 * j] *= bf16_lo(a.x);     v[8 * j + 1] *= bf16_hi(a.x);
+                                    v[8 * j + 2] *= bf16_lo(a.y); v[8 * j + 3] *= bf16_hi(a.y);
+                                    v[8 * j + 4] *= bf16_lo(a.z); v[8 * j + 5] *= bf16_hi(a.z);
+                                    v[8 * j + 6] *= bf16_lo(a.w); v[8 * j + 7] *= bf16_hi(a.w);
+                                }
                             }
                             if (p.orig != nullptr) {
-                                float o[16];
-                                load_row16(p.orig, row, p.ldr, oc, ncols, o);
+                                const float* op = p.orig + row * p.ldc + oc;
 #pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (i < ncols) v[i] = o[i] + (v[i] - o[i]) * __ldg(p.bypass_scale + oc + i);
+                                for (int i = 0; i < 32; ++i)
+                                    if (i < ncols) {
+                                        const float o = __ldg(op + i);
+                                        v[i] = o + (v[i] - o) * __ldg(p.bypass_scale + oc + i);
+                                    }
                             }
+                            store_row32(p, row, oc, ncols, v);
                         }
-                        store_row16(p, row, oc, ncols, v);
+                    }
+                    if (p.aux_mode != AUX_NONE) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&aux_empty[slot]);
                     }
                 }
             }
@@ -335,6 +388,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
+        __syncwarp();
         tc_fence_after();
         tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
     }
