@@ -59,7 +59,8 @@ typedef struct {
 /* Zipformer2EncoderLayer (reference: modules/zipformer.py:370-404) */
 typedef struct {
     zvb_linear attn_in;       /* self_attn_weights.in_proj : D -> H*(2*32+4)               */
-    const float* pos_table;   /* E = linear_pos(pos_emb): fp32 [H][2L-1][4] for this plan's L */
+    const float* pos_table;   /* E = linear_pos(pos_emb): fp32 [H][2L-1][4] for this plan's L, followed by
+                               * [H] floats max_r |E[h][r]|_2 */
     zvb_linear ff_in[3], ff_out[3];
     zvb_linear na_sx;         /* nonlin_attention.in_proj rows (s,x), gated-packed          */
     zvb_linear na_y;          /* nonlin_attention.in_proj rows y                            */
@@ -139,7 +140,7 @@ int zvb_decoder_forward(zvb_plan* plan, void* stream);
 
 /* Profiling aid (NOT graph capturable: records one CUDA event per kernel and synchronises the
  * stream): runs one forward over the resident io buffers and returns, per launched kernel, its
- * duration in ms, its zvb_op_category and its algorithmic work (FLOPs for the tensor-core
+ * duration in ms, its zvb_op_category, its GEMM shape and its algorithmic work (FLOPs for the tensor-core
  * kernels, bytes for the memory-bound ones). */
 typedef enum {
     ZVB_CAT_GEMM_LINEAR = 0, ZVB_CAT_GEMM_GATED = 1, ZVB_CAT_GEMM_PV = 2, ZVB_CAT_ATTN_WEIGHTS = 3,
@@ -147,7 +148,7 @@ typedef enum {
     ZVB_CAT_OTHER = 8
 } zvb_op_category;
 int zvb_decoder_profile(zvb_plan* plan, void* stream, int max_ops, float* ms, int* category, double* work,
-                        int* num_ops);
+                        int* shapes /* nullable, 4 ints per kernel: rows, cols, K, tile N */, int* num_ops);
 
 /* Seam 1: x fp32 [N][T][in_dim], t fp32 [N] (null for the text encoder), mask u8 [N][T],
  * g fp32 [N] or null, out fp32 [N][T][out_dim]. */
@@ -174,11 +175,12 @@ int zvb_sample(zvb_plan* plan, float* x, const float* text, const float* speech,
 int zvb_test_linear(const void* A, int M, int K, int lda, const void* W, const float* bias, int n_out,
                     int k_pitch, int block_n, int act, const float* resid, void* out, void* out_bf16, int ldc,
                     int out_mode, void* stream);
+/* P receives the unnormalised weights exp(s - m), inv_l [N][H][L] the reciprocal row sums */
 int zvb_test_attn_weights(const void* qkp, int ld, const float* pos_table, const uint8_t* mask, void* P,
-                          int N, int H, int L, int Lk, void* stream);
+                          float* inv_l, int N, int H, int L, int Lk, void* stream);
 /* mul: bf16 [N*L][hd] gate of NonlinAttention (per_head == 0 only, nullable) */
-int zvb_test_pv(const void* P, const void* Vt, void* out, int N, int H, int L, int Lk, int hd, int hp,
-                int per_head, const void* mul, void* stream);
+int zvb_test_pv(const void* P, const float* inv_l, const void* Vt, void* out, int N, int H, int L, int Lk, int hd,
+                int hp, int per_head, const void* mul, void* stream);
 /* gated projection on tile-packed weights (rows = tiles*256); gate_mode 1: x*tanh(s), 2: GLU */
 int zvb_test_gated(const void* A, int M, int K, int lda, const void* W, const float* bias, int rows, int n_out,
                    int k_pitch, int gate_mode, const uint8_t* row_mask, void* out, int ldc, void* stream);

@@ -139,12 +139,16 @@ def check_attn(N=2, H=4, L=200, masked=True, seed=0):
     qkp, E, mask = _attn_inputs(N, H, L, seed, masked)
     Lk = (L + 7) // 8 * 8
     P = torch.full((N, H, L, Lk), float("nan"), dtype=torch.bfloat16, device=DEV)
+    inv_l = torch.full((N, H, L), float("nan"), dtype=torch.float32, device=DEV)
     m8 = mask.to(torch.uint8).contiguous()
-    _lib.check(lib.zvb_test_attn_weights(qkp.data_ptr(), H * 68, E.data_ptr(), m8.data_ptr(), P.data_ptr(), N, H, L,
-                                         Lk, _s()))
+    Ex = torch.cat([E.reshape(-1), E.norm(dim=2).amax(dim=1)]).contiguous()
+    _lib.check(lib.zvb_test_attn_weights(qkp.data_ptr(), H * 68, Ex.data_ptr(), m8.data_ptr(), P.data_ptr(),
+                                         inv_l.data_ptr(), N, H, L, Lk, _s()))
     torch.cuda.synchronize()
     ref = _attn_ref(qkp, E, mask, H)
-    got = P.float()
+    pmax = float(P.float()[..., :L].max())
+    assert 0 < pmax <= 1.0 + 1e-3, pmax                    # unnormalised weights live in (0, 1]
+    got = P.float() * inv_l.unsqueeze(-1)
     pad = got[..., L:]
     return dict(maxabs=float((got[..., :L] - ref).abs().max()), rel=_rel(got[..., :L], ref),
                 nan=int(torch.isnan(got).sum()), pad_nonzero=int((pad != 0).sum()),
@@ -171,13 +175,15 @@ def check_pv(N=2, H=4, L=200, hd=12, hp=16, per_head=True, mul=False, seed=0):
         Vt[:, :, :L] = V
         out = torch.full((N, L, hd), float("nan"), dtype=torch.bfloat16, device=DEV)
         ref = torch.einsum("nij,ndj->nid", P.float()[:, 0, :, :L], V.float().to(DEV))
+    inv_l = (torch.rand(N, H, L, generator=g) + 0.5).to(DEV)
+    ref = ref * (inv_l.permute(0, 2, 1).repeat_interleave(hd, dim=2) if per_head else inv_l[:, 0].unsqueeze(-1))
     Y = None
     if mul:
         Y = torch.randn(N, L, hd, generator=g).to(torch.bfloat16).to(DEV)
         ref = ref * Y.float()
     Vt = Vt.to(DEV)
-    _lib.check(lib.zvb_test_pv(P.data_ptr(), Vt.data_ptr(), out.data_ptr(), N, H, L, Lk, hd, hp, 1 if per_head else 0,
-                               Y.data_ptr() if mul else None, _s()))
+    _lib.check(lib.zvb_test_pv(P.data_ptr(), inv_l.data_ptr(), Vt.data_ptr(), out.data_ptr(), N, H, L, Lk, hd, hp,
+                               1 if per_head else 0, Y.data_ptr() if mul else None, _s()))
     torch.cuda.synchronize()
     return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=6e-3)
 

@@ -1,11 +1,11 @@
 """End-to-end parity of the CUDA path against the golden fixtures (which the reference itself
-produced, tools/make_golden.py).  bf16 tolerances are the ones published in BASELINE.md §5:
-  decoder velocity (one fm_decoder forward, seam 1)  rel-L2 <= 1.5e-2, max-abs <= 0.15
-  solver velocity (after the CFG blend (1+g)v_c - g v_u, which amplifies the decoder error up to
-  ~(1+2g)x while t <= 0.5)                          rel-L2 <= 2.5e-2, max-abs <= 0.20
-  final state x(t_end)                              rel-L2 <= 2e-2,   max-abs <= 0.25
-For scale: the reference's own bf16-autocast run deviates from its fp32 run on these fixtures by
-0.7e-2 (decoder), 0.7-1.1e-2 (CFG velocity), 0.5e-2 (final state) -- tools/make_golden.py notes."""
+produced, tools/make_golden.py).  bf16 tolerances (published in BASELINE.md §5; all at or below the
+survey's proposal of 1.5e-2 / 2e-2, and about the reference's OWN bf16-autocast-vs-fp32 deviation on
+these fixtures, which is 0.7e-2 decoder / 0.7-1.1e-2 CFG velocity / 0.5e-2 final state):
+  decoder velocity (one fm_decoder forward, seam 1)   rel-L2 <= 8e-3,   max-abs <= 0.08
+  solver velocity (after the CFG blend)               rel-L2 <= 1.2e-2, max-abs <= 0.12
+  final state x(t_end)                                rel-L2 <= 1e-2,   max-abs <= 0.10
+Measured on B200 (round 1, fp32 residual stream): 3.1-3.3e-3 / 4.1-5.9e-3 / 1.9-3.3e-3."""
 from __future__ import annotations
 
 import torch
@@ -14,9 +14,9 @@ from zipvoice_b200.model import build_model
 from zipvoice_b200.synth import synth_state_dict, synth_utterances
 from util import CASE_CFG, load_golden, max_abs, rel_l2
 
-TOL_FM_REL, TOL_FM_ABS = 1.5e-2, 0.15
-TOL_V_REL, TOL_V_ABS, TOL_X_REL, TOL_X_ABS = 2.5e-2, 0.20, 2e-2, 0.25
-TOL_TEXT_REL = 1.5e-2
+TOL_FM_REL, TOL_FM_ABS = 8e-3, 0.08
+TOL_V_REL, TOL_V_ABS, TOL_X_REL, TOL_X_ABS = 1.2e-2, 0.12, 1e-2, 0.10
+TOL_TEXT_REL = 8e-3
 
 
 def run_case(name: str, use_cuda_graph: bool = False):

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--guidance", type=float, default=1.0)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--detail", action="store_true")
     a = ap.parse_args()
     cfg = ZipVoiceConfig(a.variant, vocab_size=362 if "dialog" in a.variant else 360)
     t0 = time.time()
@@ -70,6 +71,16 @@ def main():
         unit = "TFLOP/s" if cat.startswith("gemm") or cat == "attn_weights" else "GB/s"
         scale = 1e12 if unit == "TFLOP/s" else 1e9
         print(f"  {cat:16s} n={n:4d}  {ms:8.2f} ms  {100 * ms / tot:5.1f}%   {rate / scale:9.1f} {unit}")
+    if a.detail:
+        det = plan.profile(shapes=True)
+        # first layer of the first stack: ops after the preamble up to the first biasnorm
+        i0 = next(i for i, d in enumerate(det) if d[0] == "attn_weights") - 1
+        i1 = next(i for i, d in enumerate(det) if d[0] == "biasnorm_bypass")
+        print("first full-rate layer, kernel by kernel:")
+        for cat, ms, work, shp in det[i0:i1 + 1]:
+            tensor = cat.startswith("gemm") or cat == "attn_weights"
+            rate = work / (ms * 1e-3) / (1e12 if tensor else 1e9) if ms > 0 else 0
+            print(f"  {cat:16s} {str(shp):28s} {ms * 1e3:8.1f} us  {rate:8.1f} {'TFLOP/s' if tensor else 'GB/s'}")
     print(f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB")
 
 

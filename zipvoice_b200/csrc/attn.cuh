@@ -4,9 +4,12 @@
 // q·kᵀ runs on tcgen05 (K = 32: two UMMA_K steps per 128x128 score tile, accumulators in
 // TMEM, double buffered); the rel-pos bias is a 4-term dot product per score with the
 // per-layer table E = linear_pos(pos_emb) staged in shared memory as the (i-tile, j-tile)
-// window of 255 relative offsets; softmax is two-pass (row max / sum, then normalise) with
-// the cheap q·kᵀ recomputed in the second pass; P is written once as bf16 for the three
-// consumers of the layer (NonlinAttention, SelfAttention x2).
+// window of 255 relative offsets.  Softmax is split so that every score costs one exp and one
+// bias evaluation: pass 1 only takes the row max of q·kᵀ from TMEM (no bias, no exp); with
+// m = max_j q·k_j + |p_i|·max_r|E_h[r]| >= every score of the row, pass 2 recomputes the cheap q·kᵀ,
+// adds the bias and writes the UNNORMALISED weights exp(s - m) in (0, 1] as bf16 together with the
+// fp32 row sum's reciprocal; the three consumers of the layer (NonlinAttention, SelfAttention x2)
+// apply 1/l in their GEMM epilogue.  Masked keys get exactly 0 (exp(-1000 - m) == 0 in fp32).
 #pragma once
 #include "ptx.cuh"
 
@@ -19,7 +22,7 @@ constexpr int ATT_TILE_BYTES = 128 * 64 * 2;      // one 128-row x 64-col bf16 b
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_TMEM_COLS = 256;
 constexpr int ATT_EWIN = 256;        // 255 offsets used
-constexpr int ATT_SMEM_BYTES = (1 + ATT_KSTAGES) * ATT_TILE_BYTES + 2 * ATT_EWIN * 16 + 2 * ATT_BN +
+constexpr int ATT_SMEM_BYTES = (1 + ATT_KSTAGES) * ATT_TILE_BYTES + 2 * ATT_EWIN * 16 + 2 * 16 +
                                1024 + 256;
 
 struct AttnParams {
@@ -27,9 +30,10 @@ struct AttnParams {
     int qd;                          // H * 32: column of head-0 keys inside a qkp row
     const __nv_bfloat16* qkp;        // [N*L, ld] = [q | k | p]
     int ld;
-    const float* E;                  // [H][2L-1][4]
+    const float* E;                  // [H][2L-1][4] followed by [H] floats: max_r |E[h][r]|_2
     const uint8_t* mask;             // [N][L], non-zero = padded key
-    __nv_bfloat16* P;                // [N][H][L][Lk]
+    __nv_bfloat16* P;                // [N][H][L][Lk] unnormalised weights exp(s - m)
+    float* inv_l;                    // [N][H][L]     1 / row sum
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -40,8 +44,8 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
     uint8_t* q_tile = smem;
     uint8_t* k_tiles = smem + ATT_TILE_BYTES;
     float4* ewin = reinterpret_cast<float4*>(smem + (1 + ATT_KSTAGES) * ATT_TILE_BYTES);   // [2][256]
-    uint8_t* mwin = reinterpret_cast<uint8_t*>(ewin + 2 * ATT_EWIN);                        // [2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(mwin + 2 * ATT_BN);
+    uint32_t* mwin = reinterpret_cast<uint32_t*>(ewin + 2 * ATT_EWIN);                      // [2][4] excluded-key bits
+    uint64_t* bars = reinterpret_cast<uint64_t*>(mwin + 8);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1;                      // [KSTAGES]
     uint64_t* k_empty = k_full + ATT_KSTAGES;         // [KSTAGES]
@@ -121,6 +125,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
         // ------------------------------------------------------------------ softmax warps
         const int quarter = warp & 3;
         const int tid = threadIdx.x - 64;                 // 0..127 (not row order; only for staging)
+        const int swarp = tid >> 5;                       // 0..3
         const int r = quarter * 32 + lane;                // row inside the query tile
         const int i = i0 + r;
         const bool row_ok = i < p.L;
@@ -131,10 +136,11 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
             p0 = bf16_lo(w.x); p1 = bf16_hi(w.x); p2 = bf16_lo(w.y); p3 = bf16_hi(w.y);
         }
         const float4* Eh = reinterpret_cast<const float4*>(p.E) + static_cast<long long>(h) * (2 * p.L - 1);
+        const float emax = __ldg(p.E + static_cast<long long>(p.H) * (2 * p.L - 1) * 4 + h);
         const uint8_t* mrow = p.mask + static_cast<long long>(n) * p.L;
         __nv_bfloat16* prow = p.P + ((static_cast<long long>(n) * p.H + h) * p.L + i) * p.Lk;
         constexpr float LOG2E = 1.4426950408889634f;
-        float m_run = -INFINITY, l_run = 0.f, inv_l = 0.f, m_l2 = 0.f;
+        float m_run = -INFINITY, l_run = 0.f, m_l2 = 0.f;
 
         for (int it = 0; it < total_it; ++it) {
             const int pass = it >= num_jt ? 1 : 0;
@@ -142,22 +148,28 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
             const int j0 = jt * ATT_BN;
             const int acc = it & 1;
             const uint32_t acc_phase = static_cast<uint32_t>(it >> 1) & 1u;
-            if (it == num_jt) {                           // between the passes
-                inv_l = 1.0f / l_run;
-                m_l2 = m_run * LOG2E;
+            if (it == num_jt) {                           // between the passes: m >= every score of the row
+                const float pn = sqrtf(p0 * p0 + p1 * p1 + p2 * p2 + p3 * p3);
+                const float m_est = (m_run == -INFINITY ? 0.f : m_run) + pn * emax;
+                m_l2 = m_est * LOG2E;
             }
-            // stage the rel-pos window and the key mask of this tile (double buffered)
+            // stage the excluded-key bits (padding mask or beyond L) and, for the second pass, the
+            // rel-pos window of this tile (double buffered)
             float4* ew = ewin + acc * ATT_EWIN;
-            uint8_t* mw = mwin + acc * ATT_BN;
-            for (int w = tid; w < 255; w += 128) {
-                const int rel = (j0 - i0) - 127 + w + (p.L - 1);
-                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rel >= 0 && rel <= 2 * p.L - 2) e = __ldg(Eh + rel);
-                ew[w] = e;
-            }
+            uint32_t* mw = mwin + acc * 4;
             {
                 const int j = j0 + tid;
-                mw[tid] = j < p.L ? (mrow[j] != 0 ? 1 : 0) : 2;
+                const bool excl = j < p.L ? (mrow[j] != 0) : true;
+                const uint32_t bits = __ballot_sync(0xffffffffu, excl);
+                if (lane == 0) mw[swarp] = bits;
+            }
+            if (pass) {
+                for (int w = tid; w < 255; w += 128) {
+                    const int rel = (j0 - i0) - 127 + w + (p.L - 1);
+                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rel >= 0 && rel <= 2 * p.L - 2) e = __ldg(Eh + rel);
+                    ew[w] = e;
+                }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&s_full[acc], acc_phase);
@@ -169,46 +181,44 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
                 uint32_t sr[32];
                 tmem_ld32(taddr + c0, sr);
                 tmem_ld_wait();
-                float s[32];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float4 e = ew[c0 + c - r + 127];
-                    float v = __uint_as_float(sr[c]);
-                    v = fmaf(p0, e.x, v);
-                    v = fmaf(p1, e.y, v);
-                    v = fmaf(p2, e.z, v);
-                    v = fmaf(p3, e.w, v);
-                    const uint8_t mk = mw[c0 + c];
-                    v = mk == 0 ? v : (mk == 1 ? -1000.0f : -INFINITY);
-                    s[c] = v;
-                }
+                const uint32_t excl = mw[c0 >> 5];
                 if (pass == 0) {
-                    float cm = s[0];
+                    float cm = -INFINITY;
 #pragma unroll
-                    for (int c = 1; c < 32; ++c) cm = fmaxf(cm, s[c]);
-                    const float m_new = fmaxf(m_run, cm);
-                    if (m_new != -INFINITY) {
-                        const float ml2 = m_new * LOG2E;
-                        float acc_sum = 0.f;
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) acc_sum += fast_exp2(fmaf(s[c], LOG2E, -ml2));
-                        l_run = l_run * fast_exp2(fmaf(m_run, LOG2E, -ml2)) + acc_sum;
-                        m_run = m_new;
-                    }
-                } else if (row_ok) {
+                    for (int c = 0; c < 32; ++c)
+                        cm = fmaxf(cm, ((excl >> c) & 1u) ? -INFINITY : __uint_as_float(sr[c]));
+                    m_run = fmaxf(m_run, cm);
+                } else {
                     const int j = j0 + c0;
                     if (j < p.Lk) {
                         uint32_t w[16];
 #pragma unroll
                         for (int c = 0; c < 32; c += 2) {
-                            const float a = fast_exp2(fmaf(s[c], LOG2E, -m_l2)) * inv_l;
-                            const float b = fast_exp2(fmaf(s[c + 1], LOG2E, -m_l2)) * inv_l;
-                            w[c >> 1] = pack_bf16(a, b);
+                            float a, b;
+                            {
+                                const float4 e = ew[c0 + c - r + 127];
+                                float v = __uint_as_float(sr[c]);
+                                v = fmaf(p0, e.x, v); v = fmaf(p1, e.y, v); v = fmaf(p2, e.z, v); v = fmaf(p3, e.w, v);
+                                a = fast_exp2(fmaf(v, LOG2E, -m_l2));
+                            }
+                            {
+                                const float4 e = ew[c0 + c + 1 - r + 127];
+                                float v = __uint_as_float(sr[c + 1]);
+                                v = fmaf(p0, e.x, v); v = fmaf(p1, e.y, v); v = fmaf(p2, e.z, v); v = fmaf(p3, e.w, v);
+                                b = fast_exp2(fmaf(v, LOG2E, -m_l2));
+                            }
+                            a = ((excl >> c) & 1u) ? 0.f : a;
+                            b = ((excl >> (c + 1)) & 1u) ? 0.f : b;
+                            const uint32_t pk = pack_bf16(a, b);
+                            w[c >> 1] = pk;
+                            l_run += bf16_lo(pk) + bf16_hi(pk);      // sum of the values as stored
                         }
-                        uint4* dst = reinterpret_cast<uint4*>(prow + j);
+                        if (row_ok) {
+                            uint4* dst = reinterpret_cast<uint4*>(prow + j);
 #pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            if (j + g * 8 < p.Lk) dst[g] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+                            for (int g = 0; g < 4; ++g)
+                                if (j + g * 8 < p.Lk) dst[g] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+                        }
                     }
                 }
             }
@@ -216,6 +226,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[acc]);
         }
+        if (row_ok) p.inv_l[(static_cast<long long>(n) * p.H + h) * p.L + i] = 1.0f / l_run;
     }
 
     tc_fence_before();

@@ -120,6 +120,7 @@ struct Op {
     // kernels, bytes for the memory-bound ones)
     int cat = ZVB_CAT_OTHER;
     double work = 0.0;
+    int shape[4] = {0, 0, 0, 0};     // GEMM: rows, out cols, K, block_n
 };
 
 static int pick_block_n(int n_out, long long m_tiles) {
@@ -188,6 +189,7 @@ static int build_linear(Op& op, const bf16* A, long long M, int lda, const zvb_l
         op.has_mx = true;
     }
     set_grid(op);
+    op.shape[0] = (int)M; op.shape[1] = lin.out_features; op.shape[2] = lin.in_features; op.shape[3] = bn;
     op.cat = ZVB_CAT_GEMM_LINEAR;
     op.work = 2.0 * (double)M * lin.out_features * lin.in_features;
     return 0;
@@ -218,6 +220,7 @@ static int build_gated(Op& op, const bf16* A, long long M, int lda, const zvb_li
     TRY(make_tmap(&op.ma, A, K, M, 1, (uint64_t)lda * 2, (uint64_t)lda * 2 * M, GEMM_BLOCK_M));
     TRY(make_tmap(&op.mb, lin.w, K, lin.rows, 1, (uint64_t)lin.k_pitch * 2, (uint64_t)lin.k_pitch * 2 * lin.rows, 256));
     set_grid(op);
+    op.shape[0] = (int)M; op.shape[1] = 2 * n_out; op.shape[2] = lin.in_features; op.shape[3] = 256;
     op.cat = ZVB_CAT_GEMM_GATED;
     op.work = 2.0 * (double)M * (2.0 * n_out) * lin.in_features;
     return 0;
@@ -226,8 +229,8 @@ static int build_gated(Op& op, const bf16* A, long long M, int lda, const zvb_li
 // out[n*L+i, :] = P[n,h] · V  with V given transposed: Vt[n][rows][Lk].
 //   per_head != 0 (SelfAttention): head h uses Vt rows [h*hp, h*hp+hd) -> out cols [h*hd, (h+1)*hd)
 //   per_head == 0 (NonlinAttention): head 0 weights, all `hd` value columns, out *= mul (bf16 [N*L, ldm])
-static int build_pv(Op& op, const bf16* P, const bf16* Vt, void* out, int ldc, int N, int H, int L, int Lk, int hd,
-                    int hp, int per_head, const bf16* mul, int ldm) {
+static int build_pv(Op& op, const bf16* P, const float* inv_l, const bf16* Vt, void* out, int ldc, int N, int H, int L,
+                    int Lk, int hd, int hp, int per_head, const bf16* mul, int ldm) {
     op.type = OP_GEMM;
     op.kind = EPI_LINEAR;
     GemmParams& p = op.gp;
@@ -239,6 +242,7 @@ static int build_pv(Op& op, const bf16* P, const bf16* Vt, void* out, int ldc, i
     p.b_zb = 1;
     p.a_zb = H;
     p.out_mode = OUT_BF16; p.out = out; p.ldc = ldc;
+    p.rowscale = inv_l; p.rs_zb = H; p.rs_zn = per_head ? 1 : 0;
     int vt_rows;
     if (per_head) {
         if (hp % 16 != 0 || hd > hp) return fail(ZVB_ERR_INVALID, "pv: head pad must be a multiple of 16");
@@ -261,17 +265,18 @@ static int build_pv(Op& op, const bf16* P, const bf16* Vt, void* out, int ldc, i
     TRY(make_tmap(&op.ma, P, Lk, L, (uint64_t)N * H, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * L, GEMM_BLOCK_M));
     TRY(make_tmap(&op.mb, Vt, Lk, vt_rows, N, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * vt_rows, p.block_n));
     set_grid(op);
+    op.shape[0] = N * L; op.shape[1] = per_head ? H * hd : hd; op.shape[2] = L; op.shape[3] = p.block_n;
     op.cat = ZVB_CAT_GEMM_PV;
     op.work = 2.0 * (double)N * (per_head ? H : 1) * (double)L * L * hd;
     return 0;
 }
 
-static int build_attn(Op& op, const bf16* qkp, int ld, const float* E, const uint8_t* mask, bf16* P, int N, int H,
-                      int L, int Lk) {
+static int build_attn(Op& op, const bf16* qkp, int ld, const float* E, const uint8_t* mask, bf16* P, float* inv_l,
+                      int N, int H, int L, int Lk) {
     op.type = OP_ATTN;
     AttnParams& a = op.ap;
     a.L = L; a.Lk = Lk; a.H = H; a.N = N; a.qd = H * 32;
-    a.qkp = qkp; a.ld = ld; a.E = E; a.mask = mask; a.P = P;
+    a.qkp = qkp; a.ld = ld; a.E = E; a.mask = mask; a.P = P; a.inv_l = inv_l;
     if (ld % 8 != 0 || Lk % 8 != 0) return fail(ZVB_ERR_INVALID, "attn: pitches must be multiples of 8");
     TRY(make_tmap(&op.ma, qkp, ld, L, N, (uint64_t)ld * 2, (uint64_t)ld * 2 * L, ATT_BM));
     op.cat = ZVB_CAT_ATTN_WEIGHTS;
@@ -440,6 +445,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
     bf16* cv = c.take<bf16>(M * D);
     const int Lk0 = round8(T);
     bf16* P = c.take<bf16>((size_t)N * H * T * Lk0);
+    float* invl = c.take<float>((size_t)N * H * T);
     // per-resolution buffers (pads of the transposed V stay zero for the lifetime of the plan)
     bf16 *vtna[5] = {}, *vtsa[5] = {};
     uint8_t* mask_ds[5] = {};
@@ -538,7 +544,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             // 1. attention projections + weights (on the un-time-embedded input)
             e = LinearEpi();
             TRY(build_linear(op, srcb, Ms, D, ly.attn_in, qkp, attn_w, e)); ops.push_back(op);
-            TRY(build_attn(op, qkp, attn_w, ly.pos_table, mask_ds[ds], P, N, H, L, Lk)); ops.push_back(op);
+            TRY(build_attn(op, qkp, attn_w, ly.pos_table, mask_ds[ds], P, invl, N, H, L, Lk)); ops.push_back(op);
             // 2. feed_forward1 on src + temb:  R0 = src + temb + FF1(src + temb)
             e = LinearEpi(); e.act = ACT_SWOOSH_L;
             TRY(build_linear(op, srct, Ms, D, ly.ff_in[0], hid, m->ff_dims[0], e)); ops.push_back(op);
@@ -549,13 +555,13 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             TRY(build_gated(op, Rb[0], Ms, D, ly.na_sx, nah, GATE_TANH_SX, vtna[ds], 0, nullptr, e)); ops.push_back(op);
             e = LinearEpi();
             TRY(build_linear(op, Rb[0], Ms, D, ly.na_y, nay, nah, e)); ops.push_back(op);
-            TRY(build_pv(op, P, vtna[ds], pvna, nah, N, H, L, Lk, nah, nah, 0, nay, nah)); ops.push_back(op);
+            TRY(build_pv(op, P, invl, vtna[ds], pvna, nah, N, H, L, Lk, nah, nah, 0, nay, nah)); ops.push_back(op);
             e = stream_epi(R[0], Rb[1]);
             TRY(build_linear(op, pvna, Ms, nah, ly.na_out, R[1], D, e)); ops.push_back(op);
             // 4. self_attn1 (+ temb for the conv module that follows)
             e = t_epi(H * hp, dv, hp);
             TRY(build_linear(op, Rb[1], Ms, D, ly.sa_in[0], vtsa[ds], 0, e)); ops.push_back(op);
-            TRY(build_pv(op, P, vtsa[ds], pvsa, H * dv, N, H, L, Lk, dv, hp, 1, nullptr, 0)); ops.push_back(op);
+            TRY(build_pv(op, P, invl, vtsa[ds], pvsa, H * dv, N, H, L, Lk, dv, hp, 1, nullptr, 0)); ops.push_back(op);
             e = stream_epi(R[1], Rb[0]); e.rowbias = tb; e.rows_per_group = L;
             TRY(build_linear(op, pvsa, Ms, H * dv, ly.sa_out[0], R[0], D, e)); ops.push_back(op);
             // 5. conv_module1
@@ -574,7 +580,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             // 7. self_attn2 (+ temb)
             e = t_epi(H * hp, dv, hp);
             TRY(build_linear(op, Rb[0], Ms, D, ly.sa_in[1], vtsa[ds], 0, e)); ops.push_back(op);
-            TRY(build_pv(op, P, vtsa[ds], pvsa, H * dv, N, H, L, Lk, dv, hp, 1, nullptr, 0)); ops.push_back(op);
+            TRY(build_pv(op, P, invl, vtsa[ds], pvsa, H * dv, N, H, L, Lk, dv, hp, 1, nullptr, 0)); ops.push_back(op);
             e = stream_epi(R[0], Rb[1]); e.rowbias = tb; e.rows_per_group = L;
             TRY(build_linear(op, pvsa, Ms, H * dv, ly.sa_out[1], R[1], D, e)); ops.push_back(op);
             // 8. conv_module2
@@ -675,7 +681,7 @@ int zvb_decoder_forward(zvb_plan* plan, void* stream) {
 }
 
 int zvb_decoder_profile(zvb_plan* plan, void* stream, int max_ops, float* ms, int* category, double* work,
-                        int* num_ops) {
+                        int* shapes, int* num_ops) {
     if (plan == nullptr || ms == nullptr || category == nullptr || work == nullptr || num_ops == nullptr)
         return fail(ZVB_ERR_INVALID, "null argument");
     const int n = static_cast<int>(plan->ops.size());
@@ -695,6 +701,8 @@ int zvb_decoder_profile(zvb_plan* plan, void* stream, int max_ops, float* ms, in
         cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
         category[i] = plan->ops[i].cat;
         work[i] = plan->ops[i].work;
+        if (shapes != nullptr)
+            for (int k = 0; k < 4; ++k) shapes[4 * i + k] = plan->ops[i].shape[k];
     }
     for (auto& e : ev) cudaEventDestroy(e);
     return rc;
@@ -783,20 +791,20 @@ int zvb_test_linear(const void* A, int M, int K, int lda, const void* W, const f
     return launch_op(op, static_cast<cudaStream_t>(stream));
 }
 
-int zvb_test_attn_weights(const void* qkp, int ld, const float* pos_table, const uint8_t* mask, void* P, int N, int H,
-                          int L, int Lk, void* stream) {
+int zvb_test_attn_weights(const void* qkp, int ld, const float* pos_table, const uint8_t* mask, void* P, float* inv_l,
+                          int N, int H, int L, int Lk, void* stream) {
     TRY(init_device());
     Op op;
-    TRY(build_attn(op, (const bf16*)qkp, ld, pos_table, mask, (bf16*)P, N, H, L, Lk));
+    TRY(build_attn(op, (const bf16*)qkp, ld, pos_table, mask, (bf16*)P, inv_l, N, H, L, Lk));
     return launch_op(op, static_cast<cudaStream_t>(stream));
 }
 
-int zvb_test_pv(const void* P, const void* Vt, void* out, int N, int H, int L, int Lk, int hd, int hp, int per_head,
-                const void* mul, void* stream) {
+int zvb_test_pv(const void* P, const float* inv_l, const void* Vt, void* out, int N, int H, int L, int Lk, int hd, int hp,
+                int per_head, const void* mul, void* stream) {
     TRY(init_device());
     Op op;
     const int ldc = per_head ? H * hd : hd;
-    TRY(build_pv(op, (const bf16*)P, (const bf16*)Vt, out, ldc, N, H, L, Lk, hd, hp, per_head, (const bf16*)mul, hd));
+    TRY(build_pv(op, (const bf16*)P, inv_l, (const bf16*)Vt, out, ldc, N, H, L, Lk, hd, hp, per_head, (const bf16*)mul, hd));
     return launch_op(op, static_cast<cudaStream_t>(stream));
 }
 

@@ -54,6 +54,8 @@ struct GemmParams {
     int n_valid;           // valid accumulator columns inside one tile
     // epilogue operands (nullable)
     const float* bias;     // accumulator-column indexed, at least n_out (LINEAR) / tiles*256 (GATED)
+    const float* rowscale; // fp32 [(b*rs_zb + n_tile*rs_zn)*M + m]: accumulator row scale (softmax 1/l)
+    int rs_zb, rs_zn;
     const float* rowbias;  // fp32 [(row / rows_per_group)*ld_rowbias + outcol]
     int rows_per_group;
     int ld_rowbias;
@@ -281,6 +283,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (p.row_mask != nullptr && row_ok) masked = p.row_mask[row] != 0;
             long long grp = 0;
             if (p.rowbias != nullptr && row_ok) grp = row / p.rows_per_group;
+            float rscale = 1.0f;
+            if (p.rowscale != nullptr && row_ok)
+                rscale = __ldg(p.rowscale + static_cast<long long>(b * p.rs_zb + n_tile * p.rs_zn) * p.M + m);
 
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -333,7 +338,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         if (row_ok && ncols > 0) {
                             float v[32];
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc_r[i]) + bs[c0 + i];
+                            for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(acc_r[i]), rscale, bs[c0 + i]);
                             if (p.rowbias != nullptr) {
                                 const float* rbp = p.rowbias + grp * p.ld_rowbias + oc;
 #pragma unroll

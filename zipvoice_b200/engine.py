@@ -69,18 +69,22 @@ class DecoderPlan:
                 g32.data_ptr() if g32 is not None else None, out.data_ptr(), _stream_ptr()))
         return out
 
-    def profile(self):
+    def profile(self, shapes: bool = False):
         """One forward over the resident buffers with a CUDA event per kernel (synchronises).
-        Returns a list of (category name, milliseconds, algorithmic work)."""
+        Returns a list of (category name, milliseconds, algorithmic work[, (rows, cols, K, tile N)])."""
         import numpy as np
         cap = 4096
         ms = np.zeros(cap, dtype=np.float32)
         cat = np.zeros(cap, dtype=np.int32)
         work = np.zeros(cap, dtype=np.float64)
+        shp = np.zeros(cap * 4, dtype=np.int32)
         n = C.c_int(0)
         with torch.cuda.device(self.packed.device):
             _lib.check(self.lib.zvb_decoder_profile(self.handle, _stream_ptr(), cap, ms.ctypes.data, cat.ctypes.data,
-                                                    work.ctypes.data, C.byref(n)))
+                                                    work.ctypes.data, shp.ctypes.data, C.byref(n)))
+        if shapes:
+            return [(_lib.CATEGORIES[int(cat[i])], float(ms[i]), float(work[i]), tuple(int(x) for x in shp[4 * i: 4 * i + 4]))
+                    for i in range(n.value)]
         return [(_lib.CATEGORIES[int(cat[i])], float(ms[i]), float(work[i])) for i in range(n.value)]
 
     def sample(self, x: torch.Tensor, text: torch.Tensor, speech: torch.Tensor, mask8: torch.Tensor,

@@ -157,14 +157,16 @@ class PackedZipformer:
 
     # ------------------------------------------------------------------ struct builders
     def pos_tables(self, L: int) -> List[torch.Tensor]:
-        """Per-layer E[h][r][c] = sum_d W_pos[h*4+c][d] * pe[r][d], fp32 (H, 2L-1, 4)."""
+        """Per-layer E[h][r][c] = sum_d W_pos[h*4+c][d] * pe[r][d], fp32 (H, 2L-1, 4) flattened,
+        followed by (H,) floats max_r |E[h][r]|_2."""
         if L not in self._pos_cache:
             c = self.cfg
             pe = rel_pos_embedding(L, c.pos_dim, self.device)
             tabs = []
             for wp in self.linear_pos:
-                e = (pe @ wp.t()).reshape(2 * L - 1, c.num_heads, c.pos_head_dim).permute(1, 0, 2)
-                tabs.append(e.contiguous())
+                e = (pe @ wp.t()).reshape(2 * L - 1, c.num_heads, c.pos_head_dim).permute(1, 0, 2).contiguous()
+                emax = e.norm(dim=2).amax(dim=1)                       # (H,) bound used by the softmax shift
+                tabs.append(torch.cat([e.reshape(-1), emax]).contiguous())
             self._pos_cache[L] = tabs
         return self._pos_cache[L]
 
