@@ -149,18 +149,21 @@ upsample_combine_kernel(const float* __restrict__ orig, const float* __restrict_
 
 // Depthwise Conv1d over time (cross-correlation, zero padding K/2) + bias + SwooshR
 // (reference: modules/zipformer.py:1672-1678 with scaling.py:1200-1206).  The input is the
-// already GLU-gated and key-masked tensor.  Block = 64 channels x 64 frames; thread = one
-// channel pair x 8 consecutive frames with the 8+K-1 input window held in registers.
+// already GLU-gated and key-masked tensor.  Block = 64 channels x 128 frames staged in shared
+// memory; thread = one channel pair x 16 consecutive frames with the 16+K-1 input window held
+// packed (bf16x2) in registers, so every staged input is read from shared memory once.
+constexpr int DW_TT = 128;     // frames per block
+constexpr int DW_OT = 16;      // outputs per thread
 template <int K>
 __global__ void __launch_bounds__(256)
 dwconv_swooshr_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                       const float* __restrict__ wt /*[K][C]*/, const float* __restrict__ bias, int L,
                       int C) {
-    constexpr int TT = 64, HALF = K / 2, WIN = TT + K - 1;
+    constexpr int HALF = K / 2, WIN = DW_TT + K - 1, NW = DW_OT + K - 1;
     __shared__ uint32_t tile[WIN][32];
     __shared__ float2 wsm[K][32];
     const int c0 = blockIdx.x * 64;
-    const int t0 = blockIdx.y * TT;
+    const int t0 = blockIdx.y * DW_TT;
     const int n = blockIdx.z;
     const int cp = threadIdx.x & 31;
     const int tg = threadIdx.x >> 5;
@@ -181,30 +184,26 @@ dwconv_swooshr_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __rest
     }
     __syncthreads();
     if (2 * cp >= cvalid) return;
-    float in0[8 + K - 1], in1[8 + K - 1];
+    uint32_t win[NW];
 #pragma unroll
-    for (int q = 0; q < 8 + K - 1; ++q) {
-        const uint32_t w = tile[tg * 8 + q][cp];
-        in0[q] = bf16_lo(w);
-        in1[q] = bf16_hi(w);
-    }
+    for (int q = 0; q < NW; ++q) win[q] = tile[tg * DW_OT + q][cp];
     const float b0 = __ldg(bias + c0 + 2 * cp), b1 = __ldg(bias + c0 + 2 * cp + 1);
-    float a0[8], a1[8];
+    float a0[DW_OT], a1[DW_OT];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) { a0[o] = b0; a1[o] = b1; }
+    for (int o = 0; o < DW_OT; ++o) { a0[o] = b0; a1[o] = b1; }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const float2 w = wsm[k][cp];
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            a0[o] = fmaf(w.x, in0[o + k], a0[o]);
-            a1[o] = fmaf(w.y, in1[o + k], a1[o]);
+        for (int o = 0; o < DW_OT; ++o) {
+            a0[o] = fmaf(w.x, bf16_lo(win[o + k]), a0[o]);
+            a1[o] = fmaf(w.y, bf16_hi(win[o + k]), a1[o]);
         }
     }
     __nv_bfloat16* on = out + static_cast<long long>(n) * L * C;
 #pragma unroll
-    for (int o = 0; o < 8; ++o) {
-        const int t = t0 + tg * 8 + o;
+    for (int o = 0; o < DW_OT; ++o) {
+        const int t = t0 + tg * DW_OT + o;
         if (t < L)
             *reinterpret_cast<uint32_t*>(on + static_cast<long long>(t) * C + c0 + 2 * cp) =
                 pack_bf16(swoosh_r(a0[o]), swoosh_r(a1[o]));

@@ -72,8 +72,10 @@ static int init_device() {
     if (fn == nullptr || q != cudaDriverEntryPointSuccess)
         return fail(ZVB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_LINEAR, ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_GATED, ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(attn_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     return 0;
 }
@@ -290,10 +292,14 @@ static int launch_op(const Op& op, cudaStream_t st) {
         case OP_GEMM: {
             if (op.grid <= 0) return 0;
             const CUtensorMap& mx = op.has_mx ? op.mx : op.ma;
-            if (op.kind == EPI_LINEAR)
-                gemm_kernel<EPI_LINEAR><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, mx, op.gp);
+            if (op.kind == EPI_GATED)
+                gemm_kernel<EPI_GATED, ACT_NONE><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, mx, op.gp);
+            else if (op.gp.act == ACT_SWOOSH_L)
+                gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, mx, op.gp);
+            else if (op.gp.act == ACT_SWOOSH_R)
+                gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, mx, op.gp);
             else
-                gemm_kernel<EPI_GATED><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, mx, op.gp);
+                gemm_kernel<EPI_LINEAR, ACT_NONE><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, mx, op.gp);
             return check_launch("gemm");
         }
         case OP_ATTN: {
@@ -329,7 +335,7 @@ static int launch_op(const Op& op, cudaStream_t st) {
         }
         case OP_DWCONV: {
             const int N = op.i0, L = op.i1, C = op.i2, K = op.i3;
-            dim3 grid((C + 63) / 64, (L + 63) / 64, N);
+            dim3 grid((C + 63) / 64, (L + DW_TT - 1) / DW_TT, N);
             const bf16* x = (const bf16*)op.p0;
             bf16* o = (bf16*)op.o0;
             if (K == 7) dwconv_swooshr_kernel<7><<<grid, 256, 0, st>>>(x, o, op.f0, op.f1, L, C);

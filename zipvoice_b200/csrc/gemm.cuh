@@ -77,9 +77,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
-// Stores 32 consecutive output columns [col0, col0+32) of one row (ncols valid).
-__device__ __forceinline__ void store_row32(const GemmParams& p, long long row, int col0, int ncols,
-                                            const float* v) {
+// Direct per-thread store of 32 consecutive output columns of one row: used for the transposed
+// layout (lanes = consecutive rows -> coalesced) and for ragged / unaligned column ranges.
+__device__ __forceinline__ void store_row32_direct(const GemmParams& p, long long row, int col0, int ncols,
+                                                   const float* v) {
     if (p.out_mode == OUT_T_BF16) {
         const int n = static_cast<int>(row / p.t_L);
         const int l = static_cast<int>(row - static_cast<long long>(n) * p.t_L);
@@ -95,36 +96,82 @@ __device__ __forceinline__ void store_row32(const GemmParams& p, long long row, 
         }
         return;
     }
-    const bool full = ncols == 32 && (p.ldc & 7) == 0 && (col0 & 7) == 0;
     if (p.out_mode == OUT_F32 || p.out_mode == OUT_F32_BF16) {
         float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + col0;
-        if (full) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (i < ncols) dst[i] = v[i];
-        }
+        for (int i = 0; i < 32; ++i)
+            if (i < ncols) dst[i] = v[i];
         if (p.out_mode == OUT_F32) return;
     }
     __nv_bfloat16* dst = (p.out_mode == OUT_F32_BF16 ? p.out_bf16 : reinterpret_cast<__nv_bfloat16*>(p.out)) +
                          row * p.ldc + col0;
-    if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8)
-            *reinterpret_cast<uint4*>(dst + i) =
-                make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
-                           pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
-    } else {
+    for (int i = 0; i < 32; ++i)
+        if (i < ncols) dst[i] = __float2bfloat16(v[i]);
+}
+
+// Coalesced store of a warp's 32-row x 32-column unit: TMEM hands every thread one ROW, which as a
+// direct global store touches 32 different 128-byte lines per instruction (measured ~6 GB/s per SM).
+// The unit is therefore transposed through 4 KB of (swizzled, conflict-free) shared memory --
+// `stage`, 32 rows x 128 B -- so that each store instruction writes whole rows: 8 lanes x 16 B per
+// fp32 row, 4 lanes x 16 B per bf16 row.  `row0` = global row of the warp's first row, `rows_ok` =
+// number of valid rows among the 32, ncols a multiple of 4 (fp32) / 8 (bf16).  `cofs` = first 16-byte
+// chunk of the 128-byte row used for the bf16 staging.
+__device__ __forceinline__ void store_unit_staged(const GemmParams& p, uint8_t* stage, int lane, long long row0,
+                                                  int rows_ok, int col0, int ncols, const float* v, int cofs) {
+    const int sw = lane & 7;
+    if (p.out_mode == OUT_F32 || p.out_mode == OUT_F32_BF16) {
+        uint8_t* my = stage + lane * 128;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (i < ncols) dst[i] = __float2bfloat16(v[i]);
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(my + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        float* dst = reinterpret_cast<float*>(p.out) + row0 * p.ldc + col0;
+        const int ch = lane & 7;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int rr = 4 * k + (lane >> 3);
+            const float4 q = *reinterpret_cast<const float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
+            if (rr < rows_ok && ch * 4 < ncols) *reinterpret_cast<float4*>(dst + static_cast<long long>(rr) * p.ldc + ch * 4) = q;
+        }
+        if (p.out_mode == OUT_F32) return;
+        __syncwarp();
+    }
+    {
+        uint8_t* my = stage + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(my + (((cofs + j) ^ sw) << 4)) =
+                make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                           pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        __syncwarp();
+        __nv_bfloat16* dst = (p.out_mode == OUT_F32_BF16 ? p.out_bf16 : reinterpret_cast<__nv_bfloat16*>(p.out)) +
+                             row0 * p.ldc + col0;
+        const int ch = lane & 3;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int rr = 8 * k + (lane >> 2);
+            const uint4 q = *reinterpret_cast<const uint4*>(stage + rr * 128 + (((cofs + ch) ^ (rr & 7)) << 4));
+            if (rr < rows_ok && ch * 8 < ncols) *reinterpret_cast<uint4*>(dst + static_cast<long long>(rr) * p.ldc + ch * 8) = q;
+        }
     }
 }
 
-template <int KIND>
+// One warp stores its unit: staged+coalesced when the column range is 16-byte aligned, direct otherwise.
+__device__ __forceinline__ void store_unit(const GemmParams& p, uint8_t* stage, int lane, bool row_ok, long long row,
+                                           long long row0, int rows_ok, int col0, int ncols, const float* v, int cofs) {
+    const bool f32 = p.out_mode == OUT_F32 || p.out_mode == OUT_F32_BF16;
+    const bool aligned = p.out_mode != OUT_T_BF16 && (p.ldc & 7) == 0 && (col0 & 7) == 0 &&
+                         (ncols & (p.out_mode == OUT_F32 ? 3 : 7)) == 0 && (!f32 || (ncols & 3) == 0);
+    if (aligned) {
+        store_unit_staged(p, stage, lane, row0, rows_ok, col0, ncols, v, cofs);
+        __syncwarp();
+    } else if (row_ok) {
+        store_row32_direct(p, row, col0, ncols, v);
+    }
+}
+
+template <int KIND, int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_aux, const GemmParams p) {
@@ -258,6 +305,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const int half = (warp - 4) >> 2;                 // which of the two warps of the quarter
         const int et = threadIdx.x - 128;                 // 0..255
         const int r = quarter * 32 + lane;                // accumulator row inside the tile
+        uint8_t* private_stage = aux_smem + (warp - 4) * 4096;   // used when no aux slot is in flight
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t tile_iter = 0;
@@ -269,6 +317,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const int m = m_tile * GEMM_BLOCK_M + r;
             const bool row_ok = m < p.M;
             const long long row = static_cast<long long>(b) * p.M + m;
+            const int m0w = m_tile * GEMM_BLOCK_M + quarter * 32;          // first row of this warp
+            const long long row0 = static_cast<long long>(b) * p.M + m0w;
+            int rows_ok = p.M - m0w;
+            rows_ok = rows_ok < 0 ? 0 : (rows_ok > 32 ? 32 : rows_ok);
             const int out_base = n_tile * p.out_col_stride;
             const int acc_base = n_tile * p.block_n;
             // stage this tile's bias (double buffered by accumulator stage)
@@ -303,16 +355,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     const int oc = out_base + c0;
                     int ncols = p.n_out - oc;
                     ncols = ncols > 32 ? 32 : ncols;
-                    if (row_ok && ncols > 0) {
+                    if (ncols > 0) {
                         float v[32];
+                        const bool tanh_gate = p.gate_mode == GATE_TANH_SX;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float a = __uint_as_float(ra[i]) + bs[c0 + i];
-                            const float g = __uint_as_float(rb[i]) + bs[hcols + c0 + i];
-                            const float o = p.gate_mode == GATE_TANH_SX ? g * fast_tanh(a) : a * fast_sigmoid(g);
-                            v[i] = masked ? 0.0f : o;
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 ba = *reinterpret_cast<const float4*>(bs + c0 + 4 * j);
+                            const float4 bg = *reinterpret_cast<const float4*>(bs + hcols + c0 + 4 * j);
+                            const float ab[4] = {ba.x, ba.y, ba.z, ba.w};
+                            const float gb[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float a = __uint_as_float(ra[4 * j + e]) + ab[e];
+                                const float g = __uint_as_float(rb[4 * j + e]) + gb[e];
+                                const float o = tanh_gate ? g * fast_tanh(a) : a * fast_sigmoid(g);
+                                v[4 * j + e] = masked ? 0.0f : o;
+                            }
                         }
-                        store_row32(p, row, oc, ncols, v);
+                        store_unit(p, private_stage, lane, row_ok, row, row0, rows_ok, oc, ncols, v, 0);
                     }
                 }
             } else {
@@ -335,19 +395,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         int ncols = p.n_valid - c0;
                         if (p.n_out - oc < ncols) ncols = p.n_out - oc;
                         ncols = ncols > 32 ? 32 : ncols;
-                        if (row_ok && ncols > 0) {
+                        if (ncols > 0) {
                             float v[32];
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(acc_r[i]), rscale, bs[c0 + i]);
-                            if (p.rowbias != nullptr) {
-                                const float* rbp = p.rowbias + grp * p.ld_rowbias + oc;
-#pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    if (i < ncols) v[i] += __ldg(rbp + i);
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 bq = *reinterpret_cast<const float4*>(bs + c0 + 4 * j);
+                                v[4 * j] = fmaf(__uint_as_float(acc_r[4 * j]), rscale, bq.x);
+                                v[4 * j + 1] = fmaf(__uint_as_float(acc_r[4 * j + 1]), rscale, bq.y);
+                                v[4 * j + 2] = fmaf(__uint_as_float(acc_r[4 * j + 2]), rscale, bq.z);
+                                v[4 * j + 3] = fmaf(__uint_as_float(acc_r[4 * j + 3]), rscale, bq.w);
                             }
-                            if (p.act != ACT_NONE) {
+                            const bool vec = ncols == 32 && (p.ldc & 3) == 0;
+                            if (p.rowbias != nullptr && row_ok) {
+                                const float* rbp = p.rowbias + grp * p.ld_rowbias + oc;
+                                if (vec && (p.ld_rowbias & 3) == 0) {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float4 q = __ldg(reinterpret_cast<const float4*>(rbp) + j);
+                                        v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i)
+                                        if (i < ncols) v[i] += __ldg(rbp + i);
+                                }
+                            }
+                            if (ACT == ACT_SWOOSH_L) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = swoosh_l(v[i]);
+                            } else if (ACT == ACT_SWOOSH_R) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = swoosh_r(v[i]);
                             }
                             if (p.aux_mode == AUX_RESID_F32) {
 #pragma unroll
@@ -365,16 +443,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                     v[8 * j + 6] *= bf16_lo(a.w); v[8 * j + 7] *= bf16_hi(a.w);
                                 }
                             }
-                            if (p.orig != nullptr) {
+                            if (p.orig != nullptr && row_ok) {
                                 const float* op = p.orig + row * p.ldc + oc;
+                                const float* sp = p.bypass_scale + oc;
+                                if (vec) {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    if (i < ncols) {
-                                        const float o = __ldg(op + i);
-                                        v[i] = o + (v[i] - o) * __ldg(p.bypass_scale + oc + i);
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float4 o = __ldg(reinterpret_cast<const float4*>(op) + j);
+                                        const float4 sc = __ldg(reinterpret_cast<const float4*>(sp) + j);
+                                        v[4 * j] = fmaf(v[4 * j] - o.x, sc.x, o.x);
+                                        v[4 * j + 1] = fmaf(v[4 * j + 1] - o.y, sc.y, o.y);
+                                        v[4 * j + 2] = fmaf(v[4 * j + 2] - o.z, sc.z, o.z);
+                                        v[4 * j + 3] = fmaf(v[4 * j + 3] - o.w, sc.w, o.w);
                                     }
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i)
+                                        if (i < ncols) {
+                                            const float o = __ldg(op + i);
+                                            v[i] = o + (v[i] - o) * __ldg(sp + i);
+                                        }
+                                }
                             }
-                            store_row32(p, row, oc, ncols, v);
+                            // in place over the consumed aux rows of this warp, or in the warp's private area
+                            uint8_t* stage = p.aux_mode != AUX_NONE
+                                                 ? aux_smem + slot * GEMM_AUX_BYTES + quarter * 32 * 128
+                                                 : private_stage;
+                            __syncwarp();              // every lane has consumed its aux row
+                            store_unit(p, stage, lane, row_ok, row, row0, rows_ok, oc, ncols, v,
+                                       p.aux_mode == AUX_MUL_BF16 ? 4 * uu : 0);
                         }
                     }
                     if (p.aux_mode != AUX_NONE) {
