@@ -1,0 +1,108 @@
+"""-m gpu: BASELINE.json's full-size shapes (the oracle would need minutes to hours there), checked
+through size-independent properties of the sampler:
+  * utterances are independent: permuting the batch permutes the outputs, duplicated utterances give
+    identical rows (bit-exact: every row's arithmetic is independent of its position in a tile);
+  * one Euler step is x0 + (t1 - t0) * v(x0, t0) with v the CFG blend of two decoder rows (seam 2 ==
+    seam 1 composed by hand);
+  * outputs are finite and padded frames never leak into valid ones through the key mask."""
+import pytest
+import torch
+
+from zipvoice_b200.config import ZipVoiceConfig
+from zipvoice_b200.model import build_model, get_time_steps
+from zipvoice_b200.synth import synth_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(cfg, B, prompt, target, seed=3, ragged=False):
+    g = torch.Generator().manual_seed(seed)
+    F = cfg.feat_dim * (2 if cfg.is_stereo else 1)
+    T = prompt + target
+    x0 = torch.randn(B, T, F, generator=g)
+    text = torch.randn(B, T, cfg.feat_dim, generator=g) * 0.5
+    speech = torch.zeros(B, T, F)
+    speech[:, :prompt] = torch.randn(B, prompt, F, generator=g) * 0.3 - 0.5
+    lens = torch.full((B,), T)
+    if ragged:
+        lens = torch.randint(int(T * 0.7), T + 1, (B,), generator=g)
+        lens[0] = T
+    mask = torch.arange(T)[None, :] >= lens[:, None]
+    return [t.cuda() for t in (x0, text, speech, mask)], lens
+
+
+@pytest.fixture(scope="module")
+def base_model():
+    cfg = ZipVoiceConfig("zipvoice")
+    return cfg, build_model(cfg, synth_state_dict(cfg, 0), "cuda", use_cuda_graph=False)
+
+
+def test_c3_shape_batch_permutation_and_duplicates(base_model):
+    cfg, model = base_model
+    (x0, text, speech, mask), lens = _inputs(cfg, 6, 281, 938, ragged=True)
+    x0[5], text[5], speech[5], mask[5] = x0[2], text[2], speech[2], mask[2]        # duplicate utterance
+    kw = dict(num_step=2, guidance_scale=1.0, t_shift=0.5)
+    a = model.solver.sample(x=x0, text_condition=text, speech_condition=speech, padding_mask=mask, **kw)
+    perm = torch.tensor([3, 0, 5, 1, 4, 2], device="cuda")
+    b = model.solver.sample(x=x0[perm], text_condition=text[perm], speech_condition=speech[perm],
+                            padding_mask=mask[perm], **kw)
+    assert torch.isfinite(a).all()
+    assert torch.equal(a[perm], b)
+    assert torch.equal(a[2], a[5])
+
+
+def test_one_euler_step_is_the_cfg_blend_of_seam1(base_model):
+    cfg, model = base_model
+    (x0, text, speech, mask), _ = _inputs(cfg, 2, 281, 938)
+    g = 1.0
+    ts = get_time_steps(0.0, 1.0, 16, 0.5)
+    x1 = model.solver.sample(x=x0, text_condition=text, speech_condition=speech, padding_mask=mask,
+                             num_step=1, guidance_scale=g, t_start=float(ts[3]), t_end=float(ts[4]), t_shift=1.0)
+    t0, t1 = float(ts[3]), float(ts[4])
+    assert t0 <= 0.5                                             # uncond keeps the speech condition, g doubles
+    xin = torch.cat([torch.cat([x0, x0]), torch.cat([torch.zeros_like(text), text]),
+                     torch.cat([speech, speech])], dim=2)
+    v = model.fm_decoder(x=xin, t=torch.full((4,), t0, device="cuda"), padding_mask=torch.cat([mask, mask]))
+    vu, vc = v[:2], v[2:]
+    ref = x0 + ((1 + 2 * g) * vc - 2 * g * vu) * (torch.tensor(t1) - torch.tensor(t0)).item()
+    rel = float((x1 - ref).norm() / ref.norm())
+    assert rel < 1e-5, rel
+
+
+def test_c4_long_form_dialog_shape():
+    cfg = ZipVoiceConfig("zipvoice_dialog", vocab_size=362)
+    model = build_model(cfg, synth_state_dict(cfg, 0), "cuda", use_cuda_graph=False)
+    (x0, text, speech, mask), _ = _inputs(cfg, 2, 938, 5625)
+    x0[1], text[1], speech[1] = x0[0], text[0], speech[0]
+    out = model.solver.sample(x=x0, text_condition=text, speech_condition=speech, padding_mask=mask, num_step=1,
+                              guidance_scale=1.5, t_shift=0.5)
+    assert out.shape == (2, 6563, 100) and torch.isfinite(out).all()
+    assert torch.equal(out[0], out[1])
+
+
+def test_c5_stereo_shape_masked_frames_do_not_leak():
+    cfg = ZipVoiceConfig("zipvoice_dialog_stereo", vocab_size=362)
+    model = build_model(cfg, synth_state_dict(cfg, 0), "cuda", use_cuda_graph=False)
+    (x0, text, speech, mask), lens = _inputs(cfg, 4, 469, 1875, ragged=True)
+    kw = dict(num_step=1, guidance_scale=1.5, t_shift=0.5)
+    a = model.solver.sample(x=x0, text_condition=text, speech_condition=speech, padding_mask=mask, **kw)
+    assert a.shape == (4, 2344, 200) and torch.isfinite(a).all()
+    # change what sits in the padded frames of utterance 1: attention keys there are masked, the conv
+    # input is zeroed there; only the SimpleDownsample edge (reference zipformer.py:899-901) may see it
+    x0b = x0.clone()
+    x0b[1, int(lens[1]):] += 5.0
+    b = model.solver.sample(x=x0b, text_condition=text, speech_condition=speech, padding_mask=mask, **kw)
+    valid = int(lens[1]) - 8
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    rel = float((a[1, :valid] - b[1, :valid]).norm() / a[1, :valid].norm())
+    assert rel < 2e-2, rel
+
+
+def test_distill_four_step_sampling_shape():
+    cfg = ZipVoiceConfig("zipvoice_distill")
+    model = build_model(cfg, synth_state_dict(cfg, 0), "cuda", use_cuda_graph=True)
+    (x0, text, speech, mask), _ = _inputs(cfg, 8, 281, 938)
+    kw = dict(num_step=4, guidance_scale=3.0, t_shift=0.5)
+    a = model.solver.sample(x=x0, text_condition=text, speech_condition=speech, padding_mask=mask, **kw)
+    b = model.solver.sample(x=x0, text_condition=text, speech_condition=speech, padding_mask=mask, **kw)   # graph replay
+    assert torch.isfinite(a).all() and torch.equal(a, b)

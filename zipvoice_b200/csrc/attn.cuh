@@ -15,6 +15,8 @@
 
 namespace zvb {
 
+__device__ __forceinline__ int swarp_of(int warp) { return warp - 2; }
+
 constexpr int ATT_BM = 128;          // queries per CTA
 constexpr int ATT_BN = 128;          // keys per score tile
 constexpr int ATT_KSTAGES = 3;
@@ -22,8 +24,9 @@ constexpr int ATT_TILE_BYTES = 128 * 64 * 2;      // one 128-row x 64-col bf16 b
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_TMEM_COLS = 256;
 constexpr int ATT_EWIN = 256;        // 255 offsets used
-constexpr int ATT_SMEM_BYTES = (1 + ATT_KSTAGES) * ATT_TILE_BYTES + 2 * ATT_EWIN * 16 + 2 * 16 +
-                               1024 + 256;
+constexpr int ATT_STAGE_BYTES = 4 * 4096;            // per softmax warp: 32 rows x 128 B store staging
+constexpr int ATT_SMEM_BYTES = (1 + ATT_KSTAGES) * ATT_TILE_BYTES + ATT_STAGE_BYTES + 2 * ATT_EWIN * 16 +
+                               2 * 16 + 1024 + 256;
 
 struct AttnParams {
     int L, Lk, H, N;
@@ -43,7 +46,8 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     uint8_t* q_tile = smem;
     uint8_t* k_tiles = smem + ATT_TILE_BYTES;
-    float4* ewin = reinterpret_cast<float4*>(smem + (1 + ATT_KSTAGES) * ATT_TILE_BYTES);   // [2][256]
+    uint8_t* stage_all = smem + (1 + ATT_KSTAGES) * ATT_TILE_BYTES;                        // [4][32][128 B]
+    float4* ewin = reinterpret_cast<float4*>(stage_all + ATT_STAGE_BYTES);                  // [2][256]
     uint32_t* mwin = reinterpret_cast<uint32_t*>(ewin + 2 * ATT_EWIN);                      // [2][4] excluded-key bits
     uint64_t* bars = reinterpret_cast<uint64_t*>(mwin + 8);
     uint64_t* q_full = bars;
@@ -138,7 +142,11 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
         const float4* Eh = reinterpret_cast<const float4*>(p.E) + static_cast<long long>(h) * (2 * p.L - 1);
         const float emax = __ldg(p.E + static_cast<long long>(p.H) * (2 * p.L - 1) * 4 + h);
         const uint8_t* mrow = p.mask + static_cast<long long>(n) * p.L;
-        __nv_bfloat16* prow = p.P + ((static_cast<long long>(n) * p.H + h) * p.L + i) * p.Lk;
+        // P rows of this warp; stores are transposed through shared memory so that one instruction
+        // writes whole 128-byte row segments (8 lanes per row) instead of 32 different rows
+        __nv_bfloat16* pwarp = p.P + ((static_cast<long long>(n) * p.H + h) * p.L + i0 + quarter * 32) * p.Lk;
+        const int rows_ok = min(32, max(0, p.L - (i0 + quarter * 32)));
+        uint8_t* stage = stage_all + swarp_of(warp) * 4096;
         constexpr float LOG2E = 1.4426950408889634f;
         float m_run = -INFINITY, l_run = 0.f, m_l2 = 0.f;
 
@@ -213,12 +221,26 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
                             w[c >> 1] = pk;
                             l_run += bf16_lo(pk) + bf16_hi(pk);      // sum of the values as stored
                         }
-                        if (row_ok) {
-                            uint4* dst = reinterpret_cast<uint4*>(prow + j);
+                        // stage this thread's 32 bf16 (64 B) in its row: chunks 4*hh .. 4*hh+3 of 8
+                        const int hh = (c0 >> 5) & 1;
+                        uint8_t* my = stage + lane * 128;
 #pragma unroll
-                            for (int g = 0; g < 4; ++g)
-                                if (j + g * 8 < p.Lk) dst[g] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+                        for (int g = 0; g < 4; ++g)
+                            *reinterpret_cast<uint4*>(my + (((4 * hh + g) ^ (lane & 7)) << 4)) =
+                                make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+                    }
+                    if (c0 & 32) {                         // two chunks staged: write 64 columns, coalesced
+                        __syncwarp();
+                        const int jb = j0 + c0 - 32;
+                        const int ch = lane & 7;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int rr = 4 * k + (lane >> 3);
+                            const uint4 q = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                            if (rr < rows_ok && jb + ch * 8 < p.Lk)
+                                *reinterpret_cast<uint4*>(pwarp + static_cast<long long>(rr) * p.Lk + jb + ch * 8) = q;
                         }
+                        __syncwarp();
                     }
                 }
             }

@@ -151,7 +151,7 @@ upsample_combine_kernel(const float* __restrict__ orig, const float* __restrict_
 // (reference: modules/zipformer.py:1672-1678 with scaling.py:1200-1206).  The input is the
 // already GLU-gated and key-masked tensor.  Block = 64 channels x 128 frames staged in shared
 // memory; thread = one channel pair x 16 consecutive frames with the 16+K-1 input window held
-// packed (bf16x2) in registers, so every staged input is read from shared memory once.
+// in registers (converted to fp32 once), so every staged input is read from shared memory once.
 constexpr int DW_TT = 128;     // frames per block
 constexpr int DW_OT = 16;      // outputs per thread
 template <int K>
@@ -184,9 +184,13 @@ dwconv_swooshr_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __rest
     }
     __syncthreads();
     if (2 * cp >= cvalid) return;
-    uint32_t win[NW];
+    float w0[NW], w1[NW];                  // the input window, converted once
 #pragma unroll
-    for (int q = 0; q < NW; ++q) win[q] = tile[tg * DW_OT + q][cp];
+    for (int q = 0; q < NW; ++q) {
+        const uint32_t u = tile[tg * DW_OT + q][cp];
+        w0[q] = bf16_lo(u);
+        w1[q] = bf16_hi(u);
+    }
     const float b0 = __ldg(bias + c0 + 2 * cp), b1 = __ldg(bias + c0 + 2 * cp + 1);
     float a0[DW_OT], a1[DW_OT];
 #pragma unroll
@@ -196,8 +200,8 @@ dwconv_swooshr_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __rest
         const float2 w = wsm[k][cp];
 #pragma unroll
         for (int o = 0; o < DW_OT; ++o) {
-            a0[o] = fmaf(w.x, bf16_lo(win[o + k]), a0[o]);
-            a1[o] = fmaf(w.y, bf16_hi(win[o + k]), a1[o]);
+            a0[o] = fmaf(w.x, w0[o + k], a0[o]);
+            a1[o] = fmaf(w.y, w1[o + k], a1[o]);
         }
     }
     __nv_bfloat16* on = out + static_cast<long long>(n) * L * C;
