@@ -151,7 +151,8 @@ upsample_combine_kernel(const float* __restrict__ orig, const float* __restrict_
 // (reference: modules/zipformer.py:1672-1678 with scaling.py:1200-1206).  The input is the
 // already GLU-gated and key-masked tensor.  Block = 64 channels x 128 frames staged in shared
 // memory; thread = one channel pair x 16 consecutive frames with the 16+K-1 input window held
-// in registers (converted to fp32 once), so every staged input is read from shared memory once.
+// in registers as packed fp32x2, so every staged input is read from shared memory once and one
+// FFMA2 advances both channels.
 constexpr int DW_TT = 128;     // frames per block
 constexpr int DW_OT = 16;      // outputs per thread
 template <int K>
@@ -184,26 +185,25 @@ dwconv_swooshr_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __rest
     }
     __syncthreads();
     if (2 * cp >= cvalid) return;
-    float w0[NW], w1[NW];                  // the input window, converted once
+    f32x2 win[NW];                          // the input window of the channel pair, fp32x2 packed
 #pragma unroll
     for (int q = 0; q < NW; ++q) {
         const uint32_t u = tile[tg * DW_OT + q][cp];
-        w0[q] = bf16_lo(u);
-        w1[q] = bf16_hi(u);
+        win[q] = pack2(bf16_lo(u), bf16_hi(u));
     }
-    const float b0 = __ldg(bias + c0 + 2 * cp), b1 = __ldg(bias + c0 + 2 * cp + 1);
-    float a0[DW_OT], a1[DW_OT];
+    const f32x2 b2 = pack2(__ldg(bias + c0 + 2 * cp), __ldg(bias + c0 + 2 * cp + 1));
+    f32x2 acc[DW_OT];
 #pragma unroll
-    for (int o = 0; o < DW_OT; ++o) { a0[o] = b0; a1[o] = b1; }
+    for (int o = 0; o < DW_OT; ++o) acc[o] = b2;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const float2 w = wsm[k][cp];
+        const f32x2 w = *reinterpret_cast<const f32x2*>(&wsm[k][cp]);
 #pragma unroll
-        for (int o = 0; o < DW_OT; ++o) {
-            a0[o] = fmaf(w.x, w0[o + k], a0[o]);
-            a1[o] = fmaf(w.y, w1[o + k], a1[o]);
-        }
+        for (int o = 0; o < DW_OT; ++o) acc[o] = fma2(w, win[o + k], acc[o]);     // one FFMA2 = both channels
     }
+    float a0[DW_OT], a1[DW_OT];
+#pragma unroll
+    for (int o = 0; o < DW_OT; ++o) unpack2(acc[o], a0[o], a1[o]);
     __nv_bfloat16* on = out + static_cast<long long>(n) * L * C;
 #pragma unroll
     for (int o = 0; o < DW_OT; ++o) {

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -53,6 +54,7 @@ static int check_launch(const char* what) {
 }
 
 static int g_num_sms = 0;
+static int g_cluster_ok = 1;      // ZVB_NO_CLUSTER=1 disables the 2-CTA multicast GEMM variant
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
 static int init_device() {
@@ -66,16 +68,19 @@ static int init_device() {
     if (prop.major != 10)
         return fail(ZVB_ERR_NO_DEVICE, "device sm_%d%d is not sm_100 (B200)", prop.major, prop.minor);
     g_num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("ZVB_NO_CLUSTER")) g_cluster_ok = atoi(e) == 0;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
     CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
     if (fn == nullptr || q != cudaDriverEntryPointSuccess)
         return fail(ZVB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_LINEAR, ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<EPI_GATED, ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+#define ZVB_SMEM_ATTR(k) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES))
+    ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_NONE, 1>));     ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_NONE, 2>));
+    ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 1>)); ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 2>));
+    ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 1>)); ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 2>));
+    ZVB_SMEM_ATTR((gemm_kernel<EPI_GATED, ACT_NONE, 1>));      ZVB_SMEM_ATTR((gemm_kernel<EPI_GATED, ACT_NONE, 2>));
+#undef ZVB_SMEM_ATTR
     CUDA_TRY(cudaFuncSetAttribute(attn_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     return 0;
 }
@@ -109,7 +114,7 @@ struct Op {
     CUtensorMap ma, mb, mx;
     bool has_mx = false;
     GemmParams gp;
-    int kind = 0, grid = 0;
+    int kind = 0, grid = 0, cluster = 1;
     AttnParams ap;
     // elementwise
     const void *p0 = nullptr, *p1 = nullptr;
@@ -151,11 +156,20 @@ struct LinearEpi {
     int block_n = 0;                     // 0 = choose
 };
 
+// Decides whether the op runs as 2-CTA clusters with a multicast B tile, and the persistent grid.
 static void set_grid(Op& op) {
     const GemmParams& p = op.gp;
-    const long long tiles = (long long)p.batches * p.num_m_tiles * p.num_n_tiles;
-    op.grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+    const long long slots2 = (long long)p.batches * ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    op.cluster = (g_cluster_ok && p.block_n >= 64 && p.num_m_tiles >= 2 && slots2 >= g_num_sms / 4) ? 2 : 1;
+    if (op.cluster == 2) {
+        const long long clusters = slots2 < g_num_sms / 2 ? slots2 : g_num_sms / 2;
+        op.grid = static_cast<int>(clusters * 2);
+    } else {
+        const long long tiles = (long long)p.batches * p.num_m_tiles * p.num_n_tiles;
+        op.grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+    }
 }
+static inline uint32_t b_box_rows(const Op& op) { return op.gp.block_n / op.cluster; }
 
 // out[M, n_out] = epi(A[M, K] · W[n_out, K]ᵀ + b)
 static int build_linear(Op& op, const bf16* A, long long M, int lda, const zvb_linear& lin, void* out, int ldc,
@@ -182,15 +196,16 @@ static int build_linear(Op& op, const bf16* A, long long M, int lda, const zvb_l
     p.orig = e.orig; p.bypass_scale = e.bypass_scale;
     p.act = e.act;
     p.t_L = e.t_L; p.t_pitch = e.t_pitch; p.t_batch_rows = e.t_batch_rows; p.t_hd = e.t_hd; p.t_hp = e.t_hp;
+    set_grid(op);
     TRY(make_tmap(&op.ma, A, K, M, 1, (uint64_t)lda * 2, (uint64_t)lda * 2 * M, GEMM_BLOCK_M));
-    TRY(make_tmap(&op.mb, lin.w, K, lin.rows, 1, (uint64_t)lin.k_pitch * 2, (uint64_t)lin.k_pitch * 2 * lin.rows, bn));
+    TRY(make_tmap(&op.mb, lin.w, K, lin.rows, 1, (uint64_t)lin.k_pitch * 2, (uint64_t)lin.k_pitch * 2 * lin.rows,
+                  b_box_rows(op)));
     if (e.resid != nullptr) {
         if (ldc % 4 != 0) return fail(ZVB_ERR_INVALID, "linear: fp32 residual pitch must be a multiple of 4");
         p.aux_mode = AUX_RESID_F32; p.aux_zb = 0;
         TRY(make_tmap(&op.mx, e.resid, ldc, M, 1, (uint64_t)ldc * 4, (uint64_t)ldc * 4 * M, GEMM_BLOCK_M, true));
         op.has_mx = true;
     }
-    set_grid(op);
     op.shape[0] = (int)M; op.shape[1] = lin.out_features; op.shape[2] = lin.in_features; op.shape[3] = bn;
     op.cat = ZVB_CAT_GEMM_LINEAR;
     op.work = 2.0 * (double)M * lin.out_features * lin.in_features;
@@ -219,9 +234,10 @@ static int build_gated(Op& op, const bf16* A, long long M, int lda, const zvb_li
     p.gate_mode = gate_mode;
     p.row_mask = row_mask;
     p.t_L = e.t_L; p.t_pitch = e.t_pitch; p.t_batch_rows = e.t_batch_rows; p.t_hd = e.t_hd; p.t_hp = e.t_hp;
-    TRY(make_tmap(&op.ma, A, K, M, 1, (uint64_t)lda * 2, (uint64_t)lda * 2 * M, GEMM_BLOCK_M));
-    TRY(make_tmap(&op.mb, lin.w, K, lin.rows, 1, (uint64_t)lin.k_pitch * 2, (uint64_t)lin.k_pitch * 2 * lin.rows, 256));
     set_grid(op);
+    TRY(make_tmap(&op.ma, A, K, M, 1, (uint64_t)lda * 2, (uint64_t)lda * 2 * M, GEMM_BLOCK_M));
+    TRY(make_tmap(&op.mb, lin.w, K, lin.rows, 1, (uint64_t)lin.k_pitch * 2, (uint64_t)lin.k_pitch * 2 * lin.rows,
+                  b_box_rows(op)));
     op.shape[0] = (int)M; op.shape[1] = 2 * n_out; op.shape[2] = lin.in_features; op.shape[3] = 256;
     op.cat = ZVB_CAT_GEMM_GATED;
     op.work = 2.0 * (double)M * (2.0 * n_out) * lin.in_features;
@@ -264,9 +280,9 @@ static int build_pv(Op& op, const bf16* P, const float* inv_l, const bf16* Vt, v
             op.has_mx = true;
         }
     }
-    TRY(make_tmap(&op.ma, P, Lk, L, (uint64_t)N * H, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * L, GEMM_BLOCK_M));
-    TRY(make_tmap(&op.mb, Vt, Lk, vt_rows, N, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * vt_rows, p.block_n));
     set_grid(op);
+    TRY(make_tmap(&op.ma, P, Lk, L, (uint64_t)N * H, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * L, GEMM_BLOCK_M));
+    TRY(make_tmap(&op.mb, Vt, Lk, vt_rows, N, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * vt_rows, b_box_rows(op)));
     op.shape[0] = N * L; op.shape[1] = per_head ? H * hd : hd; op.shape[2] = L; op.shape[3] = p.block_n;
     op.cat = ZVB_CAT_GEMM_PV;
     op.work = 2.0 * (double)N * (per_head ? H : 1) * (double)L * L * hd;
@@ -292,14 +308,28 @@ static int launch_op(const Op& op, cudaStream_t st) {
         case OP_GEMM: {
             if (op.grid <= 0) return 0;
             const CUtensorMap& mx = op.has_mx ? op.mx : op.ma;
-            if (op.kind == EPI_GATED)
-                gemm_kernel<EPI_GATED, ACT_NONE><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, mx, op.gp);
-            else if (op.gp.act == ACT_SWOOSH_L)
-                gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, mx, op.gp);
-            else if (op.gp.act == ACT_SWOOSH_R)
-                gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, mx, op.gp);
-            else
-                gemm_kernel<EPI_LINEAR, ACT_NONE><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.ma, op.mb, mx, op.gp);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(op.grid);
+            cfg.blockDim = dim3(GEMM_THREADS);
+            cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = op.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            const int sel = (op.kind == EPI_GATED ? 3 : op.gp.act) * 2 + (op.cluster - 1);
+            cudaError_t e = cudaSuccess;
+            switch (sel) {
+                case 0: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 1>, op.ma, op.mb, mx, op.gp); break;
+                case 1: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 2>, op.ma, op.mb, mx, op.gp); break;
+                case 2: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 1>, op.ma, op.mb, mx, op.gp); break;
+                case 3: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 2>, op.ma, op.mb, mx, op.gp); break;
+                case 4: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 1>, op.ma, op.mb, mx, op.gp); break;
+                case 5: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 2>, op.ma, op.mb, mx, op.gp); break;
+                case 6: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 1>, op.ma, op.mb, mx, op.gp); break;
+                default: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 2>, op.ma, op.mb, mx, op.gp); break;
+            }
+            if (e != cudaSuccess) return fail(ZVB_ERR_CUDA, "launch gemm: %s", cudaGetErrorString(e));
             return check_launch("gemm");
         }
         case OP_ATTN: {

@@ -171,7 +171,12 @@ __device__ __forceinline__ void store_unit(const GemmParams& p, uint8_t* stage, 
     }
 }
 
-template <int KIND, int ACT>
+// CLUSTER == 2: two CTAs with the same n_tile and adjacent m_tiles form a cluster; each loads its own
+// A tile and HALF of the shared B tile, multicast into both CTAs' shared memory, which cuts the
+// L2->SM operand traffic per tile from (A + B) to (A + B/2) -- the K<=1920 GEMMs of this network are
+// bound by that traffic, not by the tensor pipe.  A shared-memory stage is released to both
+// producers only when both CTAs' MMAs have retired (multicast commit on the `empty` barriers).
+template <int KIND, int ACT, int CLUSTER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_aux, const GemmParams p) {
@@ -191,7 +196,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int total_tiles = p.batches * p.num_m_tiles * p.num_n_tiles;
+    // tile schedule: a "slot" is one tile per CTA of the cluster; slot s -> (b, m_group, n_tile) and the
+    // CTA of rank `crank` takes m_tile = m_group*CLUSTER + crank (a tile past num_m_tiles is all padding)
+    const int crank = CLUSTER > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int m_groups = (p.num_m_tiles + CLUSTER - 1) / CLUSTER;
+    const int total_tiles = p.batches * m_groups * p.num_n_tiles;
+    const int first_tile = blockIdx.x / CLUSTER;
+    const int tile_step = gridDim.x / CLUSTER;
     // accumulator columns are consumed in units of 32; aux sub-tiles hold 32 (fp32) or 64 (bf16) columns
     const int n_units = (p.block_n + 31) >> 5;
     const int units_per_sub = p.aux_mode == AUX_RESID_F32 ? 1 : 2;
@@ -203,7 +214,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (p.aux_mode != AUX_NONE) tma_prefetch_desc(&tma_aux);
         for (int s = 0; s < GEMM_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CLUSTER);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
@@ -221,6 +232,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();        // peers' barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
@@ -230,11 +242,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const uint32_t stage_bytes = GEMM_A_BYTES + static_cast<uint32_t>(p.block_n) * GEMM_BLOCK_K * 2;
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
                 const int n_tile = tile % p.num_n_tiles;
                 const int rest = tile / p.num_n_tiles;
-                const int m_tile = rest % p.num_m_tiles;
-                const int b = rest / p.num_m_tiles;
+                const int m_tile = (rest % m_groups) * CLUSTER + crank;
+                const int b = rest / m_groups;
                 const int az = b * p.a_zb + n_tile * p.a_zn;
                 const int bz = b * p.b_zb;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -242,8 +254,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                     uint8_t* sa = smem + stage * GEMM_STAGE_BYTES;
                     tma_load_3d(sa, &tma_a, &full_bar[stage], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M, az);
-                    tma_load_3d(sa + GEMM_A_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BLOCK_K,
-                                n_tile * p.block_n, bz);
+                    if (CLUSTER > 1) {
+                        // my half of the B tile (rows [crank*bn/2, (crank+1)*bn/2)) goes to both CTAs
+                        const int hrows = p.block_n / 2;
+                        tma_load_3d_mc(sa + GEMM_A_BYTES + crank * hrows * 128, &tma_b, &full_bar[stage],
+                                       kb * GEMM_BLOCK_K, n_tile * p.block_n + crank * hrows, bz, 0x3);
+                    } else {
+                        tma_load_3d(sa + GEMM_A_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BLOCK_K,
+                                    n_tile * p.block_n, bz);
+                    }
                     if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -256,7 +275,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc) * 256u;
@@ -272,7 +291,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
                                   idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);           // frees the smem slot when MMAs retire
+                    if (CLUSTER > 1) umma_commit_mc(&empty_bar[stage], 0x3);   // both producers wait for both MMAs
+                    else umma_commit(&empty_bar[stage]);      // frees the smem slot when MMAs retire
                     if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
                     if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -284,11 +304,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (lane == 0 && p.aux_mode != AUX_NONE) {
             const int sub_cols = p.aux_mode == AUX_RESID_F32 ? 32 : 64;
             uint32_t q = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
                 const int n_tile = tile % p.num_n_tiles;
                 const int rest = tile / p.num_n_tiles;
-                const int m_tile = rest % p.num_m_tiles;
-                const int b = rest / p.num_m_tiles;
+                const int m_tile = (rest % m_groups) * CLUSTER + crank;
+                const int b = rest / m_groups;
                 for (int s = 0; s < n_sub; ++s, ++q) {
                     const int slot = q % GEMM_AUX_SLOTS;
                     const uint32_t par = (q / GEMM_AUX_SLOTS) & 1u;
@@ -309,11 +329,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t tile_iter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+        for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++tile_iter) {
             const int n_tile = tile % p.num_n_tiles;
             const int rest = tile / p.num_n_tiles;
-            const int m_tile = rest % p.num_m_tiles;
-            const int b = rest / p.num_m_tiles;
+            const int m_tile = (rest % m_groups) * CLUSTER + crank;
+            const int b = rest / m_groups;
             const int m = m_tile * GEMM_BLOCK_M + r;
             const bool row_ok = m < p.M;
             const long long row = static_cast<long long>(b) * p.M + m;
@@ -489,6 +509,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();        // no CTA exits while a peer may still write to it
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
