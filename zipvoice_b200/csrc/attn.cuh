@@ -25,7 +25,7 @@ constexpr int ATT_THREADS = 192;
 constexpr int ATT_TMEM_COLS = 256;
 constexpr int ATT_EWIN = 256;        // 255 offsets used
 constexpr int ATT_STAGE_BYTES = 4 * 4096;            // per softmax warp: 32 rows x 128 B store staging
-constexpr int ATT_SMEM_BYTES = (1 + ATT_KSTAGES) * ATT_TILE_BYTES + ATT_STAGE_BYTES + 2 * ATT_EWIN * 32 +
+constexpr int ATT_SMEM_BYTES = (1 + ATT_KSTAGES) * ATT_TILE_BYTES + ATT_STAGE_BYTES + 2 * ATT_EWIN * 16 +
                                2 * 16 + 1024 + 256;
 
 struct AttnParams {
@@ -47,10 +47,9 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
     uint8_t* q_tile = smem;
     uint8_t* k_tiles = smem + ATT_TILE_BYTES;
     uint8_t* stage_all = smem + (1 + ATT_KSTAGES) * ATT_TILE_BYTES;                        // [4][32][128 B]
-    // rel-pos window, pre-paired for FFMA2: entry w = {E[w].x, E[w+1].x, E[w].y, E[w+1].y | .z .w likewise}
-    // (times log2 e), so the bias of the column pair (c, c+1) is four packed FMAs
-    float4* ewin = reinterpret_cast<float4*>(stage_all + ATT_STAGE_BYTES);                  // [2][256][2]
-    uint32_t* mwin = reinterpret_cast<uint32_t*>(ewin + 2 * ATT_EWIN * 2);                  // [2][4] excluded-key bits
+    // rel-pos window of the (i-tile, j-tile): 255 offsets x 4 floats, pre-scaled by log2 e
+    float4* ewin = reinterpret_cast<float4*>(stage_all + ATT_STAGE_BYTES);                  // [2][256]
+    uint32_t* mwin = reinterpret_cast<uint32_t*>(ewin + 2 * ATT_EWIN);                      // [2][4] excluded-key bits
     uint64_t* bars = reinterpret_cast<uint64_t*>(mwin + 8);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1;                      // [KSTAGES]
@@ -150,10 +149,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
         const int rows_ok = min(32, max(0, p.L - (i0 + quarter * 32)));
         uint8_t* stage = stage_all + swarp_of(warp) * 4096;
         constexpr float LOG2E = 1.4426950408889634f;
-        float m_run = -INFINITY, m_l2 = 0.f;
-        const f32x2 pp0 = pack2(p0, p0), pp1 = pack2(p1, p1), pp2 = pack2(p2, p2), pp3 = pack2(p3, p3);
-        const f32x2 l2e2 = pack2(LOG2E, LOG2E);
-        f32x2 nm2 = pack2(0.f, 0.f), lsum2 = pack2(0.f, 0.f);
+        float m_run = -INFINITY, m_l2 = 0.f, l_run = 0.f;
 
         for (int it = 0; it < total_it; ++it) {
             const int pass = it >= num_jt ? 1 : 0;
@@ -165,11 +161,10 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
                 const float pn = sqrtf(p0 * p0 + p1 * p1 + p2 * p2 + p3 * p3);
                 const float m_est = (m_run == -INFINITY ? 0.f : m_run) + pn * emax;
                 m_l2 = m_est * LOG2E;
-                nm2 = pack2(-m_l2, -m_l2);
             }
             // stage the excluded-key bits (padding mask or beyond L) and, for the second pass, the
             // rel-pos window of this tile (double buffered)
-            float4* ew = ewin + acc * ATT_EWIN * 2;
+            float4* ew = ewin + acc * ATT_EWIN;
             uint32_t* mw = mwin + acc * 4;
             {
                 const int j = j0 + tid;
@@ -180,11 +175,9 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
             if (pass) {
                 for (int w = tid; w < 255; w += 128) {
                     const int rel = (j0 - i0) - 127 + w + (p.L - 1);
-                    float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
-                    if (rel >= 0 && rel <= 2 * p.L - 2) e0 = __ldg(Eh + rel);
-                    if (rel + 1 >= 0 && rel + 1 <= 2 * p.L - 2) e1 = __ldg(Eh + rel + 1);
-                    ew[2 * w] = make_float4(e0.x * LOG2E, e1.x * LOG2E, e0.y * LOG2E, e1.y * LOG2E);
-                    ew[2 * w + 1] = make_float4(e0.z * LOG2E, e1.z * LOG2E, e0.w * LOG2E, e1.w * LOG2E);
+                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rel >= 0 && rel <= 2 * p.L - 2) e = __ldg(Eh + rel);
+                    ew[w] = make_float4(e.x * LOG2E, e.y * LOG2E, e.z * LOG2E, e.w * LOG2E);
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -214,18 +207,16 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
                     const int j = j0 + c0;
                     if (j < p.Lk) {
                         uint32_t w[16];
-                        const float4* ep = ew + 2 * (c0 - r + 127);
+                        const float4* ep = ew + (c0 - r + 127);
 #pragma unroll
                         for (int c = 0; c < 32; c += 2) {
-                            const ulonglong2 ta = *reinterpret_cast<const ulonglong2*>(ep + 2 * c);
-                            const ulonglong2 tb = *reinterpret_cast<const ulonglong2*>(ep + 2 * c + 1);
-                            f32x2 v = fma2(pack2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), l2e2, nm2);
-                            v = fma2(pp0, ta.x, v);
-                            v = fma2(pp1, ta.y, v);
-                            v = fma2(pp2, tb.x, v);
-                            v = fma2(pp3, tb.y, v);
-                            float a, b;
-                            unpack2(v, a, b);
+                            const float4 ea = ep[c], eb = ep[c + 1];
+                            float a = fmaf(__uint_as_float(sr[c]), LOG2E, -m_l2);
+                            float b = fmaf(__uint_as_float(sr[c + 1]), LOG2E, -m_l2);
+                            a = fmaf(p0, ea.x, a); b = fmaf(p0, eb.x, b);
+                            a = fmaf(p1, ea.y, a); b = fmaf(p1, eb.y, b);
+                            a = fmaf(p2, ea.z, a); b = fmaf(p2, eb.z, b);
+                            a = fmaf(p3, ea.w, a); b = fmaf(p3, eb.w, b);
                             a = fast_exp2(a);
                             b = fast_exp2(b);
                             if (excl != 0u) {
@@ -233,7 +224,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
                                 b = ((excl >> (c + 1)) & 1u) ? 0.f : b;
                             }
                             w[c >> 1] = pack_bf16(a, b);
-                            lsum2 = add2(lsum2, pack2(a, b));
+                            l_run += a + b;
                         }
                         // stage this thread's 32 bf16 (64 B) in its row: chunks 4*hh .. 4*hh+3 of 8
                         const int hh = (c0 >> 5) & 1;
@@ -262,9 +253,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[acc]);
         }
-        float la, lb;
-        unpack2(lsum2, la, lb);
-        if (row_ok) p.inv_l[(static_cast<long long>(n) * p.H + h) * p.L + i] = 1.0f / (la + lb);
+        if (row_ok) p.inv_l[(static_cast<long long>(n) * p.H + h) * p.L + i] = 1.0f / l_run;
     }
 
     tc_fence_before();

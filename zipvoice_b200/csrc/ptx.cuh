@@ -41,22 +41,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the
+// hint expires) instead of burning issue slots of the SMSP it shares with the math warps.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (globaltimer_ns() - t0 > ZVB_WAIT_TIMEOUT_NS) {
+        if ((++spins & 63u) == 0u && globaltimer_ns() - t0 > ZVB_WAIT_TIMEOUT_NS) {
             printf("zvb: mbarrier wait timeout block=(%d,%d,%d) thread=%d parity=%u\n", blockIdx.x,
                    blockIdx.y, blockIdx.z, threadIdx.x, parity);
             __trap();
