@@ -217,12 +217,17 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
                             a = fmaf(p1, ea.y, a); b = fmaf(p1, eb.y, b);
                             a = fmaf(p2, ea.z, a); b = fmaf(p2, eb.z, b);
                             a = fmaf(p3, ea.w, a); b = fmaf(p3, eb.w, b);
-                            a = fast_exp2(a);
-                            b = fast_exp2(b);
-                            if (excl != 0u) {
-                                a = ((excl >> c) & 1u) ? 0.f : a;
-                                b = ((excl >> (c + 1)) & 1u) ? 0.f : b;
-                            }
+                            sr[c] = __float_as_uint(fast_exp2(a));
+                            sr[c + 1] = __float_as_uint(fast_exp2(b));
+                        }
+                        if (excl != 0u) {       // rare: a real branch, so unmasked tiles issue no selects
+#pragma unroll
+                            for (int c = 0; c < 32; ++c)
+                                if ((excl >> c) & 1u) sr[c] = 0u;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 32; c += 2) {
+                            const float a = __uint_as_float(sr[c]), b = __uint_as_float(sr[c + 1]);
                             w[c >> 1] = pack_bf16(a, b);
                             l_run += a + b;
                         }

@@ -86,12 +86,19 @@ __device__ __forceinline__ void store_row32_direct(const GemmParams& p, long lon
         const int l = static_cast<int>(row - static_cast<long long>(n) * p.t_L);
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
                              static_cast<long long>(n) * p.t_batch_rows * p.t_pitch + l;
+        if (p.t_hp == p.t_hd) {
+            dst += static_cast<long long>(col0) * p.t_pitch;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if (i < ncols) {
-                const int c = col0 + i;
-                const int drow = c + (c / p.t_hd) * (p.t_hp - p.t_hd);
-                dst[static_cast<long long>(drow) * p.t_pitch] = __float2bfloat16(v[i]);
+            for (int i = 0; i < 32; ++i)
+                if (i < ncols) dst[static_cast<long long>(i) * p.t_pitch] = __float2bfloat16(v[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (i < ncols) {
+                    const int c = col0 + i;
+                    const int drow = c + (c / p.t_hd) * (p.t_hp - p.t_hd);
+                    dst[static_cast<long long>(drow) * p.t_pitch] = __float2bfloat16(v[i]);
+                }
             }
         }
         return;
