@@ -23,7 +23,7 @@ constexpr int GEMM_B_BYTES = 256 * GEMM_BLOCK_K * 2;            // 32 KB (block_
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
 constexpr int GEMM_AUX_SLOTS = 4;
 constexpr int GEMM_AUX_BYTES = 128 * 128;                       // 128 rows x 128 B
-constexpr int GEMM_BIAS_BYTES = 2 * 256 * 4;
+constexpr int GEMM_BIAS_BYTES = 8 * 256 * 4;               // one private copy per epilogue warp
 constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_AUX_SLOTS * GEMM_AUX_BYTES +
                                 GEMM_BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int GEMM_THREADS = 384;
@@ -191,7 +191,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     uint8_t* aux_smem = smem + GEMM_STAGES * GEMM_STAGE_BYTES;
-    float* bias_smem = reinterpret_cast<float*>(aux_smem + GEMM_AUX_SLOTS * GEMM_AUX_BYTES);   // [2][256]
+    float* bias_smem = reinterpret_cast<float*>(aux_smem + GEMM_AUX_SLOTS * GEMM_AUX_BYTES);   // [8 warps][256]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_smem) + GEMM_BIAS_BYTES);
     uint64_t* full_bar = bars;                                  // [STAGES] TMA -> MMA
     uint64_t* empty_bar = full_bar + GEMM_STAGES;               // [STAGES] MMA -> TMA
@@ -330,7 +330,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         // ------------------------------------------------------------------ epilogue (8 warps)
         const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
         const int half = (warp - 4) >> 2;                 // which of the two warps of the quarter
-        const int et = threadIdx.x - 128;                 // 0..255
         const int r = quarter * 32 + lane;                // accumulator row inside the tile
         uint8_t* private_stage = aux_smem + (warp - 4) * 4096;   // used when no aux slot is in flight
         int acc = 0;
@@ -350,14 +349,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             rows_ok = rows_ok < 0 ? 0 : (rows_ok > 32 ? 32 : rows_ok);
             const int out_base = n_tile * p.out_col_stride;
             const int acc_base = n_tile * p.block_n;
-            // stage this tile's bias (double buffered by accumulator stage)
-            float* bs = bias_smem + acc * 256;
+            // this warp's private copy of the tile's bias (minus the Swoosh offset, see swoosh_from_offset)
+            float* bs = bias_smem + (warp - 4) * 256;
             {
-                const int c = acc_base + et;
+                constexpr float off = ACT == ACT_SWOOSH_L ? SWOOSH_L_C : (ACT == ACT_SWOOSH_R ? SWOOSH_R_C : 0.0f);
                 const int lim = KIND == EPI_GATED ? p.num_n_tiles * 256 : p.n_out;
-                bs[et] = (p.bias != nullptr && et < p.block_n && c < lim) ? __ldg(p.bias + c) : 0.0f;
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int cc = q * 32 + lane;
+                    const int c = acc_base + cc;
+                    bs[cc] = ((p.bias != nullptr && cc < p.block_n && c < lim) ? __ldg(p.bias + c) : 0.0f) - off;
+                }
+                __syncwarp();
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
             bool masked = false;
             if (p.row_mask != nullptr && row_ok) masked = p.row_mask[row] != 0;
             long long grp = 0;
@@ -447,12 +452,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                         if (i < ncols) v[i] += __ldg(rbp + i);
                                 }
                             }
-                            if (ACT == ACT_SWOOSH_L) {
+                            if (ACT == ACT_SWOOSH_L) {          // v already holds x - 4 (offset folded into the bias)
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] = swoosh_l(v[i]);
+                                for (int i = 0; i < 32; ++i) v[i] = swoosh_from_offset(v[i], SWOOSH_L_K0);
                             } else if (ACT == ACT_SWOOSH_R) {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] = swoosh_r(v[i]);
+                                for (int i = 0; i < 32; ++i) v[i] = swoosh_from_offset(v[i], SWOOSH_R_K0);
                             }
                             if (p.aux_mode == AUX_RESID_F32) {
 #pragma unroll

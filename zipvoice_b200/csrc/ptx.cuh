@@ -215,25 +215,31 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-// softplus(y) = max(y,0) + log1p(exp(-|y|)); log1p on [0,1] by a degree-5 polynomial (max abs
-// error 1.2e-5) so that each activation costs one MUFU op (ex2) instead of two (ex2 + lg2): the
-// epilogue of the feed-forward GEMMs is SFU-bound otherwise.
-__device__ __forceinline__ float softplus_fast(float y) {
+// Swoosh(x) = softplus(x - c) - 0.08 x - d with softplus(y) = max(y,0) + log1p(exp(-|y|)).
+// One MUFU op (ex2) per activation instead of two (ex2 + lg2): log1p on [0,1] is a degree-5
+// polynomial (max abs error 1.2e-5), and max(y,0) - 0.08 y is folded into 0.42 y + 0.5 |y|, so the
+// whole activation is 1 FMUL + 1 MUFU + 8 FFMA on y = x - c:
+//   swoosh = t*P(t) + 0.42 y + 0.5 |y| - (0.08 c + d),   t = 2^(-|y| log2 e)
+__device__ __forceinline__ float swoosh_from_offset(float y, float k0) {
     float t;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-fabsf(y) * 1.4426950408889634f));
     float p = fmaf(t, 0.031377589387161245f, -0.1341354334221127f);
     p = fmaf(t, p, 0.2878262894239249f);
     p = fmaf(t, p, -0.491347927069251f);
     p = fmaf(t, p, 0.9994349844843187f);
-    return fmaf(t, p, fmaxf(y, 0.0f));
+    float r = fmaf(t, p, k0);
+    r = fmaf(y, 0.42f, r);
+    return fmaf(fabsf(y), 0.5f, r);
 }
+constexpr float SWOOSH_L_C = 4.0f, SWOOSH_L_K0 = -(0.08f * 4.0f + 0.035f);
+constexpr float SWOOSH_R_C = 1.0f, SWOOSH_R_K0 = -(0.08f * 1.0f + 0.313261687f);
 __device__ __forceinline__ float swoosh_l(float x) {
     // log(1+exp(x-4)) - 0.08x - 0.035 (reference: modules/scaling.py:1189-1195)
-    return softplus_fast(x - 4.0f) - 0.08f * x - 0.035f;
+    return swoosh_from_offset(x - SWOOSH_L_C, SWOOSH_L_K0);
 }
 __device__ __forceinline__ float swoosh_r(float x) {
     // log(1+exp(x-1)) - 0.08x - 0.313261687 (reference: modules/scaling.py:1200-1206)
-    return softplus_fast(x - 1.0f) - 0.08f * x - 0.313261687f;
+    return swoosh_from_offset(x - SWOOSH_R_C, SWOOSH_R_K0);
 }
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
