@@ -17,14 +17,21 @@ namespace zvb {
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_UMMA_K = 16;
-constexpr int GEMM_STAGES = 3;
 constexpr int GEMM_A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB
 constexpr int GEMM_B_BYTES = 256 * GEMM_BLOCK_K * 2;            // 32 KB (block_n <= 256)
-constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
+// single CTA: 3 stages of (A 16 KB + B 32 KB); CTA pair (cta_group::2): every CTA holds only half of
+// the B tile, 4 stages of (16 KB + 16 KB)
+constexpr int GEMM_OPERAND_BYTES = 3 * (GEMM_A_BYTES + GEMM_B_BYTES);
+template <int CLUSTER> struct GemmCfg {
+    static constexpr int STAGES = CLUSTER == 2 ? 4 : 3;
+    static constexpr int STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES / CLUSTER;
+    static_assert(STAGES * STAGE_BYTES <= GEMM_OPERAND_BYTES, "operand ring too large");
+};
+constexpr int GEMM_MAX_STAGES = 4;
 constexpr int GEMM_AUX_SLOTS = 4;
 constexpr int GEMM_AUX_BYTES = 128 * 128;                       // 128 rows x 128 B
 constexpr int GEMM_BIAS_BYTES = 8 * 256 * 4;               // one private copy per epilogue warp
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_AUX_SLOTS * GEMM_AUX_BYTES +
+constexpr int GEMM_SMEM_BYTES = GEMM_OPERAND_BYTES + GEMM_AUX_SLOTS * GEMM_AUX_BYTES +
                                 GEMM_BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_THREADS = 256;
@@ -178,11 +185,15 @@ __device__ __forceinline__ void store_unit(const GemmParams& p, uint8_t* stage, 
     }
 }
 
-// CLUSTER == 2: two CTAs with the same n_tile and adjacent m_tiles form a cluster; each loads its own
-// A tile and HALF of the shared B tile, multicast into both CTAs' shared memory, which cuts the
-// L2->SM operand traffic per tile from (A + B) to (A + B/2) -- the K<=1920 GEMMs of this network are
-// bound by that traffic, not by the tensor pipe.  A shared-memory stage is released to both
-// producers only when both CTAs' MMAs have retired (multicast commit on the `empty` barriers).
+// CLUSTER == 2: a CTA pair computes a 256 x BN tile with `tcgen05.mma.cta_group::2` (UMMA_M = 256):
+// each CTA stages its own 128 rows of A and HALF of the B tile, the leader's MMA thread consumes both
+// CTAs' shared memory, and each CTA's TMEM receives its 128 accumulator rows.  Per SM and k-block
+// this moves 16 KB + BN/2 x 128 B from L2 instead of 16 KB + BN x 128 B -- the K <= 1920 GEMMs of this
+// network are bound by that L2->SM operand traffic (~41 B/clk/SM measured), not by the tensor pipe.
+// (A 2-CTA cluster with a multicast B tile was measured first and saves nothing: L2 already
+// de-duplicates the two requests.)  Protocol: both producers wait on their LOCAL `empty` barrier and
+// complete bytes on the LEADER's `full` barrier; the leader commits with a multicast arrive to both
+// CTAs' `empty` / `tmem_full`; the peer's epilogue warps arrive remotely on the leader's `tmem_empty`.
 template <int KIND, int ACT, int CLUSTER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -190,12 +201,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    uint8_t* aux_smem = smem + GEMM_STAGES * GEMM_STAGE_BYTES;
+    constexpr int STAGES = GemmCfg<CLUSTER>::STAGES;
+    constexpr int STAGE_BYTES = GemmCfg<CLUSTER>::STAGE_BYTES;
+    uint8_t* aux_smem = smem + GEMM_OPERAND_BYTES;
     float* bias_smem = reinterpret_cast<float*>(aux_smem + GEMM_AUX_SLOTS * GEMM_AUX_BYTES);   // [8 warps][256]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_smem) + GEMM_BIAS_BYTES);
     uint64_t* full_bar = bars;                                  // [STAGES] TMA -> MMA
-    uint64_t* empty_bar = full_bar + GEMM_STAGES;               // [STAGES] MMA -> TMA
-    uint64_t* tmem_full = empty_bar + GEMM_STAGES;              // [2] MMA -> epilogue
+    uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;           // [STAGES] MMA -> TMA
+    uint64_t* tmem_full = empty_bar + GEMM_MAX_STAGES;          // [2] MMA -> epilogue
     uint64_t* tmem_empty = tmem_full + 2;                       // [2] epilogue -> MMA
     uint64_t* aux_full = tmem_empty + 2;                        // [AUX_SLOTS] TMA -> epilogue
     uint64_t* aux_empty = aux_full + GEMM_AUX_SLOTS;            // [AUX_SLOTS] epilogue -> TMA
@@ -219,13 +232,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         if (p.aux_mode != AUX_NONE) tma_prefetch_desc(&tma_aux);
-        for (int s = 0; s < GEMM_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], CLUSTER);
+            mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 8);
+            mbar_init(&tmem_empty[s], 8 * CLUSTER);
         }
         for (int s = 0; s < GEMM_AUX_SLOTS; ++s) {
             mbar_init(&aux_full[s], 1);
@@ -234,8 +247,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_holder, GEMM_TMEM_COLS);
-        tmem_relinquish();
+        if (CLUSTER == 2) { tmem_alloc_2sm(tmem_holder, GEMM_TMEM_COLS); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_holder, GEMM_TMEM_COLS); tmem_relinquish(); }
     }
     tc_fence_before();
     __syncthreads();
@@ -246,7 +259,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (A, B)
         if (lane == 0) {
-            const uint32_t stage_bytes = GEMM_A_BYTES + static_cast<uint32_t>(p.block_n) * GEMM_BLOCK_K * 2;
+            // bytes landing on the (leader's) full barrier per stage: both CTAs' A tiles + the whole B tile
+            const uint32_t stage_tx = CLUSTER * GEMM_A_BYTES + static_cast<uint32_t>(p.block_n) * GEMM_BLOCK_K * 2;
+            const int b_rows = p.block_n / CLUSTER;                    // B rows staged by this CTA
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
@@ -258,26 +273,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 const int bz = b * p.b_zb;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-                    uint8_t* sa = smem + stage * GEMM_STAGE_BYTES;
-                    tma_load_3d(sa, &tma_a, &full_bar[stage], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M, az);
-                    if (CLUSTER > 1) {
-                        // my half of the B tile (rows [crank*bn/2, (crank+1)*bn/2)) goes to both CTAs
-                        const int hrows = p.block_n / 2;
-                        tma_load_3d_mc(sa + GEMM_A_BYTES + crank * hrows * 128, &tma_b, &full_bar[stage],
-                                       kb * GEMM_BLOCK_K, n_tile * p.block_n + crank * hrows, bz, 0x3);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    if (CLUSTER == 2) {
+                        if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+                        tma_load_3d_2sm(sa, &tma_a, &full_bar[stage], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M, az);
+                        tma_load_3d_2sm(sa + GEMM_A_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BLOCK_K,
+                                        n_tile * p.block_n + crank * b_rows, bz);
                     } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+                        tma_load_3d(sa, &tma_a, &full_bar[stage], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M, az);
                         tma_load_3d(sa + GEMM_A_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BLOCK_K,
                                     n_tile * p.block_n, bz);
                     }
-                    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(static_cast<uint32_t>(p.block_n));
+        if (lane == 0 && crank == 0) {               // the leader issues for the pair
+            const uint32_t idesc = umma_idesc_bf16(static_cast<uint32_t>(p.block_n), 128u * CLUSTER);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -289,19 +304,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * GEMM_STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                     const uint64_t da = umma_desc_k_sw128(sa);
                     const uint64_t db = umma_desc_k_sw128(sa + GEMM_A_BYTES);
 #pragma unroll
                     for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
                         // advance 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in >>4 units
-                        umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                                  idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (CLUSTER == 2)
+                            umma_bf16_2sm(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                                          idesc, (kb | k) != 0 ? 1u : 0u);
+                        else
+                            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                                      idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    if (CLUSTER > 1) umma_commit_mc(&empty_bar[stage], 0x3);   // both producers wait for both MMAs
-                    else umma_commit(&empty_bar[stage]);      // frees the smem slot when MMAs retire
-                    if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
-                    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
+                    // free the smem slot (in both CTAs) when the MMAs retire; publish the accumulator
+                    if (CLUSTER == 2) {
+                        umma_commit_2sm(&empty_bar[stage], 0x3);
+                        if (kb == p.num_k_blocks - 1) umma_commit_2sm(&tmem_full[acc], 0x3);
+                    } else {
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
@@ -514,7 +538,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {                          // the leader's MMA thread owns the accumulator hand-shake
+                if (CLUSTER == 2 && crank != 0) mbar_arrive_remote(&tmem_empty[acc], 0);
+                else mbar_arrive(&tmem_empty[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }
@@ -525,7 +552,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
+        if (CLUSTER == 2) tmem_dealloc_2sm(tmem_base, GEMM_TMEM_COLS);
+        else tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
     }
 }
 
