@@ -82,6 +82,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// L2 prefetch of a box (no shared memory, no completion): hides the HBM latency of operands that a
+// later TMA load of the same box will then find in L2
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 // multicast variant: the box lands at the same shared-memory offset of every CTA in `mask` and
 // completes `bytes` on the mbarrier at the same offset in each of them
 __device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
