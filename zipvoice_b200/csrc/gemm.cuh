@@ -124,6 +124,32 @@ __device__ __forceinline__ void store_row32_direct(const GemmParams& p, long lon
         if (i < ncols) dst[i] = __float2bfloat16(v[i]);
 }
 
+// bf16 staging of one 32-column unit into 16-byte chunks cofs..cofs+3 of the thread's 128-byte row
+__device__ __forceinline__ void stage_bf16_unit(uint8_t* stage, int lane, const float* v, int cofs) {
+    uint8_t* my = stage + lane * 128;
+    const int sw = lane & 7;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(my + (((cofs + j) ^ sw) << 4)) =
+            make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                       pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+}
+// Writes the staged bf16 columns [c_lo, c_hi) (relative to `colbase`, multiples of 8, within 0..64) of
+// the warp's 32 rows: 8 lanes x 16 B = one 128-byte row segment per row, 4 rows per instruction
+// (the store path is bound by the number of <=128-byte write transactions, not by bytes).
+__device__ __forceinline__ void flush_bf16_units(__nv_bfloat16* out, int ldc, const uint8_t* stage, int lane,
+                                                 long long row0, int rows_ok, int colbase, int c_lo, int c_hi) {
+    __nv_bfloat16* dst = out + row0 * ldc + colbase;
+    const int ch = lane & 7;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int rr = 4 * k + (lane >> 3);
+        const uint4 q = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
+        if (rr < rows_ok && ch * 8 >= c_lo && ch * 8 < c_hi)
+            *reinterpret_cast<uint4*>(dst + static_cast<long long>(rr) * ldc + ch * 8) = q;
+    }
+}
+
 // Coalesced store of a warp's 32-row x 32-column unit: TMEM hands every thread one ROW, which as a
 // direct global store touches 32 different 128-byte lines per instruction (measured ~6 GB/s per SM).
 // The unit is therefore transposed through 4 KB of (swizzled, conflict-free) shared memory --
@@ -151,24 +177,10 @@ __device__ __forceinline__ void store_unit_staged(const GemmParams& p, uint8_t* 
         if (p.out_mode == OUT_F32) return;
         __syncwarp();
     }
-    {
-        uint8_t* my = stage + lane * 128;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(my + (((cofs + j) ^ sw) << 4)) =
-                make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                           pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-        __syncwarp();
-        __nv_bfloat16* dst = (p.out_mode == OUT_F32_BF16 ? p.out_bf16 : reinterpret_cast<__nv_bfloat16*>(p.out)) +
-                             row0 * p.ldc + col0;
-        const int ch = lane & 3;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int rr = 8 * k + (lane >> 2);
-            const uint4 q = *reinterpret_cast<const uint4*>(stage + rr * 128 + (((cofs + ch) ^ (rr & 7)) << 4));
-            if (rr < rows_ok && ch * 8 < ncols) *reinterpret_cast<uint4*>(dst + static_cast<long long>(rr) * p.ldc + ch * 8) = q;
-        }
-    }
+    stage_bf16_unit(stage, lane, v, cofs);
+    __syncwarp();
+    flush_bf16_units(p.out_mode == OUT_F32_BF16 ? p.out_bf16 : reinterpret_cast<__nv_bfloat16*>(p.out), p.ldc, stage,
+                     lane, row0, rows_ok, col0 - 8 * cofs, 8 * cofs, 8 * cofs + ncols);
 }
 
 // One warp stores its unit: staged+coalesced when the column range is 16-byte aligned, direct otherwise.
@@ -429,7 +441,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
             if (KIND == EPI_GATED) {
                 const int hcols = p.block_n >> 1;                       // 128
-                for (int u = half; u * 32 < hcols; u += 2) {
+                // each warp of a quarter takes two adjacent 32-column units so that their bf16 rows leave
+                // as one 128-byte segment
+                int g_lo = 0, g_hi = 0, g_col = 0;
+                for (int u = 2 * half; u < 2 * half + 2 && u * 32 < hcols; ++u) {
                     const int c0 = u * 32;
                     uint32_t ra[32], rb[32];
                     tmem_ld32(taddr + c0, ra);
@@ -455,13 +470,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                 v[4 * j + e] = masked ? 0.0f : o;
                             }
                         }
-                        store_unit(p, private_stage, lane, row_ok, row, row0, rows_ok, oc, ncols, v, 0);
+                        const bool pairable = p.out_mode == OUT_BF16 && (p.ldc & 7) == 0 && (out_base & 7) == 0 &&
+                                              (ncols & 7) == 0;
+                        if (pairable) {
+                            stage_bf16_unit(private_stage, lane, v, 4 * (u & 1));
+                            if ((u & 1) == 0) g_col = oc;
+                            else if (g_hi == 0) { g_col = oc - 32; g_lo = 32; }
+                            g_hi = 32 * (u & 1) + ncols;
+                        } else {
+                            store_unit(p, private_stage, lane, row_ok, row, row0, rows_ok, oc, ncols, v, 0);
+                        }
                     }
+                }
+                if (g_hi > 0) {
+                    __syncwarp();
+                    flush_bf16_units(reinterpret_cast<__nv_bfloat16*>(p.out), p.ldc, private_stage, lane, row0, rows_ok,
+                                     g_col, g_lo, g_hi);
+                    __syncwarp();
                 }
             } else {
                 for (int s = half; s < n_sub; s += 2) {
                     const uint8_t* aux_row = nullptr;
                     int slot = 0;
+                    int pend_lo = 0, pend_hi = 0, pend_col = 0;      // staged, not yet flushed bf16 columns
+                    uint8_t* pend_stage = nullptr;
                     if (p.aux_mode != AUX_NONE) {
                         const uint32_t q = tile_iter * static_cast<uint32_t>(n_sub) + static_cast<uint32_t>(s);
                         slot = q % GEMM_AUX_SLOTS;
@@ -553,9 +585,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                                  ? aux_smem + slot * GEMM_AUX_BYTES + quarter * 32 * 128
                                                  : private_stage;
                             __syncwarp();              // every lane has consumed its aux row
-                            store_unit(p, stage, lane, row_ok, row, row0, rows_ok, oc, ncols, v,
-                                       p.aux_mode == AUX_MUL_BF16 ? 4 * uu : 0);
+                            const bool pairable = p.out_mode == OUT_BF16 && units_per_sub == 2 && (p.ldc & 7) == 0 &&
+                                                  (out_base & 7) == 0 && (ncols & 7) == 0;
+                            if (pairable) {            // stage now, flush both units of the sub-tile together
+                                stage_bf16_unit(stage, lane, v, 4 * uu);
+                                if (uu == 0) { pend_lo = 0; pend_col = oc; }
+                                pend_hi = 32 * uu + ncols;
+                                pend_stage = stage;
+                            } else {
+                                store_unit(p, stage, lane, row_ok, row, row0, rows_ok, oc, ncols, v,
+                                           p.aux_mode == AUX_MUL_BF16 ? 4 * uu : 0);
+                            }
                         }
+                    }
+                    if (pend_hi > 0) {
+                        __syncwarp();
+                        flush_bf16_units(reinterpret_cast<__nv_bfloat16*>(p.out), p.ldc, pend_stage, lane, row0, rows_ok,
+                                         pend_col, pend_lo, pend_hi);
+                        __syncwarp();
+                        pend_hi = 0;
                     }
                     if (p.aux_mode != AUX_NONE) {
                         __syncwarp();
