@@ -283,21 +283,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 const int b = rest / m_groups;
                 const int az = b * p.a_zb + n_tile * p.a_zn;
                 const int bz = b * p.b_zb;
-                // The A operand (activations, P) streams from HBM exactly once per GEMM; with only
-                // STAGES k-blocks in flight per SM the loads are latency-bound (~2 us each).  Pull the NEXT
-                // tile's A blocks into L2 now, one tile (~5-10 us) ahead of their TMA loads.
-                {
-                    const int nt = tile + tile_step;
-                    if (nt < total_tiles) {
-                        const int n_tile2 = nt % p.num_n_tiles;
-                        const int rest2 = nt / p.num_n_tiles;
-                        const int m_tile2 = (rest2 % m_groups) * CLUSTER + crank;
-                        const int az2 = (rest2 / m_groups) * p.a_zb + n_tile2 * p.a_zn;
-                        if (m_tile2 < p.num_m_tiles)
-                            for (int kb = 0; kb < p.num_k_blocks; ++kb)
-                                tma_prefetch_3d(&tma_a, kb * GEMM_BLOCK_K, m_tile2 * GEMM_BLOCK_M, az2);
-                    }
-                }
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -367,18 +352,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 const int rest = tile / p.num_n_tiles;
                 const int m_tile = (rest % m_groups) * CLUSTER + crank;
                 const int b = rest / m_groups;
-                {   // same for the epilogue operand of the next tile
-                    const int nt = tile + tile_step;
-                    if (nt < total_tiles) {
-                        const int n_tile2 = nt % p.num_n_tiles;
-                        const int rest2 = nt / p.num_n_tiles;
-                        const int m_tile2 = (rest2 % m_groups) * CLUSTER + crank;
-                        if (m_tile2 < p.num_m_tiles)
-                            for (int s = 0; s < n_sub; ++s)
-                                tma_prefetch_3d(&tma_aux, n_tile2 * p.out_col_stride + s * sub_cols,
-                                                m_tile2 * GEMM_BLOCK_M, (rest2 / m_groups) * p.aux_zb);
-                    }
-                }
                 for (int s = 0; s < n_sub; ++s, ++q) {
                     const int slot = q % GEMM_AUX_SLOTS;
                     const uint32_t par = (q / GEMM_AUX_SLOTS) & 1u;
