@@ -48,7 +48,7 @@ def workload_config(batch_per_gpu, n_gpus):
             "utterances_per_gpu": batch_per_gpu, "global_utterances": batch_per_gpu * n_gpus,
             "prompt_frames": PROMPT_FRAMES, "target_frames": TARGET_FRAMES, "num_step": NUM_STEP,
             "parallelism": f"utterance-sharded x{n_gpus}, no data-path collective",
-            "l2": "working set (4.2 GB workspace per rank) exceeds the 126 MB L2; no explicit flush"}
+            "l2": "working set (6.3 GB workspace per rank) exceeds the 126 MB L2; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
