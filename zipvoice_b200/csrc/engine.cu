@@ -54,7 +54,8 @@ static int check_launch(const char* what) {
 }
 
 static int g_num_sms = 0;
-static int g_cluster_ok = 1;      // ZVB_NO_CLUSTER=1 disables the 2-CTA multicast GEMM variant
+static int g_cluster_ok = 1;      // ZVB_NO_CLUSTER=1 disables the CTA-pair (cta_group::2) GEMM variant
+static int g_tma_store_ok = 1;    // ZVB_NO_TMA_STORE=1 keeps the epilogue on per-thread stores
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
 static int init_device() {
@@ -69,6 +70,7 @@ static int init_device() {
         return fail(ZVB_ERR_NO_DEVICE, "device sm_%d%d is not sm_100 (B200)", prop.major, prop.minor);
     g_num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("ZVB_NO_CLUSTER")) g_cluster_ok = atoi(e) == 0;
+    if (const char* e = getenv("ZVB_NO_TMA_STORE")) g_tma_store_ok = atoi(e) == 0;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
     CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
@@ -85,9 +87,12 @@ static int init_device() {
     return 0;
 }
 
-// Tensor (dim0 fastest) viewed as 3-D, box = (128 bytes, box1, 1), 128B swizzle, zero OOB fill.
+// Tensor (dim0 fastest) viewed as 3-D, box = (128 bytes, box1, 1) with 128B swizzle -- or, with
+// half_row, box = (64 bytes, box1, 1) with 64B swizzle (the bf16 shadow of a 32-column fp32 sub-tile).
+// Out-of-range elements are zero-filled on loads and clipped on stores.
 static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
-                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box1, bool f32 = false) {
+                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box1, bool f32 = false,
+                     bool half_row = false) {
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (stride1_bytes & 15) != 0 || (stride2_bytes & 15) != 0)
         return fail(ZVB_ERR_INVALID, "tensor map: pointer/strides must be 16-byte aligned");
     if (box1 == 0 || box1 > 256 || d0 == 0 || d1 == 0 || d2 == 0)
@@ -95,12 +100,12 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
                     (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
     cuuint64_t dims[3] = {d0, d1, d2};
     cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
-    cuuint32_t box[3] = {f32 ? 32u : 64u, box1, 1};
+    cuuint32_t box[3] = {(f32 ? 32u : 64u) / (half_row ? 2u : 1u), box1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                           const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          half_row ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ZVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }
@@ -111,8 +116,8 @@ enum OpType { OP_GEMM, OP_ATTN, OP_BIASNORM, OP_PREP, OP_DOWN, OP_UP, OP_DWCONV,
 struct Op {
     OpType type;
     // GEMM / ATTN
-    CUtensorMap ma, mb, mx;
-    bool has_mx = false;
+    CUtensorMap ma, mb, mx, ms, ms2;     // A, B, epilogue operand, output, bf16 shadow output
+    bool has_mx = false, has_ms = false, has_ms2 = false;
     GemmParams gp;
     int kind = 0, grid = 0, cluster = 1;
     AttnParams ap;
@@ -131,14 +136,53 @@ struct Op {
 };
 
 static int pick_block_n(int n_out, long long m_tiles) {
+    // TMA stores move 64-column (bf16) sub-tiles, so tile widths that are multiples of 64 are preferred
+    // when they waste < 8% of the MMA work; otherwise the narrowest multiple of 16 that covers n_out.
+    if (n_out >= 64) {
+        int best = 0;
+        double best_waste = 1e9;
+        for (int bn = 256; bn >= 64; bn -= 64) {
+            const int tiles = (n_out + bn - 1) / bn;
+            if (m_tiles * tiles < g_num_sms && bn > 64) continue;       // small problems: more, narrower tiles
+            const double waste = (double)tiles * bn / n_out - 1.0;
+            if (waste < best_waste - 1e-9) { best_waste = waste; best = bn; }
+        }
+        if (best != 0 && best_waste < 0.08) return best;
+    }
     int tiles = (n_out + 255) / 256;
     int bn = (((n_out + tiles - 1) / tiles) + 15) / 16 * 16;
-    // small problems: prefer more, narrower tiles until the grid covers the SMs
     while (m_tiles * tiles < g_num_sms && bn > 64) {
         ++tiles;
         bn = (((n_out + tiles - 1) / tiles) + 15) / 16 * 16;
     }
     return bn;
+}
+
+// Output tensor maps for the TMA-store epilogue; eligible when whole 128-byte sub-tiles belong to one tile.
+static int setup_tma_store(Op& op, int batches_rows /*rows per batch*/, int nbatch) {
+    GemmParams& p = op.gp;
+    const bool f32 = p.out_mode == OUT_F32 || p.out_mode == OUT_F32_BF16;
+    const bool bf = p.out_mode == OUT_BF16;
+    if (!g_tma_store_ok || !(f32 || bf)) return 0;
+    if (op.kind == EPI_LINEAR) {
+        if (p.out_col_stride != p.block_n) return 0;
+        if (p.num_n_tiles > 1 && p.block_n % (bf ? 64 : 32) != 0) return 0;
+    } else if (!bf) {
+        return 0;
+    }
+    if ((p.ldc * (f32 ? 4 : 2)) % 16 != 0) return 0;
+    if (p.out_mode == OUT_F32_BF16 && (p.ldc * 2) % 16 != 0) return 0;
+    const uint64_t esz = f32 ? 4 : 2;
+    TRY(make_tmap(&op.ms, p.out, p.n_out, batches_rows, nbatch, (uint64_t)p.ldc * esz,
+                  (uint64_t)p.ldc * esz * batches_rows, GEMM_BLOCK_M, f32));
+    op.has_ms = true;
+    if (p.out_mode == OUT_F32_BF16) {
+        TRY(make_tmap(&op.ms2, p.out_bf16, p.n_out, batches_rows, nbatch, (uint64_t)p.ldc * 2,
+                      (uint64_t)p.ldc * 2 * batches_rows, GEMM_BLOCK_M, false, true));
+        op.has_ms2 = true;
+    }
+    p.tma_store = 1;
+    return 0;
 }
 
 static void gp_defaults(GemmParams& p) { memset(&p, 0, sizeof p); p.rows_per_group = 1; }
@@ -209,6 +253,7 @@ static int build_linear(Op& op, const bf16* A, long long M, int lda, const zvb_l
         TRY(make_tmap(&op.mx, e.resid, ldc, M, 1, (uint64_t)ldc * 4, (uint64_t)ldc * 4 * M, GEMM_BLOCK_M, true));
         op.has_mx = true;
     }
+    TRY(setup_tma_store(op, (int)M, 1));
     op.shape[0] = (int)M; op.shape[1] = lin.out_features; op.shape[2] = lin.in_features; op.shape[3] = bn;
     op.cat = ZVB_CAT_GEMM_LINEAR;
     op.work = 2.0 * (double)M * lin.out_features * lin.in_features;
@@ -241,6 +286,7 @@ static int build_gated(Op& op, const bf16* A, long long M, int lda, const zvb_li
     TRY(make_tmap(&op.ma, A, K, M, 1, (uint64_t)lda * 2, (uint64_t)lda * 2 * M, GEMM_BLOCK_M));
     TRY(make_tmap(&op.mb, lin.w, K, lin.rows, 1, (uint64_t)lin.k_pitch * 2, (uint64_t)lin.k_pitch * 2 * lin.rows,
                   b_box_rows(op)));
+    TRY(setup_tma_store(op, (int)M, 1));
     op.shape[0] = (int)M; op.shape[1] = 2 * n_out; op.shape[2] = lin.in_features; op.shape[3] = 256;
     op.cat = ZVB_CAT_GEMM_GATED;
     op.work = 2.0 * (double)M * (2.0 * n_out) * lin.in_features;
@@ -286,6 +332,7 @@ static int build_pv(Op& op, const bf16* P, const float* inv_l, const bf16* Vt, v
     set_grid(op);
     TRY(make_tmap(&op.ma, P, Lk, L, (uint64_t)N * H, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * L, GEMM_BLOCK_M));
     TRY(make_tmap(&op.mb, Vt, Lk, vt_rows, N, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * vt_rows, b_box_rows(op)));
+    if (!per_head) TRY(setup_tma_store(op, L, N));
     op.shape[0] = N * L; op.shape[1] = per_head ? H * hd : hd; op.shape[2] = L; op.shape[3] = p.block_n;
     op.cat = ZVB_CAT_GEMM_PV;
     op.work = 2.0 * (double)N * (per_head ? H : 1) * (double)L * L * hd;
@@ -311,6 +358,8 @@ static int launch_op(const Op& op, cudaStream_t st) {
         case OP_GEMM: {
             if (op.grid <= 0) return 0;
             const CUtensorMap& mx = op.has_mx ? op.mx : op.ma;
+            const CUtensorMap& ms = op.has_ms ? op.ms : op.ma;
+            const CUtensorMap& ms2 = op.has_ms2 ? op.ms2 : op.ma;
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(op.grid);
             cfg.blockDim = dim3(GEMM_THREADS);
@@ -323,14 +372,14 @@ static int launch_op(const Op& op, cudaStream_t st) {
             const int sel = (op.kind == EPI_GATED ? 3 : op.gp.act) * 2 + (op.cluster - 1);
             cudaError_t e = cudaSuccess;
             switch (sel) {
-                case 0: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 1>, op.ma, op.mb, mx, op.gp); break;
-                case 1: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 2>, op.ma, op.mb, mx, op.gp); break;
-                case 2: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 1>, op.ma, op.mb, mx, op.gp); break;
-                case 3: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 2>, op.ma, op.mb, mx, op.gp); break;
-                case 4: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 1>, op.ma, op.mb, mx, op.gp); break;
-                case 5: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 2>, op.ma, op.mb, mx, op.gp); break;
-                case 6: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 1>, op.ma, op.mb, mx, op.gp); break;
-                default: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 2>, op.ma, op.mb, mx, op.gp); break;
+                case 0: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 1>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
+                case 1: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 2>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
+                case 2: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 1>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
+                case 3: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 2>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
+                case 4: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 1>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
+                case 5: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 2>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
+                case 6: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 1>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
+                default: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 2>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
             }
             if (e != cudaSuccess) return fail(ZVB_ERR_CUDA, "launch gemm: %s", cudaGetErrorString(e));
             return check_launch("gemm");

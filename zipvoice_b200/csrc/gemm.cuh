@@ -30,9 +30,12 @@ template <int CLUSTER> struct GemmCfg {
 constexpr int GEMM_MAX_STAGES = 4;
 constexpr int GEMM_AUX_SLOTS = 4;
 constexpr int GEMM_AUX_BYTES = 128 * 128;                       // 128 rows x 128 B
-constexpr int GEMM_BIAS_BYTES = 8 * 256 * 4;               // one private copy per epilogue warp
-constexpr int GEMM_SMEM_BYTES = GEMM_OPERAND_BYTES + GEMM_AUX_SLOTS * GEMM_AUX_BYTES +
-                                GEMM_BIAS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int GEMM_BIAS_BYTES = 2 * 256 * 4;               // one copy per epilogue half (4 warps)
+constexpr int GEMM_SHADOW_BYTES = 2 * 128 * 64;            // bf16 shadow staging, 128 rows x 64 B per half
+constexpr int GEMM_LAYOUT_BYTES = GEMM_OPERAND_BYTES + GEMM_AUX_SLOTS * GEMM_AUX_BYTES + GEMM_BIAS_BYTES +
+                                  GEMM_SHADOW_BYTES + 256 /*barriers*/;
+constexpr int GEMM_SMEM_BYTES = 232448;                    // all 227 KB; layout + alignment pad must fit (checked)
+static_assert(GEMM_LAYOUT_BYTES <= GEMM_SMEM_BYTES, "shared-memory layout too large");
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_THREADS = 256;
 constexpr int GEMM_TMEM_COLS = 512;
@@ -66,6 +69,7 @@ struct GemmParams {
     const float* rowbias;  // fp32 [(row / rows_per_group)*ld_rowbias + outcol]
     int rows_per_group;
     int ld_rowbias;
+    int tma_store;         // outputs leave through TMA stores (tensor maps tma_out / tma_out2)
     int aux_mode;          // tile operand streamed by TMA: fp32 residual or bf16 multiplier
     int aux_zb;            // aux tensor-map z = b*aux_zb
     const float* orig;     // bypass: orig + (v - orig)*scale[col]; fp32, pitch ldc
@@ -209,15 +213,21 @@ __device__ __forceinline__ void store_unit(const GemmParams& p, uint8_t* stage, 
 template <int KIND, int ACT, int CLUSTER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const __grid_constant__ CUtensorMap tma_aux, const GemmParams p) {
+            const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_out,
+            const __grid_constant__ CUtensorMap tma_out2, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     constexpr int STAGES = GemmCfg<CLUSTER>::STAGES;
     constexpr int STAGE_BYTES = GemmCfg<CLUSTER>::STAGE_BYTES;
     uint8_t* aux_smem = smem + GEMM_OPERAND_BYTES;
-    float* bias_smem = reinterpret_cast<float*>(aux_smem + GEMM_AUX_SLOTS * GEMM_AUX_BYTES);   // [8 warps][256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_smem) + GEMM_BIAS_BYTES);
+    float* bias_smem = reinterpret_cast<float*>(aux_smem + GEMM_AUX_SLOTS * GEMM_AUX_BYTES);   // [2 halves][256]
+    uint8_t* shadow_smem = reinterpret_cast<uint8_t*>(bias_smem) + GEMM_BIAS_BYTES;           // [2 halves][128][64 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(shadow_smem + GEMM_SHADOW_BYTES);
+    if (threadIdx.x == 0 && (smem - smem_raw) + GEMM_LAYOUT_BYTES > GEMM_SMEM_BYTES) {
+        printf("zvb: gemm shared-memory layout does not fit (base misaligned by %d)\n", (int)(smem - smem_raw));
+        __trap();
+    }
     uint64_t* full_bar = bars;                                  // [STAGES] TMA -> MMA
     uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;           // [STAGES] MMA -> TMA
     uint64_t* tmem_full = empty_bar + GEMM_MAX_STAGES;          // [2] MMA -> epilogue
@@ -237,13 +247,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int tile_step = gridDim.x / CLUSTER;
     // accumulator columns are consumed in units of 32; aux sub-tiles hold 32 (fp32) or 64 (bf16) columns
     const int n_units = (p.block_n + 31) >> 5;
-    const int units_per_sub = p.aux_mode == AUX_RESID_F32 ? 1 : 2;
+    const bool out_f32 = p.out_mode == OUT_F32 || p.out_mode == OUT_F32_BF16;
+    const int units_per_sub = (p.aux_mode == AUX_RESID_F32 || (p.tma_store && out_f32)) ? 1 : 2;
     const int n_sub = (n_units + units_per_sub - 1) / units_per_sub;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         if (p.aux_mode != AUX_NONE) tma_prefetch_desc(&tma_aux);
+        if (p.tma_store) { tma_prefetch_desc(&tma_out); tma_prefetch_desc(&tma_out2); }
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -254,7 +266,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         for (int s = 0; s < GEMM_AUX_SLOTS; ++s) {
             mbar_init(&aux_full[s], 1);
-            mbar_init(&aux_empty[s], 4);
+            mbar_init(&aux_empty[s], p.tma_store ? 1 : 4);
         }
         fence_barrier_init();
     }
@@ -368,6 +380,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const int half = (warp - 4) >> 2;                 // which of the two warps of the quarter
         const int r = quarter * 32 + lane;                // accumulator row inside the tile
         uint8_t* private_stage = aux_smem + (warp - 4) * 4096;   // used when no aux slot is in flight
+        const bool leader = quarter == 0 && lane == 0;    // one thread per half issues the TMA stores
+        uint8_t* shadow_stage = shadow_smem + half * (128 * 64);
+        uint32_t kcount = 0;                              // sub-tiles stored by this half (staging ring)
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t tile_iter = 0;
@@ -385,19 +400,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             rows_ok = rows_ok < 0 ? 0 : (rows_ok > 32 ? 32 : rows_ok);
             const int out_base = n_tile * p.out_col_stride;
             const int acc_base = n_tile * p.block_n;
-            // this warp's private copy of the tile's bias (minus the Swoosh offset, see swoosh_from_offset)
-            float* bs = bias_smem + (warp - 4) * 256;
+            // this half's copy of the tile's bias (minus the Swoosh offset, see swoosh_from_offset)
+            float* bs = bias_smem + half * 256;
             {
                 constexpr float off = ACT == ACT_SWOOSH_L ? SWOOSH_L_C : (ACT == ACT_SWOOSH_R ? SWOOSH_R_C : 0.0f);
                 const int lim = KIND == EPI_GATED ? p.num_n_tiles * 256 : p.n_out;
-                __syncwarp();
+                named_bar_sync(2 + half, 128);            // everyone is done with the previous tile's bias
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int cc = q * 32 + lane;
+                for (int q = 0; q < 2; ++q) {
+                    const int cc = q * 128 + r;
                     const int c = acc_base + cc;
                     bs[cc] = ((p.bias != nullptr && cc < p.block_n && c < lim) ? __ldg(p.bias + c) : 0.0f) - off;
                 }
-                __syncwarp();
+                named_bar_sync(2 + half, 128);
             }
             bool masked = false;
             if (p.row_mask != nullptr && row_ok) masked = p.row_mask[row] != 0;
@@ -417,6 +432,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 // each warp of a quarter takes two adjacent 32-column units so that their bf16 rows leave
                 // as one 128-byte segment
                 int g_lo = 0, g_hi = 0, g_col = 0;
+                uint8_t* tbuf = nullptr;
+                const bool g_tma = p.tma_store && 2 * half * 32 < hcols;
+                if (g_tma) {                              // staging ring of this half: two 16 KB buffers
+                    tbuf = aux_smem + ((kcount & 1u) * 2 + half) * GEMM_AUX_BYTES;
+                    if (leader) bulk_wait_read<1>();
+                    named_bar_sync(2 + half, 128);        // the buffer's previous store has read it
+                }
                 for (int u = 2 * half; u < 2 * half + 2 && u * 32 < hcols; ++u) {
                     const int c0 = u * 32;
                     uint32_t ra[32], rb[32];
@@ -445,7 +467,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         }
                         const bool pairable = p.out_mode == OUT_BF16 && (p.ldc & 7) == 0 && (out_base & 7) == 0 &&
                                               (ncols & 7) == 0;
-                        if (pairable) {
+                        if (g_tma) {
+                            stage_bf16_unit(tbuf + quarter * 32 * 128, lane, v, 4 * (u & 1));
+                        } else if (pairable) {
                             stage_bf16_unit(private_stage, lane, v, 4 * (u & 1));
                             if ((u & 1) == 0) g_col = oc;
                             else if (g_hi == 0) { g_col = oc - 32; g_lo = 32; }
@@ -455,7 +479,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         }
                     }
                 }
-                if (g_hi > 0) {
+                if (g_tma) {
+                    fence_proxy_async_smem();
+                    named_bar_sync(2 + half, 128);        // the 128 x 64 sub-tile is staged
+                    if (leader) {
+                        tma_store_3d(&tma_out, tbuf, out_base + 64 * half, m_tile * GEMM_BLOCK_M, b);
+                        bulk_commit();
+                    }
+                    ++kcount;
+                } else if (g_hi > 0) {
                     __syncwarp();
                     flush_bf16_units(reinterpret_cast<__nv_bfloat16*>(p.out), p.ldc, private_stage, lane, row0, rows_ok,
                                      g_col, g_lo, g_hi);
@@ -473,6 +505,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         mbar_wait(&aux_full[slot], (q / GEMM_AUX_SLOTS) & 1u);
                         aux_row = aux_smem + slot * GEMM_AUX_BYTES + r * 128;
                     }
+                    uint8_t* tbuf = nullptr;                 // TMA-store staging: 128 rows x 128 B
+                    if (p.tma_store) {
+                        if (p.aux_mode != AUX_NONE) {        // in place over the consumed aux sub-tile
+                            tbuf = aux_smem + slot * GEMM_AUX_BYTES;
+                        } else {                             // staging ring of this half: two 16 KB buffers
+                            tbuf = aux_smem + ((kcount & 1u) * 2 + half) * GEMM_AUX_BYTES;
+                            if (leader) bulk_wait_read<1>();
+                        }
+                        if (p.aux_mode == AUX_NONE || p.out_mode == OUT_F32_BF16)
+                            named_bar_sync(2 + half, 128);   // previous stores have read the buffers we overwrite
+                    }
                     for (int uu = 0; uu < units_per_sub; ++uu) {
                         const int c0 = (s * units_per_sub + uu) * 32;
                         if (c0 >= p.block_n) break;
@@ -483,7 +526,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         int ncols = p.n_valid - c0;
                         if (p.n_out - oc < ncols) ncols = p.n_out - oc;
                         ncols = ncols > 32 ? 32 : ncols;
-                        if (ncols > 0) {
+                        if (ncols > 0 || p.tma_store) {
                             float v[32];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
@@ -557,6 +600,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                             uint8_t* stage = p.aux_mode != AUX_NONE
                                                  ? aux_smem + slot * GEMM_AUX_BYTES + quarter * 32 * 128
                                                  : private_stage;
+                            if (p.tma_store) {         // stage into the (swizzled) TMA box, own row only
+                                if (out_f32) {
+                                    uint8_t* my = tbuf + r * 128;
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j)
+                                        *reinterpret_cast<float4*>(my + ((j ^ (r & 7)) << 4)) =
+                                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                                    if (p.out_mode == OUT_F32_BF16) {      // 64-byte rows, 64B swizzle
+                                        uint8_t* sh = shadow_stage + r * 64;
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j)
+                                            *reinterpret_cast<uint4*>(sh + ((j ^ ((r >> 1) & 3)) << 4)) =
+                                                make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                           pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                                    }
+                                } else {
+                                    stage_bf16_unit(tbuf + quarter * 32 * 128, lane, v, 4 * uu);
+                                }
+                                continue;
+                            }
                             __syncwarp();              // every lane has consumed its aux row
                             const bool pairable = p.out_mode == OUT_BF16 && units_per_sub == 2 && (p.ldc & 7) == 0 &&
                                                   (out_base & 7) == 0 && (ncols & 7) == 0;
@@ -570,6 +633,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                            p.aux_mode == AUX_MUL_BF16 ? 4 * uu : 0);
                             }
                         }
+                    }
+                    if (p.tma_store) {
+                        fence_proxy_async_smem();            // generic-proxy writes -> visible to the TMA engine
+                        named_bar_sync(2 + half, 128);       // the whole 128-row sub-tile is staged
+                        if (leader) {
+                            const int col = out_base + s * units_per_sub * 32;
+                            tma_store_3d(&tma_out, tbuf, col, m_tile * GEMM_BLOCK_M, b);
+                            if (p.out_mode == OUT_F32_BF16) tma_store_3d(&tma_out2, shadow_stage, col, m_tile * GEMM_BLOCK_M, b);
+                            bulk_commit();
+                            if (p.aux_mode != AUX_NONE || p.out_mode == OUT_F32_BF16) {
+                                bulk_wait_read<0>();         // the slot / shadow buffer may be reused
+                                if (p.aux_mode != AUX_NONE) mbar_arrive(&aux_empty[slot]);
+                            }
+                        }
+                        ++kcount;
+                        continue;
                     }
                     if (pend_hi > 0) {
                         __syncwarp();
@@ -592,6 +671,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (p.tma_store && leader) bulk_wait_read<0>();   // staging must outlive the stores reading it
     }
 
     tc_fence_before();
