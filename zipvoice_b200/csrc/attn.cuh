@@ -10,23 +10,26 @@
 // adds the bias and writes the UNNORMALISED weights exp(s - m) in (0, 1] as bf16 together with the
 // fp32 row sum's reciprocal; the three consumers of the layer (NonlinAttention, SelfAttention x2)
 // apply 1/l in their GEMM epilogue.  Masked keys get exactly 0 (exp(-1000 - m) == 0 in fp32).
+// The softmax is latency bound (TMEM load -> LDS of the rel-pos entries -> FFMA chain -> MUFU), so a
+// CTA runs EIGHT softmax warps -- two per TMEM lane quarter, each owning 64 of the tile's 128 key
+// columns and exchanging row max / row sum through shared memory -- and two CTAs share an SM
+// (<= 102 registers per thread); P leaves through TMA box stores (32 rows x 64 columns per warp).
 #pragma once
 #include "ptx.cuh"
 
 namespace zvb {
 
-__device__ __forceinline__ int swarp_of(int warp) { return warp - 2; }
-
 constexpr int ATT_BM = 128;          // queries per CTA
 constexpr int ATT_BN = 128;          // keys per score tile
 constexpr int ATT_KSTAGES = 3;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;      // one 128-row x 64-col bf16 box (only 32 cols used)
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_SM_WARPS = 8;      // softmax warps: two per TMEM lane quarter, 64 key columns each
+constexpr int ATT_THREADS = 64 + 32 * ATT_SM_WARPS;
 constexpr int ATT_TMEM_COLS = 256;
 constexpr int ATT_EWIN = 256;        // 255 offsets used
-constexpr int ATT_STAGE_BYTES = 4 * 4096;            // per softmax warp: 32 rows x 128 B store staging
+constexpr int ATT_STAGE_BYTES = ATT_SM_WARPS * 4096; // per softmax warp: 32 rows x 128 B TMA-store staging
 constexpr int ATT_SMEM_BYTES = (1 + ATT_KSTAGES) * ATT_TILE_BYTES + ATT_STAGE_BYTES + 2 * ATT_EWIN * 16 +
-                               2 * 16 + 1024 + 256;
+                               2 * 16 + 2 * 128 * 4 + 1024 + 256;
 
 struct AttnParams {
     int L, Lk, H, N;
@@ -35,22 +38,25 @@ struct AttnParams {
     int ld;
     const float* E;                  // [H][2L-1][4] followed by [H] floats: max_r |E[h][r]|_2
     const uint8_t* mask;             // [N][L], non-zero = padded key
-    __nv_bfloat16* P;                // [N][H][L][Lk] unnormalised weights exp(s - m)
+    __nv_bfloat16* P;                // [N][H][L][Lk] unnormalised weights exp(s - m) (written through tma_p)
     float* inv_l;                    // [N][H][L]     1 / row sum
 };
 
+// tma_qk: [q | k | p] rows, box 64 x 128; tma_p: P viewed as (Lk, L, N*H), box 64 columns x 32 rows.
 __global__ void __launch_bounds__(ATT_THREADS, 2)
-attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams p) {
+attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_constant__ CUtensorMap tma_p,
+                    const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     uint8_t* q_tile = smem;
     uint8_t* k_tiles = smem + ATT_TILE_BYTES;
-    uint8_t* stage_all = smem + (1 + ATT_KSTAGES) * ATT_TILE_BYTES;                        // [4][32][128 B]
+    uint8_t* stage_all = smem + (1 + ATT_KSTAGES) * ATT_TILE_BYTES;                        // [8][32][128 B]
     // rel-pos window of the (i-tile, j-tile): 255 offsets x 4 floats, pre-scaled by log2 e
     float4* ewin = reinterpret_cast<float4*>(stage_all + ATT_STAGE_BYTES);                  // [2][256]
     uint32_t* mwin = reinterpret_cast<uint32_t*>(ewin + 2 * ATT_EWIN);                      // [2][4] excluded-key bits
-    uint64_t* bars = reinterpret_cast<uint64_t*>(mwin + 8);
+    float* xch = reinterpret_cast<float*>(mwin + 8);                                        // [2][128] half <-> half
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 256);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1;                      // [KSTAGES]
     uint64_t* k_empty = k_full + ATT_KSTAGES;         // [KSTAGES]
@@ -68,6 +74,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_qk);
+        tma_prefetch_desc(&tma_p);
         mbar_init(q_full, 1);
         for (int s = 0; s < ATT_KSTAGES; ++s) {
             mbar_init(&k_full[s], 1);
@@ -75,7 +82,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&s_full[s], 1);
-            mbar_init(&s_empty[s], 4);
+            mbar_init(&s_empty[s], ATT_SM_WARPS);
         }
         fence_barrier_init();
     }
@@ -127,10 +134,10 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
             }
         }
     } else {
-        // ------------------------------------------------------------------ softmax warps
-        const int quarter = warp & 3;
-        const int tid = threadIdx.x - 64;                 // 0..127 (not row order; only for staging)
-        const int swarp = tid >> 5;                       // 0..3
+        // ------------------------------------------------------------------ softmax warps (2..9)
+        const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
+        const int tid = threadIdx.x - 64;                 // 0..255
+        const int half = tid >> 7;                        // key columns [64*half, 64*half + 64) of every tile
         const int r = quarter * 32 + lane;                // row inside the query tile
         const int i = i0 + r;
         const bool row_ok = i < p.L;
@@ -141,13 +148,12 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
             p0 = bf16_lo(w.x); p1 = bf16_hi(w.x); p2 = bf16_lo(w.y); p3 = bf16_hi(w.y);
         }
         const float4* Eh = reinterpret_cast<const float4*>(p.E) + static_cast<long long>(h) * (2 * p.L - 1);
-        const float emax = __ldg(p.E + static_cast<long long>(p.H) * (2 * p.L - 1) * 4 + h);
         const uint8_t* mrow = p.mask + static_cast<long long>(n) * p.L;
-        // P rows of this warp; stores are transposed through shared memory so that one instruction
-        // writes whole 128-byte row segments (8 lanes per row) instead of 32 different rows
-        __nv_bfloat16* pwarp = p.P + ((static_cast<long long>(n) * p.H + h) * p.L + i0 + quarter * 32) * p.Lk;
-        const int rows_ok = min(32, max(0, p.L - (i0 + quarter * 32)));
-        uint8_t* stage = stage_all + swarp_of(warp) * 4096;
+        // P leaves through TMA stores: every warp stages 32 rows x 64 columns (128-byte rows, 128B
+        // swizzle) and one lane issues the box store; rows >= L and columns >= Lk are clipped by the map
+        uint8_t* stage = stage_all + (tid >> 5) * 4096;
+        uint8_t* my = stage + lane * 128;
+        const int sw = lane & 7;
         constexpr float LOG2E = 1.4426950408889634f;
         float m_run = -INFINITY, m_l2 = 0.f, l_run = 0.f;
 
@@ -158,40 +164,42 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
             const int acc = it & 1;
             const uint32_t acc_phase = static_cast<uint32_t>(it >> 1) & 1u;
             if (it == num_jt) {                           // between the passes: m >= every score of the row
+                xch[half * 128 + r] = m_run;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float mr = fmaxf(xch[r], xch[128 + r]);
+                const float emax = __ldg(p.E + static_cast<long long>(p.H) * (2 * p.L - 1) * 4 + h);
                 const float pn = sqrtf(p0 * p0 + p1 * p1 + p2 * p2 + p3 * p3);
-                const float m_est = (m_run == -INFINITY ? 0.f : m_run) + pn * emax;
+                const float m_est = (mr == -INFINITY ? 0.f : mr) + pn * emax;
                 m_l2 = m_est * LOG2E;
             }
             // stage the excluded-key bits (padding mask or beyond L) and, for the second pass, the
             // rel-pos window of this tile (double buffered)
             float4* ew = ewin + acc * ATT_EWIN;
             uint32_t* mw = mwin + acc * 4;
-            {
+            if (tid < 128) {
                 const int j = j0 + tid;
                 const bool excl = j < p.L ? (mrow[j] != 0) : true;
                 const uint32_t bits = __ballot_sync(0xffffffffu, excl);
-                if (lane == 0) mw[swarp] = bits;
+                if (lane == 0) mw[tid >> 5] = bits;
             }
-            if (pass) {
-                for (int w = tid; w < 255; w += 128) {
-                    const int rel = (j0 - i0) - 127 + w + (p.L - 1);
-                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rel >= 0 && rel <= 2 * p.L - 2) e = __ldg(Eh + rel);
-                    ew[w] = make_float4(e.x * LOG2E, e.y * LOG2E, e.z * LOG2E, e.w * LOG2E);
-                }
+            if (pass && tid < 255) {
+                const int rel = (j0 - i0) - 127 + tid + (p.L - 1);
+                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rel >= 0 && rel <= 2 * p.L - 2) e = __ldg(Eh + rel);
+                ew[tid] = make_float4(e.x * LOG2E, e.y * LOG2E, e.z * LOG2E, e.w * LOG2E);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&s_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * ATT_BN +
+            const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * ATT_BN + 64 * half) +
                                    (static_cast<uint32_t>(quarter * 32) << 16);
+            if (pass == 0) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
-                uint32_t sr[32];
-                tmem_ld32(taddr + c0, sr);
-                tmem_ld_wait();
-                const uint32_t excl = mw[c0 >> 5];
-                if (pass == 0) {
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t sr[32];
+                    tmem_ld32(taddr + c0, sr);
+                    tmem_ld_wait();
+                    const uint32_t excl = mw[2 * half + (c0 >> 5)];
                     float cm = -INFINITY;
                     if (excl == 0u) {
 #pragma unroll
@@ -203,54 +211,54 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
                             cm = fmaxf(cm, ((excl >> c) & 1u) ? -INFINITY : __uint_as_float(sr[c]));
                     }
                     m_run = fmaxf(m_run, cm);
-                } else {
-                    const int j = j0 + c0;
-                    if (j < p.Lk) {
-                        uint32_t w[16];
-                        const float4* ep = ew + (c0 - r + 127);
+                }
+            } else {
+                const int jh = j0 + 64 * half;            // first key column of this warp
+                if (lane == 0) bulk_wait_read<0>();       // the previous box store has read the staging rows
+                __syncwarp();
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) {
+                    if (jh + 16 * g >= p.Lk) break;
+                    uint32_t sr[16];
+                    tmem_ld16(taddr + 16 * g, sr);
+                    tmem_ld_wait();
+                    const uint32_t excl = (mw[2 * half + (g >> 1)] >> (16 * (g & 1))) & 0xffffu;
+                    const float4* ep = ew + (64 * half + 16 * g - r + 127);
+                    float ls = 0.f;
 #pragma unroll
-                        for (int c = 0; c < 32; c += 2) {
-                            const float4 ea = ep[c], eb = ep[c + 1];
-                            float a = fmaf(__uint_as_float(sr[c]), LOG2E, -m_l2);
-                            float b = fmaf(__uint_as_float(sr[c + 1]), LOG2E, -m_l2);
-                            a = fmaf(p0, ea.x, a); b = fmaf(p0, eb.x, b);
-                            a = fmaf(p1, ea.y, a); b = fmaf(p1, eb.y, b);
-                            a = fmaf(p2, ea.z, a); b = fmaf(p2, eb.z, b);
-                            a = fmaf(p3, ea.w, a); b = fmaf(p3, eb.w, b);
-                            sr[c] = __float_as_uint(fast_exp2(a));
-                            sr[c + 1] = __float_as_uint(fast_exp2(b));
-                        }
-                        if (excl != 0u) {       // rare: a real branch, so unmasked tiles issue no selects
-#pragma unroll
-                            for (int c = 0; c < 32; ++c)
-                                if ((excl >> c) & 1u) sr[c] = 0u;
-                        }
-#pragma unroll
-                        for (int c = 0; c < 32; c += 2) {
-                            const float a = __uint_as_float(sr[c]), b = __uint_as_float(sr[c + 1]);
-                            w[c >> 1] = pack_bf16(a, b);
-                            l_run += a + b;
-                        }
-                        // stage this thread's 32 bf16 (64 B) in its row: chunks 4*hh .. 4*hh+3 of 8
-                        const int hh = (c0 >> 5) & 1;
-                        uint8_t* my = stage + lane * 128;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            *reinterpret_cast<uint4*>(my + (((4 * hh + g) ^ (lane & 7)) << 4)) =
-                                make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+                    for (int c = 0; c < 16; c += 2) {
+                        const float4 ea = ep[c], eb = ep[c + 1];
+                        float a = fmaf(__uint_as_float(sr[c]), LOG2E, -m_l2);
+                        float b = fmaf(__uint_as_float(sr[c + 1]), LOG2E, -m_l2);
+                        a = fmaf(p0, ea.x, a); b = fmaf(p0, eb.x, b);
+                        a = fmaf(p1, ea.y, a); b = fmaf(p1, eb.y, b);
+                        a = fmaf(p2, ea.z, a); b = fmaf(p2, eb.z, b);
+                        a = fmaf(p3, ea.w, a); b = fmaf(p3, eb.w, b);
+                        sr[c] = __float_as_uint(fast_exp2(a));
+                        sr[c + 1] = __float_as_uint(fast_exp2(b));
                     }
-                    if (c0 & 32) {                         // two chunks staged: write 64 columns, coalesced
-                        __syncwarp();
-                        const int jb = j0 + c0 - 32;
-                        const int ch = lane & 7;
+                    if (excl != 0u) {           // rare: a real branch, so unmasked tiles issue no selects
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int rr = 4 * k + (lane >> 3);
-                            const uint4 q = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
-                            if (rr < rows_ok && jb + ch * 8 < p.Lk)
-                                *reinterpret_cast<uint4*>(pwarp + static_cast<long long>(rr) * p.Lk + jb + ch * 8) = q;
-                        }
-                        __syncwarp();
+                        for (int c = 0; c < 16; ++c)
+                            if ((excl >> c) & 1u) sr[c] = 0u;
+                    }
+                    uint32_t w[8];
+#pragma unroll
+                    for (int c = 0; c < 16; c += 2) {
+                        const float a = __uint_as_float(sr[c]), b = __uint_as_float(sr[c + 1]);
+                        w[c >> 1] = pack_bf16(a, b);
+                        ls += a + b;
+                    }
+                    l_run += ls;
+                    *reinterpret_cast<uint4*>(my + (((2 * g) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(my + (((2 * g + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+                }
+                if (jh < p.Lk) {
+                    fence_proxy_async_smem();             // generic-proxy writes -> visible to the TMA engine
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&tma_p, stage, jh, i0 + quarter * 32, n * p.H + h);
+                        bulk_commit();
                     }
                 }
             }
@@ -258,7 +266,11 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const AttnParams
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[acc]);
         }
-        if (row_ok) p.inv_l[(static_cast<long long>(n) * p.H + h) * p.L + i] = 1.0f / l_run;
+        xch[half * 128 + r] = l_run;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0 && row_ok)
+            p.inv_l[(static_cast<long long>(n) * p.H + h) * p.L + i] = 1.0f / (xch[r] + xch[128 + r]);
+        if (lane == 0) bulk_wait_read<0>();               // staging must outlive the stores reading it
     }
 
     tc_fence_before();

@@ -347,6 +347,9 @@ static int build_attn(Op& op, const bf16* qkp, int ld, const float* E, const uin
     a.qkp = qkp; a.ld = ld; a.E = E; a.mask = mask; a.P = P; a.inv_l = inv_l;
     if (ld % 8 != 0 || Lk % 8 != 0) return fail(ZVB_ERR_INVALID, "attn: pitches must be multiples of 8");
     TRY(make_tmap(&op.ma, qkp, ld, L, N, (uint64_t)ld * 2, (uint64_t)ld * 2 * L, ATT_BM));
+    // P as (Lk, L, N*H): every softmax warp stores 32-row x 64-column boxes
+    TRY(make_tmap(&op.ms, P, Lk, L, (uint64_t)N * H, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * L, 32));
+    op.has_ms = true;
     op.cat = ZVB_CAT_ATTN_WEIGHTS;
     // q.k (K = 32) + rel-pos (4-dim dot against 2L-1 offsets), reference FLOP model SURVEY.md §8d
     op.work = (double)N * H * (2.0 * L * L * 32 + 2.0 * L * (2.0 * L - 1) * 4);
@@ -386,7 +389,7 @@ static int launch_op(const Op& op, cudaStream_t st) {
         }
         case OP_ATTN: {
             dim3 grid((op.ap.L + ATT_BM - 1) / ATT_BM, op.ap.H, op.ap.N);
-            attn_weights_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(op.ma, op.ap);
+            attn_weights_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(op.ma, op.ms, op.ap);
             return check_launch("attn_weights");
         }
         case OP_BIASNORM: {
