@@ -29,10 +29,21 @@ __device__ __forceinline__ void store8f(float* p, const float* v) {
     *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
+// streaming 16-byte load that does not allocate in L1 (every element is read exactly once)
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 // BiasNorm + bypass (reference: modules/scaling.py:358-363, modules/zipformer.py:634-637,
 // 803-804):  y = x * rsqrt(mean((x-b)^2)) * exp(log_scale);  out = orig + (y-orig)*scale.
-// One warp per row, C <= 1024, C % 8 == 0.  Outputs (each nullable): fp32 stream `out`, bf16
-// shadow `out_b`, bf16 `out_t` = out + temb[row / rows_per_group].
+// One warp per row, C <= 128*KMAX, C % 4 == 0.  Lane l owns the float4 at channel 4*(32k + l): every
+// warp instruction moves one contiguous 512-byte (fp32) / 256-byte (bf16) segment, and both operands
+// of the row are requested before the reduction so each lane has 2*KMAX 16-byte loads in flight.
+// Outputs (each nullable): fp32 stream `out`, bf16 shadow `out_b`, bf16 `out_t` = out + temb[row / rows_per_group].
+template <int KMAX>
 __global__ void __launch_bounds__(256)
 biasnorm_bypass_kernel(const float* __restrict__ src, const float* __restrict__ orig,
                        float* __restrict__ out, __nv_bfloat16* __restrict__ out_b,
@@ -42,38 +53,46 @@ biasnorm_bypass_kernel(const float* __restrict__ src, const float* __restrict__ 
     const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
-    float x[4][8];
+    float4 x[KMAX], o[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int c = (k * 32 + lane) * 4;
+        if (c < C) {
+            x[k] = ld_stream_f4(src + row * C + c);
+            o[k] = ld_stream_f4(orig + row * C + c);
+        }
+    }
     float ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int c = (k * 32 + lane) * 8;
+    for (int k = 0; k < KMAX; ++k) {
+        const int c = (k * 32 + lane) * 4;
         if (c < C) {
-            load8f(src + row * C + c, x[k]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float d = x[k][i] - __ldg(nbias + c + i);
-                ss = fmaf(d, d, ss);
-            }
+            const float4 nb = __ldg(reinterpret_cast<const float4*>(nbias + c));
+            const float d0 = x[k].x - nb.x, d1 = x[k].y - nb.y, d2 = x[k].z - nb.z, d3 = x[k].w - nb.w;
+            ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    for (int q = 16; q > 0; q >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, q);
     const float scale = rsqrtf(ss / static_cast<float>(C)) * __expf(__ldg(log_scale));
     const long long grp = out_t != nullptr ? row / rows_per_group : 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int c = (k * 32 + lane) * 8;
+    for (int k = 0; k < KMAX; ++k) {
+        const int c = (k * 32 + lane) * 4;
         if (c < C) {
-            float o[8], y[8];
-            load8f(orig + row * C + c, o);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = o[i] + (x[k][i] * scale - o[i]) * __ldg(bscale + c + i);
-            if (out != nullptr) store8f(out + row * C + c, y);
-            if (out_b != nullptr) *reinterpret_cast<uint4*>(out_b + row * C + c) = pack8(y);
+            const float4 bs = __ldg(reinterpret_cast<const float4*>(bscale + c));
+            float4 y;
+            y.x = o[k].x + (x[k].x * scale - o[k].x) * bs.x;
+            y.y = o[k].y + (x[k].y * scale - o[k].y) * bs.y;
+            y.z = o[k].z + (x[k].z * scale - o[k].z) * bs.z;
+            y.w = o[k].w + (x[k].w * scale - o[k].w) * bs.w;
+            if (out != nullptr) *reinterpret_cast<float4*>(out + row * C + c) = y;
+            if (out_b != nullptr)
+                *reinterpret_cast<uint2*>(out_b + row * C + c) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
             if (out_t != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] += __ldg(temb + grp * C + c + i);
-                *reinterpret_cast<uint4*>(out_t + row * C + c) = pack8(y);
+                const float4 tb = __ldg(reinterpret_cast<const float4*>(temb + grp * C + c));
+                *reinterpret_cast<uint2*>(out_t + row * C + c) =
+                    make_uint2(pack_bf16(y.x + tb.x, y.y + tb.y), pack_bf16(y.z + tb.z, y.w + tb.w));
             }
         }
     }
@@ -149,68 +168,114 @@ upsample_combine_kernel(const float* __restrict__ orig, const float* __restrict_
 
 // Depthwise Conv1d over time (cross-correlation, zero padding K/2) + bias + SwooshR
 // (reference: modules/zipformer.py:1672-1678 with scaling.py:1200-1206).  The input is the
-// already GLU-gated and key-masked tensor.  Block = 64 channels x 128 frames staged in shared
-// memory; thread = one channel pair x 16 consecutive frames with the 16+K-1 input window held
-// in registers as packed fp32x2, so every staged input is read from shared memory once and one
-// FFMA2 advances both channels.
-constexpr int DW_TT = 128;     // frames per block
+// already GLU-gated and key-masked tensor.  The kernel is bound by the fp32 FMA pipe (K taps per
+// output), so everything else is kept off the critical path: a tile = 64 channels x 128 frames
+// (+ K-1 halo rows) arrives by ONE TMA box load (rows before the utterance start / after its end are
+// zero-filled by the tensor map = the convolution's zero padding), tiles are double buffered so the
+// next load overlaps the FMAs, and a block walks its (utterance, time-tile) list persistently with the
+// 64-channel group's taps staged once.  Thread = one channel pair x 16 consecutive frames with the
+// 16+K-1 input window in registers as packed fp32x2: one FFMA2 advances both channels.
+constexpr int DW_TT = 128;     // frames per tile
 constexpr int DW_OT = 16;      // outputs per thread
+template <int K> constexpr int dw_smem_bytes() { return 2 * (DW_TT + K - 1) * 128 + K * 32 * 8 + 128 /*align*/ + 16; }
+
+// SwooshR of a channel pair (see swoosh_from_offset): the polynomial runs as FFMA2
+__device__ __forceinline__ void swoosh_r_pair(f32x2 acc, float& o0, float& o1) {
+    float y0, y1;
+    unpack2(acc, y0, y1);
+    y0 -= SWOOSH_R_C; y1 -= SWOOSH_R_C;
+    float t0, t1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(-fabsf(y0) * 1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(-fabsf(y1) * 1.4426950408889634f));
+    const f32x2 t = pack2(t0, t1);
+    f32x2 q = fma2(t, pack2(0.031377589387161245f, 0.031377589387161245f), pack2(-0.1341354334221127f, -0.1341354334221127f));
+    q = fma2(t, q, pack2(0.2878262894239249f, 0.2878262894239249f));
+    q = fma2(t, q, pack2(-0.491347927069251f, -0.491347927069251f));
+    q = fma2(t, q, pack2(0.9994349844843187f, 0.9994349844843187f));
+    q = fma2(t, q, pack2(SWOOSH_R_K0, SWOOSH_R_K0));
+    q = fma2(pack2(y0, y1), pack2(0.42f, 0.42f), q);
+    float r0, r1;
+    unpack2(q, r0, r1);
+    o0 = fmaf(fabsf(y0), 0.5f, r0);
+    o1 = fmaf(fabsf(y1), 0.5f, r1);
+}
+
+// tma_x: x viewed as (C, L, N) bf16, box = 64 channels x (DW_TT + K - 1) frames, no swizzle.
+// grid = (blocks per channel group, channel groups); tiles = N * ceil(L / DW_TT) per channel group.
 template <int K>
-__global__ void __launch_bounds__(256)
-dwconv_swooshr_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256, 3)
+dwconv_swooshr_kernel(const __grid_constant__ CUtensorMap tma_x, __nv_bfloat16* __restrict__ out,
                       const float* __restrict__ wt /*[K][C]*/, const float* __restrict__ bias, int L,
-                      int C) {
+                      int C, int N) {
     constexpr int HALF = K / 2, WIN = DW_TT + K - 1, NW = DW_OT + K - 1;
-    __shared__ uint32_t tile[WIN][32];
-    __shared__ float2 wsm[K][32];
-    const int c0 = blockIdx.x * 64;
-    const int t0 = blockIdx.y * DW_TT;
-    const int n = blockIdx.z;
+    extern __shared__ uint8_t dw_smem_raw[];
+    const uint32_t raw = smem_u32(dw_smem_raw);
+    uint8_t* smem = dw_smem_raw + (((raw + 127u) & ~127u) - raw);
+    uint32_t* tile = reinterpret_cast<uint32_t*>(smem);                       // [2][WIN][32] bf16 pairs
+    float2* wsm = reinterpret_cast<float2*>(smem + 2 * WIN * 128);           // [K][32]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * WIN * 128 + K * 32 * 8);   // [2]
+    const int c0 = blockIdx.y * 64;
     const int cp = threadIdx.x & 31;
     const int tg = threadIdx.x >> 5;
-    const int cvalid = C - c0;            // channels valid in this block (multiple of 8)
-    const __nv_bfloat16* xn = x + static_cast<long long>(n) * L * C;
-    for (int idx = threadIdx.x; idx < WIN * 8; idx += 256) {
-        const int rr = idx >> 3, q = idx & 7;                 // 8 x 16B per 64-channel row
-        const int t = t0 - HALF + rr;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (t >= 0 && t < L && q * 8 < cvalid)
-            v = *reinterpret_cast<const uint4*>(xn + static_cast<long long>(t) * C + c0 + q * 8);
-        *reinterpret_cast<uint4*>(&tile[rr][q * 4]) = v;
-    }
+    const int n_tt = (L + DW_TT - 1) / DW_TT;
+    const int total = N * n_tt;
     for (int idx = threadIdx.x; idx < K * 32; idx += 256) {
         const int k = idx >> 5, q = idx & 31;
         const int c = c0 + 2 * q;
-        wsm[k][q] = c < C ? make_float2(__ldg(wt + k * C + c), __ldg(wt + k * C + c + 1)) : make_float2(0.f, 0.f);
+        wsm[idx] = c < C ? make_float2(__ldg(wt + k * C + c), __ldg(wt + k * C + c + 1)) : make_float2(0.f, 0.f);
+    }
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tma_x);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_barrier_init();
     }
     __syncthreads();
-    if (2 * cp >= cvalid) return;
-    f32x2 win[NW];                          // the input window of the channel pair, fp32x2 packed
-#pragma unroll
-    for (int q = 0; q < NW; ++q) {
-        const uint32_t u = tile[tg * DW_OT + q][cp];
-        win[q] = pack2(bf16_lo(u), bf16_hi(u));
+    int tl = blockIdx.x;
+    if (threadIdx.x == 0 && tl < total) {
+        mbar_arrive_expect_tx(&bar[0], WIN * 128);
+        tma_load_3d(tile, &tma_x, &bar[0], c0, (tl % n_tt) * DW_TT - HALF, tl / n_tt);
     }
-    const f32x2 b2 = pack2(__ldg(bias + c0 + 2 * cp), __ldg(bias + c0 + 2 * cp + 1));
-    f32x2 acc[DW_OT];
+    const bool ch_ok = c0 + 2 * cp < C;
+    f32x2 b2 = pack2(0.f, 0.f);
+    if (ch_ok) b2 = pack2(__ldg(bias + c0 + 2 * cp), __ldg(bias + c0 + 2 * cp + 1));
+    for (uint32_t it = 0; tl < total; tl += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u;
+        const int nxt = tl + gridDim.x;
+        if (threadIdx.x == 0 && nxt < total) {        // buffer buf^1 was drained before the last __syncthreads
+            mbar_arrive_expect_tx(&bar[buf ^ 1u], WIN * 128);
+            tma_load_3d(tile + (buf ^ 1u) * (WIN * 32), &tma_x, &bar[buf ^ 1u], c0, (nxt % n_tt) * DW_TT - HALF,
+                        nxt / n_tt);
+        }
+        mbar_wait(&bar[buf], (it >> 1) & 1u);
+        const uint32_t* tb = tile + buf * (WIN * 32) + (tg * DW_OT) * 32 + cp;
+        f32x2 win[NW];                          // the input window of the channel pair, fp32x2 packed
 #pragma unroll
-    for (int o = 0; o < DW_OT; ++o) acc[o] = b2;
+        for (int q = 0; q < NW; ++q) {
+            const uint32_t u = tb[q * 32];
+            win[q] = pack2(bf16_lo(u), bf16_hi(u));
+        }
+        f32x2 acc[DW_OT];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const f32x2 w = *reinterpret_cast<const f32x2*>(&wsm[k][cp]);
+        for (int o = 0; o < DW_OT; ++o) acc[o] = b2;
 #pragma unroll
-        for (int o = 0; o < DW_OT; ++o) acc[o] = fma2(w, win[o + k], acc[o]);     // one FFMA2 = both channels
-    }
-    float a0[DW_OT], a1[DW_OT];
+        for (int k = 0; k < K; ++k) {
+            const f32x2 w = *reinterpret_cast<const f32x2*>(&wsm[k * 32 + cp]);
 #pragma unroll
-    for (int o = 0; o < DW_OT; ++o) unpack2(acc[o], a0[o], a1[o]);
-    __nv_bfloat16* on = out + static_cast<long long>(n) * L * C;
+            for (int o = 0; o < DW_OT; ++o) acc[o] = fma2(w, win[o + k], acc[o]);     // one FFMA2 = both channels
+        }
+        const int n = tl / n_tt;
+        const int t0 = (tl - n * n_tt) * DW_TT + tg * DW_OT;
+        __nv_bfloat16* on = out + (static_cast<long long>(n) * L + t0) * C + c0 + 2 * cp;
+        if (ch_ok) {
 #pragma unroll
-    for (int o = 0; o < DW_OT; ++o) {
-        const int t = t0 + tg * DW_OT + o;
-        if (t < L)
-            *reinterpret_cast<uint32_t*>(on + static_cast<long long>(t) * C + c0 + 2 * cp) =
-                pack_bf16(swoosh_r(a0[o]), swoosh_r(a1[o]));
+            for (int o = 0; o < DW_OT; ++o) {
+                float a0, a1;
+                swoosh_r_pair(acc[o], a0, a1);
+                if (t0 + o < L) *reinterpret_cast<uint32_t*>(on + static_cast<long long>(o) * C) = pack_bf16(a0, a1);
+            }
+        }
+        __syncthreads();                        // the window reads of this buffer are done: it may be refilled
     }
 }
 

@@ -84,6 +84,10 @@ static int init_device() {
     ZVB_SMEM_ATTR((gemm_kernel<EPI_GATED, ACT_NONE, 1>));      ZVB_SMEM_ATTR((gemm_kernel<EPI_GATED, ACT_NONE, 2>));
 #undef ZVB_SMEM_ATTR
     CUDA_TRY(cudaFuncSetAttribute(attn_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_swooshr_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_swooshr_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<9>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_swooshr_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<15>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_swooshr_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<31>()));
     return 0;
 }
 
@@ -105,6 +109,24 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
     CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                           const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           half_row ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ZVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+// bf16 tensor, box = (box0 elements, box1, 1), no swizzle (rows of the box are contiguous in shared memory)
+static int make_tmap_plain(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
+                           uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (stride1_bytes & 15) != 0 || (stride2_bytes & 15) != 0)
+        return fail(ZVB_ERR_INVALID, "tensor map: pointer/strides must be 16-byte aligned");
+    if (box0 == 0 || box0 > 256 || box1 == 0 || box1 > 256 || d0 == 0 || d1 == 0 || d2 == 0)
+        return fail(ZVB_ERR_INVALID, "tensor map: bad box/dims");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ZVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
@@ -356,6 +378,32 @@ static int build_attn(Op& op, const bf16* qkp, int ld, const float* E, const uin
     return 0;
 }
 
+static int build_dwconv(Op& d, const bf16* x, bf16* out, const float* w, const float* b, int N, int L, int C, int K) {
+    d = Op();
+    d.type = OP_DWCONV; d.p0 = x; d.o0 = out; d.f0 = w; d.f1 = b;
+    d.i0 = N; d.i1 = L; d.i2 = C; d.i3 = K;
+    if (K != 7 && K != 9 && K != 15 && K != 31)
+        return fail(ZVB_ERR_INVALID, "depthwise kernel size %d not built (7, 9, 15, 31)", K);
+    if (C % 8 != 0) return fail(ZVB_ERR_INVALID, "dwconv: channels must be a multiple of 8");
+    // x as (C, L, N); a box = 64 channels x (128 + K - 1) frames, rows outside [0, L) are zero-filled
+    TRY(make_tmap_plain(&d.ma, x, C, L, N, (uint64_t)C * 2, (uint64_t)C * 2 * L, 64, DW_TT + K - 1));
+    d.cat = ZVB_CAT_DWCONV;
+    d.work = 2.0 * 2.0 * (double)N * L * C;
+    return 0;
+}
+
+template <int K>
+static void launch_dwconv(const Op& op, cudaStream_t st) {
+    const int N = op.i0, L = op.i1, C = op.i2;
+    const int groups = (C + 63) / 64;
+    const int tiles = N * ((L + DW_TT - 1) / DW_TT);
+    int per_group = (3 * g_num_sms) / groups;            // 3 resident blocks per SM
+    if (per_group < 1) per_group = 1;
+    if (per_group > tiles) per_group = tiles;
+    dim3 grid(per_group, groups);
+    dwconv_swooshr_kernel<K><<<grid, 256, dw_smem_bytes<K>(), st>>>(op.ma, (bf16*)op.o0, op.f0, op.f1, L, C, N);
+}
+
 static int launch_op(const Op& op, cudaStream_t st) {
     switch (op.type) {
         case OP_GEMM: {
@@ -394,9 +442,14 @@ static int launch_op(const Op& op, cudaStream_t st) {
         }
         case OP_BIASNORM: {
             const int blocks = static_cast<int>((op.rows + 7) / 8);
-            biasnorm_bypass_kernel<<<blocks, 256, 0, st>>>(
-                (const float*)op.p0, (const float*)op.p1, (float*)op.o0, (bf16*)op.o1, (bf16*)op.o2, op.f3, op.i1, op.f0,
-                op.f1, op.f2, op.rows, op.i0);
+            if (op.i0 <= 512)
+                biasnorm_bypass_kernel<4><<<blocks, 256, 0, st>>>(
+                    (const float*)op.p0, (const float*)op.p1, (float*)op.o0, (bf16*)op.o1, (bf16*)op.o2, op.f3, op.i1,
+                    op.f0, op.f1, op.f2, op.rows, op.i0);
+            else
+                biasnorm_bypass_kernel<8><<<blocks, 256, 0, st>>>(
+                    (const float*)op.p0, (const float*)op.p1, (float*)op.o0, (bf16*)op.o1, (bf16*)op.o2, op.f3, op.i1,
+                    op.f0, op.f1, op.f2, op.rows, op.i0);
             return check_launch("biasnorm_bypass");
         }
         case OP_PREP: {
@@ -419,14 +472,11 @@ static int launch_op(const Op& op, cudaStream_t st) {
             return check_launch("upsample_combine");
         }
         case OP_DWCONV: {
-            const int N = op.i0, L = op.i1, C = op.i2, K = op.i3;
-            dim3 grid((C + 63) / 64, (L + DW_TT - 1) / DW_TT, N);
-            const bf16* x = (const bf16*)op.p0;
-            bf16* o = (bf16*)op.o0;
-            if (K == 7) dwconv_swooshr_kernel<7><<<grid, 256, 0, st>>>(x, o, op.f0, op.f1, L, C);
-            else if (K == 9) dwconv_swooshr_kernel<9><<<grid, 256, 0, st>>>(x, o, op.f0, op.f1, L, C);
-            else if (K == 15) dwconv_swooshr_kernel<15><<<grid, 256, 0, st>>>(x, o, op.f0, op.f1, L, C);
-            else if (K == 31) dwconv_swooshr_kernel<31><<<grid, 256, 0, st>>>(x, o, op.f0, op.f1, L, C);
+            const int K = op.i3;
+            if (K == 7) launch_dwconv<7>(op, st);
+            else if (K == 9) launch_dwconv<9>(op, st);
+            else if (K == 15) launch_dwconv<15>(op, st);
+            else if (K == 31) launch_dwconv<31>(op, st);
             else return fail(ZVB_ERR_INVALID, "depthwise kernel size %d not built (7, 9, 15, 31)", K);
             return check_launch("dwconv");
         }
@@ -658,9 +708,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             // 5. conv_module1
             e = LinearEpi();
             TRY(build_gated(op, Rb[0], Ms, D, ly.conv_in[0], D, GATE_GLU_XS, glu, D, mask_ds[ds], e)); ops.push_back(op);
-            { Op d; d.type = OP_DWCONV; d.p0 = glu; d.o0 = cv; d.f0 = ly.dw_w[0]; d.f1 = ly.dw_b[0];
-              d.i0 = N; d.i1 = L; d.i2 = D; d.i3 = stk.conv_kernel;
-              d.cat = ZVB_CAT_DWCONV; d.work = 2.0 * 2.0 * (double)Ms * D; ops.push_back(d); }
+            { Op d; TRY(build_dwconv(d, glu, cv, ly.dw_w[0], ly.dw_b[0], N, L, D, stk.conv_kernel)); ops.push_back(d); }
             e = stream_epi(R[0], Rb[1]);
             TRY(build_linear(op, cv, Ms, D, ly.conv_out[0], R[1], D, e)); ops.push_back(op);
             // 6. feed_forward2 + bypass_mid
@@ -677,9 +725,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             // 8. conv_module2
             e = LinearEpi();
             TRY(build_gated(op, Rb[1], Ms, D, ly.conv_in[1], D, GATE_GLU_XS, glu, D, mask_ds[ds], e)); ops.push_back(op);
-            { Op d; d.type = OP_DWCONV; d.p0 = glu; d.o0 = cv; d.f0 = ly.dw_w[1]; d.f1 = ly.dw_b[1];
-              d.i0 = N; d.i1 = L; d.i2 = D; d.i3 = stk.conv_kernel;
-              d.cat = ZVB_CAT_DWCONV; d.work = 2.0 * 2.0 * (double)Ms * D; ops.push_back(d); }
+            { Op d; TRY(build_dwconv(d, glu, cv, ly.dw_w[1], ly.dw_b[1], N, L, D, stk.conv_kernel)); ops.push_back(d); }
             e = stream_epi(R[1], Rb[0]);
             TRY(build_linear(op, cv, Ms, D, ly.conv_out[1], R[0], D, e)); ops.push_back(op);
             // 9. feed_forward3 (only the fp32 stream is needed afterwards)
@@ -918,7 +964,8 @@ int zvb_test_biasnorm_bypass(const float* src, const float* orig, float* out, vo
 
 int zvb_test_dwconv(const void* x, void* out, const float* wt, const float* bias, int N, int L, int C, int K,
                     void* stream) {
-    Op d; d.type = OP_DWCONV; d.p0 = x; d.o0 = out; d.f0 = wt; d.f1 = bias; d.i0 = N; d.i1 = L; d.i2 = C; d.i3 = K;
+    Op d;
+    TRY(build_dwconv(d, (const bf16*)x, (bf16*)out, wt, bias, N, L, C, K));
     return launch_op(d, static_cast<cudaStream_t>(stream));
 }
 
