@@ -72,7 +72,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
     const int num_jt = (p.L + ATT_BN - 1) / ATT_BN;
     const int total_it = 2 * num_jt;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == ATT_SM_WARPS && lane == 0) {
         tma_prefetch_desc(&tma_qk);
         tma_prefetch_desc(&tma_p);
         mbar_init(q_full, 1);
@@ -86,7 +86,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
         }
         fence_barrier_init();
     }
-    if (warp == 1) {
+    if (warp == ATT_SM_WARPS + 1) {
         tmem_alloc(tmem_holder, ATT_TMEM_COLS);
         tmem_relinquish();
     }
@@ -95,7 +95,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    if (warp == 0) {
+    if (warp == ATT_SM_WARPS) {                           // TMA producer
         if (lane == 0) {
             mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
             tma_load_3d(q_tile, &tma_qk, q_full, h * 32, i0, n);
@@ -110,7 +110,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
                 if (++stage == ATT_KSTAGES) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == ATT_SM_WARPS + 1) {                // MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(ATT_BN);
             mbar_wait(q_full, 0);
@@ -134,9 +134,10 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
             }
         }
     } else {
-        // ------------------------------------------------------------------ softmax warps (2..9)
+        // ------------------------------------------------------------------ softmax warps (0..7); the two
+        // single-thread roles have the highest warp ids, which the SMSP arbiter favours
         const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
-        const int tid = threadIdx.x - 64;                 // 0..255
+        const int tid = threadIdx.x;                      // 0..255
         const int half = tid >> 7;                        // key columns [64*half, 64*half + 64) of every tile
         const int r = quarter * 32 + lane;                // row inside the query tile
         const int i = i0 + r;
@@ -275,7 +276,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == ATT_SM_WARPS + 1) {
         __syncwarp();
         tc_fence_after();
         tmem_dealloc(tmem_base, ATT_TMEM_COLS);

@@ -55,7 +55,8 @@ static int check_launch(const char* what) {
 
 static int g_num_sms = 0;
 static int g_cluster_ok = 1;      // ZVB_NO_CLUSTER=1 disables the CTA-pair (cta_group::2) GEMM variant
-static int g_tma_store_ok = 1;    // ZVB_NO_TMA_STORE=1 keeps the epilogue on per-thread stores
+static int g_tma_store_ok = 1;
+static int g_pair_min_kb = 16;    // ZVB_PAIR_MIN_KB: fewest k-blocks for which a CTA pair is used    // ZVB_NO_TMA_STORE=1 keeps the epilogue on per-thread stores
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
 static int init_device() {
@@ -71,6 +72,7 @@ static int init_device() {
     g_num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("ZVB_NO_CLUSTER")) g_cluster_ok = atoi(e) == 0;
     if (const char* e = getenv("ZVB_NO_TMA_STORE")) g_tma_store_ok = atoi(e) == 0;
+    if (const char* e = getenv("ZVB_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
     CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
@@ -138,8 +140,8 @@ enum OpType { OP_GEMM, OP_ATTN, OP_BIASNORM, OP_PREP, OP_DOWN, OP_UP, OP_DWCONV,
 struct Op {
     OpType type;
     // GEMM / ATTN
-    CUtensorMap ma, mb, mx, ms, ms2;     // A, B, epilogue operand, output, bf16 shadow output
-    bool has_mx = false, has_ms = false, has_ms2 = false;
+    CUtensorMap ma, mb, mx, ms, ms2, mo;     // A, B, epilogue operand, output, bf16 shadow output, bypass orig
+    bool has_mx = false, has_ms = false, has_ms2 = false, has_mo = false;
     GemmParams gp;
     int kind = 0, grid = 0, cluster = 1;
     AttnParams ap;
@@ -224,12 +226,12 @@ struct LinearEpi {
 
 // Decides whether the op runs as 2-CTA clusters with a multicast B tile, and the persistent grid.
 static void set_grid(Op& op) {
-    const GemmParams& p = op.gp;
+    GemmParams& p = op.gp;
     const long long slots2 = (long long)p.batches * ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     // CTA pairs pay off when the mainloop dominates the tile (measured: K = 1920 GEMMs 320 -> 279 us,
     // P.V 222 -> 195 us) and cost ~10% on the epilogue-bound K <= 512 residual-stream GEMMs
     op.cluster = (g_cluster_ok && p.block_n >= 64 && p.num_m_tiles >= 2 && slots2 >= g_num_sms / 4 &&
-                  p.num_k_blocks >= 16) ? 2 : 1;
+                  p.num_k_blocks >= g_pair_min_kb) ? 2 : 1;
     if (op.cluster == 2) {
         const long long clusters = slots2 < g_num_sms / 2 ? slots2 : g_num_sms / 2;
         op.grid = static_cast<int>(clusters * 2);
@@ -237,6 +239,7 @@ static void set_grid(Op& op) {
         const long long tiles = (long long)p.batches * p.num_m_tiles * p.num_n_tiles;
         op.grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
     }
+    gemm_ring(p.block_n, op.cluster, &op.gp.stages, &op.gp.stage_bytes);
 }
 static inline uint32_t b_box_rows(const Op& op) { return op.gp.block_n / op.cluster; }
 
@@ -276,6 +279,13 @@ static int build_linear(Op& op, const bf16* A, long long M, int lda, const zvb_l
         op.has_mx = true;
     }
     TRY(setup_tma_store(op, (int)M, 1));
+    // bypass: `orig` rides through the aux ring next to the residual sub-tiles
+    if (p.tma_store && e.orig != nullptr && p.aux_mode == AUX_RESID_F32 && lin.out_features % 32 == 0 &&
+        (reinterpret_cast<uintptr_t>(e.bypass_scale) & 15) == 0) {
+        TRY(make_tmap(&op.mo, e.orig, ldc, M, 1, (uint64_t)ldc * 4, (uint64_t)ldc * 4 * M, GEMM_BLOCK_M, true));
+        op.has_mo = true;
+        p.orig_tma = 1;
+    }
     op.shape[0] = (int)M; op.shape[1] = lin.out_features; op.shape[2] = lin.in_features; op.shape[3] = bn;
     op.cat = ZVB_CAT_GEMM_LINEAR;
     op.work = 2.0 * (double)M * lin.out_features * lin.in_features;
@@ -411,6 +421,7 @@ static int launch_op(const Op& op, cudaStream_t st) {
             const CUtensorMap& mx = op.has_mx ? op.mx : op.ma;
             const CUtensorMap& ms = op.has_ms ? op.ms : op.ma;
             const CUtensorMap& ms2 = op.has_ms2 ? op.ms2 : op.ma;
+            const CUtensorMap& mo = op.has_mo ? op.mo : op.ma;
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(op.grid);
             cfg.blockDim = dim3(GEMM_THREADS);
@@ -423,14 +434,14 @@ static int launch_op(const Op& op, cudaStream_t st) {
             const int sel = (op.kind == EPI_GATED ? 3 : op.gp.act) * 2 + (op.cluster - 1);
             cudaError_t e = cudaSuccess;
             switch (sel) {
-                case 0: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 1>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
-                case 1: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 2>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
-                case 2: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 1>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
-                case 3: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 2>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
-                case 4: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 1>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
-                case 5: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 2>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
-                case 6: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 1>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
-                default: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 2>, op.ma, op.mb, mx, ms, ms2, op.gp); break;
+                case 0: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 1>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
+                case 1: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 2>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
+                case 2: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 1>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
+                case 3: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 2>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
+                case 4: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 1>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
+                case 5: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 2>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
+                case 6: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 1>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
+                default: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 2>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
             }
             if (e != cudaSuccess) return fail(ZVB_ERR_CUDA, "launch gemm: %s", cudaGetErrorString(e));
             return check_launch("gemm");

@@ -1,12 +1,12 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C = epilogue(A · Bᵀ)
 //   A: (rows, K) bf16 K-major, B: (cols, K) bf16 K-major (an nn.Linear weight, or Vᵀ), both
-//   streamed by TMA (128B swizzle) through a 3-stage mbarrier ring; fp32 accumulators live in
+//   streamed by TMA (128B swizzle) through a 3..8-stage mbarrier ring; fp32 accumulators live in
 //   TMEM (2 stages x <=256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   The epilogue's tile-shaped operand (the fp32 residual stream, or the bf16 `y` gate of
 //   NonlinAttention) is streamed by a second TMA ring of 16 KB sub-tiles (128 rows x 128 bytes),
 //   so the epilogue threads never wait on a global load.
-//   Warp 0 = TMA producer (A/B), warp 1 = MMA issuer (+TMEM alloc), warp 2 = TMA producer (aux),
-//   warps 4..11 = epilogue (two warps per TMEM lane quarter, alternating 64-column sub-tiles).
+//   Warps 0..7 = epilogue (two warps per TMEM lane quarter, alternating sub-tiles), warp 8 = TMA producer
+//   (A/B), warp 9 = MMA issuer (+TMEM alloc), warp 10 = TMA producer (aux), warp 11 = TMA store thread.
 // Serves every dense contraction of the TTSZipformer forward (reference:
 // modules/zipformer.py:1172,1377,1393,1434-1437,1511,1534,1542,1655,1678, 265, 291).
 #pragma once
@@ -19,21 +19,24 @@ constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_UMMA_K = 16;
 constexpr int GEMM_A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB
 constexpr int GEMM_B_BYTES = 256 * GEMM_BLOCK_K * 2;            // 32 KB (block_n <= 256)
-// single CTA: 3 stages of (A 16 KB + B 32 KB); CTA pair (cta_group::2): every CTA holds only half of
-// the B tile, 4 stages of (16 KB + 16 KB)
+// The operand ring is 144 KB; a stage is A (16 KB) + the B rows this CTA stages (block_n, or block_n / 2
+// in a CTA pair, x 128 B), so narrow tiles get a deeper ring: 3 stages at block_n = 256, 4 for a CTA
+// pair, up to 8 for the 16..48-column tiles that only stream A (more bytes in flight per SM -- those
+// kernels are HBM-latency bound).  Host: gemm_ring() fills GemmParams::stages / stage_bytes.
 constexpr int GEMM_OPERAND_BYTES = 3 * (GEMM_A_BYTES + GEMM_B_BYTES);
-template <int CLUSTER> struct GemmCfg {
-    static constexpr int STAGES = CLUSTER == 2 ? 4 : 3;
-    static constexpr int STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES / CLUSTER;
-    static_assert(STAGES * STAGE_BYTES <= GEMM_OPERAND_BYTES, "operand ring too large");
-};
-constexpr int GEMM_MAX_STAGES = 4;
+constexpr int GEMM_MAX_STAGES = 8;
+inline void gemm_ring(int block_n, int cluster, int* stages, int* stage_bytes) {
+    const int sb = GEMM_A_BYTES + (block_n / cluster) * GEMM_BLOCK_K * 2;      // multiple of 1024 (block_n % 16 == 0)
+    int st = GEMM_OPERAND_BYTES / sb;
+    *stages = st > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : st;
+    *stage_bytes = sb;
+}
 constexpr int GEMM_AUX_SLOTS = 4;
 constexpr int GEMM_AUX_BYTES = 128 * 128;                       // 128 rows x 128 B
-constexpr int GEMM_BIAS_BYTES = 2 * 256 * 4;               // one copy per epilogue half (4 warps)
-constexpr int GEMM_SHADOW_BYTES = 2 * 128 * 64;            // bf16 shadow staging, 128 rows x 64 B per half
+constexpr int GEMM_BIAS_BYTES = 8 * 64 * 4;                // per epilogue warp: bias of the sub-tile in flight (64 columns)
+constexpr int GEMM_SHADOW_BYTES = 2 * 128 * 64;            // bf16 shadow staging, 128 rows x 64 B per epilogue half
 constexpr int GEMM_LAYOUT_BYTES = GEMM_OPERAND_BYTES + GEMM_AUX_SLOTS * GEMM_AUX_BYTES + GEMM_BIAS_BYTES +
-                                  GEMM_SHADOW_BYTES + 256 /*barriers*/;
+                                  GEMM_SHADOW_BYTES + 384 /*barriers*/;
 constexpr int GEMM_SMEM_BYTES = 232448;                    // all 227 KB; layout + alignment pad must fit (checked)
 static_assert(GEMM_LAYOUT_BYTES <= GEMM_SMEM_BYTES, "shared-memory layout too large");
 constexpr int GEMM_THREADS = 384;
@@ -52,6 +55,7 @@ struct GemmParams {
     int n_out;             // valid output columns per batch
     int num_k_blocks;
     int block_n;           // UMMA N: multiple of 16, <= 256 (256 for EPI_GATED)
+    int stages, stage_bytes;   // operand ring (gemm_ring)
     int num_m_tiles, num_n_tiles, batches;
     int a_zb, a_zn;        // A tensor-map z = b*a_zb + n_tile*a_zn
     int b_zb;              // B tensor-map z = b*b_zb
@@ -72,6 +76,7 @@ struct GemmParams {
     int tma_store;         // outputs leave through TMA stores (tensor maps tma_out / tma_out2)
     int aux_mode;          // tile operand streamed by TMA: fp32 residual or bf16 multiplier
     int aux_zb;            // aux tensor-map z = b*aux_zb
+    int orig_tma;          // bypass operand `orig` streamed through the aux ring (tensor map tma_orig)
     const float* orig;     // bypass: orig + (v - orig)*scale[col]; fp32, pitch ldc
     const float* bypass_scale;
     int act;
@@ -103,13 +108,13 @@ __device__ __forceinline__ void store_row32_direct(const GemmParams& p, long lon
             for (int i = 0; i < 32; ++i)
                 if (i < ncols) dst[static_cast<long long>(i) * p.t_pitch] = __float2bfloat16(v[i]);
         } else {
+            int hh = col0 / p.t_hd;                   // head of the first column, then incremental
+            int rem = col0 - hh * p.t_hd;
+            const int pad = p.t_hp - p.t_hd;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                if (i < ncols) {
-                    const int c = col0 + i;
-                    const int drow = c + (c / p.t_hd) * (p.t_hp - p.t_hd);
-                    dst[static_cast<long long>(drow) * p.t_pitch] = __float2bfloat16(v[i]);
-                }
+                if (i < ncols) dst[static_cast<long long>(col0 + i + hh * pad) * p.t_pitch] = __float2bfloat16(v[i]);
+                if (++rem == p.t_hd) { rem = 0; ++hh; }
             }
         }
         return;
@@ -214,16 +219,17 @@ template <int KIND, int ACT, int CLUSTER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_out,
-            const __grid_constant__ CUtensorMap tma_out2, const GemmParams p) {
+            const __grid_constant__ CUtensorMap tma_out2, const __grid_constant__ CUtensorMap tma_orig,
+            const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    constexpr int STAGES = GemmCfg<CLUSTER>::STAGES;
-    constexpr int STAGE_BYTES = GemmCfg<CLUSTER>::STAGE_BYTES;
+    const int STAGES = p.stages;
+    const int STAGE_BYTES = p.stage_bytes;
     uint8_t* aux_smem = smem + GEMM_OPERAND_BYTES;
-    float* bias_smem = reinterpret_cast<float*>(aux_smem + GEMM_AUX_SLOTS * GEMM_AUX_BYTES);   // [2 halves][256]
-    uint8_t* shadow_smem = reinterpret_cast<uint8_t*>(bias_smem) + GEMM_BIAS_BYTES;           // [2 halves][128][64 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(shadow_smem + GEMM_SHADOW_BYTES);
+    uint8_t* shadow_smem = aux_smem + GEMM_AUX_SLOTS * GEMM_AUX_BYTES;                         // [8 warps][32][64 B]
+    float* bias_smem = reinterpret_cast<float*>(shadow_smem + GEMM_SHADOW_BYTES);              // [8 warps][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_smem) + GEMM_BIAS_BYTES);
     if (threadIdx.x == 0 && (smem - smem_raw) + GEMM_LAYOUT_BYTES > GEMM_SMEM_BYTES) {
         printf("zvb: gemm shared-memory layout does not fit (base misaligned by %d)\n", (int)(smem - smem_raw));
         __trap();
@@ -234,10 +240,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint64_t* tmem_empty = tmem_full + 2;                       // [2] epilogue -> MMA
     uint64_t* aux_full = tmem_empty + 2;                        // [AUX_SLOTS] TMA -> epilogue
     uint64_t* aux_empty = aux_full + GEMM_AUX_SLOTS;            // [AUX_SLOTS] epilogue -> TMA
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(aux_empty + GEMM_AUX_SLOTS);
+    uint64_t* staged = aux_empty + GEMM_AUX_SLOTS;              // [2 halves][2] epilogue -> store thread
+    uint64_t* sfree = staged + 4;                               // [2 halves][2] store thread -> epilogue
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(sfree + 4);
 
+    // Roles: warps 0..7 = epilogue, 8 = TMA producer (A/B), 9 = MMA issuer (+TMEM alloc), 10 = TMA producer
+    // (aux), 11 = TMA store thread.  The single-thread roles sit in the HIGHEST warp ids because the
+    // SMSP arbiter favours higher warp ids: an MMA issue or TMA request then never queues behind the
+    // FFMA streams of the epilogue warps sharing its scheduler.
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    constexpr int W_TMA = 8, W_MMA = 9, W_AUX = 10, W_STORE = 11;
     // tile schedule: a "slot" is one tile per CTA of the cluster; slot s -> (b, m_group, n_tile) and the
     // CTA of rank `crank` takes m_tile = m_group*CLUSTER + crank (a tile past num_m_tiles is all padding)
     const int crank = CLUSTER > 1 ? static_cast<int>(cluster_ctarank()) : 0;
@@ -248,14 +261,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     // accumulator columns are consumed in units of 32; aux sub-tiles hold 32 (fp32) or 64 (bf16) columns
     const int n_units = (p.block_n + 31) >> 5;
     const bool out_f32 = p.out_mode == OUT_F32 || p.out_mode == OUT_F32_BF16;
-    const int units_per_sub = (p.aux_mode == AUX_RESID_F32 || (p.tma_store && out_f32)) ? 1 : 2;
+    const int units_per_sub =
+        (p.aux_mode == AUX_RESID_F32 || (p.tma_store && out_f32) || p.out_mode == OUT_T_BF16) ? 1 : 2;
+    const int aux_parts = p.orig_tma ? 2 : 1;          // ring entries per sub-tile: operand (+ bypass `orig`)
     const int n_sub = (n_units + units_per_sub - 1) / units_per_sub;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == W_TMA && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         if (p.aux_mode != AUX_NONE) tma_prefetch_desc(&tma_aux);
         if (p.tma_store) { tma_prefetch_desc(&tma_out); tma_prefetch_desc(&tma_out2); }
+        if (p.orig_tma) tma_prefetch_desc(&tma_orig);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -267,10 +283,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         for (int s = 0; s < GEMM_AUX_SLOTS; ++s) {
             mbar_init(&aux_full[s], 1);
             mbar_init(&aux_empty[s], p.tma_store ? 1 : 4);
+            mbar_init(&staged[s], 4);
+            mbar_init(&sfree[s], 1);
         }
         fence_barrier_init();
     }
-    if (warp == 1) {
+    if (warp == W_MMA) {
         if (CLUSTER == 2) { tmem_alloc_2sm(tmem_holder, GEMM_TMEM_COLS); tmem_relinquish_2sm(); }
         else { tmem_alloc(tmem_holder, GEMM_TMEM_COLS); tmem_relinquish(); }
     }
@@ -280,7 +298,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    if (warp == 0) {
+    if (warp == W_TMA) {
         // ------------------------------------------------------------------ TMA producer (A, B)
         if (lane == 0) {
             // bytes landing on the (leader's) full barrier per stage: both CTAs' A tiles + the whole B tile
@@ -313,7 +331,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0 && crank == 0) {               // the leader issues for the pair
             const uint32_t idesc = umma_idesc_bf16(static_cast<uint32_t>(p.block_n), 128u * CLUSTER);
@@ -354,7 +372,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
-    } else if (warp == 2) {
+    } else if (warp == W_AUX) {
         // ------------------------------------------------------------------ TMA producer (aux tiles)
         if (lane == 0 && p.aux_mode != AUX_NONE) {
             const int sub_cols = p.aux_mode == AUX_RESID_F32 ? 32 : 64;
@@ -364,25 +382,93 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 const int rest = tile / p.num_n_tiles;
                 const int m_tile = (rest % m_groups) * CLUSTER + crank;
                 const int b = rest / m_groups;
-                for (int s = 0; s < n_sub; ++s, ++q) {
-                    const int slot = q % GEMM_AUX_SLOTS;
-                    const uint32_t par = (q / GEMM_AUX_SLOTS) & 1u;
-                    mbar_wait(&aux_empty[slot], par ^ 1u);
-                    mbar_arrive_expect_tx(&aux_full[slot], GEMM_AUX_BYTES);
-                    tma_load_3d(aux_smem + slot * GEMM_AUX_BYTES, &tma_aux, &aux_full[slot],
-                                n_tile * p.out_col_stride + s * sub_cols, m_tile * GEMM_BLOCK_M, b * p.aux_zb);
+                for (int s = 0; s < n_sub; ++s) {
+                    for (int part = 0; part < aux_parts; ++part, ++q) {
+                        const int slot = q % GEMM_AUX_SLOTS;
+                        const uint32_t par = (q / GEMM_AUX_SLOTS) & 1u;
+                        mbar_wait(&aux_empty[slot], par ^ 1u);
+                        mbar_arrive_expect_tx(&aux_full[slot], GEMM_AUX_BYTES);
+                        tma_load_3d(aux_smem + slot * GEMM_AUX_BYTES, part == 0 ? &tma_aux : &tma_orig, &aux_full[slot],
+                                    n_tile * p.out_col_stride + s * sub_cols, m_tile * GEMM_BLOCK_M, b * p.aux_zb);
+                    }
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp == W_STORE) {
+        // ------------------------------------------------------------------ TMA store thread
+        // Epilogue halves (4 warps each) stage 128-row x 128-byte sub-tiles and signal `staged`; this
+        // thread issues the box stores (16 KB each: few, large TMA operations -- per-warp 4 KB stores
+        // were measured to delay the operand loads), waits until the store has read its source and hands
+        // the buffers back (`sfree`, and the aux slot that was staged in place).
+        if (lane == 0 && p.tma_store) {
+            const int subs = KIND == EPI_GATED ? 2 : n_sub;
+            uint32_t kc[2] = {0u, 0u};
+            uint32_t tile_iter = 0;
+            for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++tile_iter) {
+                const int n_tile = tile % p.num_n_tiles;
+                const int rest = tile / p.num_n_tiles;
+                const int m_tile = (rest % m_groups) * CLUSTER + crank;
+                const int b = rest / m_groups;
+                const int out_base = n_tile * p.out_col_stride;
+                for (int s = 0; s < subs; ++s) {
+                    const int h = s & 1;
+                    const uint32_t k = kc[h]++;
+                    const int bi = h * 2 + static_cast<int>(k & 1u);
+                    int slot = 0, slot2 = 0;
+                    const uint8_t* src = aux_smem + ((k & 1u) * 2 + h) * GEMM_AUX_BYTES;
+                    int col = out_base + 64 * h;
+                    if (KIND != EPI_GATED) {
+                        col = out_base + s * units_per_sub * 32;
+                        if (p.aux_mode != AUX_NONE) {
+                            const uint32_t q = (tile_iter * static_cast<uint32_t>(n_sub) + static_cast<uint32_t>(s)) *
+                                               static_cast<uint32_t>(aux_parts);
+                            slot = q % GEMM_AUX_SLOTS;
+                            slot2 = (q + 1) % GEMM_AUX_SLOTS;
+                            src = aux_smem + slot * GEMM_AUX_BYTES;
+                        }
+                    }
+                    mbar_wait(&staged[bi], (k >> 1) & 1u);
+                    if (aux_parts == 2) mbar_arrive(&aux_empty[slot2]);      // `orig` rows are consumed
+                    tma_store_3d(&tma_out, src, col, m_tile * GEMM_BLOCK_M, b);
+                    if (p.out_mode == OUT_F32_BF16)
+                        tma_store_3d(&tma_out2, shadow_smem + h * (128 * 64), col, m_tile * GEMM_BLOCK_M, b);
+                    bulk_commit();
+                    bulk_wait_read<0>();
+                    mbar_arrive(&sfree[bi]);
+                    if (p.aux_mode != AUX_NONE) mbar_arrive(&aux_empty[slot]);
+                }
+            }
+        }
+    } else {
         // ------------------------------------------------------------------ epilogue (8 warps)
+        // A warp owns 32 accumulator rows (its TMEM lane quarter) of every other sub-tile and stages them
+        // into its rows of the half's 128-row staging box: in place over the consumed aux sub-tile, or in
+        // the half's two-buffer ring.  No block-level barrier: one lane per warp arrives on `staged`, the
+        // store thread (warp 3) issues the box store and returns the buffer through `sfree`.
         const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
-        const int half = (warp - 4) >> 2;                 // which of the two warps of the quarter
+        const int ew = warp;
+        const int half = ew >> 2;                         // which of the two warps of the quarter
         const int r = quarter * 32 + lane;                // accumulator row inside the tile
-        uint8_t* private_stage = aux_smem + (warp - 4) * 4096;   // used when no aux slot is in flight
-        const bool leader = quarter == 0 && lane == 0;    // one thread per half issues the TMA stores
-        uint8_t* shadow_stage = shadow_smem + half * (128 * 64);
-        uint32_t kcount = 0;                              // sub-tiles stored by this half (staging ring)
+        uint8_t* private_stage = aux_smem + ew * 4096;    // staging of the non-TMA store paths
+        uint8_t* shadow_stage = shadow_smem + half * (128 * 64) + quarter * 2048;  // this warp's 32 rows x 64 B
+        uint32_t kcount = 0;                              // sub-tiles this half handed to the store thread
+        // a staging buffer may be rewritten once the store of `depth` sub-tiles ago has read it: the
+        // shadow box is single buffered, everything else has two buffers (or lives in an aux slot)
+        const uint32_t depth = p.out_mode == OUT_F32_BF16 ? 1u : 2u;
+        auto wait_sfree = [&]() {
+            if (kcount >= depth) {
+                const uint32_t kd = kcount - depth;
+                mbar_wait(&sfree[half * 2 + (kd & 1u)], (kd >> 1) & 1u);
+            }
+        };
+        auto signal_staged = [&]() {
+            fence_proxy_async_smem();                     // generic-proxy writes -> visible to the TMA engine
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&staged[half * 2 + (kcount & 1u)]);
+            ++kcount;
+        };
+        // bias staging of this warp: 64 floats (LINEAR), or 128 floats in the unused shadow area (GATED)
+        float* bs = KIND == EPI_GATED ? reinterpret_cast<float*>(shadow_stage) : bias_smem + ew * 64;
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t tile_iter = 0;
@@ -400,19 +486,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             rows_ok = rows_ok < 0 ? 0 : (rows_ok > 32 ? 32 : rows_ok);
             const int out_base = n_tile * p.out_col_stride;
             const int acc_base = n_tile * p.block_n;
-            // this half's copy of the tile's bias (minus the Swoosh offset, see swoosh_from_offset)
-            float* bs = bias_smem + half * 256;
-            {
-                constexpr float off = ACT == ACT_SWOOSH_L ? SWOOSH_L_C : (ACT == ACT_SWOOSH_R ? SWOOSH_R_C : 0.0f);
-                const int lim = KIND == EPI_GATED ? p.num_n_tiles * 256 : p.n_out;
-                named_bar_sync(2 + half, 128);            // everyone is done with the previous tile's bias
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int cc = q * 128 + r;
-                    const int c = acc_base + cc;
-                    bs[cc] = ((p.bias != nullptr && cc < p.block_n && c < lim) ? __ldg(p.bias + c) : 0.0f) - off;
-                }
-                named_bar_sync(2 + half, 128);
+            const int bias_lim = KIND == EPI_GATED ? p.num_n_tiles * 256 : p.n_out;
+            // bias of accumulator column cc of this tile (zero outside the valid range)
+            auto bias_at = [&](int cc) -> float {
+                const int c = acc_base + cc;
+                return (p.bias != nullptr && cc < p.block_n && c < bias_lim) ? __ldg(p.bias + c) : 0.0f;
+            };
+            // requested before the accumulator wait: the bias values of this warp's first sub-tile
+            float nb[4];
+            if (KIND == EPI_GATED) {
+                const int hc = p.block_n >> 1;
+                nb[0] = bias_at(64 * half + lane);      nb[1] = bias_at(64 * half + 32 + lane);
+                nb[2] = bias_at(hc + 64 * half + lane); nb[3] = bias_at(hc + 64 * half + 32 + lane);
+            } else {
+                nb[0] = bias_at(half * units_per_sub * 32 + lane);
+                nb[1] = units_per_sub == 2 ? bias_at(half * 64 + 32 + lane) : 0.0f;
             }
             bool masked = false;
             if (p.row_mask != nullptr && row_ok) masked = p.row_mask[row] != 0;
@@ -432,15 +520,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 // each warp of a quarter takes two adjacent 32-column units so that their bf16 rows leave
                 // as one 128-byte segment
                 int g_lo = 0, g_hi = 0, g_col = 0;
-                uint8_t* tbuf = nullptr;
                 const bool g_tma = p.tma_store && 2 * half * 32 < hcols;
-                if (g_tma) {                              // staging ring of this half: two 16 KB buffers
-                    tbuf = aux_smem + ((kcount & 1u) * 2 + half) * GEMM_AUX_BYTES;
-                    if (leader) bulk_wait_read<1>();
-                    named_bar_sync(2 + half, 128);        // the buffer's previous store has read it
-                }
+                // this warp's rows of the half's staging ring (two 16 KB buffers)
+                uint8_t* tbuf = aux_smem + ((kcount & 1u) * 2 + half) * GEMM_AUX_BYTES + quarter * 4096;
+                if (g_tma) wait_sfree();
+                bs[lane] = nb[0]; bs[32 + lane] = nb[1]; bs[64 + lane] = nb[2]; bs[96 + lane] = nb[3];
+                __syncwarp();
                 for (int u = 2 * half; u < 2 * half + 2 && u * 32 < hcols; ++u) {
                     const int c0 = u * 32;
+                    const float* ba = bs + 32 * (u & 1);
                     uint32_t ra[32], rb[32];
                     tmem_ld32(taddr + c0, ra);
                     tmem_ld32(taddr + hcols + c0, rb);
@@ -453,14 +541,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         const bool tanh_gate = p.gate_mode == GATE_TANH_SX;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 ba = *reinterpret_cast<const float4*>(bs + c0 + 4 * j);
-                            const float4 bg = *reinterpret_cast<const float4*>(bs + hcols + c0 + 4 * j);
-                            const float ab[4] = {ba.x, ba.y, ba.z, ba.w};
-                            const float gb[4] = {bg.x, bg.y, bg.z, bg.w};
+                            const float4 b4 = *reinterpret_cast<const float4*>(ba + 4 * j);
+                            const float4 g4 = *reinterpret_cast<const float4*>(ba + 64 + 4 * j);
+                            const float abv[4] = {b4.x, b4.y, b4.z, b4.w};
+                            const float gbv[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const float a = __uint_as_float(ra[4 * j + e]) + ab[e];
-                                const float g = __uint_as_float(rb[4 * j + e]) + gb[e];
+                                const float a = __uint_as_float(ra[4 * j + e]) + abv[e];
+                                const float g = __uint_as_float(rb[4 * j + e]) + gbv[e];
                                 const float o = tanh_gate ? g * fast_tanh(a) : a * fast_sigmoid(g);
                                 v[4 * j + e] = masked ? 0.0f : o;
                             }
@@ -468,7 +556,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         const bool pairable = p.out_mode == OUT_BF16 && (p.ldc & 7) == 0 && (out_base & 7) == 0 &&
                                               (ncols & 7) == 0;
                         if (g_tma) {
-                            stage_bf16_unit(tbuf + quarter * 32 * 128, lane, v, 4 * (u & 1));
+                            stage_bf16_unit(tbuf, lane, v, 4 * (u & 1));
                         } else if (pairable) {
                             stage_bf16_unit(private_stage, lane, v, 4 * (u & 1));
                             if ((u & 1) == 0) g_col = oc;
@@ -480,13 +568,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     }
                 }
                 if (g_tma) {
-                    fence_proxy_async_smem();
-                    named_bar_sync(2 + half, 128);        // the 128 x 64 sub-tile is staged
-                    if (leader) {
-                        tma_store_3d(&tma_out, tbuf, out_base + 64 * half, m_tile * GEMM_BLOCK_M, b);
-                        bulk_commit();
-                    }
-                    ++kcount;
+                    signal_staged();
                 } else if (g_hi > 0) {
                     __syncwarp();
                     flush_bf16_units(reinterpret_cast<__nv_bfloat16*>(p.out), p.ldc, private_stage, lane, row0, rows_ok,
@@ -496,25 +578,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             } else {
                 for (int s = half; s < n_sub; s += 2) {
                     const uint8_t* aux_row = nullptr;
-                    int slot = 0;
+                    const uint8_t* orig_row = nullptr;
+                    int slot = 0, slot2 = 0;
                     int pend_lo = 0, pend_hi = 0, pend_col = 0;      // staged, not yet flushed bf16 columns
                     uint8_t* pend_stage = nullptr;
                     if (p.aux_mode != AUX_NONE) {
-                        const uint32_t q = tile_iter * static_cast<uint32_t>(n_sub) + static_cast<uint32_t>(s);
+                        const uint32_t q = (tile_iter * static_cast<uint32_t>(n_sub) + static_cast<uint32_t>(s)) *
+                                           static_cast<uint32_t>(aux_parts);
                         slot = q % GEMM_AUX_SLOTS;
                         mbar_wait(&aux_full[slot], (q / GEMM_AUX_SLOTS) & 1u);
                         aux_row = aux_smem + slot * GEMM_AUX_BYTES + r * 128;
-                    }
-                    uint8_t* tbuf = nullptr;                 // TMA-store staging: 128 rows x 128 B
-                    if (p.tma_store) {
-                        if (p.aux_mode != AUX_NONE) {        // in place over the consumed aux sub-tile
-                            tbuf = aux_smem + slot * GEMM_AUX_BYTES;
-                        } else {                             // staging ring of this half: two 16 KB buffers
-                            tbuf = aux_smem + ((kcount & 1u) * 2 + half) * GEMM_AUX_BYTES;
-                            if (leader) bulk_wait_read<1>();
+                        if (aux_parts == 2) {
+                            slot2 = (q + 1) % GEMM_AUX_SLOTS;
+                            mbar_wait(&aux_full[slot2], ((q + 1) / GEMM_AUX_SLOTS) & 1u);
+                            orig_row = aux_smem + slot2 * GEMM_AUX_BYTES + r * 128;
                         }
-                        if (p.aux_mode == AUX_NONE || p.out_mode == OUT_F32_BF16)
-                            named_bar_sync(2 + half, 128);   // previous stores have read the buffers we overwrite
+                    }
+                    // TMA-store staging of this warp's 32 rows x 128 B: in place over its rows of the consumed
+                    // aux sub-tile, else the private two-buffer ring
+                    uint8_t* tbuf = (p.aux_mode != AUX_NONE ? aux_smem + slot * GEMM_AUX_BYTES
+                                                            : aux_smem + ((kcount & 1u) * 2 + half) * GEMM_AUX_BYTES) +
+                                    quarter * 4096;
+                    __syncwarp();                            // the previous sub-tile's bias reads are done
+                    bs[lane] = nb[0];
+                    bs[32 + lane] = nb[1];
+                    __syncwarp();
+                    if (s + 2 < n_sub) {                     // request the next sub-tile's bias now
+                        nb[0] = bias_at((s + 2) * units_per_sub * 32 + lane);
+                        nb[1] = units_per_sub == 2 ? bias_at((s + 2) * 64 + 32 + lane) : 0.0f;
                     }
                     for (int uu = 0; uu < units_per_sub; ++uu) {
                         const int c0 = (s * units_per_sub + uu) * 32;
@@ -522,15 +613,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         uint32_t acc_r[32];
                         tmem_ld32(taddr + c0, acc_r);
                         tmem_ld_wait();
+                        float v[32];
                         const int oc = out_base + c0;
                         int ncols = p.n_valid - c0;
                         if (p.n_out - oc < ncols) ncols = p.n_out - oc;
                         ncols = ncols > 32 ? 32 : ncols;
                         if (ncols > 0 || p.tma_store) {
-                            float v[32];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const float4 bq = *reinterpret_cast<const float4*>(bs + c0 + 4 * j);
+                                const float4 bq = *reinterpret_cast<const float4*>(bs + 32 * uu + 4 * j);
                                 v[4 * j] = fmaf(__uint_as_float(acc_r[4 * j]), rscale, bq.x);
                                 v[4 * j + 1] = fmaf(__uint_as_float(acc_r[4 * j + 1]), rscale, bq.y);
                                 v[4 * j + 2] = fmaf(__uint_as_float(acc_r[4 * j + 2]), rscale, bq.z);
@@ -551,12 +642,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                         if (i < ncols) v[i] += __ldg(rbp + i);
                                 }
                             }
-                            if (ACT == ACT_SWOOSH_L) {          // v already holds x - 4 (offset folded into the bias)
+                            if (ACT == ACT_SWOOSH_L) {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] = swoosh_from_offset(v[i], SWOOSH_L_K0);
+                                for (int i = 0; i < 32; ++i) v[i] = swoosh_direct(v[i], SWOOSH_L_C, SWOOSH_L_K0);
                             } else if (ACT == ACT_SWOOSH_R) {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] = swoosh_from_offset(v[i], SWOOSH_R_K0);
+                                for (int i = 0; i < 32; ++i) v[i] = swoosh_direct(v[i], SWOOSH_R_C, SWOOSH_R_K0);
                             }
                             if (p.aux_mode == AUX_RESID_F32) {
 #pragma unroll
@@ -574,7 +665,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                     v[8 * j + 6] *= bf16_lo(a.w); v[8 * j + 7] *= bf16_hi(a.w);
                                 }
                             }
-                            if (p.orig != nullptr && row_ok) {
+                            if (orig_row != nullptr) {        // bypass, `orig` sub-tile staged by TMA
+                                const float* sp = p.bypass_scale + oc;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 o = *reinterpret_cast<const float4*>(orig_row + ((j ^ (r & 7)) << 4));
+                                    const float4 sc = __ldg(reinterpret_cast<const float4*>(sp) + j);
+                                    v[4 * j] = fmaf(v[4 * j] - o.x, sc.x, o.x);
+                                    v[4 * j + 1] = fmaf(v[4 * j + 1] - o.y, sc.y, o.y);
+                                    v[4 * j + 2] = fmaf(v[4 * j + 2] - o.z, sc.z, o.z);
+                                    v[4 * j + 3] = fmaf(v[4 * j + 3] - o.w, sc.w, o.w);
+                                }
+                            } else if (p.orig != nullptr && row_ok) {
                                 const float* op = p.orig + row * p.ldc + oc;
                                 const float* sp = p.bypass_scale + oc;
                                 if (vec) {
@@ -596,30 +698,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                         }
                                 }
                             }
-                            // in place over the consumed aux rows of this warp, or in the warp's private area
-                            uint8_t* stage = p.aux_mode != AUX_NONE
-                                                 ? aux_smem + slot * GEMM_AUX_BYTES + quarter * 32 * 128
-                                                 : private_stage;
                             if (p.tma_store) {         // stage into the (swizzled) TMA box, own row only
+                                if (uu == 0) wait_sfree();      // earlier stores no longer read what is overwritten
                                 if (out_f32) {
-                                    uint8_t* my = tbuf + r * 128;
+                                    uint8_t* my = tbuf + lane * 128;
 #pragma unroll
                                     for (int j = 0; j < 8; ++j)
-                                        *reinterpret_cast<float4*>(my + ((j ^ (r & 7)) << 4)) =
+                                        *reinterpret_cast<float4*>(my + ((j ^ (lane & 7)) << 4)) =
                                             make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                                     if (p.out_mode == OUT_F32_BF16) {      // 64-byte rows, 64B swizzle
-                                        uint8_t* sh = shadow_stage + r * 64;
+                                        uint8_t* sh = shadow_stage + lane * 64;
 #pragma unroll
                                         for (int j = 0; j < 4; ++j)
-                                            *reinterpret_cast<uint4*>(sh + ((j ^ ((r >> 1) & 3)) << 4)) =
+                                            *reinterpret_cast<uint4*>(sh + ((j ^ ((lane >> 1) & 3)) << 4)) =
                                                 make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                                                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
                                     }
                                 } else {
-                                    stage_bf16_unit(tbuf + quarter * 32 * 128, lane, v, 4 * uu);
+                                    stage_bf16_unit(tbuf, lane, v, 4 * uu);
                                 }
                                 continue;
                             }
+                            // in place over the consumed aux rows of this warp, or in the warp's private area
+                            uint8_t* stage = p.aux_mode != AUX_NONE
+                                                 ? aux_smem + slot * GEMM_AUX_BYTES + quarter * 32 * 128
+                                                 : private_stage;
                             __syncwarp();              // every lane has consumed its aux row
                             const bool pairable = p.out_mode == OUT_BF16 && units_per_sub == 2 && (p.ldc & 7) == 0 &&
                                                   (out_base & 7) == 0 && (ncols & 7) == 0;
@@ -635,19 +738,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         }
                     }
                     if (p.tma_store) {
-                        fence_proxy_async_smem();            // generic-proxy writes -> visible to the TMA engine
-                        named_bar_sync(2 + half, 128);       // the whole 128-row sub-tile is staged
-                        if (leader) {
-                            const int col = out_base + s * units_per_sub * 32;
-                            tma_store_3d(&tma_out, tbuf, col, m_tile * GEMM_BLOCK_M, b);
-                            if (p.out_mode == OUT_F32_BF16) tma_store_3d(&tma_out2, shadow_stage, col, m_tile * GEMM_BLOCK_M, b);
-                            bulk_commit();
-                            if (p.aux_mode != AUX_NONE || p.out_mode == OUT_F32_BF16) {
-                                bulk_wait_read<0>();         // the slot / shadow buffer may be reused
-                                if (p.aux_mode != AUX_NONE) mbar_arrive(&aux_empty[slot]);
-                            }
-                        }
-                        ++kcount;
+                        signal_staged();
                         continue;
                     }
                     if (pend_hi > 0) {
@@ -659,7 +750,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     }
                     if (p.aux_mode != AUX_NONE) {
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&aux_empty[slot]);
+                        if (lane == 0) {
+                            mbar_arrive(&aux_empty[slot]);
+                            if (aux_parts == 2) mbar_arrive(&aux_empty[slot2]);
+                        }
                     }
                 }
             }
@@ -671,13 +765,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-        if (p.tma_store && leader) bulk_wait_read<0>();   // staging must outlive the stores reading it
+
     }
 
     tc_fence_before();
     __syncthreads();
     if (CLUSTER > 1) cluster_sync_all();        // no CTA exits while a peer may still write to it
-    if (warp == 1) {
+    if (warp == W_MMA) {
         __syncwarp();
         tc_fence_after();
         if (CLUSTER == 2) tmem_dealloc_2sm(tmem_base, GEMM_TMEM_COLS);

@@ -308,6 +308,21 @@ __device__ __forceinline__ float swoosh_from_offset(float y, float k0) {
     r = fmaf(y, 0.42f, r);
     return fmaf(fabsf(y), 0.5f, r);
 }
+// Same activation evaluated from x directly (no separate x - c): z = (x - c) log2 e is one FFMA, the
+// |.| and the negation ride on the MUFU operand, and the linear terms are re-expressed in x and |z|.
+__device__ __forceinline__ float swoosh_direct(float x, float c, float k0) {
+    constexpr float L2E = 1.4426950408889634f;
+    const float z = fmaf(x, L2E, -c * L2E);
+    float t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-fabsf(z)));
+    float p = fmaf(t, 0.031377589387161245f, -0.1341354334221127f);
+    p = fmaf(t, p, 0.2878262894239249f);
+    p = fmaf(t, p, -0.491347927069251f);
+    p = fmaf(t, p, 0.9994349844843187f);
+    float r = fmaf(t, p, k0 - 0.42f * c);
+    r = fmaf(x, 0.42f, r);
+    return fmaf(fabsf(z), 0.5f / L2E, r);
+}
 constexpr float SWOOSH_L_C = 4.0f, SWOOSH_L_K0 = -(0.08f * 4.0f + 0.035f);
 constexpr float SWOOSH_R_C = 1.0f, SWOOSH_R_K0 = -(0.08f * 1.0f + 0.313261687f);
 __device__ __forceinline__ float swoosh_l(float x) {
