@@ -157,6 +157,23 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
         const int sw = lane & 7;
         constexpr float LOG2E = 1.4426950408889634f;
         float m_run = -INFINITY, m_l2 = 0.f, l_run = 0.f;
+        // mask byte / rel-pos entry this thread stages for iteration `it2` (global loads, prefetched)
+        float4 e_cur = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool ex_cur = true;
+        auto fetch = [&](int it2) {
+            const int pass2 = it2 >= num_jt ? 1 : 0;
+            const int j02 = (pass2 ? it2 - num_jt : it2) * ATT_BN;
+            if (tid < 128) {
+                const int j = j02 + tid;
+                ex_cur = j < p.L ? (mrow[j] != 0) : true;
+            }
+            e_cur = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pass2 && tid < 255) {
+                const int rel = (j02 - i0) - 127 + tid + (p.L - 1);
+                if (rel >= 0 && rel <= 2 * p.L - 2) e_cur = __ldg(Eh + rel);
+            }
+        };
+        fetch(0);
 
         for (int it = 0; it < total_it; ++it) {
             const int pass = it >= num_jt ? 1 : 0;
@@ -174,22 +191,17 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
                 m_l2 = m_est * LOG2E;
             }
             // stage the excluded-key bits (padding mask or beyond L) and, for the second pass, the
-            // rel-pos window of this tile (double buffered)
+            // rel-pos window of this tile (double buffered); both were requested one iteration ago
             float4* ew = ewin + acc * ATT_EWIN;
             uint32_t* mw = mwin + acc * 4;
             if (tid < 128) {
-                const int j = j0 + tid;
-                const bool excl = j < p.L ? (mrow[j] != 0) : true;
-                const uint32_t bits = __ballot_sync(0xffffffffu, excl);
+                const uint32_t bits = __ballot_sync(0xffffffffu, ex_cur);
                 if (lane == 0) mw[tid >> 5] = bits;
             }
-            if (pass && tid < 255) {
-                const int rel = (j0 - i0) - 127 + tid + (p.L - 1);
-                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rel >= 0 && rel <= 2 * p.L - 2) e = __ldg(Eh + rel);
-                ew[tid] = make_float4(e.x * LOG2E, e.y * LOG2E, e.z * LOG2E, e.w * LOG2E);
-            }
+            if (pass && tid < 255)
+                ew[tid] = make_float4(e_cur.x * LOG2E, e_cur.y * LOG2E, e_cur.z * LOG2E, e_cur.w * LOG2E);
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (it + 1 < total_it) fetch(it + 1);         // in flight during this tile's arithmetic
             mbar_wait(&s_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * ATT_BN + 64 * half) +
