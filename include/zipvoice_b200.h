@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ZVB_ABI_VERSION 1
+#define ZVB_ABI_VERSION 2
 #define ZVB_MAX_STACKS 8
 #define ZVB_MAX_LAYERS 64
 
@@ -43,7 +43,7 @@ typedef enum {
     ZVB_ERR_NO_DEVICE = -4    /* no sm_100 device: there is no CPU fallback */
 } zvb_status;
 
-/* One nn.Linear: W is bf16 row-major (out_features, k_pitch) with k_pitch a multiple of 8,
+/* One nn.Linear: W is fp16 (IEEE half) row-major (out_features, k_pitch) with k_pitch a multiple of 8,
  * zero padded; bias is fp32 (nullable).  "Gated" projections are re-ordered per 256-row tile
  * as [128 rows of the first operand | 128 rows of the second] and zero padded to a multiple
  * of 256 rows (bias likewise), see zipvoice_b200/weights.py. */
@@ -112,7 +112,7 @@ typedef struct {
 
 /* Device buffers inside the workspace a plan reads its inputs from / writes its output to. */
 typedef struct {
-    void* xin;                /* bf16 [N][T][xin_pitch] = [x | text | speech | 0-pad]        */
+    void* xin;                /* fp16 [N][T][xin_pitch] = [x | text | speech | 0-pad]        */
     float* t;                 /* [N]                                                         */
     float* g;                 /* [N] guidance scale (distill only)                           */
     uint8_t* mask;            /* [N][T] non-zero = padded frame                              */
@@ -170,21 +170,23 @@ int zvb_sample(zvb_plan* plan, float* x, const float* text, const float* speech,
                int B, int F, int Ft, float* vrec, void* stream);
 
 /* ---- single-kernel entry points used by the parity tests -------------------------------- */
-/* C = epilogue(A·Wᵀ): A bf16 [M][lda], W bf16 [n_out][k_pitch]; act 0 none/1 SwooshL/2 SwooshR;
- * resid fp32 [M][ldc] nullable; out_mode 0: out bf16 / 1: out fp32 / 2: out fp32 + out_bf16 shadow. */
+/* C = epilogue(A·Wᵀ): A fp16 [M][lda], W fp16 [n_out][k_pitch]; act 0 none/1 SwooshL/2 SwooshR;
+ * resid fp16 [M][ldc] nullable (added); orig fp16 [M][ldc] + bypass_scale fp32 [n_out] nullable:
+ * C = orig + (C - orig)*scale (needs resid); out_mode 0: out fp16 / 1: out fp32. */
 int zvb_test_linear(const void* A, int M, int K, int lda, const void* W, const float* bias, int n_out,
-                    int k_pitch, int block_n, int act, const float* resid, void* out, void* out_bf16, int ldc,
-                    int out_mode, void* stream);
+                    int k_pitch, int block_n, int act, const void* resid, const void* orig,
+                    const float* bypass_scale, void* out, int ldc, int out_mode, void* stream);
 /* P receives the unnormalised weights exp(s - m), inv_l [N][H][L] the reciprocal row sums */
 int zvb_test_attn_weights(const void* qkp, int ld, const float* pos_table, const uint8_t* mask, void* P,
                           float* inv_l, int N, int H, int L, int Lk, void* stream);
-/* mul: bf16 [N*L][hd] gate of NonlinAttention (per_head == 0 only, nullable) */
+/* mul: fp16 [N*L][hd] gate of NonlinAttention (per_head == 0 only, nullable) */
 int zvb_test_pv(const void* P, const float* inv_l, const void* Vt, void* out, int N, int H, int L, int Lk, int hd,
                 int hp, int per_head, const void* mul, void* stream);
 /* gated projection on tile-packed weights (rows = tiles*256); gate_mode 1: x*tanh(s), 2: GLU */
 int zvb_test_gated(const void* A, int M, int K, int lda, const void* W, const float* bias, int rows, int n_out,
                    int k_pitch, int gate_mode, const uint8_t* row_mask, void* out, int ldc, void* stream);
-int zvb_test_biasnorm_bypass(const float* src, const float* orig, float* out, void* out_b, void* out_t,
+/* src, orig, out, out_t (= out + temb[row / rows_per_group], nullable): fp16 [rows][C] */
+int zvb_test_biasnorm_bypass(const void* src, const void* orig, void* out, void* out_t,
                              const float* temb, int rows_per_group, const float* nbias, const float* log_scale,
                              const float* bscale, long long rows, int C, void* stream);
 int zvb_test_dwconv(const void* x, void* out, const float* wt, const float* bias, int N, int L, int C, int K,

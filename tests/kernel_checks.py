@@ -1,7 +1,7 @@
 """Single-kernel parity checks through the C ABI test entry points, shared by
 tests/test_kernels_gpu.py (pytest, -m gpu) and tools/gpu_check.py (one process per check).
 Each check compares a CUDA kernel with a plain PyTorch fp32 computation of the same op on the
-same (bf16-rounded) inputs and returns a dict of error metrics; `assert_ok` applies the
+same (fp16-rounded) inputs and returns a dict of error metrics; `assert_ok` applies the
 tolerances written next to each check."""
 from __future__ import annotations
 
@@ -12,6 +12,7 @@ import torch
 from zipvoice_b200 import _lib
 
 DEV = "cuda"
+H16 = torch.float16          # storage type of every activation / weight on the CUDA path
 
 
 def _s():
@@ -31,25 +32,26 @@ def _swoosh_r(x):
     return torch.logaddexp(torch.zeros((), device=x.device), x - 1.0) - 0.08 * x - 0.313261687
 
 
-def check_linear(M=300, K=512, N=272, block_n=0, act=0, resid=False, out_mode=0, seed=0):
-    """tolerance: rel-L2 <= 6e-3 for bf16 outputs (rounding 2^-9), <= 1e-5 for fp32 outputs.
-    out_mode 0: bf16, 1: fp32, 2: fp32 stream + bf16 shadow; resid: fp32 residual tile (TMA aux ring)."""
+def check_linear(M=300, K=512, N=272, block_n=0, act=0, resid=False, bypass=False, out_mode=0, seed=0):
+    """tolerance: rel-L2 <= 8e-4 for fp16 outputs (rounding 2^-12), <= 2e-5 for fp32 outputs.
+    out_mode 0: fp16, 1: fp32; resid: fp16 residual-stream tile added in the epilogue (TMA aux ring);
+    bypass: out = orig + (out - orig) * scale with an fp16 `orig` tile riding the same ring."""
     lib = _lib.load()
     g = torch.Generator(device="cpu").manual_seed(seed)
     kp = (K + 7) // 8 * 8
-    A = torch.zeros(M, kp, dtype=torch.bfloat16)
-    A[:, :K] = (torch.randn(M, K, generator=g) * 1.0).to(torch.bfloat16)
-    W = torch.zeros(N, kp, dtype=torch.bfloat16)
-    W[:, :K] = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    A = torch.zeros(M, kp, dtype=H16)
+    A[:, :K] = (torch.randn(M, K, generator=g) * 1.0).to(H16)
+    W = torch.zeros(N, kp, dtype=H16)
+    W[:, :K] = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(H16)
     b = torch.randn(N, generator=g)
-    R = torch.randn(M, N, generator=g) if resid else None
+    R = torch.randn(M, N, generator=g).to(H16).to(DEV) if resid else None
+    O = torch.randn(M, N, generator=g).to(H16).to(DEV) if bypass else None
+    sc = (torch.rand(N, generator=g) * 0.6 + 0.3).to(DEV) if bypass else None
     A, W, b = A.to(DEV), W.to(DEV), b.to(DEV)
-    R = R.to(DEV) if resid else None
-    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16 if out_mode == 0 else torch.float32, device=DEV)
-    shadow = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV) if out_mode == 2 else None
+    out = torch.full((M, N), float("nan"), dtype=H16 if out_mode == 0 else torch.float32, device=DEV)
     _lib.check(lib.zvb_test_linear(A.data_ptr(), M, K, kp, W.data_ptr(), b.data_ptr(), N, kp, block_n, act,
-                                   R.data_ptr() if resid else None, out.data_ptr(),
-                                   shadow.data_ptr() if shadow is not None else None, N, out_mode, _s()))
+                                   R.data_ptr() if resid else None, O.data_ptr() if bypass else None,
+                                   sc.data_ptr() if bypass else None, out.data_ptr(), N, out_mode, _s()))
     torch.cuda.synchronize()
     ref = A.float() @ W.float().t() + b
     if act == 1:
@@ -57,31 +59,29 @@ def check_linear(M=300, K=512, N=272, block_n=0, act=0, resid=False, out_mode=0,
     elif act == 2:
         ref = _swoosh_r(ref)
     if resid:
-        ref = ref + R
+        ref = ref + R.float()
+    if bypass:
+        ref = O.float() + (ref - O.float()) * sc
     err = (out.float() - ref).abs().nan_to_num(1e9)
     am = int(err.argmax())
-    res = dict(rel=_rel(out.float().nan_to_num(0.0), ref), nan=int(torch.isnan(out.float()).sum()),
-               tol=6e-3 if out_mode == 0 else 2e-5,
-               worst=[am // N, am % N, float(out.float().flatten()[am]), float(ref.flatten()[am])],
-               bad_frac=float((err > 0.1).float().mean()),
-               bad_rows=int((err.max(dim=1).values > 0.1).sum()), bad_cols=int((err.max(dim=0).values > 0.1).sum()))
-    if shadow is not None:
-        res["shadow_rel"] = _rel(shadow.float().nan_to_num(0.0), ref)
-        res["nan"] += int(torch.isnan(shadow.float()).sum())
-    return res
+    return dict(rel=_rel(out.float().nan_to_num(0.0), ref), nan=int(torch.isnan(out.float()).sum()),
+                tol=8e-4 if out_mode == 0 else 2e-5,
+                worst=[am // N, am % N, float(out.float().flatten()[am]), float(ref.flatten()[am])],
+                bad_frac=float((err > 0.1).float().mean()),
+                bad_rows=int((err.max(dim=1).values > 0.1).sum()), bad_cols=int((err.max(dim=0).values > 0.1).sum()))
 
 
 def check_gated(M=300, K=512, n_out=384, mode=1, masked=False, seed=0):
     """Gated projection on tile-packed weights: mode 1 x*tanh(s) (rows [s|x]), mode 2 GLU x*sigmoid(s)
-    (rows [x|s]) with optional zeroed rows.  tolerance: rel-L2 <= 8e-3 (tanh.approx / fast sigmoid + bf16)."""
+    (rows [x|s]) with optional zeroed rows.  tolerance: rel-L2 <= 8e-3 (tanh.approx / fast sigmoid + fp16)."""
     lib = _lib.load()
     g = torch.Generator(device="cpu").manual_seed(seed)
-    A = torch.randn(M, K, generator=g).to(torch.bfloat16)
-    Wa = (torch.randn(n_out, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
-    Wb = (torch.randn(n_out, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    A = torch.randn(M, K, generator=g).to(H16)
+    Wa = (torch.randn(n_out, K, generator=g) / math.sqrt(K)).to(H16)
+    Wb = (torch.randn(n_out, K, generator=g) / math.sqrt(K)).to(H16)
     ba, bb = torch.randn(n_out, generator=g) * 0.3, torch.randn(n_out, generator=g) * 0.3
     tiles = (n_out + 127) // 128
-    W = torch.zeros(tiles * 256, K, dtype=torch.bfloat16)
+    W = torch.zeros(tiles * 256, K, dtype=H16)
     Bv = torch.zeros(tiles * 256)
     for t in range(tiles):
         r = min(128, n_out - t * 128)
@@ -92,7 +92,7 @@ def check_gated(M=300, K=512, n_out=384, mode=1, masked=False, seed=0):
     rm = (torch.rand(M, generator=g) < 0.3) if masked else None
     A, W, Bv = A.to(DEV), W.to(DEV), Bv.to(DEV)
     rm8 = rm.to(torch.uint8).to(DEV) if masked else None
-    out = torch.full((M, n_out), float("nan"), dtype=torch.bfloat16, device=DEV)
+    out = torch.full((M, n_out), float("nan"), dtype=H16, device=DEV)
     _lib.check(lib.zvb_test_gated(A.data_ptr(), M, K, K, W.data_ptr(), Bv.data_ptr(), tiles * 256, n_out, K, mode,
                                   rm8.data_ptr() if masked else None, out.data_ptr(), n_out, _s()))
     torch.cuda.synchronize()
@@ -109,7 +109,7 @@ def _attn_inputs(N, H, L, seed, masked):
     ld = H * 68
     qkp = torch.randn(N, L, ld, generator=g)
     qkp[..., : 2 * H * 32] *= 0.45          # q.k std ~ 1.1 ... a few units of score range
-    qkp = qkp.to(torch.bfloat16)
+    qkp = qkp.to(H16)
     E = torch.randn(H, 2 * L - 1, 4, generator=g) * 0.5
     mask = torch.zeros(N, L, dtype=torch.bool)
     if masked:
@@ -134,11 +134,11 @@ def _attn_ref(qkp, E, mask, H):
 
 
 def check_attn(N=2, H=4, L=200, masked=True, seed=0):
-    """tolerance: max-abs <= 4e-3 on probabilities (bf16 storage of P: 2^-9 relative)"""
+    """tolerance: max-abs <= 1e-3 on probabilities (fp16 storage of P: 2^-12 relative; ex2.approx)"""
     lib = _lib.load()
     qkp, E, mask = _attn_inputs(N, H, L, seed, masked)
     Lk = (L + 7) // 8 * 8
-    P = torch.full((N, H, L, Lk), float("nan"), dtype=torch.bfloat16, device=DEV)
+    P = torch.full((N, H, L, Lk), float("nan"), dtype=H16, device=DEV)
     inv_l = torch.full((N, H, L), float("nan"), dtype=torch.float32, device=DEV)
     m8 = mask.to(torch.uint8).contiguous()
     Ex = torch.cat([E.reshape(-1), E.norm(dim=2).amax(dim=1)]).contiguous()
@@ -152,84 +152,82 @@ def check_attn(N=2, H=4, L=200, masked=True, seed=0):
     pad = got[..., L:]
     return dict(maxabs=float((got[..., :L] - ref).abs().max()), rel=_rel(got[..., :L], ref),
                 nan=int(torch.isnan(got).sum()), pad_nonzero=int((pad != 0).sum()),
-                rowsum_err=float((got[..., :L].sum(-1) - 1).abs().max()), tol=4e-3)
+                rowsum_err=float((got[..., :L].sum(-1) - 1).abs().max()), tol=1e-3)
 
 
 def check_pv(N=2, H=4, L=200, hd=12, hp=16, per_head=True, mul=False, seed=0):
-    """tolerance: rel-L2 <= 6e-3"""
+    """tolerance: rel-L2 <= 8e-4 (fp16 output)"""
     lib = _lib.load()
     g = torch.Generator(device="cpu").manual_seed(seed)
     Lk = (L + 7) // 8 * 8
     P = torch.zeros(N, H, L, Lk)
     P[..., :L] = torch.rand(N, H, L, L, generator=g).pow(4)
-    P = (P / P.sum(-1, keepdim=True)).to(torch.bfloat16).to(DEV)
+    P = (P / P.sum(-1, keepdim=True)).to(H16).to(DEV)
     if per_head:
-        V = torch.randn(N, H, hd, L, generator=g).to(torch.bfloat16)
-        Vt = torch.zeros(N, H, hp, Lk, dtype=torch.bfloat16)
+        V = torch.randn(N, H, hd, L, generator=g).to(H16)
+        Vt = torch.zeros(N, H, hp, Lk, dtype=H16)
         Vt[:, :, :hd, :L] = V
-        out = torch.full((N, L, H * hd), float("nan"), dtype=torch.bfloat16, device=DEV)
+        out = torch.full((N, L, H * hd), float("nan"), dtype=H16, device=DEV)
         ref = torch.einsum("nhij,nhdj->nihd", P.float()[..., :L], V.float().to(DEV)).reshape(N, L, H * hd)
     else:
-        V = torch.randn(N, hd, L, generator=g).to(torch.bfloat16)
-        Vt = torch.zeros(N, hd, Lk, dtype=torch.bfloat16)
+        V = torch.randn(N, hd, L, generator=g).to(H16)
+        Vt = torch.zeros(N, hd, Lk, dtype=H16)
         Vt[:, :, :L] = V
-        out = torch.full((N, L, hd), float("nan"), dtype=torch.bfloat16, device=DEV)
+        out = torch.full((N, L, hd), float("nan"), dtype=H16, device=DEV)
         ref = torch.einsum("nij,ndj->nid", P.float()[:, 0, :, :L], V.float().to(DEV))
     inv_l = (torch.rand(N, H, L, generator=g) + 0.5).to(DEV)
     ref = ref * (inv_l.permute(0, 2, 1).repeat_interleave(hd, dim=2) if per_head else inv_l[:, 0].unsqueeze(-1))
     Y = None
     if mul:
-        Y = torch.randn(N, L, hd, generator=g).to(torch.bfloat16).to(DEV)
+        Y = torch.randn(N, L, hd, generator=g).to(H16).to(DEV)
         ref = ref * Y.float()
     Vt = Vt.to(DEV)
     _lib.check(lib.zvb_test_pv(P.data_ptr(), inv_l.data_ptr(), Vt.data_ptr(), out.data_ptr(), N, H, L, Lk, hd, hp,
                                1 if per_head else 0, Y.data_ptr() if mul else None, _s()))
     torch.cuda.synchronize()
-    return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=6e-3)
+    return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=8e-4)
 
 
 def check_biasnorm(rows=1000, C=512, seed=0):
-    """fp32 stream in/out + bf16 shadow + bf16 time-embedded shadow.
-    tolerance: rel-L2 <= 1e-5 (fp32 out), <= 5e-3 (bf16 shadows)"""
+    """fp16 stream in/out + fp16 time-embedded copy, fp32 arithmetic.
+    tolerance: rel-L2 <= 6e-4 (fp16 outputs)"""
     lib = _lib.load()
     g = torch.Generator(device="cpu").manual_seed(seed)
     L = 37
-    src = torch.randn(rows, C, generator=g).mul(2).to(DEV)
-    orig = torch.randn(rows, C, generator=g).to(DEV)
+    src = torch.randn(rows, C, generator=g).mul(2).to(H16).to(DEV)
+    orig = torch.randn(rows, C, generator=g).to(H16).to(DEV)
     nb = (torch.randn(C, generator=g) * 0.1).to(DEV)
     ls = torch.tensor([0.4], device=DEV)
     bs = (torch.rand(C, generator=g) * 0.6 + 0.3).to(DEV)
     temb = torch.randn((rows + L - 1) // L, C, generator=g).to(DEV)
-    out = torch.full((rows, C), float("nan"), dtype=torch.float32, device=DEV)
-    ob = torch.full((rows, C), float("nan"), dtype=torch.bfloat16, device=DEV)
-    ot = torch.full((rows, C), float("nan"), dtype=torch.bfloat16, device=DEV)
-    _lib.check(lib.zvb_test_biasnorm_bypass(src.data_ptr(), orig.data_ptr(), out.data_ptr(), ob.data_ptr(),
-                                            ot.data_ptr(), temb.data_ptr(), L, nb.data_ptr(), ls.data_ptr(),
+    out = torch.full((rows, C), float("nan"), dtype=H16, device=DEV)
+    ot = torch.full((rows, C), float("nan"), dtype=H16, device=DEV)
+    _lib.check(lib.zvb_test_biasnorm_bypass(src.data_ptr(), orig.data_ptr(), out.data_ptr(), ot.data_ptr(),
+                                            temb.data_ptr(), L, nb.data_ptr(), ls.data_ptr(),
                                             bs.data_ptr(), rows, C, _s()))
     torch.cuda.synchronize()
-    y = src * (((src - nb) ** 2).mean(-1, keepdim=True) ** -0.5) * ls.exp()
-    ref = orig + (y - orig) * bs
+    x, o = src.float(), orig.float()
+    y = x * (((x - nb) ** 2).mean(-1, keepdim=True) ** -0.5) * ls.exp()
+    ref = o + (y - o) * bs
     ref_t = ref + temb[torch.arange(rows, device=DEV) // L]
-    rel32 = _rel(out, ref)
-    relb = max(_rel(ob.float(), ref), _rel(ot.float(), ref_t))
-    return dict(rel=relb, rel_f32=rel32, nan=int(torch.isnan(out).sum() + torch.isnan(ob.float()).sum()),
-                tol=5e-3 if rel32 <= 1e-5 else 0.0)
+    rel = max(_rel(out.float(), ref), _rel(ot.float(), ref_t))
+    return dict(rel=rel, nan=int(torch.isnan(out.float()).sum() + torch.isnan(ot.float()).sum()), tol=6e-4)
 
 
 def check_dwconv(N=2, L=150, C=512, K=31, seed=0):
-    """tolerance: rel-L2 <= 5e-3 (bf16 output)"""
+    """tolerance: rel-L2 <= 8e-4 (fp16 output)"""
     lib = _lib.load()
     g = torch.Generator(device="cpu").manual_seed(seed)
-    x = torch.randn(N, L, C, generator=g).to(torch.bfloat16).to(DEV)
+    x = torch.randn(N, L, C, generator=g).to(H16).to(DEV)
     w = (torch.randn(C, 1, K, generator=g) / math.sqrt(K)).to(DEV)
     b = (torch.randn(C, generator=g) * 0.2).to(DEV)
     wt = w.reshape(C, K).t().contiguous()
-    out = torch.full((N, L, C), float("nan"), dtype=torch.bfloat16, device=DEV)
+    out = torch.full((N, L, C), float("nan"), dtype=H16, device=DEV)
     _lib.check(lib.zvb_test_dwconv(x.data_ptr(), out.data_ptr(), wt.data_ptr(), b.data_ptr(), N, L, C, K, _s()))
     torch.cuda.synchronize()
     ref = torch.nn.functional.conv1d(x.float().permute(0, 2, 1), w, b, padding=K // 2, groups=C).permute(0, 2, 1)
     ref = _swoosh_r(ref)
-    return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=5e-3)
+    return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=8e-4)
 
 
 def check_cfg_euler(B=3, T=50, F=100, cfg=1, seed=0):
@@ -264,11 +262,13 @@ def assert_ok(name, r):
 
 ALL = {
     "linear_basic": lambda: check_linear(M=300, K=512, N=272),
-    "linear_k48": lambda: check_linear(M=257, K=48, N=512, resid=True, out_mode=2),
+    "linear_k48": lambda: check_linear(M=257, K=48, N=512, resid=True),
     "linear_k300": lambda: check_linear(M=130, K=300, N=512),
     "linear_swoosh": lambda: check_linear(M=1000, K=512, N=1152, act=1),
-    "linear_big": lambda: check_linear(M=20000, K=1536, N=512, resid=True, out_mode=2),
-    "linear_resid_f32only": lambda: check_linear(M=777, K=384, N=512, resid=True, out_mode=1),
+    "linear_big": lambda: check_linear(M=20000, K=1536, N=512, resid=True),
+    "linear_bypass": lambda: check_linear(M=3000, K=1536, N=512, resid=True, bypass=True),
+    "linear_resid_n192": lambda: check_linear(M=777, K=384, N=192, resid=True),
+    "linear_bypass_n192": lambda: check_linear(M=130, K=96, N=192, resid=True, bypass=True),
     "linear_f32_n100": lambda: check_linear(M=333, K=512, N=100, out_mode=1),
     "linear_n1920_swoosh": lambda: check_linear(M=5000, K=512, N=1920, act=1),
     "gated_tanh": lambda: check_gated(M=300, n_out=384, mode=1),

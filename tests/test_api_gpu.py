@@ -10,7 +10,7 @@ from zipvoice_b200.synth import synth_state_dict, synth_utterances
 from util import CASE_CFG, load_golden, max_abs, rel_l2
 
 pytestmark = pytest.mark.gpu
-TOL_X_REL, TOL_X_ABS = 1e-2, 0.10
+TOL_X_REL, TOL_X_ABS = 4e-3, 0.04
 
 
 @pytest.fixture(scope="module")
@@ -65,7 +65,7 @@ def test_forward_fm_decoder_scalar_and_batched_t(tiny):
     oracle = orc.OracleModel(cfg, sd)
     want = orc.forward_fm_decoder(oracle.sd, oracle.fc, torch.tensor(0.37), u["x0"], gold["text_condition"],
                                   gold["speech_condition"], gold["padding_mask"])
-    assert rel_l2(a, want) <= 8e-3
+    assert rel_l2(a, want) <= 3e-3
 
 
 def test_guidance_zero_takes_the_single_pass_path(tiny):

@@ -13,18 +13,16 @@ from zipvoice_b200 import _lib  # noqa: E402
 
 def run(M, K, N, out_mode=0, act=0, resid=False, block_n=0, reps=5):
     lib = _lib.load()
-    A = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
-    W = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+    A = (torch.randn(M, K, device="cuda") * 0.5).to(torch.float16)
+    W = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(torch.float16)
     b = torch.randn(N, device="cuda")
-    R = torch.randn(M, N, device="cuda") if resid else None
-    out = torch.empty(M, N, dtype=torch.bfloat16 if out_mode == 0 else torch.float32, device="cuda")
-    sh = torch.empty(M, N, dtype=torch.bfloat16, device="cuda") if out_mode == 2 else None
+    R = torch.randn(M, N, device="cuda").to(torch.float16) if resid else None
+    out = torch.empty(M, N, dtype=torch.float16 if out_mode == 0 else torch.float32, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
 
     def go():
         _lib.check(lib.zvb_test_linear(A.data_ptr(), M, K, K, W.data_ptr(), b.data_ptr(), N, K, block_n, act,
-                                       R.data_ptr() if resid else None, out.data_ptr(),
-                                       sh.data_ptr() if sh is not None else None, N, out_mode, s))
+                                       R.data_ptr() if resid else None, None, None, out.data_ptr(), N, out_mode, s))
     go()
     torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -52,6 +50,6 @@ if __name__ == "__main__":
     for N in (256, 1024, 2048):
         run(M, 512, N)
     run(M, 512, 1536, act=1)
-    run(M, 1536, 512, out_mode=2, resid=True)
-    run(M, 512, 512, out_mode=2, resid=True)
+    run(M, 1536, 512, resid=True)
+    run(M, 512, 512, resid=True)
     run(8192, 8192, 8192)

@@ -3,6 +3,6 @@ from gemm_sweep import run
 M=156032
 for N in (1152,1536,1920):
     run(M,512,N,act=1)
-run(M,512,512); run(M,512,512,out_mode=2,resid=True)
-run(M,384,512,out_mode=2,resid=True)
+run(M,512,512); run(M,512,512,resid=True)
+run(M,384,512,resid=True)
 run(M,512,272); run(M,512,384)

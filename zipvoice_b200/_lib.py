@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libzipvoice_b200.so")
 
-ZVB_ABI_VERSION = 1
+ZVB_ABI_VERSION = 2
 ZVB_MAX_STACKS = 8
 
 
@@ -71,14 +71,14 @@ EXPORTS = {
     "zvb_decoder_forward_f32": (C.c_int, [C.c_void_p] * 7),
     "zvb_sample": (C.c_int, [C.c_void_p] * 8 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "zvb_test_linear": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
-                                  C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
-                                  C.c_void_p]),
+                                  C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_int, C.c_void_p]),
     "zvb_test_attn_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "zvb_test_pv": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),
     "zvb_test_gated": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
-    "zvb_test_biasnorm_bypass": (C.c_int, [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3 +
+    "zvb_test_biasnorm_bypass": (C.c_int, [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 3 +
                                  [C.c_longlong, C.c_int, C.c_void_p]),
     "zvb_test_dwconv": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]),
     "zvb_test_cfg_euler": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int,

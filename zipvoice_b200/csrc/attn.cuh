@@ -7,7 +7,7 @@
 // window of 255 relative offsets.  Softmax is split so that every score costs one exp and one
 // bias evaluation: pass 1 only takes the row max of q·kᵀ from TMEM (no bias, no exp); with
 // m = max_j q·k_j + |p_i|·max_r|E_h[r]| >= every score of the row, pass 2 recomputes the cheap q·kᵀ,
-// adds the bias and writes the UNNORMALISED weights exp(s - m) in (0, 1] as bf16 together with the
+// adds the bias and writes the UNNORMALISED weights exp(s - m) in (0, 1] as fp16 together with the
 // fp32 row sum's reciprocal; the three consumers of the layer (NonlinAttention, SelfAttention x2)
 // apply 1/l in their GEMM epilogue.  Masked keys get exactly 0 (exp(-1000 - m) == 0 in fp32).
 // The softmax is latency bound (TMEM load -> LDS of the rel-pos entries -> FFMA chain -> MUFU), so a
@@ -22,7 +22,7 @@ namespace zvb {
 constexpr int ATT_BM = 128;          // queries per CTA
 constexpr int ATT_BN = 128;          // keys per score tile
 constexpr int ATT_KSTAGES = 3;
-constexpr int ATT_TILE_BYTES = 128 * 64 * 2;      // one 128-row x 64-col bf16 box (only 32 cols used)
+constexpr int ATT_TILE_BYTES = 128 * 64 * 2;      // one 128-row x 64-col fp16 box (only 32 cols used)
 constexpr int ATT_SM_WARPS = 8;      // softmax warps: two per TMEM lane quarter, 64 key columns each
 constexpr int ATT_THREADS = 64 + 32 * ATT_SM_WARPS;
 constexpr int ATT_TMEM_COLS = 256;
@@ -34,11 +34,11 @@ constexpr int ATT_SMEM_BYTES = (1 + ATT_KSTAGES) * ATT_TILE_BYTES + ATT_STAGE_BY
 struct AttnParams {
     int L, Lk, H, N;
     int qd;                          // H * 32: column of head-0 keys inside a qkp row
-    const __nv_bfloat16* qkp;        // [N*L, ld] = [q | k | p]
+    const __half* qkp;        // [N*L, ld] = [q | k | p]
     int ld;
     const float* E;                  // [H][2L-1][4] followed by [H] floats: max_r |E[h][r]|_2
     const uint8_t* mask;             // [N][L], non-zero = padded key
-    __nv_bfloat16* P;                // [N][H][L][Lk] unnormalised weights exp(s - m) (written through tma_p)
+    __half* P;                // [N][H][L][Lk] unnormalised weights exp(s - m) (written through tma_p)
     float* inv_l;                    // [N][H][L]     1 / row sum
 };
 
@@ -112,7 +112,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
         }
     } else if (warp == ATT_SM_WARPS + 1) {                // MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(ATT_BN);
+            const uint32_t idesc = umma_idesc_f16(ATT_BN);
             mbar_wait(q_full, 0);
             tc_fence_after();
             const uint64_t dq = umma_desc_k_sw128(smem_u32(q_tile));
@@ -126,8 +126,8 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
                 tc_fence_after();
                 const uint64_t dk = umma_desc_k_sw128(smem_u32(k_tiles + stage * ATT_TILE_BYTES));
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc) * ATT_BN;
-                umma_bf16(tmem_d, dq, dk, idesc, 0u);            // head-dim columns  0..15
-                umma_bf16(tmem_d, dq + 2, dk + 2, idesc, 1u);    // head-dim columns 16..31
+                umma_f16(tmem_d, dq, dk, idesc, 0u);            // head-dim columns  0..15
+                umma_f16(tmem_d, dq + 2, dk + 2, idesc, 1u);    // head-dim columns 16..31
                 umma_commit(&k_empty[stage]);
                 umma_commit(&s_full[acc]);
                 if (++stage == ATT_KSTAGES) { stage = 0; phase ^= 1u; }
@@ -144,9 +144,9 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
         const bool row_ok = i < p.L;
         float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
         if (row_ok) {
-            const __nv_bfloat16* pp = p.qkp + (static_cast<long long>(n) * p.L + i) * p.ld + 2 * p.qd + h * 4;
+            const __half* pp = p.qkp + (static_cast<long long>(n) * p.L + i) * p.ld + 2 * p.qd + h * 4;
             const uint2 w = *reinterpret_cast<const uint2*>(pp);
-            p0 = bf16_lo(w.x); p1 = bf16_hi(w.x); p2 = bf16_lo(w.y); p3 = bf16_hi(w.y);
+            p0 = h2_lo(w.x); p1 = h2_hi(w.x); p2 = h2_lo(w.y); p3 = h2_hi(w.y);
         }
         const float4* Eh = reinterpret_cast<const float4*>(p.E) + static_cast<long long>(h) * (2 * p.L - 1);
         const uint8_t* mrow = p.mask + static_cast<long long>(n) * p.L;
@@ -259,7 +259,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
 #pragma unroll
                     for (int c = 0; c < 16; c += 2) {
                         const float a = __uint_as_float(sr[c]), b = __uint_as_float(sr[c + 1]);
-                        w[c >> 1] = pack_bf16(a, b);
+                        w[c >> 1] = pack_h2(a, b);
                         ls += a + b;
                     }
                     l_run += ls;

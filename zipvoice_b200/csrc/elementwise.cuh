@@ -1,5 +1,5 @@
 // Memory-bound kernels of the TTSZipformer forward and of the sampler: fused, coalesced,
-// 16-byte vectorised, warp-shuffle reductions.  Activations are (N, L, C) bf16, channel
+// 16-byte vectorised, warp-shuffle reductions.  Activations are (N, L, C) fp16, channel
 // contiguous; the ODE state and velocities are fp32.
 #pragma once
 #include "ptx.cuh"
@@ -7,69 +7,73 @@
 namespace zvb {
 
 __device__ __forceinline__ void unpack8(const uint4& w, float* v) {
-    v[0] = bf16_lo(w.x); v[1] = bf16_hi(w.x); v[2] = bf16_lo(w.y); v[3] = bf16_hi(w.y);
-    v[4] = bf16_lo(w.z); v[5] = bf16_hi(w.z); v[6] = bf16_lo(w.w); v[7] = bf16_hi(w.w);
+    v[0] = h2_lo(w.x); v[1] = h2_hi(w.x); v[2] = h2_lo(w.y); v[3] = h2_hi(w.y);
+    v[4] = h2_lo(w.z); v[5] = h2_hi(w.z); v[6] = h2_lo(w.w); v[7] = h2_hi(w.w);
 }
 __device__ __forceinline__ uint4 pack8(const float* v) {
-    return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                      pack_bf16(v[6], v[7]));
+    return make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]),
+                      pack_h2(v[6], v[7]));
 }
 
 // ---------------------------------------------------------------------------------------
-// The residual stream is fp32 (N, L, C); kernels that end a module also emit the bf16 shadow copy
-// the next tensor-core kernel consumes (and the copy with the time embedding added, reference:
-// modules/zipformer.py:532-534).
-__device__ __forceinline__ void load8f(const float* p, float* v) {
-    const float4 a = *reinterpret_cast<const float4*>(p);
-    const float4 b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void store8f(float* p, const float* v) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
+// The residual stream is fp16 (N, L, C) and is itself the A operand of the next tensor-core kernel;
+// kernels that start a module on `src + time_emb` (reference: modules/zipformer.py:532-534) read the
+// separate time-embedded copy written here.  All arithmetic is fp32.
 
 // streaming 16-byte load that does not allocate in L1 (every element is read exactly once)
-__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
+}
+__device__ __forceinline__ void load8h(const __half* p, float* v) {
+    unpack8(*reinterpret_cast<const uint4*>(p), v);
+}
+__device__ __forceinline__ void store8h(__half* p, const float* v) {
+    *reinterpret_cast<uint4*>(p) = pack8(v);
 }
 
 // BiasNorm + bypass (reference: modules/scaling.py:358-363, modules/zipformer.py:634-637,
 // 803-804):  y = x * rsqrt(mean((x-b)^2)) * exp(log_scale);  out = orig + (y-orig)*scale.
-// One warp per row, C <= 128*KMAX, C % 4 == 0.  Lane l owns the float4 at channel 4*(32k + l): every
-// warp instruction moves one contiguous 512-byte (fp32) / 256-byte (bf16) segment, and both operands
-// of the row are requested before the reduction so each lane has 2*KMAX 16-byte loads in flight.
-// Outputs (each nullable): fp32 stream `out`, bf16 shadow `out_b`, bf16 `out_t` = out + temb[row / rows_per_group].
+// One warp per row, C <= 256*KMAX, C % 8 == 0.  Lane l owns the 8 channels at 8*(32k + l): every warp
+// instruction moves one contiguous 512-byte segment, and both operands of the row are requested
+// before the reduction so each lane has 2*KMAX 16-byte loads in flight.
+// Outputs (each nullable): stream `out`, `out_t` = out + temb[row / rows_per_group].
 template <int KMAX>
 __global__ void __launch_bounds__(256)
-biasnorm_bypass_kernel(const float* __restrict__ src, const float* __restrict__ orig,
-                       float* __restrict__ out, __nv_bfloat16* __restrict__ out_b,
-                       __nv_bfloat16* __restrict__ out_t, const float* __restrict__ temb, int rows_per_group,
+biasnorm_bypass_kernel(const __half* __restrict__ src, const __half* __restrict__ orig,
+                       __half* __restrict__ out, __half* __restrict__ out_t,
+                       const float* __restrict__ temb, int rows_per_group,
                        const float* __restrict__ nbias, const float* __restrict__ log_scale,
                        const float* __restrict__ bscale, long long rows, int C) {
     const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
-    float4 x[KMAX], o[KMAX];
+    uint4 xr[KMAX], orr[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
-        const int c = (k * 32 + lane) * 4;
+        const int c = (k * 32 + lane) * 8;
         if (c < C) {
-            x[k] = ld_stream_f4(src + row * C + c);
-            o[k] = ld_stream_f4(orig + row * C + c);
+            xr[k] = ld_stream_u4(src + row * C + c);
+            orr[k] = ld_stream_u4(orig + row * C + c);
         }
     }
     float ss = 0.f;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
-        const int c = (k * 32 + lane) * 4;
+        const int c = (k * 32 + lane) * 8;
         if (c < C) {
-            const float4 nb = __ldg(reinterpret_cast<const float4*>(nbias + c));
-            const float d0 = x[k].x - nb.x, d1 = x[k].y - nb.y, d2 = x[k].z - nb.z, d3 = x[k].w - nb.w;
-            ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
+            float x[8];
+            unpack8(xr[k], x);
+            const float4 n0 = __ldg(reinterpret_cast<const float4*>(nbias + c));
+            const float4 n1 = __ldg(reinterpret_cast<const float4*>(nbias + c + 4));
+            const float nb[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float d = x[i] - nb[i];
+                ss = fmaf(d, d, ss);
+            }
         }
     }
 #pragma unroll
@@ -78,30 +82,32 @@ biasnorm_bypass_kernel(const float* __restrict__ src, const float* __restrict__ 
     const long long grp = out_t != nullptr ? row / rows_per_group : 0;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
-        const int c = (k * 32 + lane) * 4;
+        const int c = (k * 32 + lane) * 8;
         if (c < C) {
-            const float4 bs = __ldg(reinterpret_cast<const float4*>(bscale + c));
-            float4 y;
-            y.x = o[k].x + (x[k].x * scale - o[k].x) * bs.x;
-            y.y = o[k].y + (x[k].y * scale - o[k].y) * bs.y;
-            y.z = o[k].z + (x[k].z * scale - o[k].z) * bs.z;
-            y.w = o[k].w + (x[k].w * scale - o[k].w) * bs.w;
-            if (out != nullptr) *reinterpret_cast<float4*>(out + row * C + c) = y;
-            if (out_b != nullptr)
-                *reinterpret_cast<uint2*>(out_b + row * C + c) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+            float x[8], o[8], y[8];
+            unpack8(xr[k], x);
+            unpack8(orr[k], o);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bscale + c));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bscale + c + 4));
+            const float bs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = o[i] + (x[i] * scale - o[i]) * bs[i];
+            if (out != nullptr) store8h(out + row * C + c, y);
             if (out_t != nullptr) {
-                const float4 tb = __ldg(reinterpret_cast<const float4*>(temb + grp * C + c));
-                *reinterpret_cast<uint2*>(out_t + row * C + c) =
-                    make_uint2(pack_bf16(y.x + tb.x, y.y + tb.y), pack_bf16(y.z + tb.z, y.w + tb.w));
+                const float4 t0 = __ldg(reinterpret_cast<const float4*>(temb + grp * C + c));
+                const float4 t1 = __ldg(reinterpret_cast<const float4*>(temb + grp * C + c + 4));
+                y[0] += t0.x; y[1] += t0.y; y[2] += t0.z; y[3] += t0.w;
+                y[4] += t1.x; y[5] += t1.y; y[6] += t1.z; y[7] += t1.w;
+                store8h(out_t + row * C + c, y);
             }
         }
     }
 }
 
-// Stack entry: bf16 shadow of the fp32 stream and its time-embedded copy (each nullable):
-// xb = bf16(x), xt = bf16(x + temb[row / L])   (reference: modules/zipformer.py:532-534)
+// Stack entry: the time-embedded copy of the stream, xt = x + temb[row / L]
+// (reference: modules/zipformer.py:532-534)
 __global__ void __launch_bounds__(256)
-stream_prep_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, __nv_bfloat16* __restrict__ xt,
+stream_prep_kernel(const __half* __restrict__ x, __half* __restrict__ xt,
                    const float* __restrict__ temb, int rows_per_group, long long rows, int C) {
     const int cv = C >> 3;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -109,20 +115,17 @@ stream_prep_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, 
     const long long row = idx / cv;
     const int c = static_cast<int>(idx - row * cv) * 8;
     float v[8];
-    load8f(x + row * C + c, v);
-    if (xb != nullptr) *reinterpret_cast<uint4*>(xb + row * C + c) = pack8(v);
-    if (xt != nullptr) {
-        const long long grp = row / rows_per_group;
+    load8h(x + row * C + c, v);
+    const long long grp = row / rows_per_group;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += __ldg(temb + grp * C + c + i);
-        *reinterpret_cast<uint4*>(xt + row * C + c) = pack8(v);
-    }
+    for (int i = 0; i < 8; ++i) v[i] += __ldg(temb + grp * C + c + i);
+    store8h(xt + row * C + c, v);
 }
 
 // SimpleDownsample (reference: modules/zipformer.py:887-913): weighted sum over groups of ds
 // frames, right-padded by repeating frame L-1.  w = softmax(bias) precomputed on the host.
 __global__ void __launch_bounds__(256)
-downsample_kernel(const float* __restrict__ src, float* __restrict__ out, int N, int L,
+downsample_kernel(const __half* __restrict__ src, __half* __restrict__ out, int N, int L,
                   int Ld, int ds, float w0, float w1, float w2, float w3, int C) {
     const int cv = C >> 3;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -137,19 +140,19 @@ downsample_kernel(const float* __restrict__ src, float* __restrict__ out, int N,
         int l = ld * ds + k;
         l = l < L ? l : L - 1;
         float v[8];
-        load8f(src + (static_cast<long long>(n) * L + l) * C + c, v);
+        load8h(src + (static_cast<long long>(n) * L + l) * C + c, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i], w[k], acc[i]);
     }
-    store8f(out + (static_cast<long long>(n) * Ld + ld) * C + c, acc);
+    store8h(out + (static_cast<long long>(n) * Ld + ld) * C + c, acc);
 }
 
 // SimpleUpsample + truncate + out_combiner bypass (reference: modules/zipformer.py:866-870,
-// 925-935):  out[n,l] = orig[n,l] + (y[n, l/ds] - orig[n,l]) * scale   (+ optional bf16 shadow)
+// 925-935):  out[n,l] = orig[n,l] + (y[n, l/ds] - orig[n,l]) * scale
 __global__ void __launch_bounds__(256)
-upsample_combine_kernel(const float* __restrict__ orig, const float* __restrict__ y,
-                        float* __restrict__ out, __nv_bfloat16* __restrict__ out_b,
-                        const float* __restrict__ scale, int N, int L, int Ld, int ds, int C) {
+upsample_combine_kernel(const __half* __restrict__ orig, const __half* __restrict__ y,
+                        __half* __restrict__ out, const float* __restrict__ scale, int N, int L, int Ld,
+                        int ds, int C) {
     const int cv = C >> 3;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= static_cast<long long>(N) * L * cv) return;
@@ -158,12 +161,11 @@ upsample_combine_kernel(const float* __restrict__ orig, const float* __restrict_
     const int l = static_cast<int>(rl % L);
     const int n = static_cast<int>(rl / L);
     float o[8], v[8];
-    load8f(orig + rl * C + c, o);
-    load8f(y + (static_cast<long long>(n) * Ld + l / ds) * C + c, v);
+    load8h(orig + rl * C + c, o);
+    load8h(y + (static_cast<long long>(n) * Ld + l / ds) * C + c, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = o[i] + (v[i] - o[i]) * __ldg(scale + c + i);
-    store8f(out + rl * C + c, v);
-    if (out_b != nullptr) *reinterpret_cast<uint4*>(out_b + rl * C + c) = pack8(v);
+    store8h(out + rl * C + c, v);
 }
 
 // Depthwise Conv1d over time (cross-correlation, zero padding K/2) + bias + SwooshR
@@ -200,18 +202,18 @@ __device__ __forceinline__ void swoosh_r_pair(f32x2 acc, float& o0, float& o1) {
     o1 = fmaf(fabsf(y1), 0.5f, r1);
 }
 
-// tma_x: x viewed as (C, L, N) bf16, box = 64 channels x (DW_TT + K - 1) frames, no swizzle.
+// tma_x: x viewed as (C, L, N) fp16, box = 64 channels x (DW_TT + K - 1) frames, no swizzle.
 // grid = (blocks per channel group, channel groups); tiles = N * ceil(L / DW_TT) per channel group.
 template <int K>
 __global__ void __launch_bounds__(256, 3)
-dwconv_swooshr_kernel(const __grid_constant__ CUtensorMap tma_x, __nv_bfloat16* __restrict__ out,
+dwconv_swooshr_kernel(const __grid_constant__ CUtensorMap tma_x, __half* __restrict__ out,
                       const float* __restrict__ wt /*[K][C]*/, const float* __restrict__ bias, int L,
                       int C, int N) {
     constexpr int HALF = K / 2, WIN = DW_TT + K - 1, NW = DW_OT + K - 1;
     extern __shared__ uint8_t dw_smem_raw[];
     const uint32_t raw = smem_u32(dw_smem_raw);
     uint8_t* smem = dw_smem_raw + (((raw + 127u) & ~127u) - raw);
-    uint32_t* tile = reinterpret_cast<uint32_t*>(smem);                       // [2][WIN][32] bf16 pairs
+    uint32_t* tile = reinterpret_cast<uint32_t*>(smem);                       // [2][WIN][32] fp16 pairs
     float2* wsm = reinterpret_cast<float2*>(smem + 2 * WIN * 128);           // [K][32]
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * WIN * 128 + K * 32 * 8);   // [2]
     const int c0 = blockIdx.y * 64;
@@ -253,7 +255,7 @@ dwconv_swooshr_kernel(const __grid_constant__ CUtensorMap tma_x, __nv_bfloat16* 
 #pragma unroll
         for (int q = 0; q < NW; ++q) {
             const uint32_t u = tb[q * 32];
-            win[q] = pack2(bf16_lo(u), bf16_hi(u));
+            win[q] = pack2(h2_lo(u), h2_hi(u));
         }
         f32x2 acc[DW_OT];
 #pragma unroll
@@ -266,13 +268,13 @@ dwconv_swooshr_kernel(const __grid_constant__ CUtensorMap tma_x, __nv_bfloat16* 
         }
         const int n = tl / n_tt;
         const int t0 = (tl - n * n_tt) * DW_TT + tg * DW_OT;
-        __nv_bfloat16* on = out + (static_cast<long long>(n) * L + t0) * C + c0 + 2 * cp;
+        __half* on = out + (static_cast<long long>(n) * L + t0) * C + c0 + 2 * cp;
         if (ch_ok) {
 #pragma unroll
             for (int o = 0; o < DW_OT; ++o) {
                 float a0, a1;
                 swoosh_r_pair(acc[o], a0, a1);
-                if (t0 + o < L) *reinterpret_cast<uint32_t*>(on + static_cast<long long>(o) * C) = pack_bf16(a0, a1);
+                if (t0 + o < L) *reinterpret_cast<uint32_t*>(on + static_cast<long long>(o) * C) = pack_h2(a0, a1);
             }
         }
         __syncthreads();                        // the window reads of this buffer are done: it may be refilled
@@ -321,12 +323,12 @@ small_linear_kernel(const float* __restrict__ in, const float* __restrict__ W, c
 
 // ---------------------------------------------------------------------------------------
 // Decoder input assembly (reference: models/zipvoice.py:163 and modules/solver.py:83-98):
-// xin[n] = [x | text | speech] as bf16, zero-padded to `ldx` columns.  With cfg != 0 the batch
+// xin[n] = [x | text | speech] as fp16, zero-padded to `ldx` columns.  With cfg != 0 the batch
 // is doubled as [uncond ; cond]: uncond rows get text = 0 and, when drop_speech != 0
 // (t > 0.5), speech = 0.
 __global__ void __launch_bounds__(256)
 assemble_input_kernel(const float* __restrict__ x, const float* __restrict__ text,
-                      const float* __restrict__ speech, __nv_bfloat16* __restrict__ xin, int B, int T,
+                      const float* __restrict__ speech, __half* __restrict__ xin, int B, int T,
                       int F, int Ft, int ldx, int cfg, int drop_speech) {
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int N = cfg ? 2 * B : B;
@@ -341,17 +343,17 @@ assemble_input_kernel(const float* __restrict__ x, const float* __restrict__ tex
     if (c < F) v = x[r * F + c];
     else if (c < F + Ft) v = uncond ? 0.f : text[r * Ft + (c - F)];
     else if (c < 2 * F + Ft) v = (uncond && drop_speech) ? 0.f : speech[r * F + (c - F - Ft)];
-    xin[idx] = __float2bfloat16(v);
+    xin[idx] = f2h(v);
 }
 
-// fp32 (rows, C) -> bf16 (rows, ldx) zero padded (seam-1 entry: caller passes the concatenated x)
+// fp32 (rows, C) -> fp16 (rows, ldx) zero padded (seam-1 entry: caller passes the concatenated x)
 __global__ void __launch_bounds__(256)
-cast_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int C, int ldx) {
+cast_pad_kernel(const float* __restrict__ x, __half* __restrict__ out, long long rows, int C, int ldx) {
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= rows * ldx) return;
     const int c = static_cast<int>(idx % ldx);
     const long long r = idx / ldx;
-    out[idx] = __float2bfloat16(c < C ? x[r * C + c] : 0.f);
+    out[idx] = f2h(c < C ? x[r * C + c] : 0.f);
 }
 
 // CFG blend + Euler update (reference: modules/solver.py:100-110, 239):

@@ -20,7 +20,7 @@ namespace zvb { constexpr int ACT_SWOOSH_R_ = 2; }
 #include "elementwise.cuh"
 
 using namespace zvb;
-typedef __nv_bfloat16 bf16;
+typedef __half h16;
 
 // ------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -93,12 +93,10 @@ static int init_device() {
     return 0;
 }
 
-// Tensor (dim0 fastest) viewed as 3-D, box = (128 bytes, box1, 1) with 128B swizzle -- or, with
-// half_row, box = (64 bytes, box1, 1) with 64B swizzle (the bf16 shadow of a 32-column fp32 sub-tile).
+// Tensor (dim0 fastest) viewed as 3-D, box = (128 bytes, box1, 1) with 128B swizzle.
 // Out-of-range elements are zero-filled on loads and clipped on stores.
 static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
-                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box1, bool f32 = false,
-                     bool half_row = false) {
+                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box1, bool f32 = false) {
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (stride1_bytes & 15) != 0 || (stride2_bytes & 15) != 0)
         return fail(ZVB_ERR_INVALID, "tensor map: pointer/strides must be 16-byte aligned");
     if (box1 == 0 || box1 > 256 || d0 == 0 || d1 == 0 || d2 == 0)
@@ -106,17 +104,17 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
                     (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
     cuuint64_t dims[3] = {d0, d1, d2};
     cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
-    cuuint32_t box[3] = {(f32 ? 32u : 64u) / (half_row ? 2u : 1u), box1, 1};
+    cuuint32_t box[3] = {f32 ? 32u : 64u, box1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+    CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
                           const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          half_row ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ZVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }
 
-// bf16 tensor, box = (box0 elements, box1, 1), no swizzle (rows of the box are contiguous in shared memory)
+// h16 tensor, box = (box0 elements, box1, 1), no swizzle (rows of the box are contiguous in shared memory)
 static int make_tmap_plain(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
                            uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (stride1_bytes & 15) != 0 || (stride2_bytes & 15) != 0)
@@ -127,7 +125,7 @@ static int make_tmap_plain(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_
     cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
     cuuint32_t box[3] = {box0, box1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ZVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -140,8 +138,8 @@ enum OpType { OP_GEMM, OP_ATTN, OP_BIASNORM, OP_PREP, OP_DOWN, OP_UP, OP_DWCONV,
 struct Op {
     OpType type;
     // GEMM / ATTN
-    CUtensorMap ma, mb, mx, ms, ms2, mo;     // A, B, epilogue operand, output, bf16 shadow output, bypass orig
-    bool has_mx = false, has_ms = false, has_ms2 = false, has_mo = false;
+    CUtensorMap ma, mb, mx, ms, mo;          // A, B, epilogue operand, output, bypass orig
+    bool has_mx = false, has_ms = false, has_mo = false;
     GemmParams gp;
     int kind = 0, grid = 0, cluster = 1;
     AttnParams ap;
@@ -160,7 +158,7 @@ struct Op {
 };
 
 static int pick_block_n(int n_out, long long m_tiles) {
-    // TMA stores move 64-column (bf16) sub-tiles, so tile widths that are multiples of 64 are preferred
+    // TMA stores move 64-column (h16) sub-tiles, so tile widths that are multiples of 64 are preferred
     // when they waste < 8% of the MMA work; otherwise the narrowest multiple of 16 that covers n_out.
     if (n_out >= 64) {
         int best = 0;
@@ -185,8 +183,8 @@ static int pick_block_n(int n_out, long long m_tiles) {
 // Output tensor maps for the TMA-store epilogue; eligible when whole 128-byte sub-tiles belong to one tile.
 static int setup_tma_store(Op& op, int batches_rows /*rows per batch*/, int nbatch) {
     GemmParams& p = op.gp;
-    const bool f32 = p.out_mode == OUT_F32 || p.out_mode == OUT_F32_BF16;
-    const bool bf = p.out_mode == OUT_BF16;
+    const bool f32 = p.out_mode == OUT_F32;
+    const bool bf = p.out_mode == OUT_H16;
     if (!g_tma_store_ok || !(f32 || bf)) return 0;
     if (op.kind == EPI_LINEAR) {
         if (p.out_col_stride != p.block_n) return 0;
@@ -195,16 +193,10 @@ static int setup_tma_store(Op& op, int batches_rows /*rows per batch*/, int nbat
         return 0;
     }
     if ((p.ldc * (f32 ? 4 : 2)) % 16 != 0) return 0;
-    if (p.out_mode == OUT_F32_BF16 && (p.ldc * 2) % 16 != 0) return 0;
     const uint64_t esz = f32 ? 4 : 2;
     TRY(make_tmap(&op.ms, p.out, p.n_out, batches_rows, nbatch, (uint64_t)p.ldc * esz,
                   (uint64_t)p.ldc * esz * batches_rows, GEMM_BLOCK_M, f32));
     op.has_ms = true;
-    if (p.out_mode == OUT_F32_BF16) {
-        TRY(make_tmap(&op.ms2, p.out_bf16, p.n_out, batches_rows, nbatch, (uint64_t)p.ldc * 2,
-                      (uint64_t)p.ldc * 2 * batches_rows, GEMM_BLOCK_M, false, true));
-        op.has_ms2 = true;
-    }
     p.tma_store = 1;
     return 0;
 }
@@ -213,14 +205,13 @@ static void gp_defaults(GemmParams& p) { memset(&p, 0, sizeof p); p.rows_per_gro
 
 struct LinearEpi {
     int act = ACT_NONE;
-    const float* resid = nullptr;        // fp32 residual stream tile (TMA aux ring), pitch = ldc
+    const h16* resid = nullptr;          // fp16 residual stream tile (TMA aux ring), pitch = ldc
     const float* rowbias = nullptr;
     int rows_per_group = 1;
-    const float* orig = nullptr;         // fp32, pitch = ldc
+    const h16* orig = nullptr;           // bypass operand, fp16, pitch = ldc (needs resid and bypass_scale)
     const float* bypass_scale = nullptr;
-    int out_mode = OUT_BF16;
-    bf16* out_bf16 = nullptr;            // OUT_F32_BF16 shadow
-    int t_L = 0, t_pitch = 0, t_batch_rows = 0, t_hd = 1, t_hp = 1;   // OUT_T_BF16
+    int out_mode = OUT_H16;
+    int t_L = 0, t_pitch = 0, t_batch_rows = 0, t_hd = 1, t_hp = 1;   // OUT_T_H16
     int block_n = 0;                     // 0 = choose
 };
 
@@ -244,7 +235,7 @@ static void set_grid(Op& op) {
 static inline uint32_t b_box_rows(const Op& op) { return op.gp.block_n / op.cluster; }
 
 // out[M, n_out] = epi(A[M, K] · W[n_out, K]ᵀ + b)
-static int build_linear(Op& op, const bf16* A, long long M, int lda, const zvb_linear& lin, void* out, int ldc,
+static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_linear& lin, void* out, int ldc,
                         const LinearEpi& e) {
     op.type = OP_GEMM;
     op.kind = EPI_LINEAR;
@@ -261,11 +252,11 @@ static int build_linear(Op& op, const bf16* A, long long M, int lda, const zvb_l
     p.num_m_tiles = static_cast<int>(m_tiles);
     p.num_n_tiles = (lin.out_features + bn - 1) / bn;
     p.batches = 1;
-    p.out_mode = e.out_mode; p.out = out; p.out_bf16 = e.out_bf16; p.ldc = ldc;
+    p.out_mode = e.out_mode; p.out = out; p.ldc = ldc;
     p.out_col_stride = bn; p.n_valid = bn;
     p.bias = lin.b;
     p.rowbias = e.rowbias; p.rows_per_group = e.rows_per_group; p.ld_rowbias = lin.out_features;
-    p.orig = e.orig; p.bypass_scale = e.bypass_scale;
+    p.bypass_scale = e.bypass_scale;
     p.act = e.act;
     p.t_L = e.t_L; p.t_pitch = e.t_pitch; p.t_batch_rows = e.t_batch_rows; p.t_hd = e.t_hd; p.t_hp = e.t_hp;
     set_grid(op);
@@ -273,16 +264,19 @@ static int build_linear(Op& op, const bf16* A, long long M, int lda, const zvb_l
     TRY(make_tmap(&op.mb, lin.w, K, lin.rows, 1, (uint64_t)lin.k_pitch * 2, (uint64_t)lin.k_pitch * 2 * lin.rows,
                   b_box_rows(op)));
     if (e.resid != nullptr) {
-        if (ldc % 4 != 0) return fail(ZVB_ERR_INVALID, "linear: fp32 residual pitch must be a multiple of 4");
-        p.aux_mode = AUX_RESID_F32; p.aux_zb = 0;
-        TRY(make_tmap(&op.mx, e.resid, ldc, M, 1, (uint64_t)ldc * 4, (uint64_t)ldc * 4 * M, GEMM_BLOCK_M, true));
+        if (e.out_mode != OUT_H16 || ldc % 8 != 0)
+            return fail(ZVB_ERR_INVALID, "linear: a residual needs an fp16 output with a pitch that is a multiple of 8");
+        p.aux_mode = AUX_ADD_H16; p.aux_zb = 0;
+        TRY(make_tmap(&op.mx, e.resid, ldc, M, 1, (uint64_t)ldc * 2, (uint64_t)ldc * 2 * M, GEMM_BLOCK_M));
         op.has_mx = true;
     }
     TRY(setup_tma_store(op, (int)M, 1));
     // bypass: `orig` rides through the aux ring next to the residual sub-tiles
-    if (p.tma_store && e.orig != nullptr && p.aux_mode == AUX_RESID_F32 && lin.out_features % 32 == 0 &&
-        (reinterpret_cast<uintptr_t>(e.bypass_scale) & 15) == 0) {
-        TRY(make_tmap(&op.mo, e.orig, ldc, M, 1, (uint64_t)ldc * 4, (uint64_t)ldc * 4 * M, GEMM_BLOCK_M, true));
+    if (e.orig != nullptr) {
+        if (p.aux_mode != AUX_ADD_H16 || e.bypass_scale == nullptr || lin.out_features % 64 != 0 ||
+            (reinterpret_cast<uintptr_t>(e.bypass_scale) & 15) != 0)
+            return fail(ZVB_ERR_INVALID, "linear: bypass needs a residual, a 16-byte aligned scale and out_features %% 64 == 0");
+        TRY(make_tmap(&op.mo, e.orig, ldc, M, 1, (uint64_t)ldc * 2, (uint64_t)ldc * 2 * M, GEMM_BLOCK_M));
         op.has_mo = true;
         p.orig_tma = 1;
     }
@@ -293,7 +287,7 @@ static int build_linear(Op& op, const bf16* A, long long M, int lda, const zvb_l
 }
 
 // gated projection (weights packed per 256-row tile as [128 | 128]); n_out = gated outputs
-static int build_gated(Op& op, const bf16* A, long long M, int lda, const zvb_linear& lin, int n_out, int gate_mode,
+static int build_gated(Op& op, const h16* A, long long M, int lda, const zvb_linear& lin, int n_out, int gate_mode,
                        void* out, int ldc, const uint8_t* row_mask, const LinearEpi& e) {
     op.type = OP_GEMM;
     op.kind = EPI_GATED;
@@ -327,9 +321,9 @@ static int build_gated(Op& op, const bf16* A, long long M, int lda, const zvb_li
 
 // out[n*L+i, :] = P[n,h] · V  with V given transposed: Vt[n][rows][Lk].
 //   per_head != 0 (SelfAttention): head h uses Vt rows [h*hp, h*hp+hd) -> out cols [h*hd, (h+1)*hd)
-//   per_head == 0 (NonlinAttention): head 0 weights, all `hd` value columns, out *= mul (bf16 [N*L, ldm])
-static int build_pv(Op& op, const bf16* P, const float* inv_l, const bf16* Vt, void* out, int ldc, int N, int H, int L,
-                    int Lk, int hd, int hp, int per_head, const bf16* mul, int ldm) {
+//   per_head == 0 (NonlinAttention): head 0 weights, all `hd` value columns, out *= mul (h16 [N*L, ldm])
+static int build_pv(Op& op, const h16* P, const float* inv_l, const h16* Vt, void* out, int ldc, int N, int H, int L,
+                    int Lk, int hd, int hp, int per_head, const h16* mul, int ldm) {
     op.type = OP_GEMM;
     op.kind = EPI_LINEAR;
     GemmParams& p = op.gp;
@@ -340,7 +334,7 @@ static int build_pv(Op& op, const bf16* P, const float* inv_l, const bf16* Vt, v
     p.batches = N;
     p.b_zb = 1;
     p.a_zb = H;
-    p.out_mode = OUT_BF16; p.out = out; p.ldc = ldc;
+    p.out_mode = OUT_H16; p.out = out; p.ldc = ldc;
     p.rowscale = inv_l; p.rs_zb = H; p.rs_zn = per_head ? 1 : 0;
     int vt_rows;
     if (per_head) {
@@ -356,7 +350,7 @@ static int build_pv(Op& op, const bf16* P, const float* inv_l, const bf16* Vt, v
         vt_rows = hd;
         if (mul != nullptr) {
             if (ldm % 8 != 0) return fail(ZVB_ERR_INVALID, "pv: multiplier pitch must be a multiple of 8");
-            p.aux_mode = AUX_MUL_BF16; p.aux_zb = 1;
+            p.aux_mode = AUX_MUL_H16; p.aux_zb = 1;
             TRY(make_tmap(&op.mx, mul, ldm, L, N, (uint64_t)ldm * 2, (uint64_t)ldm * 2 * L, GEMM_BLOCK_M));
             op.has_mx = true;
         }
@@ -371,7 +365,7 @@ static int build_pv(Op& op, const bf16* P, const float* inv_l, const bf16* Vt, v
     return 0;
 }
 
-static int build_attn(Op& op, const bf16* qkp, int ld, const float* E, const uint8_t* mask, bf16* P, float* inv_l,
+static int build_attn(Op& op, const h16* qkp, int ld, const float* E, const uint8_t* mask, h16* P, float* inv_l,
                       int N, int H, int L, int Lk) {
     op.type = OP_ATTN;
     AttnParams& a = op.ap;
@@ -388,7 +382,7 @@ static int build_attn(Op& op, const bf16* qkp, int ld, const float* E, const uin
     return 0;
 }
 
-static int build_dwconv(Op& d, const bf16* x, bf16* out, const float* w, const float* b, int N, int L, int C, int K) {
+static int build_dwconv(Op& d, const h16* x, h16* out, const float* w, const float* b, int N, int L, int C, int K) {
     d = Op();
     d.type = OP_DWCONV; d.p0 = x; d.o0 = out; d.f0 = w; d.f1 = b;
     d.i0 = N; d.i1 = L; d.i2 = C; d.i3 = K;
@@ -411,7 +405,7 @@ static void launch_dwconv(const Op& op, cudaStream_t st) {
     if (per_group < 1) per_group = 1;
     if (per_group > tiles) per_group = tiles;
     dim3 grid(per_group, groups);
-    dwconv_swooshr_kernel<K><<<grid, 256, dw_smem_bytes<K>(), st>>>(op.ma, (bf16*)op.o0, op.f0, op.f1, L, C, N);
+    dwconv_swooshr_kernel<K><<<grid, 256, dw_smem_bytes<K>(), st>>>(op.ma, (h16*)op.o0, op.f0, op.f1, L, C, N);
 }
 
 static int launch_op(const Op& op, cudaStream_t st) {
@@ -420,7 +414,6 @@ static int launch_op(const Op& op, cudaStream_t st) {
             if (op.grid <= 0) return 0;
             const CUtensorMap& mx = op.has_mx ? op.mx : op.ma;
             const CUtensorMap& ms = op.has_ms ? op.ms : op.ma;
-            const CUtensorMap& ms2 = op.has_ms2 ? op.ms2 : op.ma;
             const CUtensorMap& mo = op.has_mo ? op.mo : op.ma;
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(op.grid);
@@ -434,14 +427,14 @@ static int launch_op(const Op& op, cudaStream_t st) {
             const int sel = (op.kind == EPI_GATED ? 3 : op.gp.act) * 2 + (op.cluster - 1);
             cudaError_t e = cudaSuccess;
             switch (sel) {
-                case 0: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 1>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
-                case 1: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 2>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
-                case 2: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 1>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
-                case 3: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 2>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
-                case 4: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 1>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
-                case 5: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 2>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
-                case 6: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 1>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
-                default: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 2>, op.ma, op.mb, mx, ms, ms2, mo, op.gp); break;
+                case 0: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 1>, op.ma, op.mb, mx, ms, mo, op.gp); break;
+                case 1: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 2>, op.ma, op.mb, mx, ms, mo, op.gp); break;
+                case 2: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 1>, op.ma, op.mb, mx, ms, mo, op.gp); break;
+                case 3: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 2>, op.ma, op.mb, mx, ms, mo, op.gp); break;
+                case 4: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 1>, op.ma, op.mb, mx, ms, mo, op.gp); break;
+                case 5: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 2>, op.ma, op.mb, mx, ms, mo, op.gp); break;
+                case 6: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 1>, op.ma, op.mb, mx, ms, mo, op.gp); break;
+                default: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 2>, op.ma, op.mb, mx, ms, mo, op.gp); break;
             }
             if (e != cudaSuccess) return fail(ZVB_ERR_CUDA, "launch gemm: %s", cudaGetErrorString(e));
             return check_launch("gemm");
@@ -454,32 +447,31 @@ static int launch_op(const Op& op, cudaStream_t st) {
         case OP_BIASNORM: {
             const int blocks = static_cast<int>((op.rows + 7) / 8);
             if (op.i0 <= 512)
-                biasnorm_bypass_kernel<4><<<blocks, 256, 0, st>>>(
-                    (const float*)op.p0, (const float*)op.p1, (float*)op.o0, (bf16*)op.o1, (bf16*)op.o2, op.f3, op.i1,
+                biasnorm_bypass_kernel<2><<<blocks, 256, 0, st>>>(
+                    (const h16*)op.p0, (const h16*)op.p1, (h16*)op.o0, (h16*)op.o1, op.f3, op.i1,
                     op.f0, op.f1, op.f2, op.rows, op.i0);
             else
-                biasnorm_bypass_kernel<8><<<blocks, 256, 0, st>>>(
-                    (const float*)op.p0, (const float*)op.p1, (float*)op.o0, (bf16*)op.o1, (bf16*)op.o2, op.f3, op.i1,
+                biasnorm_bypass_kernel<4><<<blocks, 256, 0, st>>>(
+                    (const h16*)op.p0, (const h16*)op.p1, (h16*)op.o0, (h16*)op.o1, op.f3, op.i1,
                     op.f0, op.f1, op.f2, op.rows, op.i0);
             return check_launch("biasnorm_bypass");
         }
         case OP_PREP: {
             const long long n = op.rows * (op.i0 / 8);
-            stream_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)op.p0, (bf16*)op.o0, (bf16*)op.o1,
-                                                                           op.f0, op.i1, op.rows, op.i0);
+            stream_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const h16*)op.p0, (h16*)op.o0, op.f0, op.i1,
+                                                                           op.rows, op.i0);
             return check_launch("stream_prep");
         }
         case OP_DOWN: {
             const long long n = (long long)op.i0 * op.i2 * (op.i4 / 8);
             downsample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-                (const float*)op.p0, (float*)op.o0, op.i0, op.i1, op.i2, op.i3, op.w[0], op.w[1], op.w[2], op.w[3], op.i4);
+                (const h16*)op.p0, (h16*)op.o0, op.i0, op.i1, op.i2, op.i3, op.w[0], op.w[1], op.w[2], op.w[3], op.i4);
             return check_launch("downsample");
         }
         case OP_UP: {
             const long long n = (long long)op.i0 * op.i1 * (op.i4 / 8);
             upsample_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-                (const float*)op.p0, (const float*)op.p1, (float*)op.o0, (bf16*)op.o1, op.f0, op.i0, op.i1, op.i2, op.i3,
-                op.i4);
+                (const h16*)op.p0, (const h16*)op.p1, (h16*)op.o0, op.f0, op.i0, op.i1, op.i2, op.i3, op.i4);
             return check_launch("upsample_combine");
         }
         case OP_DWCONV: {
@@ -545,9 +537,9 @@ static Op small_op(const float* in, const float* W, const float* b, const float*
 
 // Builds the plan; with ws == nullptr only measures the workspace.
 //
-// Residual stream: fp32 (as the reference under bf16 autocast effectively keeps it: BiasNorm and the
-// bypass return fp32).  Every kernel that updates the stream also writes the bf16 shadow that the
-// next tensor-core kernel reads as its A operand.
+// Residual stream: ONE fp16 tensor per stage, read by the next tensor-core kernel as its A operand and
+// by the next residual-adding epilogue through the TMA aux ring (4 bytes of HBM traffic per element and
+// update, against 10 for an fp32 stream with a 16-bit operand shadow).
 static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_out, zvb_plan* plan) {
     if (m == nullptr || m->abi_version != ZVB_ABI_VERSION) return fail(ZVB_ERR_INVALID, "model description: ABI version mismatch");
     if (N <= 0 || T <= 0) return fail(ZVB_ERR_INVALID, "N and T must be positive");
@@ -563,7 +555,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
     const long long M = (long long)N * T;
 
     Carver c(ws);
-    bf16* xin = c.take<bf16>(M * xin_pitch);
+    h16* xin = c.take<h16>(M * xin_pitch);
     float* tbuf = c.take<float>(N);
     float* gbuf = c.take<float>(N);
     uint8_t* mask = c.take<uint8_t>(M);
@@ -580,34 +572,31 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
         te3 = c.take<float>((size_t)N * td);
         for (int s = 0; s < m->num_stacks; ++s) temb[s] = c.take<float>((size_t)N * D);
     }
-    float* cur0 = c.take<float>(M * D);           // full-rate fp32 stream (ping-pong)
-    float* cur1 = c.take<float>(M * D);
-    bf16* curb = c.take<bf16>(M * D);             // bf16 shadow of the final stream (out_proj operand)
-    float* S[2] = {c.take<float>(M * D), c.take<float>(M * D)};     // layer inputs inside a stack
-    bf16* Sb[2] = {c.take<bf16>(M * D), c.take<bf16>(M * D)};       // their bf16 shadows
-    bf16* St[2] = {c.take<bf16>(M * D), c.take<bf16>(M * D)};       // bf16(src + temb)
-    float* R[2] = {c.take<float>(M * D), c.take<float>(M * D)};     // stream inside a layer
-    bf16* Rb[2] = {c.take<bf16>(M * D), c.take<bf16>(M * D)};
-    bf16* qkp = c.take<bf16>(M * attn_w);
-    bf16* hid = c.take<bf16>(M * ffmax);
-    bf16* nay = c.take<bf16>(M * nah);
-    bf16* pvna = c.take<bf16>(M * nah);
-    bf16* pvsa = c.take<bf16>(M * H * dv);
-    bf16* glu = c.take<bf16>(M * D);
-    bf16* cv = c.take<bf16>(M * D);
+    h16* cur0 = c.take<h16>(M * D);             // full-rate stream (ping-pong)
+    h16* cur1 = c.take<h16>(M * D);
+    h16* S[2] = {c.take<h16>(M * D), c.take<h16>(M * D)};        // layer inputs inside a stack
+    h16* St[2] = {c.take<h16>(M * D), c.take<h16>(M * D)};       // src + temb
+    h16* R[2] = {c.take<h16>(M * D), c.take<h16>(M * D)};        // stream inside a layer
+    h16* qkp = c.take<h16>(M * attn_w);
+    h16* hid = c.take<h16>(M * ffmax);
+    h16* nay = c.take<h16>(M * nah);
+    h16* pvna = c.take<h16>(M * nah);
+    h16* pvsa = c.take<h16>(M * H * dv);
+    h16* glu = c.take<h16>(M * D);
+    h16* cv = c.take<h16>(M * D);
     const int Lk0 = round8(T);
-    bf16* P = c.take<bf16>((size_t)N * H * T * Lk0);
+    h16* P = c.take<h16>((size_t)N * H * T * Lk0);
     float* invl = c.take<float>((size_t)N * H * T);
     // per-resolution buffers (pads of the transposed V stay zero for the lifetime of the plan)
-    bf16 *vtna[5] = {}, *vtsa[5] = {};
+    h16 *vtna[5] = {}, *vtsa[5] = {};
     uint8_t* mask_ds[5] = {};
     for (int ds = 1; ds <= 4; ds *= 2) {
         bool used = false;
         for (int s = 0; s < m->num_stacks; ++s) used |= m->stacks[s].downsample == ds;
         if (!used) continue;
         const int L = (T + ds - 1) / ds, Lk = round8(L);
-        vtna[ds] = c.take<bf16>((size_t)N * nah * Lk);
-        vtsa[ds] = c.take<bf16>((size_t)N * H * hp * Lk);
+        vtna[ds] = c.take<h16>((size_t)N * nah * Lk);
+        vtsa[ds] = c.take<h16>((size_t)N * H * hp * Lk);
         mask_ds[ds] = ds == 1 ? mask : c.take<uint8_t>((size_t)N * L);
     }
     if (bytes_out) *bytes_out = (c.off + 255) & ~static_cast<size_t>(255);
@@ -643,20 +632,18 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             ops.push_back(small_op(te3, m->stacks[s].time_w, m->stacks[s].time_b, nullptr, temb[s], N, td, D,
                                    ACT_SWOOSH_R_, 0));
     }
-    // in_proj (reference: modules/zipformer.py:264-265) -> fp32 stream
+    // in_proj (reference: modules/zipformer.py:264-265) -> stream
     {
-        Op op; LinearEpi e; e.out_mode = OUT_F32;
+        Op op; LinearEpi e;
         TRY(build_linear(op, xin, M, xin_pitch, m->in_proj, cur0, D, e));
         ops.push_back(op);
     }
-    float* cur = cur0;
-    float* cur_alt = cur1;
-    bool curb_valid = false;
+    h16* cur = cur0;
+    h16* cur_alt = cur1;
 
     for (int s = 0; s < m->num_stacks; ++s) {
         const zvb_stack& stk = m->stacks[s];
         const int ds = stk.downsample;
-        const bool last_stack = s == m->num_stacks - 1;
         if (ds != 1 && ds != 2 && ds != 4) return fail(ZVB_ERR_INVALID, "downsample %d unsupported", ds);
         if (stk.num_layers <= 0) return fail(ZVB_ERR_INVALID, "empty stack");
         const int L = (T + ds - 1) / ds, Lk = round8(L);
@@ -667,122 +654,110 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             Op op; op.type = OP_DOWN; op.p0 = cur; op.o0 = S[0];
             op.i0 = N; op.i1 = T; op.i2 = L; op.i3 = ds; op.i4 = D;
             for (int k = 0; k < 4; ++k) op.w[k] = stk.ds_weights[k];
-            op.cat = ZVB_CAT_RESAMPLE; op.work = 4.0 * ((double)M + (double)Ms) * D;
+            op.cat = ZVB_CAT_RESAMPLE; op.work = 2.0 * ((double)M + (double)Ms) * D;
             ops.push_back(op);
         }
-        const float* src = ds == 1 ? cur : S[0];
-        {   // bf16 shadows of the stack input: Sb[0] = bf16(src), St[0] = bf16(src + temb)
-            Op op; op.type = OP_PREP; op.p0 = src; op.o0 = Sb[0]; op.o1 = tb != nullptr ? St[0] : nullptr;
+        const h16* src = ds == 1 ? cur : S[0];
+        if (tb != nullptr) {   // time-embedded copy of the stack input: St[0] = src + temb
+            Op op; op.type = OP_PREP; op.p0 = src; op.o0 = St[0];
             op.f0 = tb; op.i0 = D; op.i1 = L; op.rows = Ms;
-            op.cat = ZVB_CAT_ELEMENTWISE; op.work = (double)Ms * D * (4.0 + 2.0 + (tb != nullptr ? 2.0 : 0.0));
+            op.cat = ZVB_CAT_ELEMENTWISE; op.work = (double)Ms * D * (2.0 + 2.0);
             ops.push_back(op);
         }
-        const bf16* srcb = Sb[0];
-        const bf16* srct = tb != nullptr ? St[0] : Sb[0];
+        const h16* srct = tb != nullptr ? St[0] : src;
         for (int j = 0; j < stk.num_layers; ++j) {
             const zvb_layer& ly = m->layers[stk.first_layer + j];
             const bool last = j == stk.num_layers - 1;
             Op op;
             LinearEpi e;
-            auto stream_epi = [&](const float* resid, bf16* shadow) {
-                LinearEpi x; x.resid = resid; x.out_mode = shadow != nullptr ? OUT_F32_BF16 : OUT_F32; x.out_bf16 = shadow;
+            auto stream_epi = [&](const h16* resid) {
+                LinearEpi x; x.resid = resid;
                 return x;
             };
             auto t_epi = [&](int batch_rows, int hd_, int hp_) {
-                LinearEpi x; x.out_mode = OUT_T_BF16; x.t_L = L; x.t_pitch = Lk; x.t_batch_rows = batch_rows;
+                LinearEpi x; x.out_mode = OUT_T_H16; x.t_L = L; x.t_pitch = Lk; x.t_batch_rows = batch_rows;
                 x.t_hd = hd_; x.t_hp = hp_;
                 return x;
             };
             // 1. attention projections + weights (on the un-time-embedded input)
             e = LinearEpi();
-            TRY(build_linear(op, srcb, Ms, D, ly.attn_in, qkp, attn_w, e)); ops.push_back(op);
+            TRY(build_linear(op, src, Ms, D, ly.attn_in, qkp, attn_w, e)); ops.push_back(op);
             TRY(build_attn(op, qkp, attn_w, ly.pos_table, mask_ds[ds], P, invl, N, H, L, Lk)); ops.push_back(op);
             // 2. feed_forward1 on src + temb:  R0 = src + temb + FF1(src + temb)
             e = LinearEpi(); e.act = ACT_SWOOSH_L;
             TRY(build_linear(op, srct, Ms, D, ly.ff_in[0], hid, m->ff_dims[0], e)); ops.push_back(op);
-            e = stream_epi(src, Rb[0]); e.rowbias = tb; e.rows_per_group = L;
+            e = stream_epi(src); e.rowbias = tb; e.rows_per_group = L;
             TRY(build_linear(op, hid, Ms, m->ff_dims[0], ly.ff_out[0], R[0], D, e)); ops.push_back(op);
             // 3. nonlin attention
             e = t_epi(nah, 1, 1);
-            TRY(build_gated(op, Rb[0], Ms, D, ly.na_sx, nah, GATE_TANH_SX, vtna[ds], 0, nullptr, e)); ops.push_back(op);
+            TRY(build_gated(op, R[0], Ms, D, ly.na_sx, nah, GATE_TANH_SX, vtna[ds], 0, nullptr, e)); ops.push_back(op);
             e = LinearEpi();
-            TRY(build_linear(op, Rb[0], Ms, D, ly.na_y, nay, nah, e)); ops.push_back(op);
+            TRY(build_linear(op, R[0], Ms, D, ly.na_y, nay, nah, e)); ops.push_back(op);
             TRY(build_pv(op, P, invl, vtna[ds], pvna, nah, N, H, L, Lk, nah, nah, 0, nay, nah)); ops.push_back(op);
-            e = stream_epi(R[0], Rb[1]);
+            e = stream_epi(R[0]);
             TRY(build_linear(op, pvna, Ms, nah, ly.na_out, R[1], D, e)); ops.push_back(op);
             // 4. self_attn1 (+ temb for the conv module that follows)
             e = t_epi(H * hp, dv, hp);
-            TRY(build_linear(op, Rb[1], Ms, D, ly.sa_in[0], vtsa[ds], 0, e)); ops.push_back(op);
+            TRY(build_linear(op, R[1], Ms, D, ly.sa_in[0], vtsa[ds], 0, e)); ops.push_back(op);
             TRY(build_pv(op, P, invl, vtsa[ds], pvsa, H * dv, N, H, L, Lk, dv, hp, 1, nullptr, 0)); ops.push_back(op);
-            e = stream_epi(R[1], Rb[0]); e.rowbias = tb; e.rows_per_group = L;
+            e = stream_epi(R[1]); e.rowbias = tb; e.rows_per_group = L;
             TRY(build_linear(op, pvsa, Ms, H * dv, ly.sa_out[0], R[0], D, e)); ops.push_back(op);
             // 5. conv_module1
             e = LinearEpi();
-            TRY(build_gated(op, Rb[0], Ms, D, ly.conv_in[0], D, GATE_GLU_XS, glu, D, mask_ds[ds], e)); ops.push_back(op);
+            TRY(build_gated(op, R[0], Ms, D, ly.conv_in[0], D, GATE_GLU_XS, glu, D, mask_ds[ds], e)); ops.push_back(op);
             { Op d; TRY(build_dwconv(d, glu, cv, ly.dw_w[0], ly.dw_b[0], N, L, D, stk.conv_kernel)); ops.push_back(d); }
-            e = stream_epi(R[0], Rb[1]);
+            e = stream_epi(R[0]);
             TRY(build_linear(op, cv, Ms, D, ly.conv_out[0], R[1], D, e)); ops.push_back(op);
             // 6. feed_forward2 + bypass_mid
             e = LinearEpi(); e.act = ACT_SWOOSH_L;
-            TRY(build_linear(op, Rb[1], Ms, D, ly.ff_in[1], hid, m->ff_dims[1], e)); ops.push_back(op);
-            e = stream_epi(R[1], Rb[0]); e.orig = src; e.bypass_scale = ly.bypass_mid_scale;
+            TRY(build_linear(op, R[1], Ms, D, ly.ff_in[1], hid, m->ff_dims[1], e)); ops.push_back(op);
+            e = stream_epi(R[1]); e.orig = src; e.bypass_scale = ly.bypass_mid_scale;
             TRY(build_linear(op, hid, Ms, m->ff_dims[1], ly.ff_out[1], R[0], D, e)); ops.push_back(op);
             // 7. self_attn2 (+ temb)
             e = t_epi(H * hp, dv, hp);
-            TRY(build_linear(op, Rb[0], Ms, D, ly.sa_in[1], vtsa[ds], 0, e)); ops.push_back(op);
+            TRY(build_linear(op, R[0], Ms, D, ly.sa_in[1], vtsa[ds], 0, e)); ops.push_back(op);
             TRY(build_pv(op, P, invl, vtsa[ds], pvsa, H * dv, N, H, L, Lk, dv, hp, 1, nullptr, 0)); ops.push_back(op);
-            e = stream_epi(R[0], Rb[1]); e.rowbias = tb; e.rows_per_group = L;
+            e = stream_epi(R[0]); e.rowbias = tb; e.rows_per_group = L;
             TRY(build_linear(op, pvsa, Ms, H * dv, ly.sa_out[1], R[1], D, e)); ops.push_back(op);
             // 8. conv_module2
             e = LinearEpi();
-            TRY(build_gated(op, Rb[1], Ms, D, ly.conv_in[1], D, GATE_GLU_XS, glu, D, mask_ds[ds], e)); ops.push_back(op);
+            TRY(build_gated(op, R[1], Ms, D, ly.conv_in[1], D, GATE_GLU_XS, glu, D, mask_ds[ds], e)); ops.push_back(op);
             { Op d; TRY(build_dwconv(d, glu, cv, ly.dw_w[1], ly.dw_b[1], N, L, D, stk.conv_kernel)); ops.push_back(d); }
-            e = stream_epi(R[1], Rb[0]);
+            e = stream_epi(R[1]);
             TRY(build_linear(op, cv, Ms, D, ly.conv_out[1], R[0], D, e)); ops.push_back(op);
-            // 9. feed_forward3 (only the fp32 stream is needed afterwards)
+            // 9. feed_forward3
             e = LinearEpi(); e.act = ACT_SWOOSH_L;
-            TRY(build_linear(op, Rb[0], Ms, D, ly.ff_in[2], hid, m->ff_dims[2], e)); ops.push_back(op);
-            e = stream_epi(R[0], nullptr);
+            TRY(build_linear(op, R[0], Ms, D, ly.ff_in[2], hid, m->ff_dims[2], e)); ops.push_back(op);
+            e = stream_epi(R[0]);
             TRY(build_linear(op, hid, Ms, m->ff_dims[2], ly.ff_out[2], R[1], D, e)); ops.push_back(op);
-            // 10. BiasNorm + bypass -> next layer input (fp32), its bf16 shadow, its time-embedded shadow
-            float* nsrc = (last && ds == 1) ? cur_alt : S[si ^ 1];   // never aliases `src`
-            bf16* nsrcb = nullptr;
-            bf16* nsrct = nullptr;
-            if (!last) {
-                nsrcb = Sb[si ^ 1];
-                nsrct = tb != nullptr ? St[si ^ 1] : nullptr;
-            } else if (ds == 1 && last_stack) {
-                nsrcb = curb;                                       // operand of out_proj
-                curb_valid = true;
-            }
-            { Op b; b.type = OP_BIASNORM; b.p0 = R[1]; b.p1 = src; b.o0 = nsrc; b.o1 = nsrcb; b.o2 = nsrct;
+            // 10. BiasNorm + bypass -> next layer input and its time-embedded copy
+            h16* nsrc = (last && ds == 1) ? cur_alt : S[si ^ 1];     // never aliases `src`
+            h16* nsrct = (!last && tb != nullptr) ? St[si ^ 1] : nullptr;
+            { Op b; b.type = OP_BIASNORM; b.p0 = R[1]; b.p1 = src; b.o0 = nsrc; b.o1 = nsrct;
               b.f0 = ly.norm_bias; b.f1 = ly.norm_log_scale; b.f2 = ly.bypass_scale; b.f3 = tb;
               b.i0 = D; b.i1 = L; b.rows = Ms;
               b.cat = ZVB_CAT_BIASNORM;
-              b.work = (double)Ms * D * (3 * 4.0 + (nsrcb != nullptr ? 2.0 : 0.0) + (nsrct != nullptr ? 2.0 : 0.0));
+              b.work = (double)Ms * D * (3 * 2.0 + (nsrct != nullptr ? 2.0 : 0.0));
               ops.push_back(b); }
             src = nsrc;
-            srcb = nsrcb;
-            srct = nsrct != nullptr ? nsrct : nsrcb;
+            srct = nsrct != nullptr ? nsrct : nsrc;
             si ^= 1;
         }
         if (ds == 1) {
             std::swap(cur, cur_alt);        // the last layer wrote into cur_alt
         } else {
-            Op op; op.type = OP_UP; op.p0 = cur; op.p1 = src; op.o0 = cur_alt; op.o1 = last_stack ? curb : nullptr;
+            Op op; op.type = OP_UP; op.p0 = cur; op.p1 = src; op.o0 = cur_alt;
             op.f0 = stk.out_combiner_scale;
             op.i0 = N; op.i1 = T; op.i2 = L; op.i3 = ds; op.i4 = D;
-            op.cat = ZVB_CAT_RESAMPLE; op.work = 4.0 * (2.0 * (double)M + (double)Ms) * D;
+            op.cat = ZVB_CAT_RESAMPLE; op.work = 2.0 * (2.0 * (double)M + (double)Ms) * D;
             ops.push_back(op);
-            if (last_stack) curb_valid = true;
             std::swap(cur, cur_alt);
         }
     }
-    if (!curb_valid) return fail(ZVB_ERR_INVALID, "internal: final stream has no bf16 shadow");
     // out_proj (reference: modules/zipformer.py:291)
     {
         Op op; LinearEpi e; e.out_mode = OUT_F32;
-        TRY(build_linear(op, curb, M, D, m->out_proj, out, m->out_dim, e));
+        TRY(build_linear(op, cur, M, D, m->out_proj, out, m->out_dim, e));
         ops.push_back(op);
     }
     return 0;
@@ -864,7 +839,7 @@ int zvb_decoder_forward_f32(zvb_plan* plan, const float* x, const float* t, cons
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long M = (long long)plan->N * plan->T;
     const long long n = M * plan->xin_pitch;
-    cast_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, (bf16*)plan->io.xin, M, plan->in_dim, plan->xin_pitch);
+    cast_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, (h16*)plan->io.xin, M, plan->in_dim, plan->xin_pitch);
     TRY(check_launch("cast_pad"));
     if (plan->has_time) CUDA_TRY(cudaMemcpyAsync(plan->io.t, t, sizeof(float) * plan->N, cudaMemcpyDeviceToDevice, st));
     if (plan->has_g) CUDA_TRY(cudaMemcpyAsync(plan->io.g, g, sizeof(float) * plan->N, cudaMemcpyDeviceToDevice, st));
@@ -913,7 +888,7 @@ int zvb_sample(zvb_plan* plan, float* x, const float* text, const float* speech,
         const float t = ts_host[step];
         const int drop_speech = t > 0.5f ? 1 : 0;                 // reference: solver.py:90-98
         assemble_input_kernel<<<(unsigned)((n_in + 255) / 256), 256, 0, st>>>(
-            x, text, speech, (bf16*)plan->io.xin, B, T, F, Ft, plan->xin_pitch, mode == 1, drop_speech);
+            x, text, speech, (h16*)plan->io.xin, B, T, F, Ft, plan->xin_pitch, mode == 1, drop_speech);
         TRY(check_launch("assemble_input"));
         fill_kernel<<<(N + 127) / 128, 128, 0, st>>>(plan->io.t, ts, step, N);
         TRY(check_launch("fill_t"));
@@ -929,13 +904,14 @@ int zvb_sample(zvb_plan* plan, float* x, const float* text, const float* speech,
 
 // ------------------------------------------------------------------------------------------ test entry points
 int zvb_test_linear(const void* A, int M, int K, int lda, const void* W, const float* bias, int n_out, int k_pitch,
-                    int block_n, int act, const float* resid, void* out, void* out_bf16, int ldc, int out_mode,
-                    void* stream) {
+                    int block_n, int act, const void* resid, const void* orig, const float* bypass_scale, void* out,
+                    int ldc, int out_mode, void* stream) {
     TRY(init_device());
     zvb_linear lin{W, bias, n_out, K, k_pitch, n_out};
-    Op op; LinearEpi e; e.act = act; e.resid = resid; e.out_mode = out_mode; e.out_bf16 = (bf16*)out_bf16;
+    Op op; LinearEpi e; e.act = act; e.resid = (const h16*)resid; e.orig = (const h16*)orig; e.bypass_scale = bypass_scale;
+    e.out_mode = out_mode;
     e.block_n = block_n;
-    TRY(build_linear(op, (const bf16*)A, M, lda, lin, out, ldc, e));
+    TRY(build_linear(op, (const h16*)A, M, lda, lin, out, ldc, e));
     return launch_op(op, static_cast<cudaStream_t>(stream));
 }
 
@@ -943,7 +919,7 @@ int zvb_test_attn_weights(const void* qkp, int ld, const float* pos_table, const
                           int N, int H, int L, int Lk, void* stream) {
     TRY(init_device());
     Op op;
-    TRY(build_attn(op, (const bf16*)qkp, ld, pos_table, mask, (bf16*)P, inv_l, N, H, L, Lk));
+    TRY(build_attn(op, (const h16*)qkp, ld, pos_table, mask, (h16*)P, inv_l, N, H, L, Lk));
     return launch_op(op, static_cast<cudaStream_t>(stream));
 }
 
@@ -952,7 +928,7 @@ int zvb_test_pv(const void* P, const float* inv_l, const void* Vt, void* out, in
     TRY(init_device());
     Op op;
     const int ldc = per_head ? H * hd : hd;
-    TRY(build_pv(op, (const bf16*)P, inv_l, (const bf16*)Vt, out, ldc, N, H, L, Lk, hd, hp, per_head, (const bf16*)mul, hd));
+    TRY(build_pv(op, (const h16*)P, inv_l, (const h16*)Vt, out, ldc, N, H, L, Lk, hd, hp, per_head, (const h16*)mul, hd));
     return launch_op(op, static_cast<cudaStream_t>(stream));
 }
 
@@ -961,22 +937,25 @@ int zvb_test_gated(const void* A, int M, int K, int lda, const void* W, const fl
     TRY(init_device());
     zvb_linear lin{W, bias, n_out, K, k_pitch, rows};
     Op op; LinearEpi e;
-    TRY(build_gated(op, (const bf16*)A, M, lda, lin, n_out, gate_mode, out, ldc, row_mask, e));
+    TRY(build_gated(op, (const h16*)A, M, lda, lin, n_out, gate_mode, out, ldc, row_mask, e));
     return launch_op(op, static_cast<cudaStream_t>(stream));
 }
 
-int zvb_test_biasnorm_bypass(const float* src, const float* orig, float* out, void* out_b, void* out_t,
+int zvb_test_biasnorm_bypass(const void* src, const void* orig, void* out, void* out_t,
                              const float* temb, int rows_per_group, const float* nbias, const float* log_scale,
                              const float* bscale, long long rows, int C, void* stream) {
-    Op b; b.type = OP_BIASNORM; b.p0 = src; b.p1 = orig; b.o0 = out; b.o1 = out_b; b.o2 = out_t;
+    TRY(init_device());
+    if (C % 8 != 0 || C > 1024) return fail(ZVB_ERR_INVALID, "biasnorm: C must be a multiple of 8, <= 1024");
+    Op b; b.type = OP_BIASNORM; b.p0 = src; b.p1 = orig; b.o0 = out; b.o1 = out_t;
     b.f0 = nbias; b.f1 = log_scale; b.f2 = bscale; b.f3 = temb; b.i0 = C; b.i1 = rows_per_group; b.rows = rows;
     return launch_op(b, static_cast<cudaStream_t>(stream));
 }
 
 int zvb_test_dwconv(const void* x, void* out, const float* wt, const float* bias, int N, int L, int C, int K,
                     void* stream) {
+    TRY(init_device());
     Op d;
-    TRY(build_dwconv(d, (const bf16*)x, (bf16*)out, wt, bias, N, L, C, K));
+    TRY(build_dwconv(d, (const h16*)x, (h16*)out, wt, bias, N, L, C, K));
     return launch_op(d, static_cast<cudaStream_t>(stream));
 }
 

@@ -1,10 +1,11 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C = epilogue(A · Bᵀ)
-//   A: (rows, K) bf16 K-major, B: (cols, K) bf16 K-major (an nn.Linear weight, or Vᵀ), both
+//   A: (rows, K) fp16 K-major, B: (cols, K) fp16 K-major (an nn.Linear weight, or Vᵀ), both
 //   streamed by TMA (128B swizzle) through a 3..8-stage mbarrier ring; fp32 accumulators live in
 //   TMEM (2 stages x <=256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   The epilogue's tile-shaped operand (the fp32 residual stream, or the bf16 `y` gate of
-//   NonlinAttention) is streamed by a second TMA ring of 16 KB sub-tiles (128 rows x 128 bytes),
-//   so the epilogue threads never wait on a global load.
+//   The epilogue's tile-shaped operands (the fp16 residual stream, the bypass `orig`, or the `y` gate
+//   of NonlinAttention) are streamed by a second TMA ring of 16 KB sub-tiles (128 rows x 64 columns),
+//   so the epilogue threads never wait on a global load; the result is staged in place over the
+//   consumed residual sub-tile and leaves as one TMA box store.
 //   Warps 0..7 = epilogue (two warps per TMEM lane quarter, alternating sub-tiles), warp 8 = TMA producer
 //   (A/B), warp 9 = MMA issuer (+TMEM alloc), warp 10 = TMA producer (aux), warp 11 = TMA store thread.
 // Serves every dense contraction of the TTSZipformer forward (reference:
@@ -33,10 +34,9 @@ inline void gemm_ring(int block_n, int cluster, int* stages, int* stage_bytes) {
 }
 constexpr int GEMM_AUX_SLOTS = 4;
 constexpr int GEMM_AUX_BYTES = 128 * 128;                       // 128 rows x 128 B
-constexpr int GEMM_BIAS_BYTES = 8 * 64 * 4;                // per epilogue warp: bias of the sub-tile in flight (64 columns)
-constexpr int GEMM_SHADOW_BYTES = 2 * 128 * 64;            // bf16 shadow staging, 128 rows x 64 B per epilogue half
+constexpr int GEMM_BIAS_BYTES = 8 * 128 * 4;               // per epilogue warp: bias of the sub-tile in flight (64 columns, 2 x 64 gated)
 constexpr int GEMM_LAYOUT_BYTES = GEMM_OPERAND_BYTES + GEMM_AUX_SLOTS * GEMM_AUX_BYTES + GEMM_BIAS_BYTES +
-                                  GEMM_SHADOW_BYTES + 384 /*barriers*/;
+                                  384 /*barriers*/;
 constexpr int GEMM_SMEM_BYTES = 232448;                    // all 227 KB; layout + alignment pad must fit (checked)
 static_assert(GEMM_LAYOUT_BYTES <= GEMM_SMEM_BYTES, "shared-memory layout too large");
 constexpr int GEMM_THREADS = 384;
@@ -46,8 +46,8 @@ constexpr int GEMM_TMEM_COLS = 512;
 enum { EPI_LINEAR = 0, EPI_GATED = 1 };
 enum { ACT_NONE = 0, ACT_SWOOSH_L = 1, ACT_SWOOSH_R = 2 };
 enum { GATE_TANH_SX = 1, GATE_GLU_XS = 2 };
-enum { AUX_NONE = 0, AUX_RESID_F32 = 1, AUX_MUL_BF16 = 2 };
-enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_BF16 = 2, OUT_T_BF16 = 3 };
+enum { AUX_NONE = 0, AUX_ADD_H16 = 1, AUX_MUL_H16 = 2 };      // tile operand: residual (added) / gate (multiplied)
+enum { OUT_H16 = 0, OUT_F32 = 1, OUT_T_H16 = 3 };
 
 struct GemmParams {
     // problem / tiling
@@ -61,9 +61,8 @@ struct GemmParams {
     int b_zb;              // B tensor-map z = b*b_zb
     // output: row = b*M + m
     int out_mode;
-    void* out;             // bf16 (OUT_BF16, OUT_T_BF16) or fp32 (OUT_F32, OUT_F32_BF16)
-    __nv_bfloat16* out_bf16;   // OUT_F32_BF16: bf16 shadow copy (GEMM operand of the next kernel)
-    int ldc;               // pitch of `out` (and of out_bf16), in elements
+    void* out;             // fp16 (OUT_H16, OUT_T_H16) or fp32 (OUT_F32)
+    int ldc;               // pitch of `out`, in elements
     int out_col_stride;    // first output column of a tile = n_tile*out_col_stride
     int n_valid;           // valid accumulator columns inside one tile
     // epilogue operands (nullable)
@@ -73,16 +72,15 @@ struct GemmParams {
     const float* rowbias;  // fp32 [(row / rows_per_group)*ld_rowbias + outcol]
     int rows_per_group;
     int ld_rowbias;
-    int tma_store;         // outputs leave through TMA stores (tensor maps tma_out / tma_out2)
-    int aux_mode;          // tile operand streamed by TMA: fp32 residual or bf16 multiplier
+    int tma_store;         // outputs leave through TMA stores (tensor map tma_out)
+    int aux_mode;          // tile operand streamed by TMA: fp16 residual (added) or fp16 multiplier
     int aux_zb;            // aux tensor-map z = b*aux_zb
-    int orig_tma;          // bypass operand `orig` streamed through the aux ring (tensor map tma_orig)
-    const float* orig;     // bypass: orig + (v - orig)*scale[col]; fp32, pitch ldc
+    int orig_tma;          // bypass: orig + (v - orig)*scale[col]; `orig` (fp16) rides through the aux ring
     const float* bypass_scale;
     int act;
     int gate_mode;
     const uint8_t* row_mask;        // [rows] non-zero -> output row is zero
-    // OUT_T_BF16: dst[(row / t_L)*t_batch_rows + drow(col)][row % t_L], pitch t_pitch,
+    // OUT_T_H16: dst[(row / t_L)*t_batch_rows + drow(col)][row % t_L], pitch t_pitch,
     // drow(col) = col + (col / t_hd)*(t_hp - t_hd)
     int t_L, t_pitch, t_batch_rows, t_hd, t_hp;
 };
@@ -97,58 +95,57 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // layout (lanes = consecutive rows -> coalesced) and for ragged / unaligned column ranges.
 __device__ __forceinline__ void store_row32_direct(const GemmParams& p, long long row, int col0, int ncols,
                                                    const float* v) {
-    if (p.out_mode == OUT_T_BF16) {
+    if (p.out_mode == OUT_T_H16) {
         const int n = static_cast<int>(row / p.t_L);
         const int l = static_cast<int>(row - static_cast<long long>(n) * p.t_L);
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
+        __half* dst = reinterpret_cast<__half*>(p.out) +
                              static_cast<long long>(n) * p.t_batch_rows * p.t_pitch + l;
         if (p.t_hp == p.t_hd) {
             dst += static_cast<long long>(col0) * p.t_pitch;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-                if (i < ncols) dst[static_cast<long long>(i) * p.t_pitch] = __float2bfloat16(v[i]);
+                if (i < ncols) dst[static_cast<long long>(i) * p.t_pitch] = f2h(v[i]);
         } else {
             int hh = col0 / p.t_hd;                   // head of the first column, then incremental
             int rem = col0 - hh * p.t_hd;
             const int pad = p.t_hp - p.t_hd;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                if (i < ncols) dst[static_cast<long long>(col0 + i + hh * pad) * p.t_pitch] = __float2bfloat16(v[i]);
+                if (i < ncols) dst[static_cast<long long>(col0 + i + hh * pad) * p.t_pitch] = f2h(v[i]);
                 if (++rem == p.t_hd) { rem = 0; ++hh; }
             }
         }
         return;
     }
-    if (p.out_mode == OUT_F32 || p.out_mode == OUT_F32_BF16) {
+    if (p.out_mode == OUT_F32) {
         float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + col0;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
             if (i < ncols) dst[i] = v[i];
-        if (p.out_mode == OUT_F32) return;
+        return;
     }
-    __nv_bfloat16* dst = (p.out_mode == OUT_F32_BF16 ? p.out_bf16 : reinterpret_cast<__nv_bfloat16*>(p.out)) +
-                         row * p.ldc + col0;
+    __half* dst = reinterpret_cast<__half*>(p.out) + row * p.ldc + col0;
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-        if (i < ncols) dst[i] = __float2bfloat16(v[i]);
+        if (i < ncols) dst[i] = f2h(v[i]);
 }
 
-// bf16 staging of one 32-column unit into 16-byte chunks cofs..cofs+3 of the thread's 128-byte row
-__device__ __forceinline__ void stage_bf16_unit(uint8_t* stage, int lane, const float* v, int cofs) {
+// fp16 staging of one 32-column unit into 16-byte chunks cofs..cofs+3 of the thread's 128-byte row
+__device__ __forceinline__ void stage_h16_unit(uint8_t* stage, int lane, const float* v, int cofs) {
     uint8_t* my = stage + lane * 128;
     const int sw = lane & 7;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(my + (((cofs + j) ^ sw) << 4)) =
-            make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                       pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]),
+                       pack_h2(v[8 * j + 4], v[8 * j + 5]), pack_h2(v[8 * j + 6], v[8 * j + 7]));
 }
-// Writes the staged bf16 columns [c_lo, c_hi) (relative to `colbase`, multiples of 8, within 0..64) of
+// Writes the staged fp16 columns [c_lo, c_hi) (relative to `colbase`, multiples of 8, within 0..64) of
 // the warp's 32 rows: 8 lanes x 16 B = one 128-byte row segment per row, 4 rows per instruction
 // (the store path is bound by the number of <=128-byte write transactions, not by bytes).
-__device__ __forceinline__ void flush_bf16_units(__nv_bfloat16* out, int ldc, const uint8_t* stage, int lane,
+__device__ __forceinline__ void flush_h16_units(__half* out, int ldc, const uint8_t* stage, int lane,
                                                  long long row0, int rows_ok, int colbase, int c_lo, int c_hi) {
-    __nv_bfloat16* dst = out + row0 * ldc + colbase;
+    __half* dst = out + row0 * ldc + colbase;
     const int ch = lane & 7;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -163,13 +160,13 @@ __device__ __forceinline__ void flush_bf16_units(__nv_bfloat16* out, int ldc, co
 // direct global store touches 32 different 128-byte lines per instruction (measured ~6 GB/s per SM).
 // The unit is therefore transposed through 4 KB of (swizzled, conflict-free) shared memory --
 // `stage`, 32 rows x 128 B -- so that each store instruction writes whole rows: 8 lanes x 16 B per
-// fp32 row, 4 lanes x 16 B per bf16 row.  `row0` = global row of the warp's first row, `rows_ok` =
-// number of valid rows among the 32, ncols a multiple of 4 (fp32) / 8 (bf16).  `cofs` = first 16-byte
-// chunk of the 128-byte row used for the bf16 staging.
+// fp32 row, 4 lanes x 16 B per fp16 row.  `row0` = global row of the warp's first row, `rows_ok` =
+// number of valid rows among the 32, ncols a multiple of 4 (fp32) / 8 (fp16).  `cofs` = first 16-byte
+// chunk of the 128-byte row used for the fp16 staging.
 __device__ __forceinline__ void store_unit_staged(const GemmParams& p, uint8_t* stage, int lane, long long row0,
                                                   int rows_ok, int col0, int ncols, const float* v, int cofs) {
     const int sw = lane & 7;
-    if (p.out_mode == OUT_F32 || p.out_mode == OUT_F32_BF16) {
+    if (p.out_mode == OUT_F32) {
         uint8_t* my = stage + lane * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -183,20 +180,19 @@ __device__ __forceinline__ void store_unit_staged(const GemmParams& p, uint8_t* 
             const float4 q = *reinterpret_cast<const float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
             if (rr < rows_ok && ch * 4 < ncols) *reinterpret_cast<float4*>(dst + static_cast<long long>(rr) * p.ldc + ch * 4) = q;
         }
-        if (p.out_mode == OUT_F32) return;
-        __syncwarp();
+        return;
     }
-    stage_bf16_unit(stage, lane, v, cofs);
+    stage_h16_unit(stage, lane, v, cofs);
     __syncwarp();
-    flush_bf16_units(p.out_mode == OUT_F32_BF16 ? p.out_bf16 : reinterpret_cast<__nv_bfloat16*>(p.out), p.ldc, stage,
-                     lane, row0, rows_ok, col0 - 8 * cofs, 8 * cofs, 8 * cofs + ncols);
+    flush_h16_units(reinterpret_cast<__half*>(p.out), p.ldc, stage, lane, row0, rows_ok, col0 - 8 * cofs, 8 * cofs,
+                    8 * cofs + ncols);
 }
 
 // One warp stores its unit: staged+coalesced when the column range is 16-byte aligned, direct otherwise.
 __device__ __forceinline__ void store_unit(const GemmParams& p, uint8_t* stage, int lane, bool row_ok, long long row,
                                            long long row0, int rows_ok, int col0, int ncols, const float* v, int cofs) {
-    const bool f32 = p.out_mode == OUT_F32 || p.out_mode == OUT_F32_BF16;
-    const bool aligned = p.out_mode != OUT_T_BF16 && (p.ldc & 7) == 0 && (col0 & 7) == 0 &&
+    const bool f32 = p.out_mode == OUT_F32;
+    const bool aligned = p.out_mode != OUT_T_H16 && (p.ldc & 7) == 0 && (col0 & 7) == 0 &&
                          (ncols & (p.out_mode == OUT_F32 ? 3 : 7)) == 0 && (!f32 || (ncols & 3) == 0);
     if (aligned) {
         store_unit_staged(p, stage, lane, row0, rows_ok, col0, ncols, v, cofs);
@@ -219,7 +215,7 @@ template <int KIND, int ACT, int CLUSTER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_out,
-            const __grid_constant__ CUtensorMap tma_out2, const __grid_constant__ CUtensorMap tma_orig,
+            const __grid_constant__ CUtensorMap tma_orig,
             const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -227,8 +223,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int STAGES = p.stages;
     const int STAGE_BYTES = p.stage_bytes;
     uint8_t* aux_smem = smem + GEMM_OPERAND_BYTES;
-    uint8_t* shadow_smem = aux_smem + GEMM_AUX_SLOTS * GEMM_AUX_BYTES;                         // [8 warps][32][64 B]
-    float* bias_smem = reinterpret_cast<float*>(shadow_smem + GEMM_SHADOW_BYTES);              // [8 warps][64]
+    float* bias_smem = reinterpret_cast<float*>(aux_smem + GEMM_AUX_SLOTS * GEMM_AUX_BYTES);   // [8 warps][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_smem) + GEMM_BIAS_BYTES);
     if (threadIdx.x == 0 && (smem - smem_raw) + GEMM_LAYOUT_BYTES > GEMM_SMEM_BYTES) {
         printf("zvb: gemm shared-memory layout does not fit (base misaligned by %d)\n", (int)(smem - smem_raw));
@@ -258,11 +253,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int total_tiles = p.batches * m_groups * p.num_n_tiles;
     const int first_tile = blockIdx.x / CLUSTER;
     const int tile_step = gridDim.x / CLUSTER;
-    // accumulator columns are consumed in units of 32; aux sub-tiles hold 32 (fp32) or 64 (bf16) columns
+    // accumulator columns are consumed in units of 32; a 128-byte sub-tile row holds 64 fp16 (2 units) or
+    // 32 fp32 (1 unit) columns
     const int n_units = (p.block_n + 31) >> 5;
-    const bool out_f32 = p.out_mode == OUT_F32 || p.out_mode == OUT_F32_BF16;
-    const int units_per_sub =
-        (p.aux_mode == AUX_RESID_F32 || (p.tma_store && out_f32) || p.out_mode == OUT_T_BF16) ? 1 : 2;
+    const bool out_f32 = p.out_mode == OUT_F32;
+    const int units_per_sub = ((p.tma_store && out_f32) || p.out_mode == OUT_T_H16) ? 1 : 2;
     const int aux_parts = p.orig_tma ? 2 : 1;          // ring entries per sub-tile: operand (+ bypass `orig`)
     const int n_sub = (n_units + units_per_sub - 1) / units_per_sub;
 
@@ -270,7 +265,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         if (p.aux_mode != AUX_NONE) tma_prefetch_desc(&tma_aux);
-        if (p.tma_store) { tma_prefetch_desc(&tma_out); tma_prefetch_desc(&tma_out2); }
+        if (p.tma_store) tma_prefetch_desc(&tma_out);
         if (p.orig_tma) tma_prefetch_desc(&tma_orig);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -334,7 +329,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     } else if (warp == W_MMA) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0 && crank == 0) {               // the leader issues for the pair
-            const uint32_t idesc = umma_idesc_bf16(static_cast<uint32_t>(p.block_n), 128u * CLUSTER);
+            const uint32_t idesc = umma_idesc_f16(static_cast<uint32_t>(p.block_n), 128u * CLUSTER);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -351,12 +346,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     const uint64_t db = umma_desc_k_sw128(sa + GEMM_A_BYTES);
 #pragma unroll
                     for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
-                        // advance 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in >>4 units
+                        // advance 16 fp16 = 32 bytes inside the 128B swizzle atom: +2 in >>4 units
                         if (CLUSTER == 2)
-                            umma_bf16_2sm(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                            umma_f16_2sm(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
                                           idesc, (kb | k) != 0 ? 1u : 0u);
                         else
-                            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                            umma_f16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
                                       idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     // free the smem slot (in both CTAs) when the MMAs retire; publish the accumulator
@@ -375,7 +370,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     } else if (warp == W_AUX) {
         // ------------------------------------------------------------------ TMA producer (aux tiles)
         if (lane == 0 && p.aux_mode != AUX_NONE) {
-            const int sub_cols = p.aux_mode == AUX_RESID_F32 ? 32 : 64;
+            constexpr int sub_cols = 64;
             uint32_t q = 0;
             for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
                 const int n_tile = tile % p.num_n_tiles;
@@ -430,8 +425,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     mbar_wait(&staged[bi], (k >> 1) & 1u);
                     if (aux_parts == 2) mbar_arrive(&aux_empty[slot2]);      // `orig` rows are consumed
                     tma_store_3d(&tma_out, src, col, m_tile * GEMM_BLOCK_M, b);
-                    if (p.out_mode == OUT_F32_BF16)
-                        tma_store_3d(&tma_out2, shadow_smem + h * (128 * 64), col, m_tile * GEMM_BLOCK_M, b);
                     bulk_commit();
                     bulk_wait_read<0>();
                     mbar_arrive(&sfree[bi]);
@@ -450,11 +443,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const int half = ew >> 2;                         // which of the two warps of the quarter
         const int r = quarter * 32 + lane;                // accumulator row inside the tile
         uint8_t* private_stage = aux_smem + ew * 4096;    // staging of the non-TMA store paths
-        uint8_t* shadow_stage = shadow_smem + half * (128 * 64) + quarter * 2048;  // this warp's 32 rows x 64 B
         uint32_t kcount = 0;                              // sub-tiles this half handed to the store thread
-        // a staging buffer may be rewritten once the store of `depth` sub-tiles ago has read it: the
-        // shadow box is single buffered, everything else has two buffers (or lives in an aux slot)
-        const uint32_t depth = p.out_mode == OUT_F32_BF16 ? 1u : 2u;
+        // a staging buffer may be rewritten once the store of `depth` sub-tiles ago has read it (two
+        // buffers per half, or the consumed aux slot)
+        constexpr uint32_t depth = 2u;
         auto wait_sfree = [&]() {
             if (kcount >= depth) {
                 const uint32_t kd = kcount - depth;
@@ -467,8 +459,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (lane == 0) mbar_arrive(&staged[half * 2 + (kcount & 1u)]);
             ++kcount;
         };
-        // bias staging of this warp: 64 floats (LINEAR), or 128 floats in the unused shadow area (GATED)
-        float* bs = KIND == EPI_GATED ? reinterpret_cast<float*>(shadow_stage) : bias_smem + ew * 64;
+        // bias staging of this warp: 64 floats (LINEAR) or 2 x 64 (GATED)
+        float* bs = bias_smem + ew * 128;
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t tile_iter = 0;
@@ -517,7 +509,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
             if (KIND == EPI_GATED) {
                 const int hcols = p.block_n >> 1;                       // 128
-                // each warp of a quarter takes two adjacent 32-column units so that their bf16 rows leave
+                // each warp of a quarter takes two adjacent 32-column units so that their fp16 rows leave
                 // as one 128-byte segment
                 int g_lo = 0, g_hi = 0, g_col = 0;
                 const bool g_tma = p.tma_store && 2 * half * 32 < hcols;
@@ -553,12 +545,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                 v[4 * j + e] = masked ? 0.0f : o;
                             }
                         }
-                        const bool pairable = p.out_mode == OUT_BF16 && (p.ldc & 7) == 0 && (out_base & 7) == 0 &&
+                        const bool pairable = p.out_mode == OUT_H16 && (p.ldc & 7) == 0 && (out_base & 7) == 0 &&
                                               (ncols & 7) == 0;
                         if (g_tma) {
-                            stage_bf16_unit(tbuf, lane, v, 4 * (u & 1));
+                            stage_h16_unit(tbuf, lane, v, 4 * (u & 1));
                         } else if (pairable) {
-                            stage_bf16_unit(private_stage, lane, v, 4 * (u & 1));
+                            stage_h16_unit(private_stage, lane, v, 4 * (u & 1));
                             if ((u & 1) == 0) g_col = oc;
                             else if (g_hi == 0) { g_col = oc - 32; g_lo = 32; }
                             g_hi = 32 * (u & 1) + ncols;
@@ -571,7 +563,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     signal_staged();
                 } else if (g_hi > 0) {
                     __syncwarp();
-                    flush_bf16_units(reinterpret_cast<__nv_bfloat16*>(p.out), p.ldc, private_stage, lane, row0, rows_ok,
+                    flush_h16_units(reinterpret_cast<__half*>(p.out), p.ldc, private_stage, lane, row0, rows_ok,
                                      g_col, g_lo, g_hi);
                     __syncwarp();
                 }
@@ -580,7 +572,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     const uint8_t* aux_row = nullptr;
                     const uint8_t* orig_row = nullptr;
                     int slot = 0, slot2 = 0;
-                    int pend_lo = 0, pend_hi = 0, pend_col = 0;      // staged, not yet flushed bf16 columns
+                    int pend_lo = 0, pend_hi = 0, pend_col = 0;      // staged, not yet flushed fp16 columns
                     uint8_t* pend_stage = nullptr;
                     if (p.aux_mode != AUX_NONE) {
                         const uint32_t q = (tile_iter * static_cast<uint32_t>(n_sub) + static_cast<uint32_t>(s)) *
@@ -649,53 +641,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) v[i] = swoosh_direct(v[i], SWOOSH_R_C, SWOOSH_R_K0);
                             }
-                            if (p.aux_mode == AUX_RESID_F32) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float4 a = *reinterpret_cast<const float4*>(aux_row + ((j ^ (r & 7)) << 4));
-                                    v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
-                                }
-                            } else if (p.aux_mode == AUX_MUL_BF16) {
+                            if (p.aux_mode == AUX_ADD_H16) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     const uint4 a = *reinterpret_cast<const uint4*>(aux_row + (((4 * uu + j) ^ (r & 7)) << 4));
-                                    v[8 * j] *= bf16_lo(a.x);     v[8 * j + 1] *= bf16_hi(a.x);
-                                    v[8 * j + 2] *= bf16_lo(a.y); v[8 * j + 3] *= bf16_hi(a.y);
-                                    v[8 * j + 4] *= bf16_lo(a.z); v[8 * j + 5] *= bf16_hi(a.z);
-                                    v[8 * j + 6] *= bf16_lo(a.w); v[8 * j + 7] *= bf16_hi(a.w);
+                                    v[8 * j] += h2_lo(a.x);     v[8 * j + 1] += h2_hi(a.x);
+                                    v[8 * j + 2] += h2_lo(a.y); v[8 * j + 3] += h2_hi(a.y);
+                                    v[8 * j + 4] += h2_lo(a.z); v[8 * j + 5] += h2_hi(a.z);
+                                    v[8 * j + 6] += h2_lo(a.w); v[8 * j + 7] += h2_hi(a.w);
+                                }
+                            } else if (p.aux_mode == AUX_MUL_H16) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint4 a = *reinterpret_cast<const uint4*>(aux_row + (((4 * uu + j) ^ (r & 7)) << 4));
+                                    v[8 * j] *= h2_lo(a.x);     v[8 * j + 1] *= h2_hi(a.x);
+                                    v[8 * j + 2] *= h2_lo(a.y); v[8 * j + 3] *= h2_hi(a.y);
+                                    v[8 * j + 4] *= h2_lo(a.z); v[8 * j + 5] *= h2_hi(a.z);
+                                    v[8 * j + 6] *= h2_lo(a.w); v[8 * j + 7] *= h2_hi(a.w);
                                 }
                             }
                             if (orig_row != nullptr) {        // bypass, `orig` sub-tile staged by TMA
                                 const float* sp = p.bypass_scale + oc;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float4 o = *reinterpret_cast<const float4*>(orig_row + ((j ^ (r & 7)) << 4));
-                                    const float4 sc = __ldg(reinterpret_cast<const float4*>(sp) + j);
-                                    v[4 * j] = fmaf(v[4 * j] - o.x, sc.x, o.x);
-                                    v[4 * j + 1] = fmaf(v[4 * j + 1] - o.y, sc.y, o.y);
-                                    v[4 * j + 2] = fmaf(v[4 * j + 2] - o.z, sc.z, o.z);
-                                    v[4 * j + 3] = fmaf(v[4 * j + 3] - o.w, sc.w, o.w);
-                                }
-                            } else if (p.orig != nullptr && row_ok) {
-                                const float* op = p.orig + row * p.ldc + oc;
-                                const float* sp = p.bypass_scale + oc;
-                                if (vec) {
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) {
-                                        const float4 o = __ldg(reinterpret_cast<const float4*>(op) + j);
-                                        const float4 sc = __ldg(reinterpret_cast<const float4*>(sp) + j);
-                                        v[4 * j] = fmaf(v[4 * j] - o.x, sc.x, o.x);
-                                        v[4 * j + 1] = fmaf(v[4 * j + 1] - o.y, sc.y, o.y);
-                                        v[4 * j + 2] = fmaf(v[4 * j + 2] - o.z, sc.z, o.z);
-                                        v[4 * j + 3] = fmaf(v[4 * j + 3] - o.w, sc.w, o.w);
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < 32; ++i)
-                                        if (i < ncols) {
-                                            const float o = __ldg(op + i);
-                                            v[i] = o + (v[i] - o) * __ldg(sp + i);
-                                        }
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint4 o4 = *reinterpret_cast<const uint4*>(orig_row + (((4 * uu + j) ^ (r & 7)) << 4));
+                                    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp) + 2 * j);
+                                    const float4 s1 = __ldg(reinterpret_cast<const float4*>(sp) + 2 * j + 1);
+                                    float o;
+                                    o = h2_lo(o4.x); v[8 * j] = fmaf(v[8 * j] - o, s0.x, o);
+                                    o = h2_hi(o4.x); v[8 * j + 1] = fmaf(v[8 * j + 1] - o, s0.y, o);
+                                    o = h2_lo(o4.y); v[8 * j + 2] = fmaf(v[8 * j + 2] - o, s0.z, o);
+                                    o = h2_hi(o4.y); v[8 * j + 3] = fmaf(v[8 * j + 3] - o, s0.w, o);
+                                    o = h2_lo(o4.z); v[8 * j + 4] = fmaf(v[8 * j + 4] - o, s1.x, o);
+                                    o = h2_hi(o4.z); v[8 * j + 5] = fmaf(v[8 * j + 5] - o, s1.y, o);
+                                    o = h2_lo(o4.w); v[8 * j + 6] = fmaf(v[8 * j + 6] - o, s1.z, o);
+                                    o = h2_hi(o4.w); v[8 * j + 7] = fmaf(v[8 * j + 7] - o, s1.w, o);
                                 }
                             }
                             if (p.tma_store) {         // stage into the (swizzled) TMA box, own row only
@@ -706,16 +686,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                     for (int j = 0; j < 8; ++j)
                                         *reinterpret_cast<float4*>(my + ((j ^ (lane & 7)) << 4)) =
                                             make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                                    if (p.out_mode == OUT_F32_BF16) {      // 64-byte rows, 64B swizzle
-                                        uint8_t* sh = shadow_stage + lane * 64;
-#pragma unroll
-                                        for (int j = 0; j < 4; ++j)
-                                            *reinterpret_cast<uint4*>(sh + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                                                make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                           pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                                    }
                                 } else {
-                                    stage_bf16_unit(tbuf, lane, v, 4 * uu);
+                                    stage_h16_unit(tbuf, lane, v, 4 * uu);
                                 }
                                 continue;
                             }
@@ -724,16 +696,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                                  ? aux_smem + slot * GEMM_AUX_BYTES + quarter * 32 * 128
                                                  : private_stage;
                             __syncwarp();              // every lane has consumed its aux row
-                            const bool pairable = p.out_mode == OUT_BF16 && units_per_sub == 2 && (p.ldc & 7) == 0 &&
+                            const bool pairable = p.out_mode == OUT_H16 && units_per_sub == 2 && (p.ldc & 7) == 0 &&
                                                   (out_base & 7) == 0 && (ncols & 7) == 0;
                             if (pairable) {            // stage now, flush both units of the sub-tile together
-                                stage_bf16_unit(stage, lane, v, 4 * uu);
+                                stage_h16_unit(stage, lane, v, 4 * uu);
                                 if (uu == 0) { pend_lo = 0; pend_col = oc; }
                                 pend_hi = 32 * uu + ncols;
                                 pend_stage = stage;
                             } else {
                                 store_unit(p, stage, lane, row_ok, row, row0, rows_ok, oc, ncols, v,
-                                           p.aux_mode == AUX_MUL_BF16 ? 4 * uu : 0);
+                                           p.aux_mode != AUX_NONE ? 4 * uu : 0);
                             }
                         }
                     }
@@ -743,7 +715,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     }
                     if (pend_hi > 0) {
                         __syncwarp();
-                        flush_bf16_units(reinterpret_cast<__nv_bfloat16*>(p.out), p.ldc, pend_stage, lane, row0, rows_ok,
+                        flush_h16_units(reinterpret_cast<__half*>(p.out), p.ldc, pend_stage, lane, row0, rows_ok,
                                          pend_col, pend_lo, pend_hi);
                         __syncwarp();
                         pend_hi = 0;

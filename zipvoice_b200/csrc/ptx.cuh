@@ -3,7 +3,7 @@
 // PTX ISA directly (no CUTLASS dependency).
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -163,7 +163,7 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
 }
 // D[tmem of both CTAs, 256 rows] (+)= A[128 rows in each CTA's smem] * B[N/2 rows in each CTA's smem]^T,
 // issued by the leader CTA only; descriptors hold the leader's addresses (same offsets in the peer).
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                               uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -200,8 +200,8 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, single-CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate, single-CTA.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -251,7 +251,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "memory");
 }
 
-// K-major operand tile in shared memory, rows of 128 bytes (64 bf16), 128B swizzle as written
+// K-major operand tile in shared memory, rows of 128 bytes (64 fp16), 128B swizzle as written
 // by a TMA load with CU_TENSOR_MAP_SWIZZLE_128B into a 1024B-aligned buffer.
 //   bits [0,14)  start address >> 4          bits [16,30) leading byte offset >> 4 (unused: 1)
 //   bits [32,46) stride byte offset >> 4 = 1024 >> 4 (next group of 8 rows)
@@ -265,9 +265,10 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t n, uint32_t m = 128) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=fp16 (formats, bits 7-9 / 10-12 = 0),
+// both K-major, M=m, N=n.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t n, uint32_t m = 128) {
+    return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------- math
@@ -346,11 +347,23 @@ __device__ __forceinline__ float fast_tanh(float x) {
 __device__ __forceinline__ float fast_sigmoid(float x) {
     return __fdividef(1.0f, 1.0f + __expf(-x));
 }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
+// 16-bit storage type of every activation / weight: IEEE fp16 (11-bit significand; the residual stream
+// is kept in it, so its rounding -- not bf16's 8 bits -- bounds the per-module accumulation error).
+// Conversions saturate to +-65504 instead of producing inf.
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
-__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ __half f2h(float v) {
+    const uint32_t w = pack_h2(v, 0.0f);
+    return __ushort_as_half(static_cast<unsigned short>(w & 0xFFFFu));
+}
+__device__ __forceinline__ float h2_lo(uint32_t w) {
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xFFFFu)));
+}
+__device__ __forceinline__ float h2_hi(uint32_t w) {
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16)));
+}
 
 }  // namespace zvb

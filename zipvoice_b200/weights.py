@@ -1,6 +1,6 @@
 """Weight packer: reference-format fp32 `state_dict` -> device buffers laid out for the kernels.
 
-* every nn.Linear weight becomes bf16 row-major (out, k_pitch) with k_pitch = ceil8(in), zero
+* every nn.Linear weight becomes fp16 row-major (out, k_pitch) with k_pitch = ceil8(in), zero
   padded (TMA needs 16-byte row pitches; out-of-range rows/cols are zero-filled by TMA);
 * projections followed by a gate are re-ordered per 256-row tile as [128 | 128] so that both
   gate operands of an output column land in one accumulator tile:
@@ -98,8 +98,8 @@ class PackedZipformer:
     def _pack_w(self, w: torch.Tensor) -> torch.Tensor:
         out_f, in_f = w.shape
         kp = _ceil8(in_f)
-        buf = torch.zeros(out_f, kp, dtype=torch.bfloat16)
-        buf[:, :in_f] = w.to(torch.bfloat16)
+        buf = torch.zeros(out_f, kp, dtype=torch.float16)
+        buf[:, :in_f] = w.clamp(-65504.0, 65504.0).to(torch.float16)
         return self._dev(buf)
 
     def _mk(self, w_dev: torch.Tensor, b_dev: Optional[torch.Tensor], out_f: int, in_f: int):
