@@ -6,8 +6,8 @@
 //   of NonlinAttention) are streamed by a second TMA ring of 16 KB sub-tiles (128 rows x 64 columns),
 //   so the epilogue threads never wait on a global load; the result is staged in place over the
 //   consumed residual sub-tile and leaves as one TMA box store.
-//   Warps 0..7 = epilogue (two warps per TMEM lane quarter, alternating sub-tiles), warp 8 = TMA producer
-//   (A/B), warp 9 = MMA issuer (+TMEM alloc), warp 10 = TMA producer (aux), warp 11 = TMA store thread.
+//   Warps 0..15 = epilogue (four warps per TMEM lane quarter), warp 16 = TMA producer (A/B), warp 17 = MMA
+//   issuer (+TMEM alloc), warp 18 = TMA producer (aux), warp 19 = TMA store thread.
 // Serves every dense contraction of the TTSZipformer forward (reference:
 // modules/zipformer.py:1172,1377,1393,1434-1437,1511,1534,1542,1655,1678, 265, 291).
 #pragma once
@@ -34,13 +34,13 @@ inline void gemm_ring(int block_n, int cluster, int* stages, int* stage_bytes) {
 }
 constexpr int GEMM_AUX_SLOTS = 4;
 constexpr int GEMM_AUX_BYTES = 128 * 128;                       // 128 rows x 128 B
-constexpr int GEMM_BIAS_BYTES = 8 * 128 * 4;               // per epilogue warp: bias of the sub-tile in flight (64 columns, 2 x 64 gated)
+constexpr int GEMM_BIAS_BYTES = 16 * 64 * 4;               // per epilogue warp: bias of the unit in flight (32 columns, 2 x 32 gated)
 constexpr int GEMM_LAYOUT_BYTES = GEMM_OPERAND_BYTES + GEMM_AUX_SLOTS * GEMM_AUX_BYTES + GEMM_BIAS_BYTES +
                                   384 /*barriers*/;
 constexpr int GEMM_SMEM_BYTES = 232448;                    // all 227 KB; layout + alignment pad must fit (checked)
 static_assert(GEMM_LAYOUT_BYTES <= GEMM_SMEM_BYTES, "shared-memory layout too large");
-constexpr int GEMM_THREADS = 384;
-constexpr int GEMM_EPI_THREADS = 256;
+constexpr int GEMM_THREADS = 640;
+constexpr int GEMM_EPI_WARPS = 16;
 constexpr int GEMM_TMEM_COLS = 512;
 
 enum { EPI_LINEAR = 0, EPI_GATED = 1 };
@@ -239,13 +239,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint64_t* sfree = staged + 4;                               // [2 halves][2] store thread -> epilogue
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(sfree + 4);
 
-    // Roles: warps 0..7 = epilogue, 8 = TMA producer (A/B), 9 = MMA issuer (+TMEM alloc), 10 = TMA producer
-    // (aux), 11 = TMA store thread.  The single-thread roles sit in the HIGHEST warp ids because the
+    // Roles: warps 0..15 = epilogue, 16 = TMA producer (A/B), 17 = MMA issuer (+TMEM alloc), 18 = TMA producer
+    // (aux), 19 = TMA store thread.  The single-thread roles sit in the HIGHEST warp ids because the
     // SMSP arbiter favours higher warp ids: an MMA issue or TMA request then never queues behind the
     // FFMA streams of the epilogue warps sharing its scheduler.
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    constexpr int W_TMA = 8, W_MMA = 9, W_AUX = 10, W_STORE = 11;
+    constexpr int W_TMA = GEMM_EPI_WARPS, W_MMA = W_TMA + 1, W_AUX = W_TMA + 2, W_STORE = W_TMA + 3;
     // tile schedule: a "slot" is one tile per CTA of the cluster; slot s -> (b, m_group, n_tile) and the
     // CTA of rank `crank` takes m_tile = m_group*CLUSTER + crank (a tile past num_m_tiles is all padding)
     const int crank = CLUSTER > 1 ? static_cast<int>(cluster_ctarank()) : 0;
@@ -273,12 +273,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 8 * CLUSTER);
+            mbar_init(&tmem_empty[s], GEMM_EPI_WARPS * CLUSTER);
         }
         for (int s = 0; s < GEMM_AUX_SLOTS; ++s) {
             mbar_init(&aux_full[s], 1);
-            mbar_init(&aux_empty[s], p.tma_store ? 1 : 4);
-            mbar_init(&staged[s], 4);
+            mbar_init(&aux_empty[s], p.tma_store ? 1 : (units_per_sub == 2 ? 8 : 4));
+            mbar_init(&staged[s], units_per_sub == 2 ? 8 : 4);
             mbar_init(&sfree[s], 1);
         }
         fence_barrier_init();
@@ -433,14 +433,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (8 warps)
-        // A warp owns 32 accumulator rows (its TMEM lane quarter) of every other sub-tile and stages them
-        // into its rows of the half's 128-row staging box: in place over the consumed aux sub-tile, or in
+        // ------------------------------------------------------------------ epilogue (16 warps)
+        // Four warps share a TMEM lane quarter (32 accumulator rows): `half` selects every other 128-byte
+        // wide sub-tile, `part` the 32-column unit inside a 64-column fp16 sub-tile, so the two parts fill
+        // the two halves of the same staging rows.  The tile-shaped math (bias, activation, residual,
+        // bypass, conversion) is latency bound per warp; four warps per scheduler keep the FMA/MUFU pipes
+        // busy (8 warps: 5.8 activations/clk/SM, 32 warps: 9.6, tools/microbench/epi_math.cu).
+        // Results are staged into the half's 128-row box -- in place over the consumed aux sub-tile, or in
         // the half's two-buffer ring.  No block-level barrier: one lane per warp arrives on `staged`, the
-        // store thread (warp 3) issues the box store and returns the buffer through `sfree`.
+        // store thread issues the box store and returns the buffer through `sfree`.
         const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
-        const int ew = warp;
-        const int half = ew >> 2;                         // which of the two warps of the quarter
+        const int ew = warp;                              // 0..15
+        const int half = (ew >> 2) & 1;
+        const int part = ew >> 3;
         const int r = quarter * 32 + lane;                // accumulator row inside the tile
         uint8_t* private_stage = aux_smem + ew * 4096;    // staging of the non-TMA store paths
         uint32_t kcount = 0;                              // sub-tiles this half handed to the store thread
@@ -459,8 +464,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (lane == 0) mbar_arrive(&staged[half * 2 + (kcount & 1u)]);
             ++kcount;
         };
-        // bias staging of this warp: 64 floats (LINEAR) or 2 x 64 (GATED)
-        float* bs = bias_smem + ew * 128;
+        float* bs = bias_smem + ew * 64;                  // this warp's bias staging: 32 floats (2 x 32 gated)
+        // LINEAR: which sub-tiles / unit this warp takes.  64-column sub-tiles: both parts work on the same
+        // sub-tile; 32-column sub-tiles: with TMA stores the staging ring is per half (part 1 idles, only
+        // the small fp32 outputs take this path), otherwise the four groups alternate.
+        const int s_step = units_per_sub == 2 ? 2 : (p.tma_store ? 2 : 4);
+        const int s_first = units_per_sub == 2 ? half : (p.tma_store ? half : half + 2 * part);
+        const bool lin_active = units_per_sub == 2 || !p.tma_store || part == 0;
+        const int uu = units_per_sub == 2 ? part : 0;     // unit inside the sub-tile
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t tile_iter = 0;
@@ -484,15 +495,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 const int c = acc_base + cc;
                 return (p.bias != nullptr && cc < p.block_n && c < bias_lim) ? __ldg(p.bias + c) : 0.0f;
             };
-            // requested before the accumulator wait: the bias values of this warp's first sub-tile
-            float nb[4];
+            // requested before the accumulator wait: the bias values of this warp's first unit
+            float nb0, nb1 = 0.0f;
             if (KIND == EPI_GATED) {
-                const int hc = p.block_n >> 1;
-                nb[0] = bias_at(64 * half + lane);      nb[1] = bias_at(64 * half + 32 + lane);
-                nb[2] = bias_at(hc + 64 * half + lane); nb[3] = bias_at(hc + 64 * half + 32 + lane);
+                const int u = 2 * half + part;
+                nb0 = bias_at(32 * u + lane);
+                nb1 = bias_at((p.block_n >> 1) + 32 * u + lane);
             } else {
-                nb[0] = bias_at(half * units_per_sub * 32 + lane);
-                nb[1] = units_per_sub == 2 ? bias_at(half * 64 + 32 + lane) : 0.0f;
+                nb0 = bias_at((s_first * units_per_sub + uu) * 32 + lane);
             }
             bool masked = false;
             if (p.row_mask != nullptr && row_ok) masked = p.row_mask[row] != 0;
@@ -509,71 +519,50 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
             if (KIND == EPI_GATED) {
                 const int hcols = p.block_n >> 1;                       // 128
-                // each warp of a quarter takes two adjacent 32-column units so that their fp16 rows leave
-                // as one 128-byte segment
-                int g_lo = 0, g_hi = 0, g_col = 0;
+                // the two parts of a (quarter, half) take adjacent 32-column units so that their fp16 rows
+                // leave as one 128-byte segment
+                const int u = 2 * half + part;
                 const bool g_tma = p.tma_store && 2 * half * 32 < hcols;
                 // this warp's rows of the half's staging ring (two 16 KB buffers)
                 uint8_t* tbuf = aux_smem + ((kcount & 1u) * 2 + half) * GEMM_AUX_BYTES + quarter * 4096;
                 if (g_tma) wait_sfree();
-                bs[lane] = nb[0]; bs[32 + lane] = nb[1]; bs[64 + lane] = nb[2]; bs[96 + lane] = nb[3];
                 __syncwarp();
-                for (int u = 2 * half; u < 2 * half + 2 && u * 32 < hcols; ++u) {
-                    const int c0 = u * 32;
-                    const float* ba = bs + 32 * (u & 1);
+                bs[lane] = nb0; bs[32 + lane] = nb1;
+                __syncwarp();
+                const int c0 = u * 32;
+                const int oc = out_base + c0;
+                int ncols = p.n_out - oc;
+                ncols = ncols > 32 ? 32 : ncols;
+                if (c0 < hcols && (ncols > 0 || g_tma)) {
                     uint32_t ra[32], rb[32];
                     tmem_ld32(taddr + c0, ra);
                     tmem_ld32(taddr + hcols + c0, rb);
                     tmem_ld_wait();
-                    const int oc = out_base + c0;
-                    int ncols = p.n_out - oc;
-                    ncols = ncols > 32 ? 32 : ncols;
-                    if (ncols > 0) {
-                        float v[32];
-                        const bool tanh_gate = p.gate_mode == GATE_TANH_SX;
+                    float v[32];
+                    const bool tanh_gate = p.gate_mode == GATE_TANH_SX;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(ba + 4 * j);
-                            const float4 g4 = *reinterpret_cast<const float4*>(ba + 64 + 4 * j);
-                            const float abv[4] = {b4.x, b4.y, b4.z, b4.w};
-                            const float gbv[4] = {g4.x, g4.y, g4.z, g4.w};
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * j);
+                        const float4 g4 = *reinterpret_cast<const float4*>(bs + 32 + 4 * j);
+                        const float abv[4] = {b4.x, b4.y, b4.z, b4.w};
+                        const float gbv[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float a = __uint_as_float(ra[4 * j + e]) + abv[e];
-                                const float g = __uint_as_float(rb[4 * j + e]) + gbv[e];
-                                const float o = tanh_gate ? g * fast_tanh(a) : a * fast_sigmoid(g);
-                                v[4 * j + e] = masked ? 0.0f : o;
-                            }
-                        }
-                        const bool pairable = p.out_mode == OUT_H16 && (p.ldc & 7) == 0 && (out_base & 7) == 0 &&
-                                              (ncols & 7) == 0;
-                        if (g_tma) {
-                            stage_h16_unit(tbuf, lane, v, 4 * (u & 1));
-                        } else if (pairable) {
-                            stage_h16_unit(private_stage, lane, v, 4 * (u & 1));
-                            if ((u & 1) == 0) g_col = oc;
-                            else if (g_hi == 0) { g_col = oc - 32; g_lo = 32; }
-                            g_hi = 32 * (u & 1) + ncols;
-                        } else {
-                            store_unit(p, private_stage, lane, row_ok, row, row0, rows_ok, oc, ncols, v, 0);
+                        for (int e = 0; e < 4; ++e) {
+                            const float a = __uint_as_float(ra[4 * j + e]) + abv[e];
+                            const float g = __uint_as_float(rb[4 * j + e]) + gbv[e];
+                            const float o = tanh_gate ? g * fast_tanh(a) : a * fast_sigmoid(g);
+                            v[4 * j + e] = masked ? 0.0f : o;
                         }
                     }
+                    if (g_tma) stage_h16_unit(tbuf, lane, v, 4 * part);
+                    else store_unit(p, private_stage, lane, row_ok, row, row0, rows_ok, oc, ncols, v, 0);
                 }
-                if (g_tma) {
-                    signal_staged();
-                } else if (g_hi > 0) {
-                    __syncwarp();
-                    flush_h16_units(reinterpret_cast<__half*>(p.out), p.ldc, private_stage, lane, row0, rows_ok,
-                                     g_col, g_lo, g_hi);
-                    __syncwarp();
-                }
-            } else {
-                for (int s = half; s < n_sub; s += 2) {
+                if (g_tma) signal_staged();
+            } else if (lin_active) {
+                for (int s = s_first; s < n_sub; s += s_step) {
                     const uint8_t* aux_row = nullptr;
                     const uint8_t* orig_row = nullptr;
                     int slot = 0, slot2 = 0;
-                    int pend_lo = 0, pend_hi = 0, pend_col = 0;      // staged, not yet flushed fp16 columns
-                    uint8_t* pend_stage = nullptr;
                     if (p.aux_mode != AUX_NONE) {
                         const uint32_t q = (tile_iter * static_cast<uint32_t>(n_sub) + static_cast<uint32_t>(s)) *
                                            static_cast<uint32_t>(aux_parts);
@@ -587,138 +576,118 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         }
                     }
                     // TMA-store staging of this warp's 32 rows x 128 B: in place over its rows of the consumed
-                    // aux sub-tile, else the private two-buffer ring
+                    // aux sub-tile, else the half's two-buffer ring
                     uint8_t* tbuf = (p.aux_mode != AUX_NONE ? aux_smem + slot * GEMM_AUX_BYTES
                                                             : aux_smem + ((kcount & 1u) * 2 + half) * GEMM_AUX_BYTES) +
                                     quarter * 4096;
                     __syncwarp();                            // the previous sub-tile's bias reads are done
-                    bs[lane] = nb[0];
-                    bs[32 + lane] = nb[1];
+                    bs[lane] = nb0;
                     __syncwarp();
-                    if (s + 2 < n_sub) {                     // request the next sub-tile's bias now
-                        nb[0] = bias_at((s + 2) * units_per_sub * 32 + lane);
-                        nb[1] = units_per_sub == 2 ? bias_at((s + 2) * 64 + 32 + lane) : 0.0f;
-                    }
-                    for (int uu = 0; uu < units_per_sub; ++uu) {
-                        const int c0 = (s * units_per_sub + uu) * 32;
-                        if (c0 >= p.block_n) break;
+                    if (s + s_step < n_sub)                  // request the next unit's bias now
+                        nb0 = bias_at(((s + s_step) * units_per_sub + uu) * 32 + lane);
+                    const int c0 = (s * units_per_sub + uu) * 32;
+                    const int oc = out_base + c0;
+                    int ncols = p.n_valid - c0;
+                    if (p.n_out - oc < ncols) ncols = p.n_out - oc;
+                    ncols = ncols > 32 ? 32 : ncols;
+                    if (c0 < p.block_n && (ncols > 0 || p.tma_store)) {
                         uint32_t acc_r[32];
                         tmem_ld32(taddr + c0, acc_r);
                         tmem_ld_wait();
                         float v[32];
-                        const int oc = out_base + c0;
-                        int ncols = p.n_valid - c0;
-                        if (p.n_out - oc < ncols) ncols = p.n_out - oc;
-                        ncols = ncols > 32 ? 32 : ncols;
-                        if (ncols > 0 || p.tma_store) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 bq = *reinterpret_cast<const float4*>(bs + 32 * uu + 4 * j);
-                                v[4 * j] = fmaf(__uint_as_float(acc_r[4 * j]), rscale, bq.x);
-                                v[4 * j + 1] = fmaf(__uint_as_float(acc_r[4 * j + 1]), rscale, bq.y);
-                                v[4 * j + 2] = fmaf(__uint_as_float(acc_r[4 * j + 2]), rscale, bq.z);
-                                v[4 * j + 3] = fmaf(__uint_as_float(acc_r[4 * j + 3]), rscale, bq.w);
-                            }
-                            const bool vec = ncols == 32 && (p.ldc & 3) == 0;
-                            if (p.rowbias != nullptr && row_ok) {
-                                const float* rbp = p.rowbias + grp * p.ld_rowbias + oc;
-                                if (vec && (p.ld_rowbias & 3) == 0) {
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bq = *reinterpret_cast<const float4*>(bs + 4 * j);
+                            v[4 * j] = fmaf(__uint_as_float(acc_r[4 * j]), rscale, bq.x);
+                            v[4 * j + 1] = fmaf(__uint_as_float(acc_r[4 * j + 1]), rscale, bq.y);
+                            v[4 * j + 2] = fmaf(__uint_as_float(acc_r[4 * j + 2]), rscale, bq.z);
+                            v[4 * j + 3] = fmaf(__uint_as_float(acc_r[4 * j + 3]), rscale, bq.w);
+                        }
+                        const bool vec = ncols == 32 && (p.ldc & 3) == 0;
+                        if (p.rowbias != nullptr && row_ok) {
+                            const float* rbp = p.rowbias + grp * p.ld_rowbias + oc;
+                            if (vec && (p.ld_rowbias & 3) == 0) {
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) {
-                                        const float4 q = __ldg(reinterpret_cast<const float4*>(rbp) + j);
-                                        v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < 32; ++i)
-                                        if (i < ncols) v[i] += __ldg(rbp + i);
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 q = __ldg(reinterpret_cast<const float4*>(rbp) + j);
+                                    v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
                                 }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    if (i < ncols) v[i] += __ldg(rbp + i);
                             }
-                            if (ACT == ACT_SWOOSH_L) {
+                        }
+                        if (ACT == ACT_SWOOSH_L) {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] = swoosh_direct(v[i], SWOOSH_L_C, SWOOSH_L_K0);
-                            } else if (ACT == ACT_SWOOSH_R) {
+                            for (int i = 0; i < 32; ++i) v[i] = swoosh_direct(v[i], SWOOSH_L_C, SWOOSH_L_K0);
+                        } else if (ACT == ACT_SWOOSH_R) {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] = swoosh_direct(v[i], SWOOSH_R_C, SWOOSH_R_K0);
+                            for (int i = 0; i < 32; ++i) v[i] = swoosh_direct(v[i], SWOOSH_R_C, SWOOSH_R_K0);
+                        }
+                        if (p.aux_mode == AUX_ADD_H16) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint4 a = *reinterpret_cast<const uint4*>(aux_row + (((4 * uu + j) ^ (r & 7)) << 4));
+                                v[8 * j] += h2_lo(a.x);     v[8 * j + 1] += h2_hi(a.x);
+                                v[8 * j + 2] += h2_lo(a.y); v[8 * j + 3] += h2_hi(a.y);
+                                v[8 * j + 4] += h2_lo(a.z); v[8 * j + 5] += h2_hi(a.z);
+                                v[8 * j + 6] += h2_lo(a.w); v[8 * j + 7] += h2_hi(a.w);
                             }
-                            if (p.aux_mode == AUX_ADD_H16) {
+                        } else if (p.aux_mode == AUX_MUL_H16) {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const uint4 a = *reinterpret_cast<const uint4*>(aux_row + (((4 * uu + j) ^ (r & 7)) << 4));
-                                    v[8 * j] += h2_lo(a.x);     v[8 * j + 1] += h2_hi(a.x);
-                                    v[8 * j + 2] += h2_lo(a.y); v[8 * j + 3] += h2_hi(a.y);
-                                    v[8 * j + 4] += h2_lo(a.z); v[8 * j + 5] += h2_hi(a.z);
-                                    v[8 * j + 6] += h2_lo(a.w); v[8 * j + 7] += h2_hi(a.w);
-                                }
-                            } else if (p.aux_mode == AUX_MUL_H16) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const uint4 a = *reinterpret_cast<const uint4*>(aux_row + (((4 * uu + j) ^ (r & 7)) << 4));
-                                    v[8 * j] *= h2_lo(a.x);     v[8 * j + 1] *= h2_hi(a.x);
-                                    v[8 * j + 2] *= h2_lo(a.y); v[8 * j + 3] *= h2_hi(a.y);
-                                    v[8 * j + 4] *= h2_lo(a.z); v[8 * j + 5] *= h2_hi(a.z);
-                                    v[8 * j + 6] *= h2_lo(a.w); v[8 * j + 7] *= h2_hi(a.w);
-                                }
+                            for (int j = 0; j < 4; ++j) {
+                                const uint4 a = *reinterpret_cast<const uint4*>(aux_row + (((4 * uu + j) ^ (r & 7)) << 4));
+                                v[8 * j] *= h2_lo(a.x);     v[8 * j + 1] *= h2_hi(a.x);
+                                v[8 * j + 2] *= h2_lo(a.y); v[8 * j + 3] *= h2_hi(a.y);
+                                v[8 * j + 4] *= h2_lo(a.z); v[8 * j + 5] *= h2_hi(a.z);
+                                v[8 * j + 6] *= h2_lo(a.w); v[8 * j + 7] *= h2_hi(a.w);
                             }
-                            if (orig_row != nullptr) {        // bypass, `orig` sub-tile staged by TMA
-                                const float* sp = p.bypass_scale + oc;
+                        }
+                        if (orig_row != nullptr) {        // bypass, `orig` sub-tile staged by TMA
+                            const float* sp = p.bypass_scale + oc;
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const uint4 o4 = *reinterpret_cast<const uint4*>(orig_row + (((4 * uu + j) ^ (r & 7)) << 4));
-                                    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp) + 2 * j);
-                                    const float4 s1 = __ldg(reinterpret_cast<const float4*>(sp) + 2 * j + 1);
-                                    float o;
-                                    o = h2_lo(o4.x); v[8 * j] = fmaf(v[8 * j] - o, s0.x, o);
-                                    o = h2_hi(o4.x); v[8 * j + 1] = fmaf(v[8 * j + 1] - o, s0.y, o);
-                                    o = h2_lo(o4.y); v[8 * j + 2] = fmaf(v[8 * j + 2] - o, s0.z, o);
-                                    o = h2_hi(o4.y); v[8 * j + 3] = fmaf(v[8 * j + 3] - o, s0.w, o);
-                                    o = h2_lo(o4.z); v[8 * j + 4] = fmaf(v[8 * j + 4] - o, s1.x, o);
-                                    o = h2_hi(o4.z); v[8 * j + 5] = fmaf(v[8 * j + 5] - o, s1.y, o);
-                                    o = h2_lo(o4.w); v[8 * j + 6] = fmaf(v[8 * j + 6] - o, s1.z, o);
-                                    o = h2_hi(o4.w); v[8 * j + 7] = fmaf(v[8 * j + 7] - o, s1.w, o);
-                                }
+                            for (int j = 0; j < 4; ++j) {
+                                const uint4 o4 = *reinterpret_cast<const uint4*>(orig_row + (((4 * uu + j) ^ (r & 7)) << 4));
+                                const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp) + 2 * j);
+                                const float4 s1 = __ldg(reinterpret_cast<const float4*>(sp) + 2 * j + 1);
+                                float o;
+                                o = h2_lo(o4.x); v[8 * j] = fmaf(v[8 * j] - o, s0.x, o);
+                                o = h2_hi(o4.x); v[8 * j + 1] = fmaf(v[8 * j + 1] - o, s0.y, o);
+                                o = h2_lo(o4.y); v[8 * j + 2] = fmaf(v[8 * j + 2] - o, s0.z, o);
+                                o = h2_hi(o4.y); v[8 * j + 3] = fmaf(v[8 * j + 3] - o, s0.w, o);
+                                o = h2_lo(o4.z); v[8 * j + 4] = fmaf(v[8 * j + 4] - o, s1.x, o);
+                                o = h2_hi(o4.z); v[8 * j + 5] = fmaf(v[8 * j + 5] - o, s1.y, o);
+                                o = h2_lo(o4.w); v[8 * j + 6] = fmaf(v[8 * j + 6] - o, s1.z, o);
+                                o = h2_hi(o4.w); v[8 * j + 7] = fmaf(v[8 * j + 7] - o, s1.w, o);
                             }
-                            if (p.tma_store) {         // stage into the (swizzled) TMA box, own row only
-                                if (uu == 0) wait_sfree();      // earlier stores no longer read what is overwritten
-                                if (out_f32) {
-                                    uint8_t* my = tbuf + lane * 128;
+                        }
+                        if (p.tma_store) {             // stage into the (swizzled) TMA box, own row only
+                            wait_sfree();              // earlier stores no longer read what is overwritten
+                            if (out_f32) {
+                                uint8_t* my = tbuf + lane * 128;
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j)
-                                        *reinterpret_cast<float4*>(my + ((j ^ (lane & 7)) << 4)) =
-                                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                                } else {
-                                    stage_h16_unit(tbuf, lane, v, 4 * uu);
-                                }
-                                continue;
+                                for (int j = 0; j < 8; ++j)
+                                    *reinterpret_cast<float4*>(my + ((j ^ (lane & 7)) << 4)) =
+                                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            } else {
+                                stage_h16_unit(tbuf, lane, v, 4 * uu);
                             }
+                        } else {
                             // in place over the consumed aux rows of this warp, or in the warp's private area
                             uint8_t* stage = p.aux_mode != AUX_NONE
                                                  ? aux_smem + slot * GEMM_AUX_BYTES + quarter * 32 * 128
                                                  : private_stage;
                             __syncwarp();              // every lane has consumed its aux row
-                            const bool pairable = p.out_mode == OUT_H16 && units_per_sub == 2 && (p.ldc & 7) == 0 &&
-                                                  (out_base & 7) == 0 && (ncols & 7) == 0;
-                            if (pairable) {            // stage now, flush both units of the sub-tile together
-                                stage_h16_unit(stage, lane, v, 4 * uu);
-                                if (uu == 0) { pend_lo = 0; pend_col = oc; }
-                                pend_hi = 32 * uu + ncols;
-                                pend_stage = stage;
-                            } else {
-                                store_unit(p, stage, lane, row_ok, row, row0, rows_ok, oc, ncols, v,
-                                           p.aux_mode != AUX_NONE ? 4 * uu : 0);
-                            }
+                            store_unit(p, stage, lane, row_ok, row, row0, rows_ok, oc, ncols, v,
+                                       p.aux_mode != AUX_NONE ? 4 * uu : 0);
                         }
+                    } else if (p.tma_store) {
+                        wait_sfree();                  // keeps the buffer hand-shake in step (no columns to stage)
                     }
                     if (p.tma_store) {
                         signal_staged();
                         continue;
-                    }
-                    if (pend_hi > 0) {
-                        __syncwarp();
-                        flush_h16_units(reinterpret_cast<__half*>(p.out), p.ldc, pend_stage, lane, row0, rows_ok,
-                                         pend_col, pend_lo, pend_hi);
-                        __syncwarp();
-                        pend_hi = 0;
                     }
                     if (p.aux_mode != AUX_NONE) {
                         __syncwarp();
