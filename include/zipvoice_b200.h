@@ -59,8 +59,10 @@ typedef struct {
 /* Zipformer2EncoderLayer (reference: modules/zipformer.py:370-404) */
 typedef struct {
     zvb_linear attn_in;       /* self_attn_weights.in_proj : D -> H*(2*32+4)               */
-    const float* pos_table;   /* E = linear_pos(pos_emb): fp32 [H][2L-1][4] for this plan's L, followed by
-                               * [H] floats max_r |E[h][r]|_2 */
+    const void* pos_table;    /* E = linear_pos(pos_emb) for this plan's L, folded on the host into
+                               * [H][2L-1+256] 16-byte entries of fp16 column pairs {log2e*E[r][d],
+                               * log2e*E[r+1][d]} (d = 0..3, entry = r + 128, zeros outside), followed by
+                               * [H] fp32 max_r |E[h][r]|_2 (zipvoice_b200/weights.py: pack_pos_table) */
     zvb_linear ff_in[3], ff_out[3];
     zvb_linear na_sx;         /* nonlin_attention.in_proj rows (s,x), gated-packed          */
     zvb_linear na_y;          /* nonlin_attention.in_proj rows y                            */
@@ -176,9 +178,10 @@ int zvb_sample(zvb_plan* plan, float* x, const float* text, const float* speech,
 int zvb_test_linear(const void* A, int M, int K, int lda, const void* W, const float* bias, int n_out,
                     int k_pitch, int block_n, int act, const void* resid, const void* orig,
                     const float* bypass_scale, void* out, int ldc, int out_mode, void* stream);
-/* P receives the unnormalised weights exp(s - m), inv_l [N][H][L] the reciprocal row sums */
-int zvb_test_attn_weights(const void* qkp, int ld, const float* pos_table, const uint8_t* mask, void* P,
-                          float* inv_l, int N, int H, int L, int Lk, void* stream);
+/* P receives the unnormalised weights 2^12 exp(s - m), inv_l [N][H][L] the reciprocal row sums;
+ * pos_table as in zvb_layer; scratch: N * 4 * ceil(L/128) 32-bit words (excluded-key bits) */
+int zvb_test_attn_weights(const void* qkp, int ld, const void* pos_table, const uint8_t* mask, void* scratch,
+                          void* P, float* inv_l, int N, int H, int L, int Lk, void* stream);
 /* mul: fp16 [N*L][hd] gate of NonlinAttention (per_head == 0 only, nullable) */
 int zvb_test_pv(const void* P, const float* inv_l, const void* Vt, void* out, int N, int H, int L, int Lk, int hd,
                 int hp, int per_head, const void* mul, void* stream);

@@ -10,6 +10,7 @@ import math
 import torch
 
 from zipvoice_b200 import _lib
+from zipvoice_b200.weights import pack_pos_table
 
 DEV = "cuda"
 H16 = torch.float16          # storage type of every activation / weight on the CUDA path
@@ -134,25 +135,27 @@ def _attn_ref(qkp, E, mask, H):
 
 
 def check_attn(N=2, H=4, L=200, masked=True, seed=0):
-    """tolerance: max-abs <= 1e-3 on probabilities (fp16 storage of P: 2^-12 relative; ex2.approx)"""
+    """tolerance: max-abs <= 2.5e-3 on probabilities (the rel-pos bias and the exponent are evaluated in
+    packed fp16: ~2^-9 absolute on an exponent of a few units; fp16 storage of P)"""
     lib = _lib.load()
     qkp, E, mask = _attn_inputs(N, H, L, seed, masked)
     Lk = (L + 7) // 8 * 8
     P = torch.full((N, H, L, Lk), float("nan"), dtype=H16, device=DEV)
     inv_l = torch.full((N, H, L), float("nan"), dtype=torch.float32, device=DEV)
     m8 = mask.to(torch.uint8).contiguous()
-    Ex = torch.cat([E.reshape(-1), E.norm(dim=2).amax(dim=1)]).contiguous()
-    _lib.check(lib.zvb_test_attn_weights(qkp.data_ptr(), H * 68, Ex.data_ptr(), m8.data_ptr(), P.data_ptr(),
-                                         inv_l.data_ptr(), N, H, L, Lk, _s()))
+    Ex = pack_pos_table(E)
+    scratch = torch.zeros(N * 4 * ((L + 127) // 128), dtype=torch.int32, device=DEV)
+    _lib.check(lib.zvb_test_attn_weights(qkp.data_ptr(), H * 68, Ex.data_ptr(), m8.data_ptr(), scratch.data_ptr(),
+                                         P.data_ptr(), inv_l.data_ptr(), N, H, L, Lk, _s()))
     torch.cuda.synchronize()
     ref = _attn_ref(qkp, E, mask, H)
     pmax = float(P.float()[..., :L].max())
-    assert 0 < pmax <= 1.0 + 1e-3, pmax                    # unnormalised weights live in (0, 1]
+    assert 0 < pmax <= 4096.0 * 1.01, pmax                 # unnormalised weights live in (0, 2^12]
     got = P.float() * inv_l.unsqueeze(-1)
     pad = got[..., L:]
     return dict(maxabs=float((got[..., :L] - ref).abs().max()), rel=_rel(got[..., :L], ref),
                 nan=int(torch.isnan(got).sum()), pad_nonzero=int((pad != 0).sum()),
-                rowsum_err=float((got[..., :L].sum(-1) - 1).abs().max()), tol=1e-3)
+                rowsum_err=float((got[..., :L].sum(-1) - 1).abs().max()), tol=2.5e-3)
 
 
 def check_pv(N=2, H=4, L=200, hd=12, hp=16, per_head=True, mul=False, seed=0):

@@ -7,9 +7,15 @@
 // window of 255 relative offsets.  Softmax is split so that every score costs one exp and one
 // bias evaluation: pass 1 only takes the row max of q·kᵀ from TMEM (no bias, no exp); with
 // m = max_j q·k_j + |p_i|·max_r|E_h[r]| >= every score of the row, pass 2 recomputes the cheap q·kᵀ,
-// adds the bias and writes the UNNORMALISED weights exp(s - m) in (0, 1] as fp16 together with the
-// fp32 row sum's reciprocal; the three consumers of the layer (NonlinAttention, SelfAttention x2)
-// apply 1/l in their GEMM epilogue.  Masked keys get exactly 0 (exp(-1000 - m) == 0 in fp32).
+// adds the bias and writes the UNNORMALISED weights 2^12·exp(s - m) as fp16 together with the fp32
+// row sum's reciprocal; the three consumers of the layer (NonlinAttention, SelfAttention x2) apply 1/l
+// in their GEMM epilogue.  Masked keys get exactly 0 (the reference's -1000 fill underflows as well).
+// Pass 2 runs on packed half2: the (q·k - m)·log2e pair is formed in fp32 and converted once, the
+// 4-term bias is 1 HMUL2 + 3 HFMA2 against the window stored as column PAIRS (one 16-byte LDS per two
+// scores), the exponential is MUFU.EX2.F16 and its result IS the stored fp16 weight -- 7 instructions
+// per score instead of 18 with fp32 arithmetic.  The bound m may exceed the true row max by up to
+// 2·|p_i|·max|E|; the 2^12 head-room keeps the weights of such rows in fp16's normal range (a row only
+// degrades once the bound is loose by more than 2^26, far beyond the reference's own score limit).
 // The softmax is latency bound (TMEM load -> LDS of the rel-pos entries -> FFMA chain -> MUFU), so a
 // CTA runs EIGHT softmax warps -- two per TMEM lane quarter, each owning 64 of the tile's 128 key
 // columns and exchanging row max / row sum through shared memory -- and two CTAs share an SM
@@ -27,17 +33,21 @@ constexpr int ATT_SM_WARPS = 8;      // softmax warps: two per TMEM lane quarter
 constexpr int ATT_THREADS = 64 + 32 * ATT_SM_WARPS;
 constexpr int ATT_TMEM_COLS = 256;
 constexpr int ATT_EWIN = 256;        // 255 offsets used
+constexpr int ATT_POS_PAD = 128;     // zero entries on both sides of the rel-pos table (weights.py: POS_PAD)
+constexpr int ATT_EWIN_BYTES = 255 * 16;
 constexpr int ATT_STAGE_BYTES = ATT_SM_WARPS * 4096; // per softmax warp: 32 rows x 128 B TMA-store staging
 constexpr int ATT_SMEM_BYTES = (1 + ATT_KSTAGES) * ATT_TILE_BYTES + ATT_STAGE_BYTES + 2 * ATT_EWIN * 16 +
-                               2 * 16 + 2 * 128 * 4 + 1024 + 256;
+                               2 * 128 * 4 + 1024 + 256;
 
 struct AttnParams {
     int L, Lk, H, N;
     int qd;                          // H * 32: column of head-0 keys inside a qkp row
     const __half* qkp;        // [N*L, ld] = [q | k | p]
     int ld;
-    const float* E;                  // [H][2L-1][4] followed by [H] floats: max_r |E[h][r]|_2
-    const uint8_t* mask;             // [N][L], non-zero = padded key
+    const uint4* Epair;              // [H][2L-1 + 2*ATT_POS_PAD] fp16 column pairs (weights.py: pack_pos_table)
+    const float* emax;               // [H] max_r |E[h][r]|_2
+    const uint32_t* maskw;           // [N][mask_words] bit j%32 of word j/32 set = key j excluded (padded or >= L)
+    int mask_words;                  // 4 * ceil(L / 128)
     __half* P;                // [N][H][L][Lk] unnormalised weights exp(s - m) (written through tma_p)
     float* inv_l;                    // [N][H][L]     1 / row sum
 };
@@ -52,17 +62,19 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
     uint8_t* q_tile = smem;
     uint8_t* k_tiles = smem + ATT_TILE_BYTES;
     uint8_t* stage_all = smem + (1 + ATT_KSTAGES) * ATT_TILE_BYTES;                        // [8][32][128 B]
-    // rel-pos window of the (i-tile, j-tile): 255 offsets x 4 floats, pre-scaled by log2 e
-    float4* ewin = reinterpret_cast<float4*>(stage_all + ATT_STAGE_BYTES);                  // [2][256]
-    uint32_t* mwin = reinterpret_cast<uint32_t*>(ewin + 2 * ATT_EWIN);                      // [2][4] excluded-key bits
-    float* xch = reinterpret_cast<float*>(mwin + 8);                                        // [2][128] half <-> half
+    // rel-pos window of the (i-tile, j-tile), pre-scaled by log2 e, as fp16 column pairs: entry e holds
+    // {E[e][d], E[e+1][d]} for d = 0..3, so the pair of columns (c, c+1) of row r reads entry c - r + 127
+    uint4* ewin = reinterpret_cast<uint4*>(stage_all + ATT_STAGE_BYTES);                    // [2][256]
+    float* xch = reinterpret_cast<float*>(ewin + 2 * ATT_EWIN);                             // [2][128] half <-> half
     uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 256);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1;                      // [KSTAGES]
     uint64_t* k_empty = k_full + ATT_KSTAGES;         // [KSTAGES]
     uint64_t* s_full = k_empty + ATT_KSTAGES;         // [2]
     uint64_t* s_empty = s_full + 2;                   // [2]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(s_empty + 2);
+    uint64_t* e_full = s_empty + 2;                   // [2] rel-pos window landed
+    uint64_t* e_empty = e_full + 2;                   // [2] rel-pos window consumed (second pass only)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(e_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -83,6 +95,8 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
         for (int s = 0; s < 2; ++s) {
             mbar_init(&s_full[s], 1);
             mbar_init(&s_empty[s], ATT_SM_WARPS);
+            mbar_init(&e_full[s], 1);
+            mbar_init(&e_empty[s], ATT_SM_WARPS);
         }
         fence_barrier_init();
     }
@@ -101,6 +115,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
             tma_load_3d(q_tile, &tma_qk, q_full, h * 32, i0, n);
             int stage = 0;
             uint32_t phase = 0;
+            const uint4* Eh = p.Epair + static_cast<long long>(h) * (2 * p.L - 1 + 2 * ATT_POS_PAD);
             for (int it = 0; it < total_it; ++it) {
                 const int jt = it >= num_jt ? it - num_jt : it;
                 mbar_wait(&k_empty[stage], phase ^ 1u);
@@ -108,6 +123,16 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
                 tma_load_3d(k_tiles + stage * ATT_TILE_BYTES, &tma_qk, &k_full[stage], p.qd + h * 32,
                             jt * ATT_BN, n);
                 if (++stage == ATT_KSTAGES) { stage = 0; phase ^= 1u; }
+                if (it >= num_jt) {
+                    // rel-pos window of this (i-tile, j-tile): 255 consecutive pair entries, first offset
+                    // (j0 - i0) - 127, into buffer it & 1 (its own full/empty pair: this thread runs up to
+                    // three tiles ahead of the softmax warps, so it cannot share the accumulator hand-shake)
+                    const int eb = it & 1;
+                    mbar_wait(&e_empty[eb], (static_cast<uint32_t>((it - num_jt) >> 1) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&e_full[eb], ATT_EWIN_BYTES);
+                    bulk_load_1d(ewin + eb * ATT_EWIN, Eh + ((jt * ATT_BN - i0) - 127 + (p.L - 1) + ATT_POS_PAD),
+                                 ATT_EWIN_BYTES, &e_full[eb]);
+                }
             }
         }
     } else if (warp == ATT_SM_WARPS + 1) {                // MMA issuer
@@ -143,13 +168,16 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
         const int i = i0 + r;
         const bool row_ok = i < p.L;
         float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+        uint32_t ph0 = 0u, ph1 = 0u, ph2 = 0u, ph3 = 0u;          // p_d duplicated into both halves
         if (row_ok) {
             const __half* pp = p.qkp + (static_cast<long long>(n) * p.L + i) * p.ld + 2 * p.qd + h * 4;
             const uint2 w = *reinterpret_cast<const uint2*>(pp);
             p0 = h2_lo(w.x); p1 = h2_hi(w.x); p2 = h2_lo(w.y); p3 = h2_hi(w.y);
+            ph0 = __byte_perm(w.x, 0u, 0x1010); ph1 = __byte_perm(w.x, 0u, 0x3232);
+            ph2 = __byte_perm(w.y, 0u, 0x1010); ph3 = __byte_perm(w.y, 0u, 0x3232);
         }
-        const float4* Eh = reinterpret_cast<const float4*>(p.E) + static_cast<long long>(h) * (2 * p.L - 1);
-        const uint8_t* mrow = p.mask + static_cast<long long>(n) * p.L;
+        // excluded-key bits of this warp's 64 columns of tile jt: words 2*half, 2*half + 1 of the tile's four
+        const uint32_t* mwrow = p.maskw + static_cast<long long>(n) * p.mask_words + 2 * half;
         // P leaves through TMA stores: every warp stages 32 rows x 64 columns (128-byte rows, 128B
         // swizzle) and one lane issues the box store; rows >= L and columns >= Lk are clipped by the map
         uint8_t* stage = stage_all + (tid >> 5) * 4096;
@@ -157,24 +185,6 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
         const int sw = lane & 7;
         constexpr float LOG2E = 1.4426950408889634f;
         float m_run = -INFINITY, m_l2 = 0.f, l_run = 0.f;
-        // mask byte / rel-pos entry this thread stages for iteration `it2` (global loads, prefetched)
-        float4 e_cur = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool ex_cur = true;
-        auto fetch = [&](int it2) {
-            const int pass2 = it2 >= num_jt ? 1 : 0;
-            const int j02 = (pass2 ? it2 - num_jt : it2) * ATT_BN;
-            if (tid < 128) {
-                const int j = j02 + tid;
-                ex_cur = j < p.L ? (mrow[j] != 0) : true;
-            }
-            e_cur = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pass2 && tid < 255) {
-                const int rel = (j02 - i0) - 127 + tid + (p.L - 1);
-                if (rel >= 0 && rel <= 2 * p.L - 2) e_cur = __ldg(Eh + rel);
-            }
-        };
-        fetch(0);
-
         for (int it = 0; it < total_it; ++it) {
             const int pass = it >= num_jt ? 1 : 0;
             const int jt = pass ? it - num_jt : it;
@@ -185,23 +195,14 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
                 xch[half * 128 + r] = m_run;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const float mr = fmaxf(xch[r], xch[128 + r]);
-                const float emax = __ldg(p.E + static_cast<long long>(p.H) * (2 * p.L - 1) * 4 + h);
+                const float emax = __ldg(p.emax + h);
                 const float pn = sqrtf(p0 * p0 + p1 * p1 + p2 * p2 + p3 * p3);
                 const float m_est = (mr == -INFINITY ? 0.f : mr) + pn * emax;
-                m_l2 = m_est * LOG2E;
+                m_l2 = m_est * LOG2E - 12.0f;            // weights are stored scaled by 2^12
             }
-            // stage the excluded-key bits (padding mask or beyond L) and, for the second pass, the
-            // rel-pos window of this tile (double buffered); both were requested one iteration ago
-            float4* ew = ewin + acc * ATT_EWIN;
-            uint32_t* mw = mwin + acc * 4;
-            if (tid < 128) {
-                const uint32_t bits = __ballot_sync(0xffffffffu, ex_cur);
-                if (lane == 0) mw[tid >> 5] = bits;
-            }
-            if (pass && tid < 255)
-                ew[tid] = make_float4(e_cur.x * LOG2E, e_cur.y * LOG2E, e_cur.z * LOG2E, e_cur.w * LOG2E);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (it + 1 < total_it) fetch(it + 1);         // in flight during this tile's arithmetic
+            const uint4* ew = ewin + acc * ATT_EWIN;
+            const uint32_t mw0 = __ldg(mwrow + 4 * jt), mw1 = __ldg(mwrow + 4 * jt + 1);
+            if (pass) mbar_wait(&e_full[acc], static_cast<uint32_t>((it - num_jt) >> 1) & 1u);
             mbar_wait(&s_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * ATT_BN + 64 * half) +
@@ -212,7 +213,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
                     uint32_t sr[32];
                     tmem_ld32(taddr + c0, sr);
                     tmem_ld_wait();
-                    const uint32_t excl = mw[2 * half + (c0 >> 5)];
+                    const uint32_t excl = c0 ? mw1 : mw0;
                     float cm = -INFINITY;
                     if (excl == 0u) {
 #pragma unroll
@@ -235,34 +236,33 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
                     uint32_t sr[16];
                     tmem_ld16(taddr + 16 * g, sr);
                     tmem_ld_wait();
-                    const uint32_t excl = (mw[2 * half + (g >> 1)] >> (16 * (g & 1))) & 0xffffu;
-                    const float4* ep = ew + (64 * half + 16 * g - r + 127);
-                    float ls = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 16; c += 2) {
-                        const float4 ea = ep[c], eb = ep[c + 1];
-                        float a = fmaf(__uint_as_float(sr[c]), LOG2E, -m_l2);
-                        float b = fmaf(__uint_as_float(sr[c + 1]), LOG2E, -m_l2);
-                        a = fmaf(p0, ea.x, a); b = fmaf(p0, eb.x, b);
-                        a = fmaf(p1, ea.y, a); b = fmaf(p1, eb.y, b);
-                        a = fmaf(p2, ea.z, a); b = fmaf(p2, eb.z, b);
-                        a = fmaf(p3, ea.w, a); b = fmaf(p3, eb.w, b);
-                        sr[c] = __float_as_uint(fast_exp2(a));
-                        sr[c + 1] = __float_as_uint(fast_exp2(b));
-                    }
-                    if (excl != 0u) {           // rare: a real branch, so unmasked tiles issue no selects
-#pragma unroll
-                        for (int c = 0; c < 16; ++c)
-                            if ((excl >> c) & 1u) sr[c] = 0u;
-                    }
+                    const uint32_t excl = ((g & 2 ? mw1 : mw0) >> (16 * (g & 1))) & 0xffffu;
+                    const uint4* ep = ew + (64 * half + 16 * g - r + 127);
                     uint32_t w[8];
 #pragma unroll
                     for (int c = 0; c < 16; c += 2) {
-                        const float a = __uint_as_float(sr[c]), b = __uint_as_float(sr[c + 1]);
-                        w[c >> 1] = pack_h2(a, b);
-                        ls += a + b;
+                        const uint4 e4 = ep[c];
+                        const float a = fmaf(__uint_as_float(sr[c]), LOG2E, -m_l2);
+                        const float b = fmaf(__uint_as_float(sr[c + 1]), LOG2E, -m_l2);
+                        uint32_t bias = hmul2(ph0, e4.x);
+                        bias = hfma2(ph1, e4.y, bias);
+                        bias = hfma2(ph2, e4.z, bias);
+                        bias = hfma2(ph3, e4.w, bias);
+                        const uint32_t pw = ex2_h2(hadd2(bias, pack_h2(a, b)));
+                        w[c >> 1] = pw;
                     }
-                    l_run += ls;
+                    if (excl != 0u) {           // rare: a real branch, so unmasked tiles issue no selects
+#pragma unroll
+                        for (int c = 0; c < 16; c += 2) {
+                            const uint32_t keep = (((excl >> c) & 1u) ? 0u : 0x0000FFFFu) |
+                                                  (((excl >> (c + 1)) & 1u) ? 0u : 0xFFFF0000u);
+                            w[c >> 1] &= keep;
+                        }
+                    }
+                    // half2 partial row sum of the group (<= 8 x 2^12 per half), then fp32
+                    const uint32_t sum2 = hadd2(hadd2(hadd2(w[0], w[1]), hadd2(w[2], w[3])),
+                                                hadd2(hadd2(w[4], w[5]), hadd2(w[6], w[7])));
+                    l_run += h2_lo(sum2) + h2_hi(sum2);
                     *reinterpret_cast<uint4*>(my + (((2 * g) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                     *reinterpret_cast<uint4*>(my + (((2 * g + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
                 }
@@ -277,12 +277,18 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[acc]);
+            if (lane == 0) {
+                mbar_arrive(&s_empty[acc]);
+                if (pass) mbar_arrive(&e_empty[acc]);
+            }
         }
         xch[half * 128 + r] = l_run;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (half == 0 && row_ok)
-            p.inv_l[(static_cast<long long>(n) * p.H + h) * p.L + i] = 1.0f / (xch[r] + xch[128 + r]);
+        {
+            const float l = xch[r] + xch[128 + r];
+            p.inv_l[(static_cast<long long>(n) * p.H + h) * p.L + i] = l > 0.f ? 1.0f / l : 0.f;
+        }
         if (lane == 0) bulk_wait_read<0>();               // staging must outlive the stores reading it
     }
 

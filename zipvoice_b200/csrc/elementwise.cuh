@@ -388,4 +388,20 @@ __global__ void stride_mask_kernel(const uint8_t* __restrict__ mask, uint8_t* __
     out[idx] = mask[static_cast<long long>(n) * T + l * ds];
 }
 
+// Excluded-key bit words for the attention kernel: bit (j % 32) of word j / 32 is set when key j of the
+// utterance is padded or j >= L; `words` per utterance covers whole 128-key tiles.
+__global__ void mask_words_kernel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ out, int N, int L,
+                                  int words) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * words) return;
+    const int n = idx / words, w = idx - n * words;
+    uint32_t bits = 0u;
+    for (int b = 0; b < 32; ++b) {
+        const int j = w * 32 + b;
+        const bool ex = j < L ? mask[static_cast<long long>(n) * L + j] != 0 : true;
+        bits |= (ex ? 1u : 0u) << b;
+    }
+    out[idx] = bits;
+}
+
 }  // namespace zvb

@@ -133,7 +133,7 @@ static int make_tmap_plain(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_
 }
 
 // ------------------------------------------------------------------------------------------ ops
-enum OpType { OP_GEMM, OP_ATTN, OP_BIASNORM, OP_PREP, OP_DOWN, OP_UP, OP_DWCONV, OP_MASK, OP_TSEMB, OP_SMALL };
+enum OpType { OP_GEMM, OP_ATTN, OP_BIASNORM, OP_PREP, OP_DOWN, OP_UP, OP_DWCONV, OP_MASK, OP_MASKW, OP_TSEMB, OP_SMALL };
 
 struct Op {
     OpType type;
@@ -365,12 +365,19 @@ static int build_pv(Op& op, const h16* P, const float* inv_l, const h16* Vt, voi
     return 0;
 }
 
-static int build_attn(Op& op, const h16* qkp, int ld, const float* E, const uint8_t* mask, h16* P, float* inv_l,
-                      int N, int H, int L, int Lk) {
+static inline int attn_mask_words(int L) { return 4 * ((L + ATT_BN - 1) / ATT_BN); }
+
+// pos_table: the layout of weights.py:pack_pos_table for this L; maskw: [N][attn_mask_words(L)] (mask_words_op)
+static int build_attn(Op& op, const h16* qkp, int ld, const void* pos_table, const uint32_t* maskw, h16* P,
+                      float* inv_l, int N, int H, int L, int Lk) {
     op.type = OP_ATTN;
     AttnParams& a = op.ap;
     a.L = L; a.Lk = Lk; a.H = H; a.N = N; a.qd = H * 32;
-    a.qkp = qkp; a.ld = ld; a.E = E; a.mask = mask; a.P = P; a.inv_l = inv_l;
+    a.qkp = qkp; a.ld = ld; a.P = P; a.inv_l = inv_l;
+    if ((reinterpret_cast<uintptr_t>(pos_table) & 15) != 0) return fail(ZVB_ERR_INVALID, "attn: pos table must be 16-byte aligned");
+    a.Epair = reinterpret_cast<const uint4*>(pos_table);
+    a.emax = reinterpret_cast<const float*>(a.Epair + static_cast<size_t>(H) * (2 * L - 1 + 2 * ATT_POS_PAD));
+    a.maskw = maskw; a.mask_words = attn_mask_words(L);
     if (ld % 8 != 0 || Lk % 8 != 0) return fail(ZVB_ERR_INVALID, "attn: pitches must be multiples of 8");
     TRY(make_tmap(&op.ma, qkp, ld, L, N, (uint64_t)ld * 2, (uint64_t)ld * 2 * L, ATT_BM));
     // P as (Lk, L, N*H): every softmax warp stores 32-row x 64-column boxes
@@ -380,6 +387,11 @@ static int build_attn(Op& op, const h16* qkp, int ld, const float* E, const uint
     // q.k (K = 32) + rel-pos (4-dim dot against 2L-1 offsets), reference FLOP model SURVEY.md §8d
     op.work = (double)N * H * (2.0 * L * L * 32 + 2.0 * L * (2.0 * L - 1) * 4);
     return 0;
+}
+
+static Op mask_words_op(const uint8_t* mask, uint32_t* out, int N, int L) {
+    Op op; op.type = OP_MASKW; op.p0 = mask; op.o0 = out; op.i0 = N; op.i1 = L; op.i2 = attn_mask_words(L);
+    return op;
 }
 
 static int build_dwconv(Op& d, const h16* x, h16* out, const float* w, const float* b, int N, int L, int C, int K) {
@@ -489,6 +501,11 @@ static int launch_op(const Op& op, cudaStream_t st) {
                                                                  op.i2, op.i3);
             return check_launch("stride_mask");
         }
+        case OP_MASKW: {
+            const int n = op.i0 * op.i2;
+            mask_words_kernel<<<(n + 255) / 256, 256, 0, st>>>((const uint8_t*)op.p0, (uint32_t*)op.o0, op.i0, op.i1, op.i2);
+            return check_launch("mask_words");
+        }
         case OP_TSEMB: {
             const int n = op.i0 * (op.i1 / 2);
             timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, st>>>(op.f0, (float*)op.o0, op.i0, op.i1);
@@ -590,6 +607,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
     // per-resolution buffers (pads of the transposed V stay zero for the lifetime of the plan)
     h16 *vtna[5] = {}, *vtsa[5] = {};
     uint8_t* mask_ds[5] = {};
+    uint32_t* maskw_ds[5] = {};
     for (int ds = 1; ds <= 4; ds *= 2) {
         bool used = false;
         for (int s = 0; s < m->num_stacks; ++s) used |= m->stacks[s].downsample == ds;
@@ -598,6 +616,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
         vtna[ds] = c.take<h16>((size_t)N * nah * Lk);
         vtsa[ds] = c.take<h16>((size_t)N * H * hp * Lk);
         mask_ds[ds] = ds == 1 ? mask : c.take<uint8_t>((size_t)N * L);
+        maskw_ds[ds] = c.take<uint32_t>((size_t)N * attn_mask_words(L));
     }
     if (bytes_out) *bytes_out = (c.off + 255) & ~static_cast<size_t>(255);
     if (!building) return 0;
@@ -615,6 +634,8 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
         op.i0 = N; op.i1 = T; op.i2 = (T + ds - 1) / ds; op.i3 = ds;
         ops.push_back(op);
     }
+    for (int ds = 1; ds <= 4; ds *= 2)
+        if (maskw_ds[ds] != nullptr) ops.push_back(mask_words_op(mask_ds[ds], maskw_ds[ds], N, (T + ds - 1) / ds));
     // time embedding chain (reference: modules/zipformer.py:267-278, 676-680, 727-729)
     if (td > 0) {
         Op e; e.type = OP_TSEMB; e.f0 = tbuf; e.o0 = te0; e.i0 = N; e.i1 = td;
@@ -682,7 +703,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             // 1. attention projections + weights (on the un-time-embedded input)
             e = LinearEpi();
             TRY(build_linear(op, src, Ms, D, ly.attn_in, qkp, attn_w, e)); ops.push_back(op);
-            TRY(build_attn(op, qkp, attn_w, ly.pos_table, mask_ds[ds], P, invl, N, H, L, Lk)); ops.push_back(op);
+            TRY(build_attn(op, qkp, attn_w, ly.pos_table, maskw_ds[ds], P, invl, N, H, L, Lk)); ops.push_back(op);
             // 2. feed_forward1 on src + temb:  R0 = src + temb + FF1(src + temb)
             e = LinearEpi(); e.act = ACT_SWOOSH_L;
             TRY(build_linear(op, srct, Ms, D, ly.ff_in[0], hid, m->ff_dims[0], e)); ops.push_back(op);
@@ -915,11 +936,13 @@ int zvb_test_linear(const void* A, int M, int K, int lda, const void* W, const f
     return launch_op(op, static_cast<cudaStream_t>(stream));
 }
 
-int zvb_test_attn_weights(const void* qkp, int ld, const float* pos_table, const uint8_t* mask, void* P, float* inv_l,
-                          int N, int H, int L, int Lk, void* stream) {
+int zvb_test_attn_weights(const void* qkp, int ld, const void* pos_table, const uint8_t* mask, void* scratch, void* P,
+                          float* inv_l, int N, int H, int L, int Lk, void* stream) {
     TRY(init_device());
+    if (scratch == nullptr) return fail(ZVB_ERR_INVALID, "attn: scratch (N * 4 * ceil(L/128) words) is null");
+    TRY(launch_op(mask_words_op(mask, (uint32_t*)scratch, N, L), static_cast<cudaStream_t>(stream)));
     Op op;
-    TRY(build_attn(op, (const h16*)qkp, ld, pos_table, mask, (h16*)P, inv_l, N, H, L, Lk));
+    TRY(build_attn(op, (const h16*)qkp, ld, pos_table, (const uint32_t*)scratch, (h16*)P, inv_l, N, H, L, Lk));
     return launch_op(op, static_cast<cudaStream_t>(stream));
 }
 

@@ -26,6 +26,24 @@ def _ceil8(x: int) -> int:
     return (x + 7) // 8 * 8
 
 
+POS_PAD = 128        # zero entries before / after the 2L-1 offsets (a tile's 255-offset window never leaves the table)
+
+
+def pack_pos_table(e: torch.Tensor) -> torch.Tensor:
+    """E[h][r][d] = linear_pos(pos_emb) fp32 (H, 2L-1, 4) -> the attention kernel's table (uint8 tensor):
+    [H][2L-1 + 2*POS_PAD] entries of 16 bytes = fp16 column PAIRS {log2e*E[r][d], log2e*E[r+1][d]}, d = 0..3
+    (entry index = r + POS_PAD, zeros outside the table: one contiguous 4080-byte bulk copy stages the
+    window of a score tile, one 16-byte read serves two adjacent key columns), followed by [H] fp32:
+    max_r |E[h][r]|_2, the bound of the softmax shift (reference: modules/zipformer.py:1215-1248)."""
+    H, R, D = e.shape
+    assert D == 4
+    emax = e.float().norm(dim=2).amax(dim=1).contiguous()
+    pad = torch.zeros(H, R + 2 * POS_PAD + 1, 4, dtype=torch.float32, device=e.device)
+    pad[:, POS_PAD:POS_PAD + R] = e.float() * 1.4426950408889634
+    pairs = torch.stack([pad[:, :-1], pad[:, 1:]], dim=-1).to(torch.float16).contiguous()   # (H, R+2P, 4, 2)
+    return torch.cat([pairs.view(torch.uint8).reshape(-1), emax.view(torch.uint8).reshape(-1)]).contiguous()
+
+
 def rel_pos_embedding(L: int, pos_dim: int, device) -> torch.Tensor:
     """CompactRelPositionalEncoding rows for offsets -(L-1)..(L-1) (reference:
     modules/zipformer.py:995-1056), shape (2L-1, pos_dim) fp32."""
@@ -157,16 +175,14 @@ class PackedZipformer:
 
     # ------------------------------------------------------------------ struct builders
     def pos_tables(self, L: int) -> List[torch.Tensor]:
-        """Per-layer E[h][r][c] = sum_d W_pos[h*4+c][d] * pe[r][d], fp32 (H, 2L-1, 4) flattened,
-        followed by (H,) floats max_r |E[h][r]|_2."""
+        """Per-layer rel-pos table in the kernel's layout (see pack_pos_table), one byte tensor per layer."""
         if L not in self._pos_cache:
             c = self.cfg
             pe = rel_pos_embedding(L, c.pos_dim, self.device)
             tabs = []
             for wp in self.linear_pos:
                 e = (pe @ wp.t()).reshape(2 * L - 1, c.num_heads, c.pos_head_dim).permute(1, 0, 2).contiguous()
-                emax = e.norm(dim=2).amax(dim=1)                       # (H,) bound used by the softmax shift
-                tabs.append(torch.cat([e.reshape(-1), emax]).contiguous())
+                tabs.append(pack_pos_table(e))
             self._pos_cache[L] = tabs
         return self._pos_cache[L]
 
