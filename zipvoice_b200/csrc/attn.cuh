@@ -231,12 +231,18 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
                 if (lane == 0) bulk_wait_read<0>();       // the previous box store has read the staging rows
                 __syncwarp();
 #pragma unroll 1
-                for (int g = 0; g < 4; ++g) {
-                    if (jh + 16 * g >= p.Lk) break;
-                    uint32_t sr[16];
-                    tmem_ld16(taddr + 16 * g, sr);
+                for (int gg = 0; gg < 2; ++gg) {
+                    if (jh + 32 * gg >= p.Lk) break;
+                    uint32_t sr32[32];
+                    tmem_ld32(taddr + 32 * gg, sr32);            // one exposed TMEM latency per 32 columns
                     tmem_ld_wait();
-                    const uint32_t excl = ((g & 2 ? mw1 : mw0) >> (16 * (g & 1))) & 0xffffu;
+                    const uint32_t excl32 = gg ? mw1 : mw0;
+#pragma unroll
+                for (int gl = 0; gl < 2; ++gl) {
+                    const int g = 2 * gg + gl;
+                    if (jh + 16 * g >= p.Lk) break;
+                    const uint32_t* sr = sr32 + 16 * gl;
+                    const uint32_t excl = (excl32 >> (16 * gl)) & 0xffffu;
                     const uint4* ep = ew + (64 * half + 16 * g - r + 127);
                     uint32_t w[8];
 #pragma unroll
@@ -265,6 +271,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
                     l_run += h2_lo(sum2) + h2_hi(sum2);
                     *reinterpret_cast<uint4*>(my + (((2 * g) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                     *reinterpret_cast<uint4*>(my + (((2 * g + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+                }
                 }
                 if (jh < p.Lk) {
                     fence_proxy_async_smem();             // generic-proxy writes -> visible to the TMA engine

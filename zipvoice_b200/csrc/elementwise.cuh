@@ -181,25 +181,27 @@ constexpr int DW_TT = 128;     // frames per tile
 constexpr int DW_OT = 16;      // outputs per thread
 template <int K> constexpr int dw_smem_bytes() { return 2 * (DW_TT + K - 1) * 128 + K * 32 * 8 + 128 /*align*/ + 16; }
 
-// SwooshR of a channel pair (see swoosh_from_offset): the polynomial runs as FFMA2
+// SwooshR of a channel pair (see swoosh_direct): everything but the two MUFU ops runs as FFMA2 --
+// 8 packed FMAs per pair; |z| is two ALU-pipe LOP3s, the negation rides on the MUFU operand.
 __device__ __forceinline__ void swoosh_r_pair(f32x2 acc, float& o0, float& o1) {
-    float y0, y1;
-    unpack2(acc, y0, y1);
-    y0 -= SWOOSH_R_C; y1 -= SWOOSH_R_C;
+    constexpr float L2E = 1.4426950408889634f;
+    const f32x2 z = fma2(acc, pack2(L2E, L2E), pack2(-SWOOSH_R_C * L2E, -SWOOSH_R_C * L2E));
+    float z0, z1;
+    unpack2(z, z0, z1);
+    const float a0 = fabsf(z0), a1 = fabsf(z1);
     float t0, t1;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(-fabsf(y0) * 1.4426950408889634f));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(-fabsf(y1) * 1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(-a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(-a1));
     const f32x2 t = pack2(t0, t1);
     f32x2 q = fma2(t, pack2(0.031377589387161245f, 0.031377589387161245f), pack2(-0.1341354334221127f, -0.1341354334221127f));
     q = fma2(t, q, pack2(0.2878262894239249f, 0.2878262894239249f));
     q = fma2(t, q, pack2(-0.491347927069251f, -0.491347927069251f));
     q = fma2(t, q, pack2(0.9994349844843187f, 0.9994349844843187f));
-    q = fma2(t, q, pack2(SWOOSH_R_K0, SWOOSH_R_K0));
-    q = fma2(pack2(y0, y1), pack2(0.42f, 0.42f), q);
-    float r0, r1;
-    unpack2(q, r0, r1);
-    o0 = fmaf(fabsf(y0), 0.5f, r0);
-    o1 = fmaf(fabsf(y1), 0.5f, r1);
+    constexpr float K = SWOOSH_R_K0 - 0.42f * SWOOSH_R_C;
+    q = fma2(t, q, pack2(K, K));
+    q = fma2(acc, pack2(0.42f, 0.42f), q);
+    q = fma2(pack2(a0, a1), pack2(0.5f / L2E, 0.5f / L2E), q);
+    unpack2(q, o0, o1);
 }
 
 // tma_x: x viewed as (C, L, N) fp16, box = 64 channels x (DW_TT + K - 1) frames, no swizzle.
