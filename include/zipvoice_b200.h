@@ -150,6 +150,7 @@ typedef enum {
     ZVB_CAT_OTHER = 8
 } zvb_op_category;
 int zvb_decoder_profile(zvb_plan* plan, void* stream, int max_ops, float* ms, int* category, double* work,
+                        double* bytes /* nullable: algorithmic HBM bytes of every kernel */,
                         int* shapes /* nullable, 4 ints per kernel: rows, cols, K, tile N */, int* num_ops);
 
 /* Seam 1: x fp32 [N][T][in_dim], t fp32 [N] (null for the text encoder), mask u8 [N][T],

@@ -72,15 +72,17 @@ def main():
         scale = 1e12 if unit == "TFLOP/s" else 1e9
         print(f"  {cat:16s} n={n:4d}  {ms:8.2f} ms  {100 * ms / tot:5.1f}%   {rate / scale:9.1f} {unit}")
     if a.detail:
-        det = plan.profile(shapes=True)
+        det = plan.profile(shapes=True, with_bytes=True)
         # first layer of the first stack: ops after the preamble up to the first biasnorm
         i0 = next(i for i, d in enumerate(det) if d[0] == "attn_weights") - 1
         i1 = next(i for i, d in enumerate(det) if d[0] == "biasnorm_bypass")
-        print("first full-rate layer, kernel by kernel:")
-        for cat, ms, work, shp in det[i0:i1 + 1]:
+        print("first full-rate layer, kernel by kernel (roof = max(FLOPs / 1349.8 TF/s, bytes / 6532.9 GB/s)):")
+        for cat, ms, work, nbytes, shp in det[i0:i1 + 1]:
             tensor = cat.startswith("gemm") or cat == "attn_weights"
-            rate = work / (ms * 1e-3) / (1e12 if tensor else 1e9) if ms > 0 else 0
-            print(f"  {cat:16s} {str(shp):28s} {ms * 1e3:8.1f} us  {rate:8.1f} {'TFLOP/s' if tensor else 'GB/s'}")
+            tf = work / (ms * 1e-3) / 1e12 if tensor and ms > 0 else 0.0
+            gb = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            roof = max((work / 1349.8e12 if tensor else 0.0), nbytes / 6532.9e9) * 1e3
+            print(f"  {cat:16s} {str(shp):28s} {ms * 1e3:8.1f} us  {tf:7.1f} TFLOP/s {gb:7.0f} GB/s  roof {roof * 1e3:6.1f} us = {100 * roof / ms:4.0f}%")
     print(f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB")
 
 

@@ -67,7 +67,7 @@ EXPORTS = {
     "zvb_plan_io": (C.c_int, [C.c_void_p, C.POINTER(zvb_io)]),
     "zvb_decoder_forward": (C.c_int, [C.c_void_p, C.c_void_p]),
     "zvb_decoder_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                      C.c_void_p, C.POINTER(C.c_int)]),
+                                      C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "zvb_decoder_forward_f32": (C.c_int, [C.c_void_p] * 7),
     "zvb_sample": (C.c_int, [C.c_void_p] * 8 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "zvb_test_linear": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,

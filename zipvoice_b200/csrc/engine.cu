@@ -154,6 +154,7 @@ struct Op {
     // kernels, bytes for the memory-bound ones)
     int cat = ZVB_CAT_OTHER;
     double work = 0.0;
+    double bytes = 0.0;              // algorithmic HBM bytes: every operand read once, every result written once
     int shape[4] = {0, 0, 0, 0};     // GEMM: rows, out cols, K, block_n
 };
 
@@ -283,6 +284,8 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
     op.shape[0] = (int)M; op.shape[1] = lin.out_features; op.shape[2] = lin.in_features; op.shape[3] = bn;
     op.cat = ZVB_CAT_GEMM_LINEAR;
     op.work = 2.0 * (double)M * lin.out_features * lin.in_features;
+    op.bytes = 2.0 * ((double)M * lin.in_features + (double)lin.out_features * lin.in_features) +
+               (double)M * lin.out_features * ((e.out_mode == OUT_F32 ? 4.0 : 2.0) + (e.resid ? 2.0 : 0.0) + (e.orig ? 2.0 : 0.0));
     return 0;
 }
 
@@ -316,6 +319,7 @@ static int build_gated(Op& op, const h16* A, long long M, int lda, const zvb_lin
     op.shape[0] = (int)M; op.shape[1] = 2 * n_out; op.shape[2] = lin.in_features; op.shape[3] = 256;
     op.cat = ZVB_CAT_GEMM_GATED;
     op.work = 2.0 * (double)M * (2.0 * n_out) * lin.in_features;
+    op.bytes = 2.0 * ((double)M * lin.in_features + 2.0 * n_out * lin.in_features + (double)M * n_out);
     return 0;
 }
 
@@ -362,6 +366,8 @@ static int build_pv(Op& op, const h16* P, const float* inv_l, const h16* Vt, voi
     op.shape[0] = N * L; op.shape[1] = per_head ? H * hd : hd; op.shape[2] = L; op.shape[3] = p.block_n;
     op.cat = ZVB_CAT_GEMM_PV;
     op.work = 2.0 * (double)N * (per_head ? H : 1) * (double)L * L * hd;
+    op.bytes = 2.0 * ((double)N * (per_head ? H : 1) * L * Lk + (double)N * vt_rows * Lk +
+                      (double)N * L * (per_head ? H * hd : hd) * (mul != nullptr ? 2.0 : 1.0));
     return 0;
 }
 
@@ -386,6 +392,7 @@ static int build_attn(Op& op, const h16* qkp, int ld, const void* pos_table, con
     op.cat = ZVB_CAT_ATTN_WEIGHTS;
     // q.k (K = 32) + rel-pos (4-dim dot against 2L-1 offsets), reference FLOP model SURVEY.md §8d
     op.work = (double)N * H * (2.0 * L * L * 32 + 2.0 * L * (2.0 * L - 1) * 4);
+    op.bytes = 2.0 * ((double)N * L * ld + (double)N * H * L * Lk) + 4.0 * N * H * L;
     return 0;
 }
 
@@ -405,6 +412,7 @@ static int build_dwconv(Op& d, const h16* x, h16* out, const float* w, const flo
     TRY(make_tmap_plain(&d.ma, x, C, L, N, (uint64_t)C * 2, (uint64_t)C * 2 * L, 64, DW_TT + K - 1));
     d.cat = ZVB_CAT_DWCONV;
     d.work = 2.0 * 2.0 * (double)N * L * C;
+    d.bytes = d.work;
     return 0;
 }
 
@@ -825,7 +833,7 @@ int zvb_decoder_forward(zvb_plan* plan, void* stream) {
 }
 
 int zvb_decoder_profile(zvb_plan* plan, void* stream, int max_ops, float* ms, int* category, double* work,
-                        int* shapes, int* num_ops) {
+                        double* bytes, int* shapes, int* num_ops) {
     if (plan == nullptr || ms == nullptr || category == nullptr || work == nullptr || num_ops == nullptr)
         return fail(ZVB_ERR_INVALID, "null argument");
     const int n = static_cast<int>(plan->ops.size());
@@ -845,6 +853,7 @@ int zvb_decoder_profile(zvb_plan* plan, void* stream, int max_ops, float* ms, in
         cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
         category[i] = plan->ops[i].cat;
         work[i] = plan->ops[i].work;
+        if (bytes != nullptr) bytes[i] = plan->ops[i].bytes > 0.0 ? plan->ops[i].bytes : plan->ops[i].work;
         if (shapes != nullptr)
             for (int k = 0; k < 4; ++k) shapes[4 * i + k] = plan->ops[i].shape[k];
     }

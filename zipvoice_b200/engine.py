@@ -69,23 +69,30 @@ class DecoderPlan:
                 g32.data_ptr() if g32 is not None else None, out.data_ptr(), _stream_ptr()))
         return out
 
-    def profile(self, shapes: bool = False):
+    def profile(self, shapes: bool = False, with_bytes: bool = False):
         """One forward over the resident buffers with a CUDA event per kernel (synchronises).
-        Returns a list of (category name, milliseconds, algorithmic work[, (rows, cols, K, tile N)])."""
+        Returns a list of (category name, milliseconds, algorithmic work[, algorithmic HBM bytes]
+        [, (rows, cols, K, tile N)]); work = FLOPs for the tensor-core kernels, bytes for the others."""
         import numpy as np
         cap = 4096
         ms = np.zeros(cap, dtype=np.float32)
         cat = np.zeros(cap, dtype=np.int32)
         work = np.zeros(cap, dtype=np.float64)
+        nbytes = np.zeros(cap, dtype=np.float64)
         shp = np.zeros(cap * 4, dtype=np.int32)
         n = C.c_int(0)
         with torch.cuda.device(self.packed.device):
             _lib.check(self.lib.zvb_decoder_profile(self.handle, _stream_ptr(), cap, ms.ctypes.data, cat.ctypes.data,
-                                                    work.ctypes.data, shp.ctypes.data, C.byref(n)))
-        if shapes:
-            return [(_lib.CATEGORIES[int(cat[i])], float(ms[i]), float(work[i]), tuple(int(x) for x in shp[4 * i: 4 * i + 4]))
-                    for i in range(n.value)]
-        return [(_lib.CATEGORIES[int(cat[i])], float(ms[i]), float(work[i])) for i in range(n.value)]
+                                                    work.ctypes.data, nbytes.ctypes.data, shp.ctypes.data, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            row = [_lib.CATEGORIES[int(cat[i])], float(ms[i]), float(work[i])]
+            if with_bytes:
+                row.append(float(nbytes[i]))
+            if shapes:
+                row.append(tuple(int(x) for x in shp[4 * i: 4 * i + 4]))
+            out.append(tuple(row))
+        return out
 
     def sample(self, x: torch.Tensor, text: torch.Tensor, speech: torch.Tensor, mask8: torch.Tensor,
                guidance: Optional[torch.Tensor], ts_dev: torch.Tensor, ts_host: torch.Tensor, num_step: int,
