@@ -56,6 +56,8 @@ static int check_launch(const char* what) {
 static int g_num_sms = 0;
 static int g_cluster_ok = 1;      // ZVB_NO_CLUSTER=1 disables the CTA-pair (cta_group::2) GEMM variant
 static int g_tma_store_ok = 1;
+static int g_bn192 = 0;           // ZVB_BN192=1: 192-column tiles for short-K GEMMs (measured: no gain)
+static int g_layout_ok = 1;       // ZVB_NO_LAYOUT=1 keeps the default operand-ring / aux split everywhere
 static int g_pair_min_kb = 16;    // ZVB_PAIR_MIN_KB: fewest k-blocks for which a CTA pair is used    // ZVB_NO_TMA_STORE=1 keeps the epilogue on per-thread stores
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
@@ -73,6 +75,8 @@ static int init_device() {
     if (const char* e = getenv("ZVB_NO_CLUSTER")) g_cluster_ok = atoi(e) == 0;
     if (const char* e = getenv("ZVB_NO_TMA_STORE")) g_tma_store_ok = atoi(e) == 0;
     if (const char* e = getenv("ZVB_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
+    if (const char* e = getenv("ZVB_NO_LAYOUT")) g_layout_ok = atoi(e) == 0;
+    if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
     CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
@@ -158,7 +162,10 @@ struct Op {
     int shape[4] = {0, 0, 0, 0};     // GEMM: rows, out cols, K, block_n
 };
 
-static int pick_block_n(int n_out, long long m_tiles) {
+static int pick_block_n(int n_out, long long m_tiles, int k_blocks) {
+    // short K (<= 8 k-blocks): the mainloop is bound by operand bytes in flight, and a 40 KB stage (192
+    // columns) fits four times into the wide ring where a 48 KB stage (256 columns) fits three times
+    if (g_bn192 && k_blocks <= 8 && n_out >= 768 && n_out % 192 == 0 && m_tiles * (n_out / 192) >= g_num_sms) return 192;
     // TMA stores move 64-column (h16) sub-tiles, so tile widths that are multiples of 64 are preferred
     // when they waste < 8% of the MMA work; otherwise the narrowest multiple of 16 that covers n_out.
     if (n_out >= 64) {
@@ -231,7 +238,33 @@ static void set_grid(Op& op) {
         const long long tiles = (long long)p.batches * p.num_m_tiles * p.num_n_tiles;
         op.grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
     }
-    gemm_ring(p.block_n, op.cluster, &op.gp.stages, &op.gp.stage_bytes);
+    p.ring_bytes = GEMM_OPERAND_BYTES; p.aux_slots = GEMM_AUX_SLOTS; p.stage_depth = 2;
+    gemm_ring(p.block_n, op.cluster, p.ring_bytes, &p.stages, &p.stage_bytes);
+}
+
+// Splits the 208 KB shared budget between the operand ring and the aux / staging slots (gemm.cuh); called once
+// the epilogue operands and the store path of the op are known.
+static void gemm_layout(Op& op) {
+    GemmParams& p = op.gp;
+    if (!g_layout_ok) return;
+    int sb, st;
+    gemm_ring(p.block_n, op.cluster, GEMM_OPERAND_BYTES, &st, &sb);
+    if (p.aux_mode == AUX_NONE && p.tma_store) {
+        // wide ring: one staging buffer per epilogue half, everything else to the operands
+        const int ring = GEMM_SHARED_BUDGET - 2 * GEMM_AUX_BYTES;
+        int st2, sb2;
+        gemm_ring(p.block_n, op.cluster, ring, &st2, &sb2);
+        if (st2 > st && p.num_k_blocks > st) {
+            p.ring_bytes = ring; p.aux_slots = 2; p.stage_depth = 1; p.stages = st2;
+        }
+    } else if (p.aux_mode != AUX_NONE && p.tma_store && p.num_k_blocks * 2 < st) {
+        // deep aux: the operands of two tiles are all the ring ever holds
+        const int need = 2 * p.num_k_blocks;
+        int slots = (GEMM_SHARED_BUDGET - need * sb) / GEMM_AUX_BYTES;
+        if (slots > GEMM_AUX_SLOTS_MAX) slots = GEMM_AUX_SLOTS_MAX;
+        if (p.orig_tma) slots &= ~1;          // operand + `orig` entries travel in pairs
+        p.aux_slots = slots; p.stages = need; p.ring_bytes = GEMM_SHARED_BUDGET - slots * GEMM_AUX_BYTES;
+    }
 }
 static inline uint32_t b_box_rows(const Op& op) { return op.gp.block_n / op.cluster; }
 
@@ -243,7 +276,7 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
     if (lin.k_pitch % 8 != 0 || lda % 8 != 0) return fail(ZVB_ERR_INVALID, "linear: pitches must be multiples of 8");
     const int K = lin.k_pitch < lda ? lin.k_pitch : lda;    // both zero padded beyond in_features
     const long long m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
-    const int bn = e.block_n ? e.block_n : pick_block_n(lin.out_features, m_tiles);
+    const int bn = e.block_n ? e.block_n : pick_block_n(lin.out_features, m_tiles, (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K);
     GemmParams& p = op.gp;
     gp_defaults(p);
     p.M = static_cast<int>(M);
@@ -281,6 +314,7 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
         op.has_mo = true;
         p.orig_tma = 1;
     }
+    gemm_layout(op);
     op.shape[0] = (int)M; op.shape[1] = lin.out_features; op.shape[2] = lin.in_features; op.shape[3] = bn;
     op.cat = ZVB_CAT_GEMM_LINEAR;
     op.work = 2.0 * (double)M * lin.out_features * lin.in_features;
@@ -316,6 +350,7 @@ static int build_gated(Op& op, const h16* A, long long M, int lda, const zvb_lin
     TRY(make_tmap(&op.mb, lin.w, K, lin.rows, 1, (uint64_t)lin.k_pitch * 2, (uint64_t)lin.k_pitch * 2 * lin.rows,
                   b_box_rows(op)));
     TRY(setup_tma_store(op, (int)M, 1));
+    gemm_layout(op);
     op.shape[0] = (int)M; op.shape[1] = 2 * n_out; op.shape[2] = lin.in_features; op.shape[3] = 256;
     op.cat = ZVB_CAT_GEMM_GATED;
     op.work = 2.0 * (double)M * (2.0 * n_out) * lin.in_features;
@@ -363,6 +398,7 @@ static int build_pv(Op& op, const h16* P, const float* inv_l, const h16* Vt, voi
     TRY(make_tmap(&op.ma, P, Lk, L, (uint64_t)N * H, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * L, GEMM_BLOCK_M));
     TRY(make_tmap(&op.mb, Vt, Lk, vt_rows, N, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * vt_rows, b_box_rows(op)));
     if (!per_head) TRY(setup_tma_store(op, L, N));
+    gemm_layout(op);
     op.shape[0] = N * L; op.shape[1] = per_head ? H * hd : hd; op.shape[2] = L; op.shape[3] = p.block_n;
     op.cat = ZVB_CAT_GEMM_PV;
     op.work = 2.0 * (double)N * (per_head ? H : 1) * (double)L * L * hd;

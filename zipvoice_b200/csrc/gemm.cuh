@@ -24,19 +24,28 @@ constexpr int GEMM_B_BYTES = 256 * GEMM_BLOCK_K * 2;            // 32 KB (block_
 // in a CTA pair, x 128 B), so narrow tiles get a deeper ring: 3 stages at block_n = 256, 4 for a CTA
 // pair, up to 8 for the 16..48-column tiles that only stream A (more bytes in flight per SM -- those
 // kernels are HBM-latency bound).  Host: gemm_ring() fills GemmParams::stages / stage_bytes.
-constexpr int GEMM_OPERAND_BYTES = 3 * (GEMM_A_BYTES + GEMM_B_BYTES);
+constexpr int GEMM_OPERAND_BYTES = 3 * (GEMM_A_BYTES + GEMM_B_BYTES);        // default operand ring (144 KB)
 constexpr int GEMM_MAX_STAGES = 8;
-inline void gemm_ring(int block_n, int cluster, int* stages, int* stage_bytes) {
+constexpr int GEMM_AUX_SLOTS = 4;                               // default aux / staging slots
+constexpr int GEMM_AUX_SLOTS_MAX = 8;
+constexpr int GEMM_AUX_BYTES = 128 * 128;                       // 128 rows x 128 B
+// The operand ring and the aux / staging slots share one 208 KB budget; both are latency bound (bytes in
+// flight per SM / L2 latency), so the host gives each GEMM the split its traffic wants (gemm_layout):
+//   default          ring 144 KB, 4 aux slots (a tile's residual sub-tiles, staged in place; or 2 staging
+//                    buffers per epilogue half);
+//   wide ring        no aux operand, TMA stores: 1 staging buffer per half (32 KB), ring 176 KB -- one more
+//                    stage in flight for the K = 512 feed-forward input GEMMs;
+//   deep aux         K <= 128 (SelfAttention out_proj): the ring shrinks to the k-blocks of two tiles and
+//                    the residual / output sub-tiles get up to 8 slots.
+constexpr int GEMM_SHARED_BUDGET = GEMM_OPERAND_BYTES + GEMM_AUX_SLOTS * GEMM_AUX_BYTES;
+inline void gemm_ring(int block_n, int cluster, int ring_bytes, int* stages, int* stage_bytes) {
     const int sb = GEMM_A_BYTES + (block_n / cluster) * GEMM_BLOCK_K * 2;      // multiple of 1024 (block_n % 16 == 0)
-    int st = GEMM_OPERAND_BYTES / sb;
+    int st = ring_bytes / sb;
     *stages = st > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : st;
     *stage_bytes = sb;
 }
-constexpr int GEMM_AUX_SLOTS = 4;
-constexpr int GEMM_AUX_BYTES = 128 * 128;                       // 128 rows x 128 B
 constexpr int GEMM_BIAS_BYTES = 16 * 64 * 4;               // per epilogue warp: bias of the unit in flight (32 columns, 2 x 32 gated)
-constexpr int GEMM_LAYOUT_BYTES = GEMM_OPERAND_BYTES + GEMM_AUX_SLOTS * GEMM_AUX_BYTES + GEMM_BIAS_BYTES +
-                                  384 /*barriers*/;
+constexpr int GEMM_LAYOUT_BYTES = GEMM_SHARED_BUDGET + GEMM_BIAS_BYTES + 512 /*barriers*/;
 constexpr int GEMM_SMEM_BYTES = 232448;                    // all 227 KB; layout + alignment pad must fit (checked)
 static_assert(GEMM_LAYOUT_BYTES <= GEMM_SMEM_BYTES, "shared-memory layout too large");
 constexpr int GEMM_THREADS = 640;
@@ -56,6 +65,9 @@ struct GemmParams {
     int num_k_blocks;
     int block_n;           // UMMA N: multiple of 16, <= 256 (256 for EPI_GATED)
     int stages, stage_bytes;   // operand ring (gemm_ring)
+    int ring_bytes;            // shared memory given to the operand ring; the aux slots follow it
+    int aux_slots;             // 16 KB slots of the aux / staging area (2 .. GEMM_AUX_SLOTS_MAX)
+    int stage_depth;           // staging buffers per epilogue half on the aux-less TMA-store path (1 or 2)
     int num_m_tiles, num_n_tiles, batches;
     int a_zb, a_zn;        // A tensor-map z = b*a_zb + n_tile*a_zn
     int b_zb;              // B tensor-map z = b*b_zb
@@ -222,10 +234,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     const int STAGES = p.stages;
     const int STAGE_BYTES = p.stage_bytes;
-    uint8_t* aux_smem = smem + GEMM_OPERAND_BYTES;
-    float* bias_smem = reinterpret_cast<float*>(aux_smem + GEMM_AUX_SLOTS * GEMM_AUX_BYTES);   // [8 warps][128]
+    uint8_t* aux_smem = smem + p.ring_bytes;
+    float* bias_smem = reinterpret_cast<float*>(aux_smem + p.aux_slots * GEMM_AUX_BYTES);      // [16 warps][64]
+    const int AUX_SLOTS = p.aux_slots;
+    const uint32_t dsh = static_cast<uint32_t>(p.stage_depth - 1);     // staging buffer of sub-tile k: k & dsh
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_smem) + GEMM_BIAS_BYTES);
-    if (threadIdx.x == 0 && (smem - smem_raw) + GEMM_LAYOUT_BYTES > GEMM_SMEM_BYTES) {
+    if (threadIdx.x == 0 && ((smem - smem_raw) + GEMM_LAYOUT_BYTES > GEMM_SMEM_BYTES ||
+                             p.ring_bytes + p.aux_slots * GEMM_AUX_BYTES > GEMM_SHARED_BUDGET)) {
         printf("zvb: gemm shared-memory layout does not fit (base misaligned by %d)\n", (int)(smem - smem_raw));
         __trap();
     }
@@ -234,8 +249,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint64_t* tmem_full = empty_bar + GEMM_MAX_STAGES;          // [2] MMA -> epilogue
     uint64_t* tmem_empty = tmem_full + 2;                       // [2] epilogue -> MMA
     uint64_t* aux_full = tmem_empty + 2;                        // [AUX_SLOTS] TMA -> epilogue
-    uint64_t* aux_empty = aux_full + GEMM_AUX_SLOTS;            // [AUX_SLOTS] epilogue -> TMA
-    uint64_t* staged = aux_empty + GEMM_AUX_SLOTS;              // [2 halves][2] epilogue -> store thread
+    uint64_t* aux_empty = aux_full + GEMM_AUX_SLOTS_MAX;        // [AUX_SLOTS] epilogue -> TMA
+    uint64_t* staged = aux_empty + GEMM_AUX_SLOTS_MAX;          // [2 halves][2] epilogue -> store thread
     uint64_t* sfree = staged + 4;                               // [2 halves][2] store thread -> epilogue
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(sfree + 4);
 
@@ -275,9 +290,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], GEMM_EPI_WARPS * CLUSTER);
         }
-        for (int s = 0; s < GEMM_AUX_SLOTS; ++s) {
+        for (int s = 0; s < GEMM_AUX_SLOTS_MAX; ++s) {
             mbar_init(&aux_full[s], 1);
             mbar_init(&aux_empty[s], p.tma_store ? 1 : (units_per_sub == 2 ? 8 : 4));
+        }
+        for (int s = 0; s < 4; ++s) {
             mbar_init(&staged[s], units_per_sub == 2 ? 8 : 4);
             mbar_init(&sfree[s], 1);
         }
@@ -379,8 +396,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 const int b = rest / m_groups;
                 for (int s = 0; s < n_sub; ++s) {
                     for (int part = 0; part < aux_parts; ++part, ++q) {
-                        const int slot = q % GEMM_AUX_SLOTS;
-                        const uint32_t par = (q / GEMM_AUX_SLOTS) & 1u;
+                        const int slot = q % AUX_SLOTS;
+                        const uint32_t par = (q / AUX_SLOTS) & 1u;
                         mbar_wait(&aux_empty[slot], par ^ 1u);
                         mbar_arrive_expect_tx(&aux_full[slot], GEMM_AUX_BYTES);
                         tma_load_3d(aux_smem + slot * GEMM_AUX_BYTES, part == 0 ? &tma_aux : &tma_orig, &aux_full[slot],
@@ -391,14 +408,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
     } else if (warp == W_STORE) {
         // ------------------------------------------------------------------ TMA store thread
-        // Epilogue halves (4 warps each) stage 128-row x 128-byte sub-tiles and signal `staged`; this
+        // Epilogue halves (8 warps each) stage 128-row x 128-byte sub-tiles and signal `staged`; this
         // thread issues the box stores (16 KB each: few, large TMA operations -- per-warp 4 KB stores
-        // were measured to delay the operand loads), waits until the store has read its source and hands
-        // the buffers back (`sfree`, and the aux slot that was staged in place).
+        // were measured to delay the operand loads) and hands a buffer back (`sfree`, and the aux slot
+        // that was staged in place) once its store has read it.  Up to ST_PEND stores stay in flight: a
+        // buffer is only reclaimed when a later store has been issued, or when no staged sub-tile is
+        // waiting (then everything outstanding is drained first -- the epilogue may need those buffers).
         if (lane == 0 && p.tma_store) {
             const int subs = KIND == EPI_GATED ? 2 : n_sub;
             uint32_t kc[2] = {0u, 0u};
             uint32_t tile_iter = 0;
+            constexpr uint32_t ST_PEND = 2;
+            int pend_bi[4], pend_slot[4];
+            uint32_t issued = 0, freed = 0;
+            auto release_oldest = [&]() {
+                const int bi0 = pend_bi[freed & 3u], sl0 = pend_slot[freed & 3u];
+                mbar_arrive(&sfree[bi0]);
+                if (p.aux_mode != AUX_NONE) mbar_arrive(&aux_empty[sl0]);
+                ++freed;
+            };
             for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++tile_iter) {
                 const int n_tile = tile % p.num_n_tiles;
                 const int rest = tile / p.num_n_tiles;
@@ -408,29 +436,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 for (int s = 0; s < subs; ++s) {
                     const int h = s & 1;
                     const uint32_t k = kc[h]++;
-                    const int bi = h * 2 + static_cast<int>(k & 1u);
+                    const int bi = h * 2 + static_cast<int>(k & dsh);
                     int slot = 0, slot2 = 0;
-                    const uint8_t* src = aux_smem + ((k & 1u) * 2 + h) * GEMM_AUX_BYTES;
+                    const uint8_t* src = aux_smem + ((k & dsh) * 2 + h) * GEMM_AUX_BYTES;
                     int col = out_base + 64 * h;
                     if (KIND != EPI_GATED) {
                         col = out_base + s * units_per_sub * 32;
                         if (p.aux_mode != AUX_NONE) {
                             const uint32_t q = (tile_iter * static_cast<uint32_t>(n_sub) + static_cast<uint32_t>(s)) *
                                                static_cast<uint32_t>(aux_parts);
-                            slot = q % GEMM_AUX_SLOTS;
-                            slot2 = (q + 1) % GEMM_AUX_SLOTS;
+                            slot = q % AUX_SLOTS;
+                            slot2 = (q + 1) % AUX_SLOTS;
                             src = aux_smem + slot * GEMM_AUX_BYTES;
                         }
                     }
-                    mbar_wait(&staged[bi], (k >> 1) & 1u);
+                    if (!mbar_test(&staged[bi], (k >> dsh) & 1u)) {
+                        bulk_wait_read<0>();                                 // nothing to issue: drain
+                        while (freed < issued) release_oldest();
+                        mbar_wait(&staged[bi], (k >> dsh) & 1u);
+                    }
                     if (aux_parts == 2) mbar_arrive(&aux_empty[slot2]);      // `orig` rows are consumed
                     tma_store_3d(&tma_out, src, col, m_tile * GEMM_BLOCK_M, b);
                     bulk_commit();
-                    bulk_wait_read<0>();
-                    mbar_arrive(&sfree[bi]);
-                    if (p.aux_mode != AUX_NONE) mbar_arrive(&aux_empty[slot]);
+                    pend_bi[issued & 3u] = bi; pend_slot[issued & 3u] = slot;
+                    ++issued;
+                    if (issued - freed > ST_PEND) {
+                        bulk_wait_read<ST_PEND>();
+                        release_oldest();
+                    }
                 }
             }
+            bulk_wait_read<0>();
+            while (freed < issued) release_oldest();
         }
     } else {
         // ------------------------------------------------------------------ epilogue (16 warps)
@@ -449,19 +486,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const int r = quarter * 32 + lane;                // accumulator row inside the tile
         uint8_t* private_stage = aux_smem + ew * 4096;    // staging of the non-TMA store paths
         uint32_t kcount = 0;                              // sub-tiles this half handed to the store thread
-        // a staging buffer may be rewritten once the store of `depth` sub-tiles ago has read it (two
-        // buffers per half, or the consumed aux slot)
-        constexpr uint32_t depth = 2u;
+        // a staging buffer may be rewritten once the store of `depth` sub-tiles ago has read it (one or
+        // two buffers per half, or the consumed aux slot)
+        const uint32_t depth = dsh + 1u;
         auto wait_sfree = [&]() {
             if (kcount >= depth) {
                 const uint32_t kd = kcount - depth;
-                mbar_wait(&sfree[half * 2 + (kd & 1u)], (kd >> 1) & 1u);
+                mbar_wait(&sfree[half * 2 + (kd & dsh)], (kd >> dsh) & 1u);
             }
         };
         auto signal_staged = [&]() {
             fence_proxy_async_smem();                     // generic-proxy writes -> visible to the TMA engine
             __syncwarp();
-            if (lane == 0) mbar_arrive(&staged[half * 2 + (kcount & 1u)]);
+            if (lane == 0) mbar_arrive(&staged[half * 2 + (kcount & dsh)]);
             ++kcount;
         };
         float* bs = bias_smem + ew * 64;                  // this warp's bias staging: 32 floats (2 x 32 gated)
@@ -524,7 +561,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 const int u = 2 * half + part;
                 const bool g_tma = p.tma_store && 2 * half * 32 < hcols;
                 // this warp's rows of the half's staging ring (two 16 KB buffers)
-                uint8_t* tbuf = aux_smem + ((kcount & 1u) * 2 + half) * GEMM_AUX_BYTES + quarter * 4096;
+                uint8_t* tbuf = aux_smem + ((kcount & dsh) * 2 + half) * GEMM_AUX_BYTES + quarter * 4096;
                 if (g_tma) wait_sfree();
                 __syncwarp();
                 bs[lane] = nb0; bs[32 + lane] = nb1;
@@ -566,19 +603,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     if (p.aux_mode != AUX_NONE) {
                         const uint32_t q = (tile_iter * static_cast<uint32_t>(n_sub) + static_cast<uint32_t>(s)) *
                                            static_cast<uint32_t>(aux_parts);
-                        slot = q % GEMM_AUX_SLOTS;
-                        mbar_wait(&aux_full[slot], (q / GEMM_AUX_SLOTS) & 1u);
+                        slot = q % AUX_SLOTS;
+                        mbar_wait(&aux_full[slot], (q / AUX_SLOTS) & 1u);
                         aux_row = aux_smem + slot * GEMM_AUX_BYTES + r * 128;
                         if (aux_parts == 2) {
-                            slot2 = (q + 1) % GEMM_AUX_SLOTS;
-                            mbar_wait(&aux_full[slot2], ((q + 1) / GEMM_AUX_SLOTS) & 1u);
+                            slot2 = (q + 1) % AUX_SLOTS;
+                            mbar_wait(&aux_full[slot2], ((q + 1) / AUX_SLOTS) & 1u);
                             orig_row = aux_smem + slot2 * GEMM_AUX_BYTES + r * 128;
                         }
                     }
                     // TMA-store staging of this warp's 32 rows x 128 B: in place over its rows of the consumed
                     // aux sub-tile, else the half's two-buffer ring
                     uint8_t* tbuf = (p.aux_mode != AUX_NONE ? aux_smem + slot * GEMM_AUX_BYTES
-                                                            : aux_smem + ((kcount & 1u) * 2 + half) * GEMM_AUX_BYTES) +
+                                                            : aux_smem + ((kcount & dsh) * 2 + half) * GEMM_AUX_BYTES) +
                                     quarter * 4096;
                     __syncwarp();                            // the previous sub-tile's bias reads are done
                     bs[lane] = nb0;
@@ -595,13 +632,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         tmem_ld32(taddr + c0, acc_r);
                         tmem_ld_wait();
                         float v[32];
+                        const f32x2 rs2 = pack2(rscale, rscale);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
+                        for (int j = 0; j < 8; ++j) {       // acc * rowscale + bias, two columns per FFMA2
                             const float4 bq = *reinterpret_cast<const float4*>(bs + 4 * j);
-                            v[4 * j] = fmaf(__uint_as_float(acc_r[4 * j]), rscale, bq.x);
-                            v[4 * j + 1] = fmaf(__uint_as_float(acc_r[4 * j + 1]), rscale, bq.y);
-                            v[4 * j + 2] = fmaf(__uint_as_float(acc_r[4 * j + 2]), rscale, bq.z);
-                            v[4 * j + 3] = fmaf(__uint_as_float(acc_r[4 * j + 3]), rscale, bq.w);
+                            const f32x2 lo = fma2(pack2(__uint_as_float(acc_r[4 * j]), __uint_as_float(acc_r[4 * j + 1])),
+                                                  rs2, pack2(bq.x, bq.y));
+                            const f32x2 hi = fma2(pack2(__uint_as_float(acc_r[4 * j + 2]), __uint_as_float(acc_r[4 * j + 3])),
+                                                  rs2, pack2(bq.z, bq.w));
+                            unpack2(lo, v[4 * j], v[4 * j + 1]);
+                            unpack2(hi, v[4 * j + 2], v[4 * j + 3]);
                         }
                         const bool vec = ncols == 32 && (p.ldc & 3) == 0;
                         if (p.rowbias != nullptr && row_ok) {
@@ -620,10 +660,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         }
                         if (ACT == ACT_SWOOSH_L) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = swoosh_direct(v[i], SWOOSH_L_C, SWOOSH_L_K0);
+                            for (int i = 0; i < 32; i += 2) swoosh_direct2(v[i], v[i + 1], SWOOSH_L_C, SWOOSH_L_K0);
                         } else if (ACT == ACT_SWOOSH_R) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = swoosh_direct(v[i], SWOOSH_R_C, SWOOSH_R_K0);
+                            for (int i = 0; i < 32; i += 2) swoosh_direct2(v[i], v[i + 1], SWOOSH_R_C, SWOOSH_R_K0);
                         }
                         if (p.aux_mode == AUX_ADD_H16) {
 #pragma unroll

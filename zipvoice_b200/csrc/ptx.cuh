@@ -54,6 +54,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking poll (test_wait never suspends the thread)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const uint64_t t0 = globaltimer_ns();
@@ -146,12 +158,14 @@ __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMa
         "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-// arrive on the mbarrier at the same offset in CTA `rank` of the cluster
+// arrive on the mbarrier at the same offset in CTA `rank` of the cluster.  Relaxed: the arrival only says
+// "this warp's tcgen05.ld of the accumulator have completed" (they were waited for and fenced); no generic
+// memory is published, and a release here costs a cluster-wide fence (ERRBAR) per warp and tile.
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(smem_u32(bar)), "r"(rank)
         : "memory");
 }
@@ -330,6 +344,30 @@ __device__ __forceinline__ float swoosh_direct(float x, float c, float k0) {
     float r = fmaf(t, p, k0 - 0.42f * c);
     r = fmaf(x, 0.42f, r);
     return fmaf(fabsf(z), 0.5f / L2E, r);
+}
+// swoosh_direct on a pair: 8 FFMA2 + 2 MUFU.  The fp32 FMA pipe issues one 3-register FFMA per two
+// cycles and scheduler, an FFMA2 in the same two cycles -- packing doubles what the epilogue warps get out
+// of it (tools/microbench/epi_math.cu: 5.8 -> 7.8 activations/clk/SM at 8 warps).
+__device__ __forceinline__ void swoosh_direct2(float& x0, float& x1, float c, float k0) {
+    constexpr float L2E = 1.4426950408889634f;
+    const f32x2 x = pack2(x0, x1);
+    const f32x2 z = fma2(x, pack2(L2E, L2E), pack2(-c * L2E, -c * L2E));
+    float z0, z1;
+    unpack2(z, z0, z1);
+    const float a0 = fabsf(z0), a1 = fabsf(z1);
+    float t0, t1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(-a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(-a1));
+    const f32x2 t = pack2(t0, t1);
+    f32x2 q = fma2(t, pack2(0.031377589387161245f, 0.031377589387161245f), pack2(-0.1341354334221127f, -0.1341354334221127f));
+    q = fma2(t, q, pack2(0.2878262894239249f, 0.2878262894239249f));
+    q = fma2(t, q, pack2(-0.491347927069251f, -0.491347927069251f));
+    q = fma2(t, q, pack2(0.9994349844843187f, 0.9994349844843187f));
+    const float k = k0 - 0.42f * c;
+    q = fma2(t, q, pack2(k, k));
+    q = fma2(x, pack2(0.42f, 0.42f), q);
+    q = fma2(pack2(a0, a1), pack2(0.5f / L2E, 0.5f / L2E), q);
+    unpack2(q, x0, x1);
 }
 constexpr float SWOOSH_L_C = 4.0f, SWOOSH_L_K0 = -(0.08f * 4.0f + 0.035f);
 constexpr float SWOOSH_R_C = 1.0f, SWOOSH_R_K0 = -(0.08f * 1.0f + 0.313261687f);
