@@ -45,3 +45,25 @@ for rep in sorted(p for p in os.listdir("gpurun_out") if p.endswith(f"_{tag}.ncu
         for r in rows:
             w.writerow([r[i] for i in idx])
     print(open(f"{out_dir}/{name}.csv").read())
+
+# DRAM traffic of every gemm_kernel launch of one decoder forward (ncu_capture.sh: gemm_traffic_<tag>.csv)
+tcsv = f"gpurun_out/gemm_traffic_{tag}.csv"
+if os.path.exists(tcsv):
+    import json
+    rows = list(csv.DictReader(l for l in open(tcsv) if l.startswith('"')))
+    per = collections.OrderedDict()
+    for r in rows:
+        d = per.setdefault(r["ID"], {})
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r["Metric Unit"]
+        v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0}.get(unit, 1)
+        d[r["Metric Name"]] = v
+    rd = sum(d.get("dram__bytes_read.sum", 0.0) for d in per.values())
+    wr = sum(d.get("dram__bytes_write.sum", 0.0) for d in per.values())
+    ms = sum(d.get("gpu__time_duration.sum", 0.0) for d in per.values())
+    out = {"gemm_kernel_dram_bytes_per_launch": (rd + wr) / max(1, len(per)), "launches": len(per),
+           "dram_read_bytes_total": rd, "dram_write_bytes_total": wr, "serialized_time_ms_total": ms,
+           "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:gemm_kernel: every gemm_kernel "
+                     f"launch of one decoder forward (N=128, T=1219), tools/ncu_capture.sh {tag}"}
+    json.dump(out, open(f"{out_dir}/traffic_r1.json", "w"), indent=1)
+    print(json.dumps(out, indent=1))

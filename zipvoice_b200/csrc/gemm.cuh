@@ -577,18 +577,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     tmem_ld_wait();
                     float v[32];
                     const bool tanh_gate = p.gate_mode == GATE_TANH_SX;
+                    constexpr float NL2E = -1.4426950408889634f;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 8; ++j) {           // two columns per packed fp32x2 instruction
                         const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * j);
                         const float4 g4 = *reinterpret_cast<const float4*>(bs + 32 + 4 * j);
                         const float abv[4] = {b4.x, b4.y, b4.z, b4.w};
                         const float gbv[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float a = __uint_as_float(ra[4 * j + e]) + abv[e];
-                            const float g = __uint_as_float(rb[4 * j + e]) + gbv[e];
-                            const float o = tanh_gate ? g * fast_tanh(a) : a * fast_sigmoid(g);
-                            v[4 * j + e] = masked ? 0.0f : o;
+                        for (int e = 0; e < 4; e += 2) {
+                            const f32x2 a2 = add2(pack2(__uint_as_float(ra[4 * j + e]), __uint_as_float(ra[4 * j + e + 1])),
+                                                  pack2(abv[e], abv[e + 1]));
+                            const f32x2 g2 = add2(pack2(__uint_as_float(rb[4 * j + e]), __uint_as_float(rb[4 * j + e + 1])),
+                                                  pack2(gbv[e], gbv[e + 1]));
+                            f32x2 o2;
+                            if (tanh_gate) {                 // x * tanh(s): a = s, g = x
+                                float a0, a1;
+                                unpack2(a2, a0, a1);
+                                o2 = mul2(g2, pack2(fast_tanh(a0), fast_tanh(a1)));
+                            } else {                         // GLU x * sigmoid(s): a = x, g = s
+                                float z0, z1;
+                                unpack2(mul2(g2, pack2(NL2E, NL2E)), z0, z1);
+                                const f32x2 d2 = add2(pack2(fast_exp2(z0), fast_exp2(z1)), pack2(1.0f, 1.0f));
+                                float d0, d1;
+                                unpack2(d2, d0, d1);
+                                o2 = mul2(a2, pack2(fast_rcp(d0), fast_rcp(d1)));
+                            }
+                            float o0, o1;
+                            unpack2(o2, o0, o1);
+                            v[4 * j + e] = masked ? 0.0f : o0;
+                            v[4 * j + e + 1] = masked ? 0.0f : o1;
                         }
                     }
                     if (g_tma) stage_h16_unit(tbuf, lane, v, 4 * part);

@@ -314,6 +314,16 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // Swoosh(x) = softplus(x - c) - 0.08 x - d with softplus(y) = max(y,0) + log1p(exp(-|y|)).
 // One MUFU op (ex2) per activation instead of two (ex2 + lg2): log1p on [0,1] is a degree-5
 // polynomial (max abs error 1.2e-5), and max(y,0) - 0.08 y is folded into 0.42 y + 0.5 |y|, so the
