@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libzipvoice_b200.so")
+# ZVB_LIB: an alternative in-tree build of the same sources (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("ZVB_LIB") or os.path.join(HERE, "libzipvoice_b200.so")
 
 ZVB_ABI_VERSION = 2
 ZVB_MAX_STACKS = 8

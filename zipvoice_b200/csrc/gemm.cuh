@@ -419,7 +419,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             uint32_t kc[2] = {0u, 0u};
             uint32_t tile_iter = 0;
             constexpr uint32_t ST_PEND = 2;
-            int pend_bi[4], pend_slot[4];
+            int pend_bi[4] = {0, 0, 0, 0}, pend_slot[4] = {0, 0, 0, 0};
             uint32_t issued = 0, freed = 0;
             auto release_oldest = [&]() {
                 const int bi0 = pend_bi[freed & 3u], sl0 = pend_slot[freed & 3u];
