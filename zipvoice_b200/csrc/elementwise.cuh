@@ -105,21 +105,36 @@ biasnorm_bypass_kernel(const __half* __restrict__ src, const __half* __restrict_
 }
 
 // Stack entry: the time-embedded copy of the stream, xt = x + temb[row / L]
-// (reference: modules/zipformer.py:532-534)
+// (reference: modules/zipformer.py:532-534).  One thread = 8 channels of 4 rows (the four 16-byte loads
+// are issued before anything is consumed; a warp covers 256 contiguous channels of a row).
 __global__ void __launch_bounds__(256)
 stream_prep_kernel(const __half* __restrict__ x, __half* __restrict__ xt,
                    const float* __restrict__ temb, int rows_per_group, long long rows, int C) {
+    constexpr int RPT = 4;
     const int cv = C >> 3;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (idx >= rows * cv) return;
-    const long long row = idx / cv;
-    const int c = static_cast<int>(idx - row * cv) * 8;
-    float v[8];
-    load8h(x + row * C + c, v);
-    const long long grp = row / rows_per_group;
+    const long long rgroups = (rows + RPT - 1) / RPT;
+    if (idx >= rgroups * cv) return;
+    const long long rg = idx / cv;
+    const int c = static_cast<int>(idx - rg * cv) * 8;
+    const long long row0 = rg * RPT;
+    uint4 w[RPT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += __ldg(temb + grp * C + c + i);
-    store8h(xt + row * C + c, v);
+    for (int i = 0; i < RPT; ++i)
+        if (row0 + i < rows) w[i] = ld_stream_u4(x + (row0 + i) * C + c);
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const long long row = row0 + i;
+        if (row >= rows) break;
+        const float* tp = temb + (row / rows_per_group) * C + c;
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(tp));
+        const float4 t1 = __ldg(reinterpret_cast<const float4*>(tp + 4));
+        float v[8];
+        unpack8(w[i], v);
+        v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
+        v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+        store8h(xt + row * C + c, v);
+    }
 }
 
 // SimpleDownsample (reference: modules/zipformer.py:887-913): weighted sum over groups of ds

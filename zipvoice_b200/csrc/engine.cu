@@ -513,7 +513,7 @@ static int launch_op(const Op& op, cudaStream_t st) {
             return check_launch("biasnorm_bypass");
         }
         case OP_PREP: {
-            const long long n = op.rows * (op.i0 / 8);
+            const long long n = ((op.rows + 3) / 4) * (op.i0 / 8);
             stream_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const h16*)op.p0, (h16*)op.o0, op.f0, op.i1,
                                                                            op.rows, op.i0);
             return check_launch("stream_prep");
