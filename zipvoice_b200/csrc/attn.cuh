@@ -108,6 +108,8 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();                 // set-up above overlaps the previous kernel's tail
+    pdl_launch();
 
     if (warp == ATT_SM_WARPS) {                           // TMA producer
         if (lane == 0) {

@@ -47,6 +47,8 @@ biasnorm_bypass_kernel(const __half* __restrict__ src, const __half* __restrict_
                        const float* __restrict__ temb, int rows_per_group,
                        const float* __restrict__ nbias, const float* __restrict__ log_scale,
                        const float* __restrict__ bscale, long long rows, int C) {
+    pdl_wait();
+    pdl_launch();
     const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -110,6 +112,8 @@ biasnorm_bypass_kernel(const __half* __restrict__ src, const __half* __restrict_
 __global__ void __launch_bounds__(256)
 stream_prep_kernel(const __half* __restrict__ x, __half* __restrict__ xt,
                    const float* __restrict__ temb, int rows_per_group, long long rows, int C) {
+    pdl_wait();
+    pdl_launch();
     constexpr int RPT = 4;
     const int cv = C >> 3;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -142,6 +146,8 @@ stream_prep_kernel(const __half* __restrict__ x, __half* __restrict__ xt,
 __global__ void __launch_bounds__(256)
 downsample_kernel(const __half* __restrict__ src, __half* __restrict__ out, int N, int L,
                   int Ld, int ds, float w0, float w1, float w2, float w3, int C) {
+    pdl_wait();
+    pdl_launch();
     const int cv = C >> 3;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ld * cv) return;
@@ -168,6 +174,8 @@ __global__ void __launch_bounds__(256)
 upsample_combine_kernel(const __half* __restrict__ orig, const __half* __restrict__ y,
                         __half* __restrict__ out, const float* __restrict__ scale, int N, int L, int Ld,
                         int ds, int C) {
+    pdl_wait();
+    pdl_launch();
     const int cv = C >> 3;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= static_cast<long long>(N) * L * cv) return;
@@ -250,6 +258,8 @@ dwconv_swooshr_kernel(const __grid_constant__ CUtensorMap tma_x, __half* __restr
         fence_barrier_init();
     }
     __syncthreads();
+    pdl_wait();                 // the taps above are constants; the input tile is the predecessor's output
+    pdl_launch();
     int tl = blockIdx.x;
     if (threadIdx.x == 0 && tl < total) {
         mbar_arrive_expect_tx(&bar[0], WIN * 128);
@@ -301,6 +311,8 @@ dwconv_swooshr_kernel(const __grid_constant__ CUtensorMap tma_x, __half* __restr
 // ---------------------------------------------------------------------------------------
 // Time / guidance embedding (reference: modules/zipformer.py:47-69): out[n] = [cos(t f) | sin(t f)]
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int N, int dim) {
+    pdl_wait();
+    pdl_launch();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int half = dim >> 1;
     if (idx >= N * half) return;
@@ -318,6 +330,8 @@ __global__ void __launch_bounds__(256)
 small_linear_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
                     const float* __restrict__ addend, float* __restrict__ out, int N, int K, int O,
                     int act_in, int act_out) {
+    pdl_wait();
+    pdl_launch();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (gw >= N * O) return;
@@ -347,6 +361,8 @@ __global__ void __launch_bounds__(256)
 assemble_input_kernel(const float* __restrict__ x, const float* __restrict__ text,
                       const float* __restrict__ speech, __half* __restrict__ xin, int B, int T,
                       int F, int Ft, int ldx, int cfg, int drop_speech) {
+    pdl_wait();
+    pdl_launch();
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int N = cfg ? 2 * B : B;
     if (idx >= static_cast<long long>(N) * T * ldx) return;
@@ -366,6 +382,8 @@ assemble_input_kernel(const float* __restrict__ x, const float* __restrict__ tex
 // fp32 (rows, C) -> fp16 (rows, ldx) zero padded (seam-1 entry: caller passes the concatenated x)
 __global__ void __launch_bounds__(256)
 cast_pad_kernel(const float* __restrict__ x, __half* __restrict__ out, long long rows, int C, int ldx) {
+    pdl_wait();
+    pdl_launch();
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= rows * ldx) return;
     const int c = static_cast<int>(idx % ldx);
@@ -381,6 +399,8 @@ __global__ void __launch_bounds__(256)
 cfg_euler_kernel(float* __restrict__ x, const float* __restrict__ v, const float* __restrict__ guidance,
                  float gscale, const float* __restrict__ ts, int step, float* __restrict__ vout, int B,
                  long long per_utt, int cfg) {
+    pdl_wait();
+    pdl_launch();
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= static_cast<long long>(B) * per_utt) return;
     const float dt = ts[step + 1] - ts[step];
@@ -399,6 +419,8 @@ cfg_euler_kernel(float* __restrict__ x, const float* __restrict__ v, const float
 // mask[n, ::ds] (reference: modules/zipformer.py:857-858)
 __global__ void stride_mask_kernel(const uint8_t* __restrict__ mask, uint8_t* __restrict__ out, int N, int T,
                                    int Ld, int ds) {
+    pdl_wait();
+    pdl_launch();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * Ld) return;
     const int n = idx / Ld, l = idx - n * Ld;
@@ -409,6 +431,8 @@ __global__ void stride_mask_kernel(const uint8_t* __restrict__ mask, uint8_t* __
 // utterance is padded or j >= L; `words` per utterance covers whole 128-key tiles.
 __global__ void mask_words_kernel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ out, int N, int L,
                                   int words) {
+    pdl_wait();
+    pdl_launch();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * words) return;
     const int n = idx / words, w = idx - n * words;

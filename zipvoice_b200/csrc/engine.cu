@@ -54,6 +54,19 @@ static int check_launch(const char* what) {
 }
 
 static int g_num_sms = 0;
+static int g_pdl = 1;             // ZVB_NO_PDL=1: plain stream serialization between the kernels of a plan
+
+// Every kernel goes through here: programmatic dependent launch (ptx.cuh: pdl_wait / pdl_launch).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 static int g_cluster_ok = 1;      // ZVB_NO_CLUSTER=1 disables the CTA-pair (cta_group::2) GEMM variant
 static int g_tma_store_ok = 1;
 static int g_bn192 = 0;           // ZVB_BN192=1: 192-column tiles for short-K GEMMs (measured: no gain)
@@ -76,6 +89,7 @@ static int init_device() {
     if (const char* e = getenv("ZVB_NO_TMA_STORE")) g_tma_store_ok = atoi(e) == 0;
     if (const char* e = getenv("ZVB_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
     if (const char* e = getenv("ZVB_NO_LAYOUT")) g_layout_ok = atoi(e) == 0;
+    if (const char* e = getenv("ZVB_NO_PDL")) g_pdl = atoi(e) == 0;
     if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -461,7 +475,7 @@ static void launch_dwconv(const Op& op, cudaStream_t st) {
     if (per_group < 1) per_group = 1;
     if (per_group > tiles) per_group = tiles;
     dim3 grid(per_group, groups);
-    dwconv_swooshr_kernel<K><<<grid, 256, dw_smem_bytes<K>(), st>>>(op.ma, (h16*)op.o0, op.f0, op.f1, L, C, N);
+    launch_k(dwconv_swooshr_kernel<K>, dim3(grid), dim3(256), dw_smem_bytes<K>(), st, op.ma, (h16*)op.o0, op.f0, op.f1, L, C, N);
 }
 
 static int launch_op(const Op& op, cudaStream_t st) {
@@ -476,10 +490,12 @@ static int launch_op(const Op& op, cudaStream_t st) {
             cfg.blockDim = dim3(GEMM_THREADS);
             cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
             cfg.stream = st;
-            cudaLaunchAttribute attr[1];
+            cudaLaunchAttribute attr[2];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = op.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = g_pdl ? 2 : 1;
             const int sel = (op.kind == EPI_GATED ? 3 : op.gp.act) * 2 + (op.cluster - 1);
             cudaError_t e = cudaSuccess;
             switch (sel) {
@@ -497,36 +513,36 @@ static int launch_op(const Op& op, cudaStream_t st) {
         }
         case OP_ATTN: {
             dim3 grid((op.ap.L + ATT_BM - 1) / ATT_BM, op.ap.H, op.ap.N);
-            attn_weights_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(op.ma, op.ms, op.ap);
+            launch_k(attn_weights_kernel, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, st, op.ma, op.ms, op.ap);
             return check_launch("attn_weights");
         }
         case OP_BIASNORM: {
             const int blocks = static_cast<int>((op.rows + 7) / 8);
             if (op.i0 <= 512)
-                biasnorm_bypass_kernel<2><<<blocks, 256, 0, st>>>(
+                launch_k(biasnorm_bypass_kernel<2>, dim3(blocks), dim3(256), 0, st, 
                     (const h16*)op.p0, (const h16*)op.p1, (h16*)op.o0, (h16*)op.o1, op.f3, op.i1,
                     op.f0, op.f1, op.f2, op.rows, op.i0);
             else
-                biasnorm_bypass_kernel<4><<<blocks, 256, 0, st>>>(
+                launch_k(biasnorm_bypass_kernel<4>, dim3(blocks), dim3(256), 0, st, 
                     (const h16*)op.p0, (const h16*)op.p1, (h16*)op.o0, (h16*)op.o1, op.f3, op.i1,
                     op.f0, op.f1, op.f2, op.rows, op.i0);
             return check_launch("biasnorm_bypass");
         }
         case OP_PREP: {
             const long long n = ((op.rows + 3) / 4) * (op.i0 / 8);
-            stream_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const h16*)op.p0, (h16*)op.o0, op.f0, op.i1,
+            launch_k(stream_prep_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const h16*)op.p0, (h16*)op.o0, op.f0, op.i1,
                                                                            op.rows, op.i0);
             return check_launch("stream_prep");
         }
         case OP_DOWN: {
             const long long n = (long long)op.i0 * op.i2 * (op.i4 / 8);
-            downsample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            launch_k(downsample_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 
                 (const h16*)op.p0, (h16*)op.o0, op.i0, op.i1, op.i2, op.i3, op.w[0], op.w[1], op.w[2], op.w[3], op.i4);
             return check_launch("downsample");
         }
         case OP_UP: {
             const long long n = (long long)op.i0 * op.i1 * (op.i4 / 8);
-            upsample_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            launch_k(upsample_combine_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 
                 (const h16*)op.p0, (const h16*)op.p1, (h16*)op.o0, op.f0, op.i0, op.i1, op.i2, op.i3, op.i4);
             return check_launch("upsample_combine");
         }
@@ -541,23 +557,23 @@ static int launch_op(const Op& op, cudaStream_t st) {
         }
         case OP_MASK: {
             const int n = op.i0 * op.i2;
-            stride_mask_kernel<<<(n + 255) / 256, 256, 0, st>>>((const uint8_t*)op.p0, (uint8_t*)op.o0, op.i0, op.i1,
+            launch_k(stride_mask_kernel, dim3((n + 255) / 256), dim3(256), 0, st, (const uint8_t*)op.p0, (uint8_t*)op.o0, op.i0, op.i1,
                                                                  op.i2, op.i3);
             return check_launch("stride_mask");
         }
         case OP_MASKW: {
             const int n = op.i0 * op.i2;
-            mask_words_kernel<<<(n + 255) / 256, 256, 0, st>>>((const uint8_t*)op.p0, (uint32_t*)op.o0, op.i0, op.i1, op.i2);
+            launch_k(mask_words_kernel, dim3((n + 255) / 256), dim3(256), 0, st, (const uint8_t*)op.p0, (uint32_t*)op.o0, op.i0, op.i1, op.i2);
             return check_launch("mask_words");
         }
         case OP_TSEMB: {
             const int n = op.i0 * (op.i1 / 2);
-            timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, st>>>(op.f0, (float*)op.o0, op.i0, op.i1);
+            launch_k(timestep_embedding_kernel, dim3((n + 127) / 128), dim3(128), 0, st, op.f0, (float*)op.o0, op.i0, op.i1);
             return check_launch("timestep_embedding");
         }
         case OP_SMALL: {
             const long long warps = (long long)op.i0 * op.i2;
-            small_linear_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+            launch_k(small_linear_kernel, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, st, 
                 op.f0, op.f1, op.f2, op.f3, (float*)op.o0, op.i0, op.i1, op.i2, op.i3, op.i4);
             return check_launch("small_linear");
         }
@@ -905,7 +921,7 @@ int zvb_decoder_forward_f32(zvb_plan* plan, const float* x, const float* t, cons
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long M = (long long)plan->N * plan->T;
     const long long n = M * plan->xin_pitch;
-    cast_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, (h16*)plan->io.xin, M, plan->in_dim, plan->xin_pitch);
+    launch_k(cast_pad_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, (h16*)plan->io.xin, M, plan->in_dim, plan->xin_pitch);
     TRY(check_launch("cast_pad"));
     if (plan->has_time) CUDA_TRY(cudaMemcpyAsync(plan->io.t, t, sizeof(float) * plan->N, cudaMemcpyDeviceToDevice, st));
     if (plan->has_g) CUDA_TRY(cudaMemcpyAsync(plan->io.g, g, sizeof(float) * plan->N, cudaMemcpyDeviceToDevice, st));
@@ -917,10 +933,14 @@ int zvb_decoder_forward_f32(zvb_plan* plan, const float* x, const float* t, cons
 
 // fills a device float array with one value (captured as a kernel so graphs stay replayable)
 __global__ void fill_kernel(float* p, const float* src, int idx, int n) {
+    pdl_wait();
+    pdl_launch();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = src[idx];
 }
 __global__ void copy_scaled_kernel(float* dst, const float* src, float scale, int n) {
+    pdl_wait();
+    pdl_launch();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i] * scale;
 }
@@ -945,7 +965,7 @@ int zvb_sample(zvb_plan* plan, float* x, const float* text, const float* speech,
     CUDA_TRY(cudaMemcpyAsync(plan->io.mask, mask, mbytes, cudaMemcpyDeviceToDevice, st));
     if (mode == 1) CUDA_TRY(cudaMemcpyAsync(plan->io.mask + mbytes, mask, mbytes, cudaMemcpyDeviceToDevice, st));
     if (mode == 2) {
-        copy_scaled_kernel<<<(N + 127) / 128, 128, 0, st>>>(plan->io.g, guidance, 1.0f, N);
+        launch_k(copy_scaled_kernel, dim3((N + 127) / 128), dim3(128), 0, st, plan->io.g, guidance, 1.0f, N);
         TRY(check_launch("copy_guidance"));
     }
     const long long n_in = (long long)N * T * plan->xin_pitch;
@@ -953,14 +973,14 @@ int zvb_sample(zvb_plan* plan, float* x, const float* text, const float* speech,
     for (int step = 0; step < num_step; ++step) {
         const float t = ts_host[step];
         const int drop_speech = t > 0.5f ? 1 : 0;                 // reference: solver.py:90-98
-        assemble_input_kernel<<<(unsigned)((n_in + 255) / 256), 256, 0, st>>>(
+        launch_k(assemble_input_kernel, dim3((unsigned)((n_in + 255) / 256)), dim3(256), 0, st, 
             x, text, speech, (h16*)plan->io.xin, B, T, F, Ft, plan->xin_pitch, mode == 1, drop_speech);
         TRY(check_launch("assemble_input"));
-        fill_kernel<<<(N + 127) / 128, 128, 0, st>>>(plan->io.t, ts, step, N);
+        launch_k(fill_kernel, dim3((N + 127) / 128), dim3(128), 0, st, plan->io.t, ts, step, N);
         TRY(check_launch("fill_t"));
         TRY(zvb_decoder_forward(plan, stream));
         const float gscale = (mode == 1 && !drop_speech) ? 2.0f : 1.0f;
-        cfg_euler_kernel<<<(unsigned)((n_x + 255) / 256), 256, 0, st>>>(
+        launch_k(cfg_euler_kernel, dim3((unsigned)((n_x + 255) / 256)), dim3(256), 0, st, 
             x, plan->io.out, guidance, gscale, ts, step, vrec ? vrec + (long long)step * n_x : nullptr, B, per_utt,
             mode == 1);
         TRY(check_launch("cfg_euler"));
@@ -1030,7 +1050,7 @@ int zvb_test_dwconv(const void* x, void* out, const float* wt, const float* bias
 int zvb_test_cfg_euler(float* x, const float* v, const float* guidance, float gscale, const float* ts, int step, int B,
                        long long per_utt, int cfg, void* stream) {
     const long long n = (long long)B * per_utt;
-    cfg_euler_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    launch_k(cfg_euler_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         x, v, guidance, gscale, ts, step, nullptr, B, per_utt, cfg);
     return check_launch("cfg_euler");
 }

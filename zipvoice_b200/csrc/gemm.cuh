@@ -309,6 +309,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (CLUSTER > 1) cluster_sync_all();        // peers' barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();                 // set-up above overlaps the previous kernel's tail
+    pdl_launch();
 
     if (warp == W_TMA) {
         // ------------------------------------------------------------------ TMA producer (A, B)

@@ -23,6 +23,14 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     return t;
 }
 
+// ------------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the plan is launched with programmatic stream serialization: its CTAs may become resident
+// (and run their set-up: barrier init, TMEM allocation, tensor-map prefetch, constant staging) while the
+// previous kernel drains.  pdl_wait() blocks until the previous grid has completed and its writes are visible;
+// nothing written by a predecessor may be touched before it.  pdl_launch() lets the NEXT grid start launching.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
