@@ -105,13 +105,13 @@ def check_gated(M=300, K=512, n_out=384, mode=1, masked=False, seed=0):
     return dict(rel=_rel(out.float().nan_to_num(0.0), ref), nan=int(torch.isnan(out.float()).sum()), tol=8e-3)
 
 
-def _attn_inputs(N, H, L, seed, masked):
+def _attn_inputs(N, H, L, seed, masked, pos_scale=0.5):
     g = torch.Generator(device="cpu").manual_seed(seed)
     ld = H * 68
     qkp = torch.randn(N, L, ld, generator=g)
     qkp[..., : 2 * H * 32] *= 0.45          # q.k std ~ 1.1 ... a few units of score range
     qkp = qkp.to(H16)
-    E = torch.randn(H, 2 * L - 1, 4, generator=g) * 0.5
+    E = torch.randn(H, 2 * L - 1, 4, generator=g) * pos_scale
     mask = torch.zeros(N, L, dtype=torch.bool)
     if masked:
         lens = torch.randint(max(1, L // 2), L + 1, (N,), generator=g)
@@ -134,11 +134,11 @@ def _attn_ref(qkp, E, mask, H):
     return s.softmax(-1)
 
 
-def check_attn(N=2, H=4, L=200, masked=True, seed=0):
+def check_attn(N=2, H=4, L=200, masked=True, seed=0, pos_scale=0.5, tol=2.5e-3):
     """tolerance: max-abs <= 2.5e-3 on probabilities (the rel-pos bias and the exponent are evaluated in
     packed fp16: ~2^-9 absolute on an exponent of a few units; fp16 storage of P)"""
     lib = _lib.load()
-    qkp, E, mask = _attn_inputs(N, H, L, seed, masked)
+    qkp, E, mask = _attn_inputs(N, H, L, seed, masked, pos_scale)
     Lk = (L + 7) // 8 * 8
     P = torch.full((N, H, L, Lk), float("nan"), dtype=H16, device=DEV)
     inv_l = torch.full((N, H, L), float("nan"), dtype=torch.float32, device=DEV)
@@ -150,12 +150,12 @@ def check_attn(N=2, H=4, L=200, masked=True, seed=0):
     torch.cuda.synchronize()
     ref = _attn_ref(qkp, E, mask, H)
     pmax = float(P.float()[..., :L].max())
-    assert 0 < pmax <= 4096.0 * 1.01, pmax                 # unnormalised weights live in (0, 2^12]
+    assert 0 < pmax <= 4096.0 * 1.05, pmax                 # unnormalised weights live in (0, 2^12]
     got = P.float() * inv_l.unsqueeze(-1)
     pad = got[..., L:]
     return dict(maxabs=float((got[..., :L] - ref).abs().max()), rel=_rel(got[..., :L], ref),
                 nan=int(torch.isnan(got).sum()), pad_nonzero=int((pad != 0).sum()),
-                rowsum_err=float((got[..., :L].sum(-1) - 1).abs().max()), tol=2.5e-3)
+                rowsum_err=float((got[..., :L].sum(-1) - 1).abs().max()), tol=tol)
 
 
 def check_pv(N=2, H=4, L=200, hd=12, hp=16, per_head=True, mul=False, seed=0):
@@ -282,6 +282,10 @@ ALL = {
     "attn_small": lambda: check_attn(N=2, H=4, L=100, masked=False),
     "attn_masked": lambda: check_attn(N=3, H=4, L=333, masked=True),
     "attn_long": lambda: check_attn(N=1, H=4, L=1219, masked=True),
+    # strong rel-pos bias: |p|.max|E| ~ 15, the softmax shift bound is loose by up to ~2^40 and most rows
+    # sit far below it; weights must stay normal fp16 numbers thanks to the 2^12 head-room (looser
+    # tolerance: the fp16 bias sum carries ~2^-6 absolute error at magnitudes of 16..32)
+    "attn_strong_pos": lambda: check_attn(N=2, H=4, L=333, masked=True, pos_scale=2.5, tol=3e-2),
     "pv_heads": lambda: check_pv(N=2, H=4, L=333, per_head=True),
     "pv_wide": lambda: check_pv(N=2, H=4, L=333, hd=384, hp=384, per_head=False),
     "pv_wide96": lambda: check_pv(N=2, H=4, L=81, hd=96, hp=96, per_head=False),

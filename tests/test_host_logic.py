@@ -94,3 +94,30 @@ def test_ragged_synthetic_batch_is_sorted_and_consistent():
     assert u["target_lens"].tolist() == sorted(u["target_lens"].tolist(), reverse=True)
     assert int(u["features_lens"].max()) == u["x0"].shape[1]
     assert float(u["prompt_features"][1, int(u["prompt_features_lens"][1]):].abs().sum()) == 0.0
+
+
+def test_pos_table_pair_layout():
+    """weights.pack_pos_table: fp16 column pairs {log2e*E[r][d], log2e*E[r+1][d]} at entry r + POS_PAD, zeros
+    outside the 2L-1 offsets, followed by max_r |E[h][r]|_2 per head (the layout include/zipvoice_b200.h
+    documents for zvb_layer.pos_table)."""
+    from zipvoice_b200.weights import POS_PAD, pack_pos_table
+    H, L = 3, 37
+    R = 2 * L - 1
+    g = torch.Generator().manual_seed(3)
+    e = torch.randn(H, R, 4, generator=g)
+    raw = pack_pos_table(e)
+    n_entries = R + 2 * POS_PAD
+    assert raw.dtype == torch.uint8 and raw.numel() == H * n_entries * 16 + H * 4
+    pairs = raw[: H * n_entries * 16].view(torch.float16).reshape(H, n_entries, 4, 2).float()
+    emax = raw[H * n_entries * 16:].view(torch.float32)
+    want = torch.zeros(H, n_entries + 1, 4)
+    want[:, POS_PAD:POS_PAD + R] = e * 1.4426950408889634
+    assert torch.allclose(pairs[..., 0], want[:, :-1], rtol=1e-3, atol=1e-4)       # fp16 rounding
+    assert torch.allclose(pairs[..., 1], want[:, 1:], rtol=1e-3, atol=1e-4)
+    assert float(pairs[:, :POS_PAD - 1].abs().max()) == 0.0 and float(pairs[:, POS_PAD + R:].abs().max()) == 0.0
+    assert torch.allclose(emax, e.norm(dim=2).amax(dim=1))
+    # every 255-entry window a score tile can ask for lies inside the table
+    for i0 in range(0, L, 128):
+        for j0 in range(0, L, 128):
+            start = (j0 - i0) - 127 + (L - 1) + POS_PAD
+            assert 0 <= start and start + 255 <= n_entries

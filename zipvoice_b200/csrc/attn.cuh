@@ -14,8 +14,9 @@
 // 4-term bias is 1 HMUL2 + 3 HFMA2 against the window stored as column PAIRS (one 16-byte LDS per two
 // scores), the exponential is MUFU.EX2.F16 and its result IS the stored fp16 weight -- 7 instructions
 // per score instead of 18 with fp32 arithmetic.  The bound m may exceed the true row max by up to
-// 2·|p_i|·max|E|; the 2^12 head-room keeps the weights of such rows in fp16's normal range (a row only
-// degrades once the bound is loose by more than 2^26, far beyond the reference's own score limit).
+// 2·|p_i|·max|E|; the 2^12 head-room keeps the weights of such rows in fp16's normal range while that
+// slack stays below ATT_BOUND_SLACK_L2 (checked per CTA); a CTA with a stronger rel-pos bias takes the
+// EXACT row maximum instead: its first pass evaluates the bias too (same packed-half2 code).
 // The softmax is latency bound (TMEM load -> LDS of the rel-pos entries -> FFMA chain -> MUFU), so a
 // CTA runs EIGHT softmax warps -- two per TMEM lane quarter, each owning 64 of the tile's 128 key
 // columns and exchanging row max / row sum through shared memory -- and two CTAs share an SM
@@ -35,6 +36,7 @@ constexpr int ATT_TMEM_COLS = 256;
 constexpr int ATT_EWIN = 256;        // 255 offsets used
 constexpr int ATT_POS_PAD = 128;     // zero entries on both sides of the rel-pos table (weights.py: POS_PAD)
 constexpr int ATT_EWIN_BYTES = 255 * 16;
+constexpr float ATT_BOUND_SLACK_L2 = 10.0f;  // log2 units of slack the cheap softmax shift may have (weights >= 2^2)
 constexpr int ATT_STAGE_BYTES = ATT_SM_WARPS * 4096; // per softmax warp: 32 rows x 128 B TMA-store staging
 constexpr int ATT_SMEM_BYTES = (1 + ATT_KSTAGES) * ATT_TILE_BYTES + ATT_STAGE_BYTES + 2 * ATT_EWIN * 16 +
                                2 * 128 * 4 + 1024 + 256;
@@ -111,6 +113,33 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
     pdl_wait();                 // set-up above overlaps the previous kernel's tail
     pdl_launch();
 
+    // The cheap softmax shift m = max_j q.k_j + |p_i| max_r |E[r]| can exceed the true row maximum by up to
+    // 2 |p_i| max|E|; the stored weights 2^12 exp(s - m) stay normal fp16 numbers while that slack is below
+    // ~2^26.  A CTA whose rows may exceed ATT_BOUND_SLACK_L2 log2 units of slack (strong rel-pos bias)
+    // switches -- CTA-uniformly, the rel-pos window in shared memory is common to its eight warps -- to the
+    // EXACT row maximum: pass 1 then evaluates the bias as well (packed half2, like pass 2).
+    bool exact_max;
+    {
+        float bi = 0.f;
+        if (warp < ATT_SM_WARPS / 2) {                    // one warp per lane quarter computes its rows' |p_i|
+            const int i = i0 + warp * 32 + lane;
+            if (i < p.L) {
+                const __half* pp = p.qkp + (static_cast<long long>(n) * p.L + i) * p.ld + 2 * p.qd + h * 4;
+                const uint2 w = *reinterpret_cast<const uint2*>(pp);
+                const float a0 = h2_lo(w.x), a1 = h2_hi(w.x), a2 = h2_lo(w.y), a3 = h2_hi(w.y);
+                bi = sqrtf(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3);
+            }
+#pragma unroll
+            for (int q = 16; q > 0; q >>= 1) bi = fmaxf(bi, __shfl_xor_sync(0xffffffffu, bi, q));
+            if (lane == 0) xch[warp] = bi;
+        }
+        __syncthreads();
+        const float pmax = fmaxf(fmaxf(xch[0], xch[1]), fmaxf(xch[2], xch[3]));
+        exact_max = 2.0f * pmax * __ldg(p.emax + h) * 1.4426950408889634f > ATT_BOUND_SLACK_L2;
+        __syncthreads();                                  // xch is reused by the softmax warps
+    }
+    const int e_first = exact_max ? 0 : num_jt;           // first iteration that needs the rel-pos window
+
     if (warp == ATT_SM_WARPS) {                           // TMA producer
         if (lane == 0) {
             mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
@@ -125,12 +154,12 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
                 tma_load_3d(k_tiles + stage * ATT_TILE_BYTES, &tma_qk, &k_full[stage], p.qd + h * 32,
                             jt * ATT_BN, n);
                 if (++stage == ATT_KSTAGES) { stage = 0; phase ^= 1u; }
-                if (it >= num_jt) {
+                if (it >= e_first) {
                     // rel-pos window of this (i-tile, j-tile): 255 consecutive pair entries, first offset
                     // (j0 - i0) - 127, into buffer it & 1 (its own full/empty pair: this thread runs up to
                     // three tiles ahead of the softmax warps, so it cannot share the accumulator hand-shake)
                     const int eb = it & 1;
-                    mbar_wait(&e_empty[eb], (static_cast<uint32_t>((it - num_jt) >> 1) & 1u) ^ 1u);
+                    mbar_wait(&e_empty[eb], (static_cast<uint32_t>((it - e_first) >> 1) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(&e_full[eb], ATT_EWIN_BYTES);
                     bulk_load_1d(ewin + eb * ATT_EWIN, Eh + ((jt * ATT_BN - i0) - 127 + (p.L - 1) + ATT_POS_PAD),
                                  ATT_EWIN_BYTES, &e_full[eb]);
@@ -197,19 +226,49 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
                 xch[half * 128 + r] = m_run;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const float mr = fmaxf(xch[r], xch[128 + r]);
-                const float emax = __ldg(p.emax + h);
-                const float pn = sqrtf(p0 * p0 + p1 * p1 + p2 * p2 + p3 * p3);
-                const float m_est = (mr == -INFINITY ? 0.f : mr) + pn * emax;
-                m_l2 = m_est * LOG2E - 12.0f;            // weights are stored scaled by 2^12
+                if (exact_max) {                          // exact (fp16) row maximum of the biased scores, log2 units
+                    m_l2 = (mr == -INFINITY ? 0.f : mr) - 12.0f;
+                } else {
+                    const float emax = __ldg(p.emax + h);
+                    const float pn = sqrtf(p0 * p0 + p1 * p1 + p2 * p2 + p3 * p3);
+                    const float m_est = (mr == -INFINITY ? 0.f : mr) + pn * emax;
+                    m_l2 = m_est * LOG2E - 12.0f;        // weights are stored scaled by 2^12
+                }
             }
             const uint4* ew = ewin + acc * ATT_EWIN;
             const uint32_t mw0 = __ldg(mwrow + 4 * jt), mw1 = __ldg(mwrow + 4 * jt + 1);
-            if (pass) mbar_wait(&e_full[acc], static_cast<uint32_t>((it - num_jt) >> 1) & 1u);
+            if (it >= e_first) mbar_wait(&e_full[acc], static_cast<uint32_t>((it - e_first) >> 1) & 1u);
             mbar_wait(&s_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * ATT_BN + 64 * half) +
                                    (static_cast<uint32_t>(quarter * 32) << 16);
-            if (pass == 0) {
+            if (pass == 0 && exact_max) {
+                // exact row maximum: (q.k) log2e + bias per column pair in packed half2, as in pass 2
+                uint32_t hm = 0xFC00FC00u;                // (-inf, -inf)
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t sr[32];
+                    tmem_ld32(taddr + c0, sr);
+                    tmem_ld_wait();
+                    const uint32_t excl = c0 ? mw1 : mw0;
+                    const uint4* ep = ew + (64 * half + c0 - r + 127);
+#pragma unroll
+                    for (int c = 0; c < 32; c += 2) {
+                        const uint4 e4 = ep[c];
+                        uint32_t bias = hmul2(ph0, e4.x);
+                        bias = hfma2(ph1, e4.y, bias);
+                        bias = hfma2(ph2, e4.z, bias);
+                        bias = hfma2(ph3, e4.w, bias);
+                        uint32_t v = hadd2(bias, pack_h2(__uint_as_float(sr[c]) * LOG2E, __uint_as_float(sr[c + 1]) * LOG2E));
+                        if (excl != 0u) {
+                            if ((excl >> c) & 1u) v = (v & 0xFFFF0000u) | 0x0000FC00u;
+                            if ((excl >> (c + 1)) & 1u) v = (v & 0x0000FFFFu) | 0xFC000000u;
+                        }
+                        hm = hmax2(hm, v);
+                    }
+                }
+                m_run = fmaxf(m_run, fmaxf(h2_lo(hm), h2_hi(hm)));
+            } else if (pass == 0) {
 #pragma unroll 1
                 for (int c0 = 0; c0 < 64; c0 += 32) {
                     uint32_t sr[32];
@@ -288,7 +347,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&s_empty[acc]);
-                if (pass) mbar_arrive(&e_empty[acc]);
+                if (it >= e_first) mbar_arrive(&e_empty[acc]);
             }
         }
         xch[half * 128 + r] = l_run;

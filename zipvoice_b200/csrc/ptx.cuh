@@ -428,6 +428,9 @@ __device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {
 __device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) {
     uint32_t d; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
 }
+__device__ __forceinline__ uint32_t hmax2(uint32_t a, uint32_t b) {
+    uint32_t d; asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
+}
 __device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {      // 2^x on both halves (MUFU.EX2.F16)
     uint32_t y; asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y;
 }
