@@ -143,9 +143,56 @@ stream_prep_kernel(const __half* __restrict__ x, __half* __restrict__ xt,
 
 // SimpleDownsample (reference: modules/zipformer.py:887-913): weighted sum over groups of ds
 // frames, right-padded by repeating frame L-1.  w = softmax(bias) precomputed on the host.
+// One thread = 8 channels of two output frames; all 2*ds 16-byte loads are issued before the first use.
 __global__ void __launch_bounds__(256)
 downsample_kernel(const __half* __restrict__ src, __half* __restrict__ out, int N, int L,
                   int Ld, int ds, float w0, float w1, float w2, float w3, int C) {
+    pdl_wait();
+    pdl_launch();
+    constexpr int RPT = 2;
+    const int cv = C >> 3;
+    const int Lg = (Ld + RPT - 1) / RPT;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<long long>(N) * Lg * cv) return;
+    const int c = static_cast<int>(idx % cv) * 8;
+    const long long rl = idx / cv;
+    const int lg = static_cast<int>(rl % Lg);
+    const int n = static_cast<int>(rl / Lg);
+    const float w[4] = {w0, w1, w2, w3};
+    uint4 in[RPT][4];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int l = (lg * RPT + i) * ds + k;
+            l = l < L ? l : L - 1;
+            if (k < ds) in[i][k] = ld_stream_u4(src + (static_cast<long long>(n) * L + l) * C + c);
+        }
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int ld = lg * RPT + i;
+        if (ld >= Ld) break;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < ds) {
+                float v[8];
+                unpack8(in[i][k], v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], w[k], acc[e]);
+            }
+        }
+        store8h(out + (static_cast<long long>(n) * Ld + ld) * C + c, acc);
+    }
+}
+
+// SimpleUpsample + truncate + out_combiner bypass (reference: modules/zipformer.py:866-870,
+// 925-935):  out[n,l] = orig[n,l] + (y[n, l/ds] - orig[n,l]) * scale
+// One thread = 8 channels of the ds frames that share one low-rate frame (loads first).
+__global__ void __launch_bounds__(256)
+upsample_combine_kernel(const __half* __restrict__ orig, const __half* __restrict__ y,
+                        __half* __restrict__ out, const float* __restrict__ scale, int N, int L, int Ld,
+                        int ds, int C) {
     pdl_wait();
     pdl_launch();
     const int cv = C >> 3;
@@ -155,40 +202,29 @@ downsample_kernel(const __half* __restrict__ src, __half* __restrict__ out, int 
     const long long rl = idx / cv;
     const int ld = static_cast<int>(rl % Ld);
     const int n = static_cast<int>(rl / Ld);
-    const float w[4] = {w0, w1, w2, w3};
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < ds; ++k) {
-        int l = ld * ds + k;
-        l = l < L ? l : L - 1;
-        float v[8];
-        load8h(src + (static_cast<long long>(n) * L + l) * C + c, v);
+    const uint4 yv = ld_stream_u4(y + (static_cast<long long>(n) * Ld + ld) * C + c);
+    uint4 ov[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i], w[k], acc[i]);
+    for (int k = 0; k < 4; ++k) {
+        const int l = ld * ds + k;
+        if (k < ds && l < L) ov[k] = ld_stream_u4(orig + (static_cast<long long>(n) * L + l) * C + c);
     }
-    store8h(out + (static_cast<long long>(n) * Ld + ld) * C + c, acc);
-}
-
-// SimpleUpsample + truncate + out_combiner bypass (reference: modules/zipformer.py:866-870,
-// 925-935):  out[n,l] = orig[n,l] + (y[n, l/ds] - orig[n,l]) * scale
-__global__ void __launch_bounds__(256)
-upsample_combine_kernel(const __half* __restrict__ orig, const __half* __restrict__ y,
-                        __half* __restrict__ out, const float* __restrict__ scale, int N, int L, int Ld,
-                        int ds, int C) {
-    pdl_wait();
-    pdl_launch();
-    const int cv = C >> 3;
-    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (idx >= static_cast<long long>(N) * L * cv) return;
-    const int c = static_cast<int>(idx % cv) * 8;
-    const long long rl = idx / cv;
-    const int l = static_cast<int>(rl % L);
-    const int n = static_cast<int>(rl / L);
-    float o[8], v[8];
-    load8h(orig + rl * C + c, o);
-    load8h(y + (static_cast<long long>(n) * Ld + l / ds) * C + c, v);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    float v[8];
+    unpack8(yv, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = o[i] + (v[i] - o[i]) * __ldg(scale + c + i);
-    store8h(out + rl * C + c, v);
+    for (int k = 0; k < 4; ++k) {
+        const int l = ld * ds + k;
+        if (k < ds && l < L) {
+            float o[8], r[8];
+            unpack8(ov[k], o);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) r[e] = o[e] + (v[e] - o[e]) * sc[e];
+            store8h(out + (static_cast<long long>(n) * L + l) * C + c, r);
+        }
+    }
 }
 
 // Depthwise Conv1d over time (cross-correlation, zero padding K/2) + bias + SwooshR

@@ -535,13 +535,13 @@ static int launch_op(const Op& op, cudaStream_t st) {
             return check_launch("stream_prep");
         }
         case OP_DOWN: {
-            const long long n = (long long)op.i0 * op.i2 * (op.i4 / 8);
+            const long long n = (long long)op.i0 * ((op.i2 + 1) / 2) * (op.i4 / 8);
             launch_k(downsample_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 
                 (const h16*)op.p0, (h16*)op.o0, op.i0, op.i1, op.i2, op.i3, op.w[0], op.w[1], op.w[2], op.w[3], op.i4);
             return check_launch("downsample");
         }
         case OP_UP: {
-            const long long n = (long long)op.i0 * op.i1 * (op.i4 / 8);
+            const long long n = (long long)op.i0 * op.i2 * (op.i4 / 8);
             launch_k(upsample_combine_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, 
                 (const h16*)op.p0, (const h16*)op.p1, (h16*)op.o0, op.f0, op.i0, op.i1, op.i2, op.i3, op.i4);
             return check_launch("upsample_combine");
