@@ -68,7 +68,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
     // {E[e][d], E[e+1][d]} for d = 0..3, so the pair of columns (c, c+1) of row r reads entry c - r + 127
     uint4* ewin = reinterpret_cast<uint4*>(stage_all + ATT_STAGE_BYTES);                    // [2][256]
     float* xch = reinterpret_cast<float*>(ewin + 2 * ATT_EWIN);                             // [2][128] half <-> half
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 256);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 256 + 8);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1;                      // [KSTAGES]
     uint64_t* k_empty = k_full + ATT_KSTAGES;         // [KSTAGES]
@@ -118,42 +118,39 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
     // ~2^26.  A CTA whose rows may exceed ATT_BOUND_SLACK_L2 log2 units of slack (strong rel-pos bias)
     // switches -- CTA-uniformly, the rel-pos window in shared memory is common to its eight warps -- to the
     // EXACT row maximum: pass 1 then evaluates the bias as well (packed half2, like pass 2).
-    bool exact_max;
-    {
-        float bi = 0.f;
-        if (warp < ATT_SM_WARPS / 2) {                    // one warp per lane quarter computes its rows' |p_i|
-            const int i = i0 + warp * 32 + lane;
-            if (i < p.L) {
-                const __half* pp = p.qkp + (static_cast<long long>(n) * p.L + i) * p.ld + 2 * p.qd + h * 4;
-                const uint2 w = *reinterpret_cast<const uint2*>(pp);
-                const float a0 = h2_lo(w.x), a1 = h2_hi(w.x), a2 = h2_lo(w.y), a3 = h2_hi(w.y);
-                bi = sqrtf(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3);
-            }
-#pragma unroll
-            for (int q = 16; q > 0; q >>= 1) bi = fmaxf(bi, __shfl_xor_sync(0xffffffffu, bi, q));
-            if (lane == 0) xch[warp] = bi;
-        }
-        __syncthreads();
-        const float pmax = fmaxf(fmaxf(xch[0], xch[1]), fmaxf(xch[2], xch[3]));
-        exact_max = 2.0f * pmax * __ldg(p.emax + h) * 1.4426950408889634f > ATT_BOUND_SLACK_L2;
-        __syncthreads();                                  // xch is reused by the softmax warps
-    }
-    const int e_first = exact_max ? 0 : num_jt;           // first iteration that needs the rel-pos window
+    // The decision is taken by the softmax warps from the p rows they load anyway and shared with the TMA
+    // producer through `flag` and named barrier 2 (the producer has the Q tile and the first K tiles in
+    // flight by then).
+    float* flag = xch + 256;                              // [8] per-warp max |p_i|
 
     if (warp == ATT_SM_WARPS) {                           // TMA producer
+        int stage = 0;
+        uint32_t phase = 0;
+        auto load_k = [&](int it) {
+            const int jt = it >= num_jt ? it - num_jt : it;
+            mbar_wait(&k_empty[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&k_full[stage], ATT_TILE_BYTES);
+            tma_load_3d(k_tiles + stage * ATT_TILE_BYTES, &tma_qk, &k_full[stage], p.qd + h * 32,
+                        jt * ATT_BN, n);
+            if (++stage == ATT_KSTAGES) { stage = 0; phase ^= 1u; }
+        };
+        const int prefill = total_it < ATT_KSTAGES ? total_it : ATT_KSTAGES;
         if (lane == 0) {
             mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
             tma_load_3d(q_tile, &tma_qk, q_full, h * 32, i0, n);
-            int stage = 0;
-            uint32_t phase = 0;
+            for (int it = 0; it < prefill; ++it) load_k(it);       // in flight while the softmax warps decide
+        }
+        __syncwarp();
+        asm volatile("bar.sync 2, 288;" ::: "memory");             // whole warp, converged
+        if (lane == 0) {
+            float pmax = flag[0];
+            for (int w = 1; w < ATT_SM_WARPS; ++w) pmax = fmaxf(pmax, flag[w]);
+            const bool exact_max = 2.0f * pmax * __ldg(p.emax + h) * 1.4426950408889634f > ATT_BOUND_SLACK_L2;
+            const int e_first = exact_max ? 0 : num_jt;            // first iteration that needs the rel-pos window
             const uint4* Eh = p.Epair + static_cast<long long>(h) * (2 * p.L - 1 + 2 * ATT_POS_PAD);
             for (int it = 0; it < total_it; ++it) {
                 const int jt = it >= num_jt ? it - num_jt : it;
-                mbar_wait(&k_empty[stage], phase ^ 1u);
-                mbar_arrive_expect_tx(&k_full[stage], ATT_TILE_BYTES);
-                tma_load_3d(k_tiles + stage * ATT_TILE_BYTES, &tma_qk, &k_full[stage], p.qd + h * 32,
-                            jt * ATT_BN, n);
-                if (++stage == ATT_KSTAGES) { stage = 0; phase ^= 1u; }
+                if (it >= prefill) load_k(it);
                 if (it >= e_first) {
                     // rel-pos window of this (i-tile, j-tile): 255 consecutive pair entries, first offset
                     // (j0 - i0) - 127, into buffer it & 1 (its own full/empty pair: this thread runs up to
@@ -207,6 +204,18 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
             ph0 = __byte_perm(w.x, 0u, 0x1010); ph1 = __byte_perm(w.x, 0u, 0x3232);
             ph2 = __byte_perm(w.y, 0u, 0x1010); ph3 = __byte_perm(w.y, 0u, 0x3232);
         }
+        {   // CTA-uniform choice between the cheap and the exact softmax shift (see above)
+            float bi = sqrtf(p0 * p0 + p1 * p1 + p2 * p2 + p3 * p3);
+#pragma unroll
+            for (int q = 16; q > 0; q >>= 1) bi = fmaxf(bi, __shfl_xor_sync(0xffffffffu, bi, q));
+            if (lane == 0) flag[warp] = bi;
+        }
+        asm volatile("bar.sync 2, 288;" ::: "memory");
+        float pmax_cta = flag[0];
+#pragma unroll
+        for (int w = 1; w < ATT_SM_WARPS; ++w) pmax_cta = fmaxf(pmax_cta, flag[w]);
+        const bool exact_max = 2.0f * pmax_cta * __ldg(p.emax + h) * 1.4426950408889634f > ATT_BOUND_SLACK_L2;
+        const int e_first = exact_max ? 0 : num_jt;       // first iteration that needs the rel-pos window
         // excluded-key bits of this warp's 64 columns of tile jt: words 2*half, 2*half + 1 of the tile's four
         const uint32_t* mwrow = p.maskw + static_cast<long long>(n) * p.mask_words + 2 * half;
         // P leaves through TMA stores: every warp stages 32 rows x 64 columns (128-byte rows, 128B
