@@ -71,7 +71,7 @@ static int g_cluster_ok = 1;      // ZVB_NO_CLUSTER=1 disables the CTA-pair (cta
 static int g_tma_store_ok = 1;
 static int g_bn192 = 0;           // ZVB_BN192=1: 192-column tiles for short-K GEMMs (measured: no gain)
 static int g_layout_ok = 1;       // ZVB_NO_LAYOUT=1 keeps the default operand-ring / aux split everywhere
-static int g_pair_min_kb = 16;    // ZVB_PAIR_MIN_KB: fewest k-blocks for which a CTA pair is used    // ZVB_NO_TMA_STORE=1 keeps the epilogue on per-thread stores
+static int g_pair_min_kb = 8;     // ZVB_PAIR_MIN_KB: fewest k-blocks for which a CTA pair is used    // ZVB_NO_TMA_STORE=1 keeps the epilogue on per-thread stores
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
 static int init_device() {
@@ -242,7 +242,9 @@ static void set_grid(Op& op) {
     GemmParams& p = op.gp;
     const long long slots2 = (long long)p.batches * ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     // CTA pairs pay off when the mainloop dominates the tile (measured: K = 1920 GEMMs 320 -> 279 us,
-    // P.V 222 -> 195 us) and cost ~10% on the epilogue-bound K <= 512 residual-stream GEMMs
+    // P.V 222 -> 195 us).  For K = 512 they were a loss until the peer's accumulator hand-off stopped fencing
+    // (relaxed remote arrive) and the epilogue arithmetic was packed; since then 8 k-blocks are worth it
+    // (-30% L2->SM operand bytes; 790 -> 770 ms per sample, A/B on one box), fewer make no difference
     op.cluster = (g_cluster_ok && p.block_n >= 64 && p.num_m_tiles >= 2 && slots2 >= g_num_sms / 4 &&
                   p.num_k_blocks >= g_pair_min_kb) ? 2 : 1;
     if (op.cluster == 2) {
