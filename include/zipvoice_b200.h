@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ZVB_ABI_VERSION 2
+#define ZVB_ABI_VERSION 3
 #define ZVB_MAX_STACKS 8
 #define ZVB_MAX_LAYERS 64
 
@@ -102,12 +102,14 @@ typedef struct {
     int32_t na_hidden;
     int32_t time_dim;         /* 192, or 0 when the network takes no time embedding          */
     int32_t use_guidance_embed;
+    int32_t guidance_dim;     /* width of timestep_embedding(guidance_scale) = guidance_w's in_features
+                               * (reference: zipformer.py:128, 233-238: 192, independent of time_dim)   */
     int32_t num_stacks;
     int32_t num_layers;
     zvb_linear in_proj, out_proj;
     const float* time0_w; const float* time0_b;   /* time_embed.0 fp32 [2*time_dim][time_dim] */
     const float* time2_w; const float* time2_b;   /* time_embed.2 fp32 [time_dim][2*time_dim] */
-    const float* guidance_w;                      /* guidance_scale_embed.weight (nullable)   */
+    const float* guidance_w;                      /* guidance_scale_embed.weight fp32 [time_dim][guidance_dim] (nullable) */
     zvb_stack stacks[ZVB_MAX_STACKS];
     const zvb_layer* layers;  /* host array of num_layers entries                            */
 } zvb_model;
@@ -126,6 +128,8 @@ typedef struct zvb_plan zvb_plan;
 
 const char* zvb_last_error(void);
 int zvb_abi_version(void);
+/* sha256 of the sources the library was built from (zipvoice_b200/build.py rebuilds on mismatch) */
+const char* zvb_source_hash(void);
 /* number of kernels of this library launched by the calling thread since process start */
 long long zvb_launch_count(void);
 
@@ -139,6 +143,11 @@ int zvb_plan_io(const zvb_plan* plan, zvb_io* io);
 
 /* Forward over the resident io buffers: out = fm_decoder(xin, t, mask[, g]). */
 int zvb_decoder_forward(zvb_plan* plan, void* stream);
+
+/* Parity aid: with a non-null device counter every forward of the plan also counts, kernel by kernel, the
+ * fp16 outputs that reached the largest finite fp16 magnitude (the conversions of the path saturate) or are
+ * inf / NaN, and adds them to *counter.  null switches the check off again. */
+int zvb_plan_set_saturation_counter(zvb_plan* plan, unsigned long long* counter);
 
 /* Profiling aid (NOT graph capturable: records one CUDA event per kernel and synchronises the
  * stream): runs one forward over the resident io buffers and returns, per launched kernel, its
@@ -197,6 +206,26 @@ int zvb_test_dwconv(const void* x, void* out, const float* wt, const float* bias
                     void* stream);
 int zvb_test_cfg_euler(float* x, const float* v, const float* guidance, float gscale, const float* ts,
                        int step, int B, long long per_utt, int cfg, void* stream);
+/* linear with the transposed store of the value projections: out[(row / t_L)*t_batch_rows + drow(col)][row % t_L],
+ * pitch t_pitch, drow(col) = col + (col / t_hd)*(t_hp - t_hd) (SelfAttention heads padded t_hd -> t_hp rows) */
+int zvb_test_linear_t(const void* A, int M, int K, int lda, const void* W, const float* bias, int n_out, int k_pitch,
+                      void* out, int t_L, int t_pitch, int t_batch_rows, int t_hd, int t_hp, void* stream);
+/* SimpleDownsample / SimpleUpsample + out_combiner on fp16 [N][L][C] (reference: zipformer.py:873-935) */
+int zvb_test_downsample(const void* src, void* out, int N, int L, int ds, const float* w4, int C, void* stream);
+int zvb_test_upsample_combine(const void* orig, const void* y, void* out, const float* scale, int N, int L, int ds,
+                              int C, void* stream);
+/* xt = x + temb[row / rows_per_group] */
+int zvb_test_stream_prep(const void* x, void* xt, const float* temb, int rows_per_group, long long rows, int C,
+                         void* stream);
+/* decoder input [x | text | speech | 0] as fp16 with the CFG doubling (reference: solver.py:83-98) */
+int zvb_test_assemble_input(const float* x, const float* text, const float* speech, void* xin, int B, int T, int F,
+                            int Ft, int ldx, int cfg, int drop_speech, void* stream);
+/* out = act_out(addend + bias + W * act_in(in)), fp32 (time-embedding MLPs); act 0 none / 2 SwooshR */
+int zvb_test_small_linear(const float* in, const float* W, const float* bias, const float* addend, float* out,
+                          int N, int K, int O, int act_in, int act_out, void* stream);
+int zvb_test_timestep_embedding(const float* t, float* out, int N, int dim, void* stream);
+/* strided key mask mask[:, ::ds] and the attention kernel's excluded-key bit words (either output nullable) */
+int zvb_test_masks(const uint8_t* mask, int N, int T, int ds, uint8_t* strided, uint32_t* words, void* stream);
 
 #ifdef __cplusplus
 }

@@ -254,8 +254,152 @@ def check_cfg_euler(B=3, T=50, F=100, cfg=1, seed=0):
     return dict(rel=_rel(x, ref), tol=1e-6)
 
 
+def check_linear_t(N=3, L=77, K=512, H=4, hd=12, hp=16, seed=0):
+    """Value projection with the transposed store (SelfAttention: heads padded hd -> hp rows; NonlinAttention:
+    hd = hp = 1 i.e. plain transpose): out[n][drow(col)][l].  tolerance: rel-L2 <= 8e-4; pad rows/cols stay 0."""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    M, n_out = N * L, H * hd
+    Lk = (L + 7) // 8 * 8
+    A = torch.randn(M, K, generator=g).to(H16).to(DEV)
+    W = (torch.randn(n_out, K, generator=g) / math.sqrt(K)).to(H16).to(DEV)
+    b = torch.randn(n_out, generator=g).to(DEV)
+    rows = H * hp
+    out = torch.zeros(N, rows, Lk, dtype=H16, device=DEV)
+    _lib.check(lib.zvb_test_linear_t(A.data_ptr(), M, K, K, W.data_ptr(), b.data_ptr(), n_out, K, out.data_ptr(),
+                                     L, Lk, rows, hd, hp, _s()))
+    torch.cuda.synchronize()
+    ref = (A.float() @ W.float().t() + b).reshape(N, L, H, hd).permute(0, 2, 3, 1)          # (N, H, hd, L)
+    got = out.float().reshape(N, H, hp, Lk)
+    pad = int((got[:, :, hd:] != 0).sum() + (got[..., L:] != 0).sum())
+    return dict(rel=_rel(got[:, :, :hd, :L], ref), nan=int(torch.isnan(got).sum()), pad_bad=pad, tol=8e-4)
+
+
+def check_resample(N=3, L=333, ds=2, C=512, seed=0):
+    """SimpleDownsample (weighted sum over groups of ds frames, last frame repeated) and SimpleUpsample +
+    out_combiner (reference: zipformer.py:873-935).  tolerance: rel-L2 <= 6e-4 (fp16 outputs)."""
+    import ctypes as C_
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(N, L, C, generator=g).to(H16).to(DEV)
+    w = torch.softmax(torch.randn(ds, generator=g), 0)
+    w4 = (C_.c_float * 4)(*(w.tolist() + [0.0] * (4 - ds)))
+    Ld = (L + ds - 1) // ds
+    down = torch.full((N, Ld, C), float("nan"), dtype=H16, device=DEV)
+    _lib.check(lib.zvb_test_downsample(x.data_ptr(), down.data_ptr(), N, L, ds, w4, C, _s()))
+    xf = x.float()
+    pad = Ld * ds - L
+    xp = torch.cat([xf, xf[:, -1:].expand(N, pad, C)], dim=1) if pad else xf
+    ref_d = (xp.reshape(N, Ld, ds, C) * w.to(DEV)[None, None, :, None]).sum(2)
+    y = torch.randn(N, Ld, C, generator=g).to(H16).to(DEV)
+    sc = (torch.rand(C, generator=g) * 0.6 + 0.3).to(DEV)
+    up = torch.full((N, L, C), float("nan"), dtype=H16, device=DEV)
+    _lib.check(lib.zvb_test_upsample_combine(x.data_ptr(), y.data_ptr(), up.data_ptr(), sc.data_ptr(), N, L, ds, C, _s()))
+    torch.cuda.synchronize()
+    yu = y.float().repeat_interleave(ds, dim=1)[:, :L]
+    ref_u = xf + (yu - xf) * sc
+    return dict(rel=max(_rel(down.float(), ref_d), _rel(up.float(), ref_u)),
+                nan=int(torch.isnan(down.float()).sum() + torch.isnan(up.float()).sum()), tol=6e-4)
+
+
+def check_stream_prep(rows=1001, C=512, L=37, seed=0):
+    """xt = x + temb[row / L].  tolerance: rel-L2 <= 6e-4 (fp16 output)."""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(rows, C, generator=g).to(H16).to(DEV)
+    temb = torch.randn((rows + L - 1) // L, C, generator=g).to(DEV)
+    out = torch.full((rows, C), float("nan"), dtype=H16, device=DEV)
+    _lib.check(lib.zvb_test_stream_prep(x.data_ptr(), out.data_ptr(), temb.data_ptr(), L, rows, C, _s()))
+    torch.cuda.synchronize()
+    ref = x.float() + temb[torch.arange(rows, device=DEV) // L]
+    return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=6e-4)
+
+
+def check_assemble(B=3, T=41, F=100, Ft=100, cfg=1, drop=0, seed=0):
+    """Decoder input [x | text | speech | 0] as fp16 with the CFG doubling [uncond ; cond] (reference:
+    solver.py:83-98, zipvoice.py:163).  Bit-exact against torch's fp32 -> fp16 rounding."""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(B, T, F, generator=g).to(DEV)
+    text = torch.randn(B, T, Ft, generator=g).to(DEV)
+    speech = torch.randn(B, T, F, generator=g).to(DEV)
+    ldx = (2 * F + Ft + 7) // 8 * 8
+    N = 2 * B if cfg else B
+    out = torch.full((N, T, ldx), float("nan"), dtype=H16, device=DEV)
+    _lib.check(lib.zvb_test_assemble_input(x.data_ptr(), text.data_ptr(), speech.data_ptr(), out.data_ptr(), B, T, F, Ft,
+                                           ldx, cfg, drop, _s()))
+    torch.cuda.synchronize()
+    z = torch.zeros(B, T, ldx - 2 * F - Ft, device=DEV)
+    cond = torch.cat([x, text, speech, z], dim=2)
+    if cfg:
+        unc = torch.cat([x, torch.zeros_like(text), torch.zeros_like(speech) if drop else speech, z], dim=2)
+        ref = torch.cat([unc, cond], dim=0)
+    else:
+        ref = cond
+    return dict(rel=0.0 if torch.equal(out, ref.to(H16)) else 1.0, nan=int(torch.isnan(out.float()).sum()), tol=0.0)
+
+
+def check_small_linear(N=5, K=192, O=384, act_in=0, act_out=2, addend=False, seed=0):
+    """fp32 time-embedding MLP layer.  tolerance: rel-L2 <= 2e-5 (SwooshR uses the fast exp/log path)."""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(N, K, generator=g).to(DEV)
+    W = (torch.randn(O, K, generator=g) / math.sqrt(K)).to(DEV)
+    b = torch.randn(O, generator=g).to(DEV)
+    add = torch.randn(N, O, generator=g).to(DEV) if addend else None
+    out = torch.full((N, O), float("nan"), device=DEV)
+    _lib.check(lib.zvb_test_small_linear(x.data_ptr(), W.data_ptr(), b.data_ptr(), add.data_ptr() if addend else None,
+                                         out.data_ptr(), N, K, O, act_in, act_out, _s()))
+    torch.cuda.synchronize()
+    xi = _swoosh_r(x) if act_in == 2 else x
+    ref = xi @ W.t() + b
+    if addend:
+        ref = ref + add
+    if act_out == 2:
+        ref = _swoosh_r(ref)
+    return dict(rel=_rel(out, ref), nan=int(torch.isnan(out).sum()), tol=2e-5)
+
+
+def check_timestep_embedding(N=7, dim=192):
+    """[cos(t f) | sin(t f)], f_i = 10000^(-i/half) (reference: zipformer.py:47-69).  tolerance: max-abs <= 2e-5
+    (arguments up to ~10 rad in fp32; guidance scales reach 3)."""
+    lib = _lib.load()
+    t = torch.linspace(0.0, 3.0, N, device=DEV)
+    out = torch.full((N, dim), float("nan"), device=DEV)
+    _lib.check(lib.zvb_test_timestep_embedding(t.data_ptr(), out.data_ptr(), N, dim, _s()))
+    torch.cuda.synchronize()
+    half = dim // 2
+    f = torch.exp(-math.log(10000.0) * torch.arange(half, device=DEV, dtype=torch.float32) / half)
+    a = t[:, None].double() * f[None].double()
+    ref = torch.cat([a.cos(), a.sin()], dim=-1)
+    return dict(rel=float((out.double() - ref).abs().max()), nan=int(torch.isnan(out).sum()), tol=2e-5)
+
+
+def check_masks(N=3, T=333, ds=2, seed=0):
+    """mask[:, ::ds] and the attention kernel's excluded-key bit words.  Bit-exact."""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    lens = torch.randint(T // 2, T + 1, (N,), generator=g)
+    mask = (torch.arange(T)[None, :] >= lens[:, None]).to(torch.uint8).to(DEV)
+    L = (T + ds - 1) // ds
+    words = 4 * ((L + 127) // 128)
+    st = torch.full((N, L), 7, dtype=torch.uint8, device=DEV)
+    wd = torch.zeros(N, words, dtype=torch.int32, device=DEV)
+    _lib.check(lib.zvb_test_masks(mask.data_ptr(), N, T, ds, st.data_ptr() if ds != 1 else None, wd.data_ptr(), _s()))
+    torch.cuda.synchronize()
+    ref_m = mask[:, ::ds]
+    ok = ds == 1 or torch.equal(st, ref_m)
+    bits = torch.ones(N, words * 32, dtype=torch.int64, device=DEV)
+    bits[:, :L] = ref_m.long()
+    ref_w = (bits.reshape(N, words, 32) << torch.arange(32, device=DEV)).sum(-1)
+    got_w = wd.long() & 0xFFFFFFFF
+    ok = ok and torch.equal(got_w, ref_w)
+    return dict(rel=0.0 if ok else 1.0, tol=0.0)
+
+
 def assert_ok(name, r):
     assert r.get("nan", 0) == 0, (name, r)
+    assert r.get("pad_bad", 0) == 0, (name, r)
     if "maxabs" in r:
         assert r["maxabs"] <= r["tol"], (name, r)
         assert r.get("pad_nonzero", 0) == 0, (name, r)
@@ -297,6 +441,22 @@ ALL = {
     "dwconv15": lambda: check_dwconv(K=15, L=77),
     "dwconv7": lambda: check_dwconv(K=7, L=64, C=128),
     "dwconv9": lambda: check_dwconv(K=9, L=20, C=192),
+    "linear_t_heads": lambda: check_linear_t(N=3, L=77, H=4, hd=12, hp=16),
+    "linear_t_plain": lambda: check_linear_t(N=2, L=333, H=1, hd=48, hp=48),
+    "resample_ds2": lambda: check_resample(N=3, L=333, ds=2),
+    "resample_ds4": lambda: check_resample(N=2, L=1219, ds=4),
+    "resample_ds4_c128": lambda: check_resample(N=2, L=50, ds=4, C=128),
+    "stream_prep": lambda: check_stream_prep(),
+    "assemble_cfg_keep": lambda: check_assemble(cfg=1, drop=0),
+    "assemble_cfg_drop": lambda: check_assemble(cfg=1, drop=1),
+    "assemble_stereo_nocfg": lambda: check_assemble(B=2, T=30, F=200, Ft=100, cfg=0),
+    "small_linear_swoosh_out": lambda: check_small_linear(),
+    "small_linear_swoosh_in": lambda: check_small_linear(K=192, O=512, act_in=2, act_out=0),
+    "small_linear_addend": lambda: check_small_linear(K=192, O=192, act_in=0, act_out=0, addend=True),
+    "timestep_embedding": lambda: check_timestep_embedding(),
+    "masks_ds1": lambda: check_masks(ds=1),
+    "masks_ds2": lambda: check_masks(ds=2),
+    "masks_ds4": lambda: check_masks(N=2, T=1219, ds=4),
     "cfg_euler": lambda: check_cfg_euler(cfg=1),
     "euler_nocfg": lambda: check_cfg_euler(cfg=0),
 }

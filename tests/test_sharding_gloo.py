@@ -33,8 +33,7 @@ def _worker(rank: int, world: int, port: int, lens, out_q):
     dist.destroy_process_group()
 
 
-def test_partition_and_gather_world2():
-    lens = [37, 12, 50, 44, 9, 28, 31]
+def _run_world2(lens):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)
@@ -46,6 +45,18 @@ def test_partition_and_gather_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == {0: True, 1: True}
+
+
+def test_partition_and_gather_world2():
+    _run_world2([37, 12, 50, 44, 9, 28, 31])
+
+
+def test_skewed_lengths_world2():
+    """One long utterance against ten short ones: the frame-balanced shards hold 1 and 10 utterances."""
+    lens = [1000] + [100] * 10
+    shards = partition_utterances(lens, 2)
+    assert sorted(len(s) for s in shards) == [1, 10]
+    _run_world2(lens)
 
 
 def test_gather_single_process():

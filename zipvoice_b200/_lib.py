@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # ZVB_LIB: an alternative in-tree build of the same sources (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("ZVB_LIB") or os.path.join(HERE, "libzipvoice_b200.so")
 
-ZVB_ABI_VERSION = 2
+ZVB_ABI_VERSION = 3
 ZVB_MAX_STACKS = 8
 
 
@@ -44,7 +44,7 @@ class zvb_model(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("dim", C.c_int32), ("num_heads", C.c_int32),
                 ("value_head_dim", C.c_int32), ("in_dim", C.c_int32), ("out_dim", C.c_int32),
                 ("ff_dims", C.c_int32 * 3), ("na_hidden", C.c_int32), ("time_dim", C.c_int32),
-                ("use_guidance_embed", C.c_int32), ("num_stacks", C.c_int32),
+                ("use_guidance_embed", C.c_int32), ("guidance_dim", C.c_int32), ("num_stacks", C.c_int32),
                 ("num_layers", C.c_int32),
                 ("in_proj", zvb_linear), ("out_proj", zvb_linear),
                 ("time0_w", C.c_void_p), ("time0_b", C.c_void_p),
@@ -60,6 +60,8 @@ class zvb_io(C.Structure):
 EXPORTS = {
     "zvb_last_error": (C.c_char_p, []),
     "zvb_abi_version": (C.c_int, []),
+    "zvb_source_hash": (C.c_char_p, []),
+    "zvb_plan_set_saturation_counter": (C.c_int, [C.c_void_p, C.c_void_p]),
     "zvb_launch_count": (C.c_longlong, []),
     "zvb_plan_workspace_bytes": (C.c_int, [C.POINTER(zvb_model), C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "zvb_plan_create": (C.c_int, [C.POINTER(zvb_model), C.c_int, C.c_int, C.c_void_p, C.c_size_t,
@@ -84,6 +86,17 @@ EXPORTS = {
     "zvb_test_dwconv": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]),
     "zvb_test_cfg_euler": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
                                      C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
+    "zvb_test_linear_t": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "zvb_test_downsample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
+                                      C.c_void_p]),
+    "zvb_test_upsample_combine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_void_p]),
+    "zvb_test_stream_prep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
+    "zvb_test_assemble_input": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]),
+    "zvb_test_small_linear": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 5 + [C.c_void_p]),
+    "zvb_test_timestep_embedding": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "zvb_test_masks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

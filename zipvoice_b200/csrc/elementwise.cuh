@@ -481,4 +481,31 @@ __global__ void mask_words_kernel(const uint8_t* __restrict__ mask, uint32_t* __
     out[idx] = bits;
 }
 
+// Debug / parity aid: counts fp16 elements whose magnitude is the largest finite value or above (what the
+// saturating conversions `cvt.rn.satfinite.f16x2.f32` of the path produce on overflow, plus inf / NaN).
+__global__ void __launch_bounds__(256)
+count_saturated_kernel(const __half* __restrict__ p, long long n, unsigned long long* __restrict__ counter) {
+    pdl_wait();
+    pdl_launch();
+    const long long vec = n >> 3;
+    unsigned int c = 0;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < vec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const uint4 w = ld_stream_u4(p + i * 8);
+        const uint32_t q[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            c += ((q[k] & 0x7FFFu) >= 0x7BFFu) ? 1u : 0u;
+            c += (((q[k] >> 16) & 0x7FFFu) >= 0x7BFFu) ? 1u : 0u;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+        const unsigned short b = reinterpret_cast<const unsigned short*>(p)[vec * 8 + threadIdx.x];
+        c += ((b & 0x7FFFu) >= 0x7BFFu) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int q = 16; q > 0; q >>= 1) c += __shfl_xor_sync(0xffffffffu, c, q);
+    if ((threadIdx.x & 31) == 0 && c != 0u) atomicAdd(counter, static_cast<unsigned long long>(c));
+}
+
 }  // namespace zvb

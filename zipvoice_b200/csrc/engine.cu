@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -75,30 +76,43 @@ static int g_layout_ok = 1;       // ZVB_NO_LAYOUT=1 keeps the default operand-r
 static int g_pair_min_kb = 8;     // ZVB_PAIR_MIN_KB: fewest k-blocks for which a CTA pair is used    // ZVB_NO_TMA_STORE=1 keeps the epilogue on per-thread stores
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
+// Per-device initialisation: the opt-in shared-memory sizes (cudaFuncSetAttribute) and the SM count belong to
+// the CURRENT device, so a process that builds plans on several GPUs initialises each of them once.
+#ifndef ZVB_SOURCE_HASH
+#define ZVB_SOURCE_HASH "unknown"
+#endif
+static const char g_source_hash[] = "ZVB_SRC_HASH=" ZVB_SOURCE_HASH;     // zipvoice_b200/build.py greps this marker
+constexpr int ZVB_MAX_DEVICES = 64;
+static std::mutex g_init_mutex;
+static int g_dev_sms[ZVB_MAX_DEVICES] = {};
+
 static int init_device() {
-    if (g_encode != nullptr) return 0;
+    std::lock_guard<std::mutex> lock(g_init_mutex);
     int dev = 0, count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
         return fail(ZVB_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
     CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= ZVB_MAX_DEVICES) return fail(ZVB_ERR_INVALID, "device ordinal %d out of range", dev);
+    if (g_dev_sms[dev] != 0) { g_num_sms = g_dev_sms[dev]; return 0; }
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10)
         return fail(ZVB_ERR_NO_DEVICE, "device sm_%d%d is not sm_100 (B200)", prop.major, prop.minor);
-    g_num_sms = prop.multiProcessorCount;
-    if (const char* e = getenv("ZVB_NO_CLUSTER")) g_cluster_ok = atoi(e) == 0;
-    if (const char* e = getenv("ZVB_NO_TMA_STORE")) g_tma_store_ok = atoi(e) == 0;
-    if (const char* e = getenv("ZVB_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
-    if (const char* e = getenv("ZVB_NO_LAYOUT")) g_layout_ok = atoi(e) == 0;
-    if (const char* e = getenv("ZVB_NO_PDL")) g_pdl = atoi(e) == 0;
-    if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
-    if (const char* e = getenv("ZVB_WIDE_PREF")) g_wide_pref = atoi(e) != 0;
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-    if (fn == nullptr || q != cudaDriverEntryPointSuccess)
-        return fail(ZVB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
-    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    if (g_encode == nullptr) {
+        if (const char* e = getenv("ZVB_NO_CLUSTER")) g_cluster_ok = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_NO_TMA_STORE")) g_tma_store_ok = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
+        if (const char* e = getenv("ZVB_NO_LAYOUT")) g_layout_ok = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_NO_PDL")) g_pdl = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
+        if (const char* e = getenv("ZVB_WIDE_PREF")) g_wide_pref = atoi(e) != 0;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (fn == nullptr || q != cudaDriverEntryPointSuccess)
+            return fail(ZVB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+        g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
 #define ZVB_SMEM_ATTR(k) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES))
     ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_NONE, 1>));     ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_NONE, 2>));
     ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 1>)); ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 2>));
@@ -110,6 +124,8 @@ static int init_device() {
     CUDA_TRY(cudaFuncSetAttribute(dwconv_swooshr_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<9>()));
     CUDA_TRY(cudaFuncSetAttribute(dwconv_swooshr_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<15>()));
     CUDA_TRY(cudaFuncSetAttribute(dwconv_swooshr_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<31>()));
+    g_dev_sms[dev] = prop.multiProcessorCount;
+    g_num_sms = prop.multiProcessorCount;
     return 0;
 }
 
@@ -176,7 +192,12 @@ struct Op {
     double work = 0.0;
     double bytes = 0.0;              // algorithmic HBM bytes: every operand read once, every result written once
     int shape[4] = {0, 0, 0, 0};     // GEMM: rows, out cols, K, block_n
+    // fp16 outputs of the op (pointer, element count): scanned for saturated values when the plan has a
+    // saturation counter (zvb_plan_set_saturation_counter)
+    const void* scan_ptr[2] = {nullptr, nullptr};
+    long long scan_n[2] = {0, 0};
 };
+static inline void mark_out(Op& op, int i, const void* p, long long n) { op.scan_ptr[i] = p; op.scan_n[i] = n; }
 
 static int pick_block_n(int n_out, long long m_tiles, int k_blocks) {
     // short K (<= 8 k-blocks): the mainloop is bound by operand bytes in flight, and a 40 KB stage (192
@@ -336,6 +357,8 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
         p.orig_tma = 1;
     }
     gemm_layout(op);
+    if (e.out_mode == OUT_H16) mark_out(op, 0, out, M * ldc);
+    else if (e.out_mode == OUT_T_H16 && e.t_L > 0) mark_out(op, 0, out, (M / e.t_L) * (long long)e.t_batch_rows * e.t_pitch);
     op.shape[0] = (int)M; op.shape[1] = lin.out_features; op.shape[2] = lin.in_features; op.shape[3] = bn;
     op.cat = ZVB_CAT_GEMM_LINEAR;
     op.work = 2.0 * (double)M * lin.out_features * lin.in_features;
@@ -372,6 +395,8 @@ static int build_gated(Op& op, const h16* A, long long M, int lda, const zvb_lin
                   b_box_rows(op)));
     TRY(setup_tma_store(op, (int)M, 1));
     gemm_layout(op);
+    if (e.out_mode == OUT_H16) mark_out(op, 0, out, M * ldc);
+    else if (e.out_mode == OUT_T_H16 && e.t_L > 0) mark_out(op, 0, out, (M / e.t_L) * (long long)e.t_batch_rows * e.t_pitch);
     op.shape[0] = (int)M; op.shape[1] = 2 * n_out; op.shape[2] = lin.in_features; op.shape[3] = 256;
     op.cat = ZVB_CAT_GEMM_GATED;
     op.work = 2.0 * (double)M * (2.0 * n_out) * lin.in_features;
@@ -420,6 +445,7 @@ static int build_pv(Op& op, const h16* P, const float* inv_l, const h16* Vt, voi
     TRY(make_tmap(&op.mb, Vt, Lk, vt_rows, N, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * vt_rows, b_box_rows(op)));
     if (!per_head) TRY(setup_tma_store(op, L, N));
     gemm_layout(op);
+    mark_out(op, 0, out, (long long)N * L * ldc);
     op.shape[0] = N * L; op.shape[1] = per_head ? H * hd : hd; op.shape[2] = L; op.shape[3] = p.block_n;
     op.cat = ZVB_CAT_GEMM_PV;
     op.work = 2.0 * (double)N * (per_head ? H : 1) * (double)L * L * hd;
@@ -446,6 +472,7 @@ static int build_attn(Op& op, const h16* qkp, int ld, const void* pos_table, con
     // P as (Lk, L, N*H): every softmax warp stores 32-row x 64-column boxes
     TRY(make_tmap(&op.ms, P, Lk, L, (uint64_t)N * H, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * L, 32));
     op.has_ms = true;
+    mark_out(op, 0, P, (long long)N * H * L * Lk);
     op.cat = ZVB_CAT_ATTN_WEIGHTS;
     // q.k (K = 32) + rel-pos (4-dim dot against 2L-1 offsets), reference FLOP model SURVEY.md §8d
     op.work = (double)N * H * (2.0 * L * L * 32 + 2.0 * L * (2.0 * L - 1) * 4);
@@ -467,6 +494,7 @@ static int build_dwconv(Op& d, const h16* x, h16* out, const float* w, const flo
     if (C % 8 != 0) return fail(ZVB_ERR_INVALID, "dwconv: channels must be a multiple of 8");
     // x as (C, L, N); a box = 64 channels x (128 + K - 1) frames, rows outside [0, L) are zero-filled
     TRY(make_tmap_plain(&d.ma, x, C, L, N, (uint64_t)C * 2, (uint64_t)C * 2 * L, 64, DW_TT + K - 1));
+    mark_out(d, 0, out, (long long)N * L * C);
     d.cat = ZVB_CAT_DWCONV;
     d.work = 2.0 * 2.0 * (double)N * L * C;
     d.bytes = d.work;
@@ -594,6 +622,7 @@ struct zvb_plan {
     int D = 0, in_dim = 0, out_dim = 0, xin_pitch = 0, has_time = 0, has_g = 0;
     zvb_io io{};
     std::vector<Op> ops;
+    unsigned long long* sat_counter = nullptr;      // device counter (caller owned), see zvb_plan_set_saturation_counter
 };
 
 struct Carver {
@@ -646,11 +675,13 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
     float* out = c.take<float>(M * m->out_dim);
     // time embedding chain
     const int td = m->time_dim;
+    // guidance_scale_embed has its own input width (reference: modules/zipformer.py:128, 233-238)
+    const int gd = m->guidance_dim > 0 ? m->guidance_dim : td;
     float *te0 = nullptr, *teg = nullptr, *te1 = nullptr, *te2 = nullptr, *te3 = nullptr;
     float* temb[ZVB_MAX_STACKS] = {};
     if (td > 0) {
         te0 = c.take<float>((size_t)N * td);
-        teg = c.take<float>((size_t)N * td);
+        teg = c.take<float>((size_t)N * gd);
         te1 = c.take<float>((size_t)N * 2 * td);
         te2 = c.take<float>((size_t)N * td);
         te3 = c.take<float>((size_t)N * td);
@@ -709,9 +740,10 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
         ops.push_back(e);
         const float* t_in = te0;
         if (m->use_guidance_embed) {
-            Op eg; eg.type = OP_TSEMB; eg.f0 = gbuf; eg.o0 = teg; eg.i0 = N; eg.i1 = td;
+            if (m->guidance_w == nullptr || gd % 2 != 0) return fail(ZVB_ERR_INVALID, "guidance embedding: weight missing or odd width %d", gd);
+            Op eg; eg.type = OP_TSEMB; eg.f0 = gbuf; eg.o0 = teg; eg.i0 = N; eg.i1 = gd;
             ops.push_back(eg);
-            ops.push_back(small_op(teg, m->guidance_w, nullptr, te0, te2, N, td, td, 0, 0));   // te2 = te0 + Wg*emb(g)
+            ops.push_back(small_op(teg, m->guidance_w, nullptr, te0, te2, N, gd, td, 0, 0));   // te2 = te0 + Wg*emb(g)
             t_in = te2;
         }
         ops.push_back(small_op(t_in, m->time0_w, m->time0_b, nullptr, te1, N, td, 2 * td, 0, ACT_SWOOSH_R_));
@@ -743,6 +775,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             op.i0 = N; op.i1 = T; op.i2 = L; op.i3 = ds; op.i4 = D;
             for (int k = 0; k < 4; ++k) op.w[k] = stk.ds_weights[k];
             op.cat = ZVB_CAT_RESAMPLE; op.work = 2.0 * ((double)M + (double)Ms) * D;
+            mark_out(op, 0, S[0], Ms * D);
             ops.push_back(op);
         }
         const h16* src = ds == 1 ? cur : S[0];
@@ -750,6 +783,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             Op op; op.type = OP_PREP; op.p0 = src; op.o0 = St[0];
             op.f0 = tb; op.i0 = D; op.i1 = L; op.rows = Ms;
             op.cat = ZVB_CAT_ELEMENTWISE; op.work = (double)Ms * D * (2.0 + 2.0);
+            mark_out(op, 0, St[0], Ms * D);
             ops.push_back(op);
         }
         const h16* srct = tb != nullptr ? St[0] : src;
@@ -826,6 +860,8 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
               b.i0 = D; b.i1 = L; b.rows = Ms;
               b.cat = ZVB_CAT_BIASNORM;
               b.work = (double)Ms * D * (3 * 2.0 + (nsrct != nullptr ? 2.0 : 0.0));
+              mark_out(b, 0, nsrc, Ms * D);
+              if (nsrct != nullptr) mark_out(b, 1, nsrct, Ms * D);
               ops.push_back(b); }
             src = nsrc;
             srct = nsrct != nullptr ? nsrct : nsrc;
@@ -838,6 +874,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             op.f0 = stk.out_combiner_scale;
             op.i0 = N; op.i1 = T; op.i2 = L; op.i3 = ds; op.i4 = D;
             op.cat = ZVB_CAT_RESAMPLE; op.work = 2.0 * (2.0 * (double)M + (double)Ms) * D;
+            mark_out(op, 0, cur_alt, M * D);
             ops.push_back(op);
             std::swap(cur, cur_alt);
         }
@@ -887,9 +924,30 @@ int zvb_plan_io(const zvb_plan* plan, zvb_io* io) {
 int zvb_decoder_forward(zvb_plan* plan, void* stream) {
     if (plan == nullptr) return fail(ZVB_ERR_INVALID, "null plan");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    for (const Op& op : plan->ops) TRY(launch_op(op, st));
+    for (const Op& op : plan->ops) {
+        TRY(launch_op(op, st));
+        if (plan->sat_counter != nullptr)
+            for (int i = 0; i < 2; ++i)
+                if (op.scan_ptr[i] != nullptr && op.scan_n[i] > 0) {
+                    const long long vec = op.scan_n[i] / 8;
+                    long long blocks = (vec + 255) / 256;
+                    if (blocks > 8 * g_num_sms) blocks = 8 * g_num_sms;
+                    if (blocks < 1) blocks = 1;
+                    launch_k(count_saturated_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (const h16*)op.scan_ptr[i],
+                             op.scan_n[i], plan->sat_counter);
+                    TRY(check_launch("count_saturated"));
+                }
+    }
     return 0;
 }
+
+int zvb_plan_set_saturation_counter(zvb_plan* plan, unsigned long long* counter) {
+    if (plan == nullptr) return fail(ZVB_ERR_INVALID, "null plan");
+    plan->sat_counter = counter;
+    return 0;
+}
+
+const char* zvb_source_hash(void) { return g_source_hash + 13; }
 
 int zvb_decoder_profile(zvb_plan* plan, void* stream, int max_ops, float* ms, int* category, double* work,
                         double* bytes, int* shapes, int* num_ops) {
@@ -1052,6 +1110,79 @@ int zvb_test_dwconv(const void* x, void* out, const float* wt, const float* bias
     Op d;
     TRY(build_dwconv(d, (const h16*)x, (h16*)out, wt, bias, N, L, C, K));
     return launch_op(d, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_linear_t(const void* A, int M, int K, int lda, const void* W, const float* bias, int n_out, int k_pitch,
+                      void* out, int t_L, int t_pitch, int t_batch_rows, int t_hd, int t_hp, void* stream) {
+    TRY(init_device());
+    zvb_linear lin{W, bias, n_out, K, k_pitch, n_out};
+    Op op; LinearEpi e; e.out_mode = OUT_T_H16;
+    e.t_L = t_L; e.t_pitch = t_pitch; e.t_batch_rows = t_batch_rows; e.t_hd = t_hd; e.t_hp = t_hp;
+    TRY(build_linear(op, (const h16*)A, M, lda, lin, out, 0, e));
+    return launch_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_downsample(const void* src, void* out, int N, int L, int ds, const float* w4, int C, void* stream) {
+    TRY(init_device());
+    if (C % 8 != 0 || (ds != 1 && ds != 2 && ds != 4) || w4 == nullptr) return fail(ZVB_ERR_INVALID, "downsample: bad arguments");
+    Op op; op.type = OP_DOWN; op.p0 = src; op.o0 = out;
+    op.i0 = N; op.i1 = L; op.i2 = (L + ds - 1) / ds; op.i3 = ds; op.i4 = C;
+    for (int k = 0; k < 4; ++k) op.w[k] = w4[k];
+    return launch_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_upsample_combine(const void* orig, const void* y, void* out, const float* scale, int N, int L, int ds, int C,
+                              void* stream) {
+    TRY(init_device());
+    if (C % 8 != 0 || (ds != 1 && ds != 2 && ds != 4)) return fail(ZVB_ERR_INVALID, "upsample: bad arguments");
+    Op op; op.type = OP_UP; op.p0 = orig; op.p1 = y; op.o0 = out; op.f0 = scale;
+    op.i0 = N; op.i1 = L; op.i2 = (L + ds - 1) / ds; op.i3 = ds; op.i4 = C;
+    return launch_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_stream_prep(const void* x, void* xt, const float* temb, int rows_per_group, long long rows, int C, void* stream) {
+    TRY(init_device());
+    if (C % 8 != 0) return fail(ZVB_ERR_INVALID, "stream_prep: C must be a multiple of 8");
+    Op op; op.type = OP_PREP; op.p0 = x; op.o0 = xt; op.f0 = temb; op.i0 = C; op.i1 = rows_per_group; op.rows = rows;
+    return launch_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_assemble_input(const float* x, const float* text, const float* speech, void* xin, int B, int T, int F, int Ft,
+                            int ldx, int cfg, int drop_speech, void* stream) {
+    TRY(init_device());
+    if (ldx < 2 * F + Ft) return fail(ZVB_ERR_INVALID, "assemble: pitch %d < %d", ldx, 2 * F + Ft);
+    const long long n_in = (long long)(cfg ? 2 * B : B) * T * ldx;
+    launch_k(assemble_input_kernel, dim3((unsigned)((n_in + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+             x, text, speech, (h16*)xin, B, T, F, Ft, ldx, cfg, drop_speech);
+    return check_launch("assemble_input");
+}
+
+int zvb_test_small_linear(const float* in, const float* W, const float* bias, const float* addend, float* out, int N, int K,
+                          int O, int act_in, int act_out, void* stream) {
+    TRY(init_device());
+    return launch_op(small_op(in, W, bias, addend, out, N, K, O, act_in, act_out), static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_timestep_embedding(const float* t, float* out, int N, int dim, void* stream) {
+    TRY(init_device());
+    if (dim % 2 != 0) return fail(ZVB_ERR_INVALID, "timestep embedding: odd width");
+    Op e; e.type = OP_TSEMB; e.f0 = t; e.o0 = out; e.i0 = N; e.i1 = dim;
+    return launch_op(e, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_masks(const uint8_t* mask, int N, int T, int ds, uint8_t* strided, uint32_t* words, void* stream) {
+    TRY(init_device());
+    const int L = (T + ds - 1) / ds;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint8_t* m = mask;
+    if (ds != 1) {
+        if (strided == nullptr) return fail(ZVB_ERR_INVALID, "masks: strided output is null");
+        Op op; op.type = OP_MASK; op.p0 = mask; op.o0 = strided; op.i0 = N; op.i1 = T; op.i2 = L; op.i3 = ds;
+        TRY(launch_op(op, st));
+        m = strided;
+    }
+    if (words != nullptr) TRY(launch_op(mask_words_op(m, words, N, L), st));
+    return 0;
 }
 
 int zvb_test_cfg_euler(float* x, const float* v, const float* guidance, float gscale, const float* ts, int step, int B,

@@ -2,6 +2,7 @@
 holding the PyTorch-owned workspace and the opaque C-ABI plan handle."""
 from __future__ import annotations
 
+import collections
 import ctypes as C
 from typing import Dict, Optional, Tuple
 
@@ -37,6 +38,25 @@ class DecoderPlan:
         self.io = io
         self.out_dim = packed.out_dim
         self.in_dim = packed.in_dim
+        # CUDA graphs captured over this plan's workspace (model.B200EulerSolver) live and die with the plan:
+        # evicting the plan drops them too, so no captured graph can outlive the buffers it points into
+        self.graphs: Dict[tuple, dict] = {}
+        self._sat_counter: Optional[torch.Tensor] = None
+
+    @property
+    def nbytes(self) -> int:
+        return self.workspace_bytes + sum(st.get("nbytes", 0) for st in self.graphs.values())
+
+    def enable_saturation_check(self) -> None:
+        """Every forward of this plan also counts, kernel by kernel, fp16 outputs that hit the largest finite
+        fp16 magnitude (parity aid, include/zipvoice_b200.h: zvb_plan_set_saturation_counter)."""
+        if self._sat_counter is None:
+            self._sat_counter = torch.zeros(1, dtype=torch.int64, device=self.packed.device)
+            _lib.check(self.lib.zvb_plan_set_saturation_counter(self.handle, self._sat_counter.data_ptr()))
+            self.graphs.clear()             # graphs captured before the switch do not contain the scans
+
+    def saturated(self) -> int:
+        return int(self._sat_counter.item()) if self._sat_counter is not None else 0
 
     def __del__(self):
         try:
@@ -109,18 +129,60 @@ class DecoderPlan:
                 vrec.data_ptr() if vrec is not None else None, _stream_ptr()))
 
 
-class PlanCache:
-    """(N, T) -> DecoderPlan for one packed network."""
+def round_up(x: int, step: int) -> int:
+    return (int(x) + step - 1) // step * step if step and step > 1 else int(x)
 
-    def __init__(self, packed: PackedZipformer, max_plans: int = 8):
+
+class PlanCache:
+    """(rows, frames) -> DecoderPlan for one packed network: shape-bucketed, least-recently-used, bounded by
+    plan count AND bytes (a plan for N=128, T=1219 holds a 4.5 GB workspace).
+
+    `frame_bucket` / `row_bucket` > 1 round the requested shape up (reference counterpart: one TensorRT engine
+    serves N 1-4 / T 100-3000, zipvoice/bin/tensorrt_export.py:112-131); the caller pads its inputs and masks
+    the extra frames / rows, which is exactly the reference batching a short utterance with a longer one.
+    0 / 1 = exact shapes."""
+
+    def __init__(self, packed: PackedZipformer, max_plans: int = 12, max_bytes: Optional[int] = None,
+                 frame_bucket: int = 0, row_bucket: int = 0, factory=None):
         self.packed = packed
+        self.factory = factory or DecoderPlan
         self.max_plans = max_plans
-        self._plans: Dict[Tuple[int, int], DecoderPlan] = {}
+        self.max_bytes = max_bytes
+        self.frame_bucket = frame_bucket
+        self.row_bucket = row_bucket
+        self.check_saturation = False
+        self.created = 0
+        self._plans: "collections.OrderedDict[Tuple[int, int], DecoderPlan]" = collections.OrderedDict()
+
+    def shape_for(self, N: int, T: int) -> Tuple[int, int]:
+        return round_up(N, self.row_bucket), round_up(T, self.frame_bucket)
+
+    def _budget(self) -> int:
+        if self.max_bytes is not None:
+            return self.max_bytes
+        if self.packed.device.type == "cuda":
+            return int(0.6 * torch.cuda.get_device_properties(self.packed.device).total_memory)
+        return 1 << 62
 
     def get(self, N: int, T: int) -> DecoderPlan:
-        key = (int(N), int(T))
-        if key not in self._plans:
-            if len(self._plans) >= self.max_plans:
-                self._plans.pop(next(iter(self._plans)))
-            self._plans[key] = DecoderPlan(self.packed, N, T)
-        return self._plans[key]
+        """The plan covering (N, T): its N / T are the bucketed sizes (>= the request)."""
+        key = self.shape_for(N, T)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self.factory(self.packed, *key)
+            if self.check_saturation:
+                plan.enable_saturation_check()
+            self._plans[key] = plan
+            self.created += 1
+        self._plans.move_to_end(key)
+        budget = self._budget()
+        while len(self._plans) > 1 and (len(self._plans) > self.max_plans or
+                                        sum(p.nbytes for p in self._plans.values()) > budget):
+            self._plans.popitem(last=False)        # least recently used; its graphs go with it
+        return plan
+
+    def __len__(self) -> int:
+        return len(self._plans)
+
+    def plans(self):
+        return list(self._plans.values())

@@ -17,6 +17,7 @@ zipvoice.py:187-330, utils/common.py:252-301, restated without Python loops over
 """
 from __future__ import annotations
 
+import itertools
 from typing import Dict, List, Optional, Tuple, Union
 
 import torch
@@ -29,11 +30,13 @@ from .weights import PackedZipformer
 
 # --------------------------------------------------------------------------------- host helpers
 def pad_labels(y: List[List[int]], pad_id: int, device) -> torch.Tensor:
-    """One pad appended to every sequence, then padded to the max (reference: common.py:261-274)."""
-    n = max(len(t) for t in y) + 1
+    """One pad appended to every sequence, then padded to the max (reference: common.py:261-274).
+    One flat host tensor and one masked scatter instead of a Python loop over utterances."""
+    lens = torch.tensor([len(t) for t in y], dtype=torch.int64)
+    n = int(lens.max()) + 1 if len(y) else 1
     out = torch.full((len(y), n), pad_id, dtype=torch.int64)
-    for i, t in enumerate(y):
-        out[i, : len(t)] = torch.as_tensor(t, dtype=torch.int64)
+    flat = torch.tensor(list(itertools.chain.from_iterable(y)), dtype=torch.int64)
+    out[torch.arange(n)[None, :] < lens[:, None]] = flat
     return out.to(device)
 
 
@@ -63,11 +66,12 @@ def get_time_steps(t_start: float, t_end: float, num_step: int, t_shift: float) 
 
 # --------------------------------------------------------------------------------- seam objects
 class B200Zipformer:
-    """Callable replacement of a `TTSZipformer` (seam 1)."""
+    """Callable replacement of a `TTSZipformer` (seam 1).  Shapes are served by a bucketed LRU plan cache;
+    when the plan is larger than the call, inputs are zero padded and the extra frames / rows masked."""
 
-    def __init__(self, packed: PackedZipformer):
+    def __init__(self, packed: PackedZipformer, frame_bucket: int = 0, row_bucket: int = 0):
         self.packed = packed
-        self.plans = PlanCache(packed)
+        self.plans = PlanCache(packed, frame_bucket=frame_bucket, row_bucket=row_bucket)
 
     def __call__(self, x: torch.Tensor, t: Optional[torch.Tensor] = None, padding_mask: Optional[torch.Tensor] = None,
                  guidance_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -77,20 +81,43 @@ class B200Zipformer:
         if t is not None and t.dim() != 1:
             raise NotImplementedError("per-frame t (N,T) is a training-only input of the reference")
         plan = self.plans.get(N, T)
-        return plan.forward_f32(x, t, padding_mask, guidance_scale)
+        if (plan.N, plan.T) == (N, T):
+            return plan.forward_f32(x, t, padding_mask, guidance_scale)
+        xp = torch.zeros(plan.N, plan.T, x.shape[2], dtype=torch.float32, device=x.device)
+        xp[:N, :T] = x
+        mp = torch.ones(plan.N, plan.T, dtype=torch.bool, device=x.device)
+        mp[:N, :T] = padding_mask
+        pad1 = lambda v: None if v is None else torch.nn.functional.pad(v.float(), (0, plan.N - N))
+        return plan.forward_f32(xp, pad1(t), mp, pad1(guidance_scale))[:N, :T].contiguous()
 
 
 class B200EulerSolver:
     """`model.solver` replacement (seam 2): Euler ODE + classifier-free guidance + decoder in one
-    launch sequence, optionally replayed from a CUDA graph (reference: modules/solver.py:167-240)."""
+    launch sequence, optionally replayed from a CUDA graph (reference: modules/solver.py:167-240).
+    Graphs and their static input buffers are owned by the plan they were captured over."""
 
     def __init__(self, decoders: Dict[int, B200Zipformer], distill: bool, use_cuda_graph: bool = True):
         self.decoders = decoders          # feature width F -> decoder (stereo models have two)
         self.distill = distill
         self.use_cuda_graph = use_cuda_graph
-        self._graphs: Dict[tuple, dict] = {}
         self.last_velocities: Optional[torch.Tensor] = None
         self.record_velocities = False
+
+    @property
+    def check_saturation(self) -> bool:
+        return all(d.plans.check_saturation for d in self.decoders.values())
+
+    @check_saturation.setter
+    def check_saturation(self, on: bool) -> None:
+        for d in self.decoders.values():
+            d.plans.check_saturation = bool(on)
+            if on:
+                for p in d.plans.plans():
+                    p.enable_saturation_check()
+
+    def count_saturated(self) -> int:
+        """fp16 values at the saturation limit seen so far by the decoder plans (0 unless check_saturation)."""
+        return sum(p.saturated() for d in self.decoders.values() for p in d.plans.plans())
 
     def _mode_and_guidance(self, guidance_scale, B: int, device):
         if torch.is_tensor(guidance_scale):
@@ -114,32 +141,44 @@ class B200EulerSolver:
         B, T, F = x.shape
         mode, g = self._mode_and_guidance(guidance_scale, B, device)
         dec = self.decoders[F]
-        plan = dec.plans.get(2 * B if mode == 1 else B, T)
+        Bp, Tp = dec.plans.shape_for(B, T)
+        plan = dec.plans.get(2 * Bp if mode == 1 else Bp, Tp)
+        if mode == 1 and plan.N != 2 * Bp:               # odd row bucket: keep the CFG halves equal
+            Bp = plan.N // 2
         ts_host = get_time_steps(t_start, t_end, num_step, t_shift).contiguous()
         record = self.record_velocities
-        key = (id(plan), num_step, mode, tuple(bool(v > 0.5) for v in ts_host[:-1].tolist()), record)
-        st = self._graphs.get(key) if self.use_cuda_graph else None
+        key = (Bp, num_step, mode, tuple(bool(v > 0.5) for v in ts_host[:-1].tolist()), record)
+        st = plan.graphs.get(key) if self.use_cuda_graph else None
         if st is None:
             st = dict(
-                x=torch.empty(B, T, F, dtype=torch.float32, device=device),
-                text=torch.empty(B, T, text_condition.shape[2], dtype=torch.float32, device=device),
-                speech=torch.empty(B, T, F, dtype=torch.float32, device=device),
-                mask=torch.empty(B, T, dtype=torch.uint8, device=device),
-                g=torch.zeros(B, dtype=torch.float32, device=device),
+                x=torch.zeros(Bp, Tp, F, dtype=torch.float32, device=device),
+                text=torch.zeros(Bp, Tp, text_condition.shape[2], dtype=torch.float32, device=device),
+                speech=torch.zeros(Bp, Tp, F, dtype=torch.float32, device=device),
+                mask=torch.ones(Bp, Tp, dtype=torch.uint8, device=device),
+                g=torch.zeros(Bp, dtype=torch.float32, device=device),
                 ts=torch.empty(num_step + 1, dtype=torch.float32, device=device),
-                ts_pinned=torch.empty(num_step + 1, dtype=torch.float32).pin_memory(),
-                vrec=torch.empty(num_step, B, T, F, dtype=torch.float32, device=device) if record else None,
+                vrec=torch.empty(num_step, Bp, Tp, F, dtype=torch.float32, device=device) if record else None,
                 graph=None)
+            st["nbytes"] = sum(v.numel() * v.element_size() for v in st.values() if torch.is_tensor(v))
             if self.use_cuda_graph:
-                self._graphs[key] = st
-        st["x"].copy_(x)
-        st["text"].copy_(text_condition)
-        st["speech"].copy_(speech_condition)
-        st["mask"].copy_(padding_mask)
+                plan.graphs[key] = st
+        if (Bp, Tp) != (B, T):
+            # the ODE state is updated in place and an earlier, longer call may have left its conditions behind:
+            # the padding is cleared on every call so that a result never depends on the call history
+            st["x"].zero_()
+            st["text"].zero_()
+            st["speech"].zero_()
+            st["mask"].fill_(1)
+            st["g"].zero_()
+        st["x"][:B, :T].copy_(x)
+        st["text"][:B, :T].copy_(text_condition)
+        st["speech"][:B, :T].copy_(speech_condition)
+        st["mask"][:B, :T].copy_(padding_mask)
         if g is not None:
-            st["g"].copy_(g)
-        st["ts_pinned"].copy_(ts_host)
-        st["ts"].copy_(st["ts_pinned"], non_blocking=True)
+            st["g"][:B].copy_(g)
+        # pageable source: the copy is staged before it returns, so `ts_host` may be reused at once and an
+        # in-flight earlier sample never sees this call's time grid (stream order)
+        st["ts"].copy_(ts_host)
 
         def run():
             plan.sample(st["x"], st["text"], st["speech"], st["mask"], st["g"] if mode != 0 else None, st["ts"],
@@ -156,18 +195,27 @@ class B200EulerSolver:
         else:
             st["graph"].replay()
         if record:
-            self.last_velocities = st["vrec"].clone()
-        return st["x"].clone()
+            self.last_velocities = st["vrec"][:, :B, :T].clone()
+        return st["x"][:B, :T].clone()
 
 
 # --------------------------------------------------------------------------------- models
+# The text encoder has no down-sampling stack: padded tokens are masked keys and zeroed convolution inputs, so
+# running it on a longer, masked token axis leaves every valid position bit-identical.
+TEXT_FRAME_BUCKET = 32
+
+
 class ZipVoice:
     """The ZipVoice model on B200 (reference: zipvoice/models/zipvoice.py:35-133)."""
 
     variant = "zipvoice"
 
-    def __init__(self, use_cuda_graph: bool = True, **kwargs):
+    def __init__(self, use_cuda_graph: bool = True, frame_bucket: int = 0, row_bucket: int = 0, **kwargs):
+        """`frame_bucket` / `row_bucket`: round the decoder's (rows, frames) up to multiples of these before
+        choosing a plan / CUDA graph (0 = exact shapes; serving with ragged traffic wants e.g. 64 / 8, see
+        engine.PlanCache).  The text encoder always buckets its token axis by 32 (no effect on its result)."""
         self.cfg = ZipVoiceConfig(variant=self.variant, **kwargs)
+        self.frame_bucket, self.row_bucket = int(frame_bucket), int(row_bucket)
         self.feat_dim = self.cfg.feat_dim
         self.text_embed_dim = self.cfg.text_embed_dim
         self.pad_id = self.cfg.pad_id
@@ -204,11 +252,13 @@ class ZipVoice:
         fc = cfg.fm_decoder()
         decs = {}
         for i in range(len(fc.in_dims)):
-            dz = B200Zipformer(PackedZipformer(sd, "fm_decoder.", fc, dev, stream_index=i))
+            dz = B200Zipformer(PackedZipformer(sd, "fm_decoder.", fc, dev, stream_index=i),
+                               frame_bucket=self.frame_bucket, row_bucket=self.row_bucket)
             decs[fc.out_dims[i]] = dz
         self._decoders = decs
         self.fm_decoder = _WidthDispatch(decs, fc) if len(decs) > 1 else next(iter(decs.values()))
-        self.text_encoder = B200Zipformer(PackedZipformer(sd, "text_encoder.", cfg.text_encoder(), dev))
+        self.text_encoder = B200Zipformer(PackedZipformer(sd, "text_encoder.", cfg.text_encoder(), dev),
+                                          frame_bucket=TEXT_FRAME_BUCKET, row_bucket=self.row_bucket)
         self.solver = B200EulerSolver(decs, distill=cfg.is_distill, use_cuda_graph=self.use_cuda_graph)
         self.embed_weight = sd["embed.weight"].float().to(dev)
         if cfg.is_dialog:
@@ -364,40 +414,54 @@ class ZipVoiceDialogStereo(ZipVoice):
 MODEL_CLASSES = {c.variant: c for c in (ZipVoice, ZipVoiceDistill, ZipVoiceDialog, ZipVoiceDialogStereo)}
 
 
-def build_model(cfg: ZipVoiceConfig, sd: Dict[str, torch.Tensor], device="cuda", use_cuda_graph: bool = True) -> ZipVoice:
+def build_model(cfg: ZipVoiceConfig, sd: Dict[str, torch.Tensor], device="cuda", use_cuda_graph: bool = True,
+                frame_bucket: int = 0, row_bucket: int = 0) -> ZipVoice:
     kw = cfg.model_kwargs()
     if not cfg.is_dialog:
         kw.pop("spk_a_id", None)
         kw.pop("spk_b_id", None)
-    m = MODEL_CLASSES[cfg.variant](use_cuda_graph=use_cuda_graph, **kw)
+    m = MODEL_CLASSES[cfg.variant](use_cuda_graph=use_cuda_graph, frame_bucket=frame_bucket, row_bucket=row_bucket, **kw)
     m.load_state_dict(sd)
     return m.to(device)
 
 
-def accelerate(ref_model, use_cuda_graph: bool = True):
-    """Patch an instance of the *reference* `zipvoice.models.*` classes in place, the way
-    `load_trt` does (reference: zipvoice/utils/tensorrt.py:128-143): `fm_decoder`, `text_encoder`
-    and `solver` are replaced; `sample`/`sample_intermediate` keep running the reference code."""
+def config_from_reference(ref_model) -> ZipVoiceConfig:
+    """The hyper-parameters of an instance of the reference's `zipvoice.models.*` classes, read from the module
+    attributes and the weight shapes (reference: zipvoice/models/zipvoice.py:38-133, modules/zipformer.py:109-240)."""
     name = type(ref_model).__name__
     variant = {"ZipVoice": "zipvoice", "ZipVoiceDistill": "zipvoice_distill", "ZipVoiceDialog": "zipvoice_dialog",
                "ZipVoiceDialogStereo": "zipvoice_dialog_stereo"}[name]
     sd = ref_model.state_dict()
-    dev = next(ref_model.parameters()).device
-    fm = ref_model.fm_decoder
-    cfg = ZipVoiceConfig(
+    fm, te = ref_model.fm_decoder, ref_model.text_encoder
+    fm0 = "fm_decoder.encoders.0.layers.0."
+    H = fm.num_heads
+    return ZipVoiceConfig(
         variant=variant, fm_decoder_downsampling_factor=list(fm.downsampling_factor),
         fm_decoder_num_layers=list(fm.num_encoder_layers), fm_decoder_cnn_module_kernel=list(fm.cnn_module_kernel),
-        fm_decoder_feedforward_dim=sd["fm_decoder.encoders.0.layers.0.feed_forward2.in_proj.weight"].shape[0],
-        fm_decoder_num_heads=fm.num_heads, fm_decoder_dim=fm.encoder_dim,
-        text_encoder_num_layers=ref_model.text_encoder.num_encoder_layers[0],
+        fm_decoder_feedforward_dim=sd[fm0 + "feed_forward2.in_proj.weight"].shape[0],
+        fm_decoder_num_heads=H, fm_decoder_dim=fm.encoder_dim,
+        text_encoder_num_layers=te.num_encoder_layers[0],
         text_encoder_feedforward_dim=sd["text_encoder.encoders.0.layers.0.feed_forward2.in_proj.weight"].shape[0],
-        text_encoder_cnn_module_kernel=ref_model.text_encoder.cnn_module_kernel[0],
-        text_encoder_num_heads=ref_model.text_encoder.num_heads, text_encoder_dim=ref_model.text_encoder.encoder_dim,
+        text_encoder_cnn_module_kernel=te.cnn_module_kernel[0],
+        text_encoder_num_heads=te.num_heads, text_encoder_dim=te.encoder_dim,
         time_embed_dim=fm.time_embed_dim, text_embed_dim=ref_model.text_embed_dim,
-        query_head_dim=fm.query_head_dim, value_head_dim=fm.value_head_dim, feat_dim=ref_model.feat_dim,
-        vocab_size=sd["embed.weight"].shape[0], pad_id=ref_model.pad_id,
+        query_head_dim=fm.query_head_dim, value_head_dim=fm.value_head_dim,
+        pos_head_dim=sd[fm0 + "self_attn_weights.linear_pos.weight"].shape[0] // H,
+        pos_dim=sd[fm0 + "self_attn_weights.linear_pos.weight"].shape[1],
+        feat_dim=ref_model.feat_dim, vocab_size=sd["embed.weight"].shape[0], pad_id=ref_model.pad_id,
         spk_a_id=getattr(ref_model, "spk_a_id", 360), spk_b_id=getattr(ref_model, "spk_b_id", 361))
-    shadow = build_model(cfg, sd, dev, use_cuda_graph)
+
+
+def accelerate(ref_model, use_cuda_graph: bool = True, frame_bucket: int = 0, row_bucket: int = 0):
+    """Patch an instance of the *reference* `zipvoice.models.*` classes in place, the way
+    `load_trt` does (reference: zipvoice/utils/tensorrt.py:128-143): `fm_decoder`, `text_encoder`
+    and `solver` are replaced; `sample`/`sample_intermediate` keep running the reference code."""
+    cfg = config_from_reference(ref_model)
+    dev = next(ref_model.parameters()).device
+    if dev.type != "cuda":
+        raise _lib.ZvbError("accelerate(): move the reference model to a CUDA device first (zipvoice_b200 has no CPU path)")
+    shadow = build_model(cfg, ref_model.state_dict(), dev, use_cuda_graph, frame_bucket=frame_bucket,
+                         row_bucket=row_bucket)
     del ref_model.fm_decoder            # nn.Module child -> plain attribute, as load_trt does
     del ref_model.text_encoder
     ref_model.fm_decoder = shadow.fm_decoder

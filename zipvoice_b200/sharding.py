@@ -26,17 +26,27 @@ def partition_utterances(total_frames: Sequence[int], world_size: int) -> List[L
 
 
 def gather_mels(mel: torch.Tensor, lens: torch.Tensor, shard: Sequence[int], num_utts: int,
-                max_frames: int) -> Tuple[torch.Tensor, torch.Tensor]:
+                max_frames: int, per_rank: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """All ranks contribute their (b, T_r, F) zero-padded mels; every rank gets (num_utts, max_frames,
     F) in the original utterance order plus the lengths.  One all_gather of a fixed-size buffer
-    (NCCL over NVLink on the GPU box; gloo in the CPU tests)."""
+    (NCCL over NVLink on the GPU box; gloo in the CPU tests).
+
+    `per_rank` = utterances in the LARGEST shard (every rank passes the same value: `max(len(s) for s in
+    partition_utterances(...))`; the partition balances frames, not counts, so shards can differ by many
+    utterances).  0: the ranks agree on it with one extra all_reduce."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     F = mel.shape[2]
-    per = (num_utts + world - 1) // world + 1          # shards differ by at most one utterance
+    per = int(per_rank)
+    if per <= 0:
+        cnt = torch.tensor([len(shard)], dtype=torch.int64, device=mel.device)
+        if world > 1:
+            dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+        per = int(cnt.item())
+    if len(shard) > per:
+        raise ValueError(f"gather_mels: this rank holds {len(shard)} utterances but per_rank is {per}")
     buf = torch.zeros(per, max_frames, F, dtype=mel.dtype, device=mel.device)
     meta = torch.full((per, 2), -1, dtype=torch.int64, device=mel.device)   # (utterance id, length)
     n = len(shard)
-    assert n <= per, (n, per)
     buf[:n, : mel.shape[1]] = mel[:, :max_frames]
     meta[:n, 0] = torch.as_tensor(list(shard), dtype=torch.int64, device=mel.device)
     meta[:n, 1] = lens.to(torch.int64)

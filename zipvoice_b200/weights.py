@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 from typing import Dict, List, Optional
 
 import torch
@@ -59,6 +60,10 @@ def rel_pos_embedding(L: int, pos_dim: int, device) -> torch.Tensor:
     return pe
 
 
+class _PosTables(list):
+    """Per-layer rel-pos tables of one length (a list that can be weakly referenced)."""
+
+
 class PackedZipformer:
     """Device-resident weights of one TTSZipformer plus builders for the `zvb_model` struct."""
 
@@ -83,6 +88,17 @@ class PackedZipformer:
             self.time = dict(w0=self._f32(prefix + "time_embed.0.weight"), b0=self._f32(prefix + "time_embed.0.bias"),
                              w2=self._f32(prefix + "time_embed.2.weight"), b2=self._f32(prefix + "time_embed.2.bias"),
                              g=self._f32(prefix + "guidance_scale_embed.weight") if c.use_guidance_scale_embed else None)
+        # guidance_scale_embed maps its OWN embedding width (192 in the reference, zipformer.py:128,233-238) to
+        # time_embed_dim: the width is taken from the weight, not assumed equal to time_embed_dim
+        self.guidance_dim = 0
+        if self.time is not None:
+            te = c.time_embed_dim
+            assert tuple(self.time["w0"].shape) == (2 * te, te) and tuple(self.time["w2"].shape) == (te, 2 * te), \
+                "time_embed weights do not match time_embed_dim"
+            if self.time["g"] is not None:
+                assert self.time["g"].dim() == 2 and self.time["g"].shape[0] == te and self.time["g"].shape[1] % 2 == 0, \
+                    f"guidance_scale_embed.weight {tuple(self.time['g'].shape)} does not map an even width to {te}"
+                self.guidance_dim = int(self.time["g"].shape[1])
         self.stacks = []
         self.layers = []
         self.linear_pos = []            # per layer (H*4, pos_dim) fp32 on device
@@ -102,7 +118,8 @@ class PackedZipformer:
                 self.layers.append(self._layer(sp + f"layers.{j}.", k))
             self.stacks.append(st)
         self._sd = None
-        self._pos_cache: Dict[int, List[torch.Tensor]] = {}
+        # length -> tables, alive only while a plan of that length holds them (plans keep strong references)
+        self._pos_cache: "weakref.WeakValueDictionary[int, _PosTables]" = weakref.WeakValueDictionary()
 
     # ------------------------------------------------------------------ tensor helpers
     def _dev(self, t: torch.Tensor) -> torch.Tensor:
@@ -176,15 +193,16 @@ class PackedZipformer:
     # ------------------------------------------------------------------ struct builders
     def pos_tables(self, L: int) -> List[torch.Tensor]:
         """Per-layer rel-pos table in the kernel's layout (see pack_pos_table), one byte tensor per layer."""
-        if L not in self._pos_cache:
+        tabs = self._pos_cache.get(L)
+        if tabs is None:
             c = self.cfg
             pe = rel_pos_embedding(L, c.pos_dim, self.device)
-            tabs = []
+            tabs = _PosTables()
             for wp in self.linear_pos:
                 e = (pe @ wp.t()).reshape(2 * L - 1, c.num_heads, c.pos_head_dim).permute(1, 0, 2).contiguous()
                 tabs.append(pack_pos_table(e))
             self._pos_cache[L] = tabs
-        return self._pos_cache[L]
+        return tabs
 
     @staticmethod
     def _lin_struct(d) -> _lib.zvb_linear:
@@ -241,6 +259,7 @@ class PackedZipformer:
         m.na_hidden = c.na_hidden
         m.time_dim = c.time_embed_dim if c.time_embed_dim != -1 else 0
         m.use_guidance_embed = 1 if c.use_guidance_scale_embed else 0
+        m.guidance_dim = self.guidance_dim
         m.num_stacks, m.num_layers = len(self.stacks), nl
         m.in_proj, m.out_proj = self._lin_struct(self.in_proj), self._lin_struct(self.out_proj)
         if self.time is not None:
