@@ -79,6 +79,7 @@ def run_case(name: str, use_cuda_graph: bool = True):
         return None
     u = synth_utterances(cfg, **gold["ukw"])
     model = build_model(cfg, sd, "cuda", use_cuda_graph=use_cuda_graph)
+    model.solver.check_saturation = True          # every decoder plan counts saturated fp16 outputs, kernel by kernel
     dev = model.device
     res = {}
     cat_tokens = [p + t for p, t in zip(u["prompt_tokens"], u["tokens"])]
@@ -109,6 +110,12 @@ def run_case(name: str, use_cuda_graph: bool = True):
     res["x_rel"], res["x_abs"] = rel_l2(x1, gold["x1"]), max_abs(x1, gold["x1"])
     res["finite"] = bool(torch.isfinite(x1).all())
     res["saturated"] = model.solver.count_saturated()
+    res["sat_plans"] = sum(1 for d in model.solver.decoders.values() for p in d.plans.plans() if p._sat_counter is not None)
+    log = os.environ.get("ZVB_PARITY_LOG")
+    if log:
+        import json
+        with open(log, "a") as f:
+            f.write(json.dumps(dict(case=name, **res)) + "\n")
     return res
 
 
@@ -120,4 +127,4 @@ def assert_case(name, res):
         assert res["fm_rel"] <= TOL_FM_REL and res["fm_abs"] <= TOL_FM_ABS, (name, res)
     assert max(res["v_rel"]) <= TOL_V_REL and max(res["v_abs"]) <= TOL_V_ABS, (name, res)
     assert res["x_rel"] <= TOL_X_REL and res["x_abs"] <= TOL_X_ABS, (name, res)
-    assert res["saturated"] == 0, (name, res)
+    assert res["sat_plans"] >= 1 and res["saturated"] == 0, (name, res)
