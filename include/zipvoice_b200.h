@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ZVB_ABI_VERSION 3
+#define ZVB_ABI_VERSION 4
 #define ZVB_MAX_STACKS 8
 #define ZVB_MAX_LAYERS 64
 
@@ -63,6 +63,10 @@ typedef struct {
                                * [H][2L-1+256] 16-byte entries of fp16 column pairs {log2e*E[r][d],
                                * log2e*E[r+1][d]} (d = 0..3, entry = r + 128, zeros outside), followed by
                                * [H] fp32 max_r |E[h][r]|_2 (zipvoice_b200/weights.py: pack_pos_table) */
+    const void* pos_table_tc; /* the same E for the tensor-core bias (csrc/attn3.cuh): [H][2][LZ] entries of 4 fp16 =
+                               * log2e*E[r][0..3] at index 128 + r of copy 0 (zeros elsewhere), copy 1 = copy 0 shifted by
+                               * one entry, LZ = even(2L + 264); followed by [H] fp32 max_r |log2e*E[h][r]|_2
+                               * (zipvoice_b200/weights.py: pack_pos_table_tc).  null: the CUDA-core kernel is used */
     zvb_linear ff_in[3], ff_out[3];
     zvb_linear na_sx;         /* nonlin_attention.in_proj rows (s,x), gated-packed          */
     zvb_linear na_y;          /* nonlin_attention.in_proj rows y                            */
@@ -192,6 +196,8 @@ int zvb_test_linear(const void* A, int M, int K, int lda, const void* W, const f
  * pos_table as in zvb_layer; scratch: N * 4 * ceil(L/128) 32-bit words (excluded-key bits) */
 int zvb_test_attn_weights(const void* qkp, int ld, const void* pos_table, const uint8_t* mask, void* scratch,
                           void* P, float* inv_l, int N, int H, int L, int Lk, void* stream);
+int zvb_test_attn_weights_tc(const void* qkp, int ld, const void* pos_table_tc, const uint8_t* mask, void* scratch,
+                             void* P, float* inv_l, int N, int H, int L, int Lk, void* stream);
 /* mul: fp16 [N*L][hd] gate of NonlinAttention (per_head == 0 only, nullable) */
 int zvb_test_pv(const void* P, const float* inv_l, const void* Vt, void* out, int N, int H, int L, int Lk, int hd,
                 int hp, int per_head, const void* mul, void* stream);

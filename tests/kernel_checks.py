@@ -10,7 +10,7 @@ import math
 import torch
 
 from zipvoice_b200 import _lib
-from zipvoice_b200.weights import pack_pos_table
+from zipvoice_b200.weights import pack_pos_table, pack_pos_table_tc
 
 DEV = "cuda"
 H16 = torch.float16          # storage type of every activation / weight on the CUDA path
@@ -134,7 +134,7 @@ def _attn_ref(qkp, E, mask, H):
     return s.softmax(-1)
 
 
-def check_attn(N=2, H=4, L=200, masked=True, seed=0, pos_scale=0.5, tol=2.5e-3):
+def check_attn(N=2, H=4, L=200, masked=True, seed=0, pos_scale=0.5, tol=2.5e-3, tc=True):
     """tolerance: max-abs <= 2.5e-3 on probabilities (the rel-pos bias and the exponent are evaluated in
     packed fp16: ~2^-9 absolute on an exponent of a few units; fp16 storage of P)"""
     lib = _lib.load()
@@ -143,10 +143,11 @@ def check_attn(N=2, H=4, L=200, masked=True, seed=0, pos_scale=0.5, tol=2.5e-3):
     P = torch.full((N, H, L, Lk), float("nan"), dtype=H16, device=DEV)
     inv_l = torch.full((N, H, L), float("nan"), dtype=torch.float32, device=DEV)
     m8 = mask.to(torch.uint8).contiguous()
-    Ex = pack_pos_table(E)
+    Ex = pack_pos_table_tc(E) if tc else pack_pos_table(E)
     scratch = torch.zeros(N * 4 * ((L + 127) // 128), dtype=torch.int32, device=DEV)
-    _lib.check(lib.zvb_test_attn_weights(qkp.data_ptr(), H * 68, Ex.data_ptr(), m8.data_ptr(), scratch.data_ptr(),
-                                         P.data_ptr(), inv_l.data_ptr(), N, H, L, Lk, _s()))
+    fn = lib.zvb_test_attn_weights_tc if tc else lib.zvb_test_attn_weights
+    _lib.check(fn(qkp.data_ptr(), H * 68, Ex.data_ptr(), m8.data_ptr(), scratch.data_ptr(),
+                  P.data_ptr(), inv_l.data_ptr(), N, H, L, Lk, _s()))
     torch.cuda.synchronize()
     ref = _attn_ref(qkp, E, mask, H)
     pmax = float(P.float()[..., :L].max())
@@ -418,6 +419,12 @@ ALL = {
     "linear_bypass_n192": lambda: check_linear(M=130, K=96, N=192, resid=True, bypass=True),
     "linear_f32_n100": lambda: check_linear(M=333, K=512, N=100, out_mode=1),
     "linear_n1920_swoosh": lambda: check_linear(M=5000, K=512, N=1920, act=1),
+    # CTA pairs with the A-stationary tile order (K = 512, several n-tiles, aux-less TMA-store epilogue): odd tile
+    # counts, chunk boundaries inside an m-group, a last pair with one all-padding m-tile
+    "linear_resident_n384": lambda: check_linear(M=6001, K=512, N=384),
+    "linear_resident_swoosh_n1152": lambda: check_linear(M=9000, K=512, N=1152, act=1),
+    "linear_resident_n1536": lambda: check_linear(M=40000, K=512, N=1536, act=1),
+    "gated_glu_resident": lambda: check_gated(M=6001, n_out=512, mode=2, masked=True),
     "gated_tanh": lambda: check_gated(M=300, n_out=384, mode=1),
     "gated_tanh96": lambda: check_gated(M=81, K=128, n_out=96, mode=1),
     "gated_glu_masked": lambda: check_gated(M=1000, n_out=512, mode=2, masked=True),
@@ -430,6 +437,14 @@ ALL = {
     # sit far below it; weights must stay normal fp16 numbers thanks to the 2^12 head-room (looser
     # tolerance: the fp16 bias sum carries ~2^-6 absolute error at magnitudes of 16..32)
     "attn_strong_pos": lambda: check_attn(N=2, H=4, L=333, masked=True, pos_scale=2.5, tol=3e-2),
+    # the CUDA-core-bias kernel (attn.cuh, kept behind ZVB_ATTN_V2=1)
+    "attn_v2_masked": lambda: check_attn(N=3, H=4, L=333, masked=True, tc=False),
+    "attn_v2_strong_pos": lambda: check_attn(N=2, H=4, L=333, masked=True, pos_scale=2.5, tol=3e-2, tc=False),
+    # tensor-core bias: odd / even L (window alignment in the two table copies), one tile, tile boundaries
+    "attn_tc_L128": lambda: check_attn(N=2, H=4, L=128, masked=False),
+    "attn_tc_L129": lambda: check_attn(N=2, H=4, L=129, masked=True),
+    "attn_tc_L610": lambda: check_attn(N=2, H=4, L=610, masked=True),
+    "attn_tc_L77": lambda: check_attn(N=3, H=2, L=77, masked=True),
     "pv_heads": lambda: check_pv(N=2, H=4, L=333, per_head=True),
     "pv_wide": lambda: check_pv(N=2, H=4, L=333, hd=384, hp=384, per_head=False),
     "pv_wide96": lambda: check_pv(N=2, H=4, L=81, hd=96, hp=96, per_head=False),

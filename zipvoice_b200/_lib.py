@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # ZVB_LIB: an alternative in-tree build of the same sources (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("ZVB_LIB") or os.path.join(HERE, "libzipvoice_b200.so")
 
-ZVB_ABI_VERSION = 3
+ZVB_ABI_VERSION = 4
 ZVB_MAX_STACKS = 8
 
 
@@ -24,7 +24,7 @@ class zvb_linear(C.Structure):
 
 
 class zvb_layer(C.Structure):
-    _fields_ = [("attn_in", zvb_linear), ("pos_table", C.c_void_p),
+    _fields_ = [("attn_in", zvb_linear), ("pos_table", C.c_void_p), ("pos_table_tc", C.c_void_p),
                 ("ff_in", zvb_linear * 3), ("ff_out", zvb_linear * 3),
                 ("na_sx", zvb_linear), ("na_y", zvb_linear), ("na_out", zvb_linear),
                 ("sa_in", zvb_linear * 2), ("sa_out", zvb_linear * 2),
@@ -78,6 +78,8 @@ EXPORTS = {
                                   C.c_int, C.c_void_p]),
     "zvb_test_attn_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "zvb_test_attn_weights_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "zvb_test_pv": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),
     "zvb_test_gated": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

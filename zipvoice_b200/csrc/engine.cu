@@ -16,6 +16,7 @@
 
 #include "../../include/zipvoice_b200.h"
 #include "attn.cuh"
+#include "attn3.cuh"
 #include "gemm.cuh"
 namespace zvb { constexpr int ACT_SWOOSH_R_ = 2; }
 #include "elementwise.cuh"
@@ -73,6 +74,9 @@ static int g_tma_store_ok = 1;
 static int g_wide_pref = 1;       // ZVB_WIDE_PREF=0: exact-fit tile widths first
 static int g_bn192 = 0;           // ZVB_BN192=1: 192-column tiles for short-K GEMMs (measured: no gain)
 static int g_layout_ok = 1;       // ZVB_NO_LAYOUT=1 keeps the default operand-ring / aux split everywhere
+static int g_attn_tc = 1;         // ZVB_ATTN_V2=1: attention weights with the CUDA-core rel-pos bias (attn.cuh)
+static int g_fast_epi = 1;        // ZVB_NO_FAST_EPI=1: generic epilogue everywhere
+static int g_resident_ok = 0;     // ZVB_RESIDENT=1: A-stationary tile order for the K = 512 GEMMs (measured 5-8% SLOWER, profiles/gemm_resident_ab_r2.txt)
 static int g_pair_min_kb = 8;     // ZVB_PAIR_MIN_KB: fewest k-blocks for which a CTA pair is used    // ZVB_NO_TMA_STORE=1 keeps the epilogue on per-thread stores
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
@@ -104,6 +108,9 @@ static int init_device() {
         if (const char* e = getenv("ZVB_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
         if (const char* e = getenv("ZVB_NO_LAYOUT")) g_layout_ok = atoi(e) == 0;
         if (const char* e = getenv("ZVB_NO_PDL")) g_pdl = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_RESIDENT")) g_resident_ok = atoi(e) != 0;
+        if (const char* e = getenv("ZVB_NO_FAST_EPI")) g_fast_epi = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_ATTN_V2")) g_attn_tc = atoi(e) == 0;
         if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
         if (const char* e = getenv("ZVB_WIDE_PREF")) g_wide_pref = atoi(e) != 0;
         void* fn = nullptr;
@@ -120,6 +127,7 @@ static int init_device() {
     ZVB_SMEM_ATTR((gemm_kernel<EPI_GATED, ACT_NONE, 1>));      ZVB_SMEM_ATTR((gemm_kernel<EPI_GATED, ACT_NONE, 2>));
 #undef ZVB_SMEM_ATTR
     CUDA_TRY(cudaFuncSetAttribute(attn_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(attn_weights_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(dwconv_swooshr_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
     CUDA_TRY(cudaFuncSetAttribute(dwconv_swooshr_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<9>()));
     CUDA_TRY(cudaFuncSetAttribute(dwconv_swooshr_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<15>()));
@@ -169,7 +177,7 @@ static int make_tmap_plain(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_
 }
 
 // ------------------------------------------------------------------------------------------ ops
-enum OpType { OP_GEMM, OP_ATTN, OP_BIASNORM, OP_PREP, OP_DOWN, OP_UP, OP_DWCONV, OP_MASK, OP_MASKW, OP_TSEMB, OP_SMALL };
+enum OpType { OP_GEMM, OP_ATTN, OP_ATTN_TC, OP_BIASNORM, OP_PREP, OP_DOWN, OP_UP, OP_DWCONV, OP_MASK, OP_MASKW, OP_TSEMB, OP_SMALL };
 
 struct Op {
     OpType type;
@@ -179,6 +187,7 @@ struct Op {
     GemmParams gp;
     int kind = 0, grid = 0, cluster = 1;
     AttnParams ap;
+    Attn3Params ap3;
     // elementwise
     const void *p0 = nullptr, *p1 = nullptr;
     void *o0 = nullptr, *o1 = nullptr, *o2 = nullptr;
@@ -288,6 +297,22 @@ static void set_grid(Op& op) {
 // the epilogue operands and the store path of the op are known.
 static void gemm_layout(Op& op) {
     GemmParams& p = op.gp;
+    // A-stationary: K <= 512 GEMMs with several n-tiles per m-group are bound by the L2 -> SM operand bytes
+    // (16 KB of A + the CTA's half of B per k-block and SM, ~64 B/clk against a ~43 B/clk chip-wide L2 cap); with
+    // the pair's A tile resident for all n-tiles of its m-group only B streams (~35 B/clk).  Needs the aux-less
+    // TMA-store epilogue (two staging buffers) so that 128 KB of A and >= 3 B stages fit.
+    if (g_resident_ok && op.cluster == 2 && p.aux_mode == AUX_NONE && p.tma_store && p.num_n_tiles >= 2 &&
+        p.num_k_blocks <= 8 && p.a_zn == 0) {
+        const int a_bytes = p.num_k_blocks * GEMM_A_BYTES;
+        const int b_stage = (p.block_n / 2) * GEMM_BLOCK_K * 2;
+        int stages = (GEMM_SHARED_BUDGET - 2 * GEMM_AUX_BYTES - a_bytes) / b_stage;
+        if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
+        if (stages >= 3) {
+            p.a_resident = 1; p.a_bytes = a_bytes; p.stages = stages; p.stage_bytes = b_stage;
+            p.ring_bytes = a_bytes + stages * b_stage; p.aux_slots = 2; p.stage_depth = 1;
+            return;
+        }
+    }
     if (!g_layout_ok) return;
     int sb, st;
     gemm_ring(p.block_n, op.cluster, GEMM_OPERAND_BYTES, &st, &sb);
@@ -357,6 +382,9 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
         p.orig_tma = 1;
     }
     gemm_layout(op);
+    p.fast_epi = (g_fast_epi && p.tma_store && p.aux_mode == AUX_NONE && p.out_mode == OUT_H16 && p.rowbias == nullptr &&
+                  p.rowscale == nullptr && p.row_mask == nullptr && bn % 64 == 0 && lin.out_features % 32 == 0 &&
+                  (reinterpret_cast<uintptr_t>(lin.b) & 15) == 0) ? 1 : 0;
     if (e.out_mode == OUT_H16) mark_out(op, 0, out, M * ldc);
     else if (e.out_mode == OUT_T_H16 && e.t_L > 0) mark_out(op, 0, out, (M / e.t_L) * (long long)e.t_batch_rows * e.t_pitch);
     op.shape[0] = (int)M; op.shape[1] = lin.out_features; op.shape[2] = lin.in_features; op.shape[3] = bn;
@@ -480,6 +508,32 @@ static int build_attn(Op& op, const h16* qkp, int ld, const void* pos_table, con
     return 0;
 }
 
+// entries per copy of the tensor-core rel-pos table (weights.py: pack_pos_table_tc uses the same formula)
+static inline int attn_tc_lz(int L) { return (2 * L + 264 + 1) / 2 * 2; }
+
+static int build_attn_tc(Op& op, const h16* qkp, int ld, const void* pos_table_tc, const uint32_t* maskw, h16* P,
+                         float* inv_l, int N, int H, int L, int Lk) {
+    op.type = OP_ATTN_TC;
+    Attn3Params& a = op.ap3;
+    a.L = L; a.Lk = Lk; a.H = H; a.N = N; a.qd = H * 32;
+    a.qkp = qkp; a.ld = ld; a.P = P; a.inv_l = inv_l;
+    if (pos_table_tc == nullptr || (reinterpret_cast<uintptr_t>(pos_table_tc) & 15) != 0)
+        return fail(ZVB_ERR_INVALID, "attn: tensor-core pos table missing or not 16-byte aligned");
+    a.Z = reinterpret_cast<const uint2*>(pos_table_tc);
+    a.LZ = attn_tc_lz(L);
+    a.emax = reinterpret_cast<const float*>(a.Z + static_cast<size_t>(H) * 2 * a.LZ);
+    a.maskw = maskw; a.mask_words = attn_mask_words(L);
+    if (ld % 8 != 0 || Lk % 8 != 0) return fail(ZVB_ERR_INVALID, "attn: pitches must be multiples of 8");
+    TRY(make_tmap(&op.ma, qkp, ld, L, N, (uint64_t)ld * 2, (uint64_t)ld * 2 * L, A3_BM));
+    TRY(make_tmap(&op.ms, P, Lk, L, (uint64_t)N * H, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * L, 32));
+    op.has_ms = true;
+    mark_out(op, 0, P, (long long)N * H * L * Lk);
+    op.cat = ZVB_CAT_ATTN_WEIGHTS;
+    op.work = (double)N * H * (2.0 * L * L * 32 + 2.0 * L * (2.0 * L - 1) * 4);
+    op.bytes = 2.0 * ((double)N * L * ld + (double)N * H * L * Lk) + 4.0 * N * H * L;
+    return 0;
+}
+
 static Op mask_words_op(const uint8_t* mask, uint32_t* out, int N, int L) {
     Op op; op.type = OP_MASKW; op.p0 = mask; op.o0 = out; op.i0 = N; op.i1 = L; op.i2 = attn_mask_words(L);
     return op;
@@ -550,6 +604,11 @@ static int launch_op(const Op& op, cudaStream_t st) {
             dim3 grid((op.ap.L + ATT_BM - 1) / ATT_BM, op.ap.H, op.ap.N);
             launch_k(attn_weights_kernel, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, st, op.ma, op.ms, op.ap);
             return check_launch("attn_weights");
+        }
+        case OP_ATTN_TC: {
+            dim3 grid((op.ap3.L + A3_BM - 1) / A3_BM, op.ap3.H, op.ap3.N);
+            launch_k(attn_weights_tc_kernel, dim3(grid), dim3(A3_THREADS), A3_SMEM_BYTES, st, op.ma, op.ms, op.ap3);
+            return check_launch("attn_weights_tc");
         }
         case OP_BIASNORM: {
             const int blocks = static_cast<int>((op.rows + 7) / 8);
@@ -804,7 +863,11 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             // 1. attention projections + weights (on the un-time-embedded input)
             e = LinearEpi();
             TRY(build_linear(op, src, Ms, D, ly.attn_in, qkp, attn_w, e)); ops.push_back(op);
-            TRY(build_attn(op, qkp, attn_w, ly.pos_table, maskw_ds[ds], P, invl, N, H, L, Lk)); ops.push_back(op);
+            if (g_attn_tc && ly.pos_table_tc != nullptr)
+                TRY(build_attn_tc(op, qkp, attn_w, ly.pos_table_tc, maskw_ds[ds], P, invl, N, H, L, Lk));
+            else
+                TRY(build_attn(op, qkp, attn_w, ly.pos_table, maskw_ds[ds], P, invl, N, H, L, Lk));
+            ops.push_back(op);
             // 2. feed_forward1 on src + temb:  R0 = src + temb + FF1(src + temb)
             e = LinearEpi(); e.act = ACT_SWOOSH_L;
             TRY(build_linear(op, srct, Ms, D, ly.ff_in[0], hid, m->ff_dims[0], e)); ops.push_back(op);
@@ -1073,6 +1136,16 @@ int zvb_test_attn_weights(const void* qkp, int ld, const void* pos_table, const 
     TRY(launch_op(mask_words_op(mask, (uint32_t*)scratch, N, L), static_cast<cudaStream_t>(stream)));
     Op op;
     TRY(build_attn(op, (const h16*)qkp, ld, pos_table, (const uint32_t*)scratch, (h16*)P, inv_l, N, H, L, Lk));
+    return launch_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_attn_weights_tc(const void* qkp, int ld, const void* pos_table_tc, const uint8_t* mask, void* scratch, void* P,
+                             float* inv_l, int N, int H, int L, int Lk, void* stream) {
+    TRY(init_device());
+    if (scratch == nullptr) return fail(ZVB_ERR_INVALID, "attn: scratch (N * 4 * ceil(L/128) words) is null");
+    TRY(launch_op(mask_words_op(mask, (uint32_t*)scratch, N, L), static_cast<cudaStream_t>(stream)));
+    Op op;
+    TRY(build_attn_tc(op, (const h16*)qkp, ld, pos_table_tc, (const uint32_t*)scratch, (h16*)P, inv_l, N, H, L, Lk));
     return launch_op(op, static_cast<cudaStream_t>(stream));
 }
 

@@ -65,9 +65,15 @@ struct GemmParams {
     int num_k_blocks;
     int block_n;           // UMMA N: multiple of 16, <= 256 (256 for EPI_GATED)
     int stages, stage_bytes;   // operand ring (gemm_ring)
-    int ring_bytes;            // shared memory given to the operand ring; the aux slots follow it
+    int ring_bytes;            // shared memory given to the operands (resident A + ring); the aux slots follow it
+    int a_resident;            // A-stationary mode (CTA pairs, K <= 512): the pair walks a CONTIGUOUS range of tiles,
+                               // n-tile fastest, keeps the 128 x K A tile of its m-group in shared memory and streams
+                               // only B; `a_bytes` = num_k_blocks x 16 KB in front of the (B-only) ring
     int aux_slots;             // 16 KB slots of the aux / staging area (2 .. GEMM_AUX_SLOTS_MAX)
     int stage_depth;           // staging buffers per epilogue half on the aux-less TMA-store path (1 or 2)
+    int a_bytes;
+    int fast_epi;              // lean epilogue (EPI_LINEAR, fp16 TMA-store output, no tile operand / row scale / row bias /
+                               // row mask, block_n % 64 == 0, n_out % 32 == 0): the feed-forward input GEMMs
     int num_m_tiles, num_n_tiles, batches;
     int a_zb, a_zn;        // A tensor-map z = b*a_zb + n_tile*a_zn
     int b_zb;              // B tensor-map z = b*b_zb
@@ -252,7 +258,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint64_t* aux_empty = aux_full + GEMM_AUX_SLOTS_MAX;        // [AUX_SLOTS] epilogue -> TMA
     uint64_t* staged = aux_empty + GEMM_AUX_SLOTS_MAX;          // [2 halves][2] epilogue -> store thread
     uint64_t* sfree = staged + 4;                               // [2 halves][2] store thread -> epilogue
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(sfree + 4);
+    uint64_t* a_full = sfree + 4;                               // [8] resident A k-block landed (TMA -> MMA)
+    uint64_t* a_empty = a_full + 8;                             // [8] resident A k-block released (MMA -> TMA)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_empty + 8);
 
     // Roles: warps 0..15 = epilogue, 16 = TMA producer (A/B), 17 = MMA issuer (+TMEM alloc), 18 = TMA producer
     // (aux), 19 = TMA store thread.  The single-thread roles sit in the HIGHEST warp ids because the
@@ -268,6 +276,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int total_tiles = p.batches * m_groups * p.num_n_tiles;
     const int first_tile = blockIdx.x / CLUSTER;
     const int tile_step = gridDim.x / CLUSTER;
+    // tile range of this CTA (pair): strided over the grid, or -- A-stationary -- one contiguous range so that the
+    // n-tiles of an m-group follow each other and its A tile is loaded once
+    const bool resident = CLUSTER == 2 && p.a_resident != 0;
+    const int t_first = resident ? static_cast<int>(static_cast<long long>(total_tiles) * first_tile / tile_step) : first_tile;
+    const int t_end = resident ? static_cast<int>(static_cast<long long>(total_tiles) * (first_tile + 1) / tile_step) : total_tiles;
+    const int t_step = resident ? 1 : tile_step;
+    uint8_t* ring = smem + (resident ? p.a_bytes : 0);          // operand ring ([A | B] stages, or B-only stages)
     // accumulator columns are consumed in units of 32; a 128-byte sub-tile row holds 64 fp16 (2 units) or
     // 32 fp32 (1 unit) columns
     const int n_units = (p.block_n + 31) >> 5;
@@ -298,6 +313,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             mbar_init(&staged[s], units_per_sub == 2 ? 8 : 4);
             mbar_init(&sfree[s], 1);
         }
+        for (int s = 0; s < 8; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
         fence_barrier_init();
     }
     if (warp == W_MMA) {
@@ -320,16 +339,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const int b_rows = p.block_n / CLUSTER;                    // B rows staged by this CTA
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+            uint32_t mg = 0;                        // m-groups started so far (A-stationary mode)
+            for (int tile = t_first; tile < t_end; tile += t_step) {
                 const int n_tile = tile % p.num_n_tiles;
                 const int rest = tile / p.num_n_tiles;
                 const int m_tile = (rest % m_groups) * CLUSTER + crank;
                 const int b = rest / m_groups;
                 const int az = b * p.a_zb + n_tile * p.a_zn;
                 const int bz = b * p.b_zb;
+                if (CLUSTER == 2 && resident) {
+                    const bool new_mg = tile == t_first || n_tile == 0;
+                    const uint32_t b_tx = static_cast<uint32_t>(p.block_n) * GEMM_BLOCK_K * 2;
+                    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                        if (new_mg) {       // this k-block of the previous m-group's A has been consumed by its last n-tile
+                            mbar_wait(&a_empty[kb], (mg & 1u) ^ 1u);
+                            if (crank == 0) mbar_arrive_expect_tx(&a_full[kb], 2 * GEMM_A_BYTES);
+                            tma_load_3d_2sm(smem + kb * GEMM_A_BYTES, &tma_a, &a_full[kb], kb * GEMM_BLOCK_K,
+                                            m_tile * GEMM_BLOCK_M, az);
+                        }
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], b_tx);
+                        tma_load_3d_2sm(ring + stage * STAGE_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BLOCK_K,
+                                        n_tile * p.block_n + crank * b_rows, bz);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    if (tile == t_end - 1 || n_tile == p.num_n_tiles - 1) ++mg;
+                    continue;
+                }
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sa = ring + stage * STAGE_BYTES;
                     if (CLUSTER == 2) {
                         if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
                         tma_load_3d_2sm(sa, &tma_a, &full_bar[stage], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M, az);
@@ -353,16 +392,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+            uint32_t mg = 0;
+            for (int tile = t_first; tile < t_end; tile += t_step) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc) * 256u;
+                const int n_tile = tile % p.num_n_tiles;
+                const bool new_mg = resident && (tile == t_first || n_tile == 0);
+                const bool last_of_mg = resident && (tile == t_end - 1 || n_tile == p.num_n_tiles - 1);
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    if (new_mg) mbar_wait(&a_full[kb], mg & 1u);
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t da = umma_desc_k_sw128(sa);
-                    const uint64_t db = umma_desc_k_sw128(sa + GEMM_A_BYTES);
+                    const uint32_t sa = smem_u32(ring + stage * STAGE_BYTES);
+                    const uint64_t da = umma_desc_k_sw128(resident ? smem_u32(smem + kb * GEMM_A_BYTES) : sa);
+                    const uint64_t db = umma_desc_k_sw128(resident ? sa : sa + GEMM_A_BYTES);
 #pragma unroll
                     for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
                         // advance 16 fp16 = 32 bytes inside the 128B swizzle atom: +2 in >>4 units
@@ -376,6 +420,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     // free the smem slot (in both CTAs) when the MMAs retire; publish the accumulator
                     if (CLUSTER == 2) {
                         umma_commit_2sm(&empty_bar[stage], 0x3);
+                        if (last_of_mg) umma_commit_2sm(&a_empty[kb], 0x3);
                         if (kb == p.num_k_blocks - 1) umma_commit_2sm(&tmem_full[acc], 0x3);
                     } else {
                         umma_commit(&empty_bar[stage]);
@@ -383,6 +428,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
+                if (last_of_mg) ++mg;
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -391,7 +437,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (lane == 0 && p.aux_mode != AUX_NONE) {
             constexpr int sub_cols = 64;
             uint32_t q = 0;
-            for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+            for (int tile = t_first; tile < t_end; tile += t_step) {
                 const int n_tile = tile % p.num_n_tiles;
                 const int rest = tile / p.num_n_tiles;
                 const int m_tile = (rest % m_groups) * CLUSTER + crank;
@@ -429,7 +475,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 if (p.aux_mode != AUX_NONE) mbar_arrive(&aux_empty[sl0]);
                 ++freed;
             };
-            for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++tile_iter) {
+            for (int tile = t_first; tile < t_end; tile += t_step, ++tile_iter) {
                 const int n_tile = tile % p.num_n_tiles;
                 const int rest = tile / p.num_n_tiles;
                 const int m_tile = (rest % m_groups) * CLUSTER + crank;
@@ -511,10 +557,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const int s_first = units_per_sub == 2 ? half : (p.tma_store ? half : half + 2 * part);
         const bool lin_active = units_per_sub == 2 || !p.tma_store || part == 0;
         const int uu = units_per_sub == 2 ? part : 0;     // unit inside the sub-tile
+        // lean path (fast_epi): 32-bit shared-window addresses, computed once
+        const uint32_t fast_stage = smem_u32(aux_smem) + static_cast<uint32_t>(half * GEMM_AUX_BYTES + quarter * 4096 + lane * 128);
+        const uint32_t fast_staged = smem_u32(&staged[half * 2]);
+        const uint32_t fast_sfree = smem_u32(&sfree[half * 2]);
+        uint32_t fast_chunk[4];                           // swizzled 16-byte chunks of this warp's unit inside a staging row
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fast_chunk[j] = static_cast<uint32_t>(((4 * part + j) ^ (lane & 7)) << 4);
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t tile_iter = 0;
-        for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++tile_iter) {
+        for (int tile = t_first; tile < t_end; tile += t_step, ++tile_iter) {
             const int n_tile = tile % p.num_n_tiles;
             const int rest = tile / p.num_n_tiles;
             const int m_tile = (rest % m_groups) * CLUSTER + crank;
@@ -556,7 +609,67 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * 256u +
                                    (static_cast<uint32_t>(quarter * 32) << 16);
 
-            if (KIND == EPI_GATED) {
+            if (KIND == EPI_LINEAR && p.fast_epi) {
+                // Lean path of the feed-forward input GEMMs.  These kernels are bound by the epilogue's issue slots
+                // (ncu, round 2: 415 executed instructions per 32 x 32 unit of which 176 are FFMA2 / MUFU; tensor pipe
+                // 51%), so everything that is not arithmetic is hoisted: shared-memory and barrier addresses are
+                // 32-bit window addresses computed once per kernel, the bias is read as warp-uniform 16-byte loads
+                // (no staging through shared memory, no warp barriers), no per-unit bounds beyond `live`.
+                const float4* bias4 = reinterpret_cast<const float4*>(p.bias);
+                for (int s = half; s < n_sub; s += 2) {
+                    const int c0 = (2 * s + part) * 32;
+                    const int gc = acc_base + c0;
+                    const bool live = gc < p.n_out;               // whole unit inside the output (n_out % 32 == 0)
+                    const uint32_t buf = kcount & dsh;
+                    if (live) {
+                        uint32_t acc_r[32];
+                        tmem_ld32(taddr + c0, acc_r);
+                        f32x2 v2[16];
+                        if (bias4 != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 bq = __ldg(bias4 + (gc >> 2) + j);
+                                v2[2 * j] = pack2(bq.x, bq.y);
+                                v2[2 * j + 1] = pack2(bq.z, bq.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v2[j] = pack2(0.f, 0.f);
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            v2[j] = add2(pack2(__uint_as_float(acc_r[2 * j]), __uint_as_float(acc_r[2 * j + 1])), v2[j]);
+                        if (ACT == ACT_SWOOSH_L) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) swoosh_x2_group<4>(v2 + j, SWOOSH_L_C, SWOOSH_L_K0);
+                        } else if (ACT == ACT_SWOOSH_R) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) swoosh_x2_group<4>(v2 + j, SWOOSH_R_C, SWOOSH_R_K0);
+                        }
+                        if (kcount >= depth) {
+                            const uint32_t kd = kcount - depth;
+                            mbar_wait_u32(fast_sfree + 8u * (kd & dsh), (kd >> dsh) & 1u);
+                        }
+                        const uint32_t row_addr = fast_stage + buf * (2u * GEMM_AUX_BYTES);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float a0, a1, a2, a3, a4, a5, a6, a7;
+                            unpack2(v2[4 * j], a0, a1); unpack2(v2[4 * j + 1], a2, a3);
+                            unpack2(v2[4 * j + 2], a4, a5); unpack2(v2[4 * j + 3], a6, a7);
+                            sts128_u32(row_addr + fast_chunk[j], pack_h2(a0, a1), pack_h2(a2, a3), pack_h2(a4, a5),
+                                       pack_h2(a6, a7));
+                        }
+                    } else if (kcount >= depth) {
+                        const uint32_t kd = kcount - depth;
+                        mbar_wait_u32(fast_sfree + 8u * (kd & dsh), (kd >> dsh) & 1u);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_u32(fast_staged + 8u * buf);
+                    ++kcount;
+                }
+            } else if (KIND == EPI_GATED) {
                 const int hcols = p.block_n >> 1;                       // 128
                 // the two parts of a (quarter, half) take adjacent 32-column units so that their fp16 rows
                 // leave as one 128-byte segment

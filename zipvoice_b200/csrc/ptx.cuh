@@ -87,6 +87,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Variants on raw 32-bit shared-window addresses.  A generic pointer into shared memory is converted by
+// `cvta.to.shared`, which on sm_100 re-reads %cluster_ctaid and rebuilds the CTA's window base every time
+// (S2UR SR_CgaCtaId + 5 uniform ops in SASS): hot loops convert once and keep the u32.
+__device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_u32(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait_u32(bar, parity)) {
+        if ((++spins & 63u) == 0u && globaltimer_ns() - t0 > ZVB_WAIT_TIMEOUT_NS) {
+            printf("zvb: mbarrier wait timeout block=(%d,%d,%d) thread=%d parity=%u\n", blockIdx.x,
+                   blockIdx.y, blockIdx.z, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void sts128_u32(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ------------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -386,6 +419,76 @@ __device__ __forceinline__ void swoosh_direct2(float& x0, float& x1, float c, fl
     q = fma2(x, pack2(0.42f, 0.42f), q);
     q = fma2(pack2(a0, a1), pack2(0.5f / L2E, 0.5f / L2E), q);
     unpack2(q, x0, x1);
+}
+// the same on a packed pair, in and out
+__device__ __forceinline__ f32x2 swoosh_x2(f32x2 x, float c, float k0) {
+    constexpr float L2E = 1.4426950408889634f;
+    const f32x2 z = fma2(x, pack2(L2E, L2E), pack2(-c * L2E, -c * L2E));
+    float z0, z1;
+    unpack2(z, z0, z1);
+    const float a0 = fabsf(z0), a1 = fabsf(z1);
+    float t0, t1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(-a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(-a1));
+    const f32x2 t = pack2(t0, t1);
+    f32x2 q = fma2(t, pack2(0.031377589387161245f, 0.031377589387161245f), pack2(-0.1341354334221127f, -0.1341354334221127f));
+    q = fma2(t, q, pack2(0.2878262894239249f, 0.2878262894239249f));
+    q = fma2(t, q, pack2(-0.491347927069251f, -0.491347927069251f));
+    q = fma2(t, q, pack2(0.9994349844843187f, 0.9994349844843187f));
+    const float k = k0 - 0.42f * c;
+    q = fma2(t, q, pack2(k, k));
+    q = fma2(x, pack2(0.42f, 0.42f), q);
+    return fma2(pack2(a0, a1), pack2(0.5f / L2E, 0.5f / L2E), q);
+}
+// Scheduling-pinned variants: ptxas keeps `asm volatile` statements in program order, so chains interleaved in the
+// source stay interleaved in SASS (left alone it serialises every chain to save registers).
+__device__ __forceinline__ f32x2 fma2_o(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float ex2_neg_abs_o(float x) {
+    float y;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(-fabsf(x)));
+    return y;
+}
+// G pairs at once, the G Horner chains interleaved step by step: a single chain is a string of dependent FFMA2s
+// behind a MUFU (4-cycle issue-to-use each, ~20 for the MUFU), and an epilogue warp shares its scheduler with only
+// three others -- the independent chains are what keeps the FMA pipe fed.
+template <int G>
+__device__ __forceinline__ void swoosh_x2_group(f32x2* v, float c, float k0) {
+    constexpr float L2E = 1.4426950408889634f;
+    f32x2 z[G], t[G], q[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) z[i] = fma2_o(v[i], pack2(L2E, L2E), pack2(-c * L2E, -c * L2E));
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        float z0, z1;
+        unpack2(z[i], z0, z1);
+        const float t0 = ex2_neg_abs_o(z0);
+        const float t1 = ex2_neg_abs_o(z1);
+        t[i] = pack2(t0, t1);
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i)
+        q[i] = fma2_o(t[i], pack2(0.031377589387161245f, 0.031377589387161245f), pack2(-0.1341354334221127f, -0.1341354334221127f));
+#pragma unroll
+    for (int i = 0; i < G; ++i) q[i] = fma2_o(t[i], q[i], pack2(0.2878262894239249f, 0.2878262894239249f));
+#pragma unroll
+    for (int i = 0; i < G; ++i) q[i] = fma2_o(t[i], q[i], pack2(-0.491347927069251f, -0.491347927069251f));
+#pragma unroll
+    for (int i = 0; i < G; ++i) q[i] = fma2_o(t[i], q[i], pack2(0.9994349844843187f, 0.9994349844843187f));
+    const float k = k0 - 0.42f * c;
+#pragma unroll
+    for (int i = 0; i < G; ++i) q[i] = fma2_o(t[i], q[i], pack2(k, k));
+#pragma unroll
+    for (int i = 0; i < G; ++i) q[i] = fma2_o(v[i], pack2(0.42f, 0.42f), q[i]);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        float z0, z1;
+        unpack2(z[i], z0, z1);
+        v[i] = fma2_o(pack2(fabsf(z0), fabsf(z1)), pack2(0.5f / L2E, 0.5f / L2E), q[i]);
+    }
 }
 constexpr float SWOOSH_L_C = 4.0f, SWOOSH_L_K0 = -(0.08f * 4.0f + 0.035f);
 constexpr float SWOOSH_R_C = 1.0f, SWOOSH_R_K0 = -(0.08f * 1.0f + 0.313261687f);

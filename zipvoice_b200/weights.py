@@ -45,6 +45,32 @@ def pack_pos_table(e: torch.Tensor) -> torch.Tensor:
     return torch.cat([pairs.view(torch.uint8).reshape(-1), emax.view(torch.uint8).reshape(-1)]).contiguous()
 
 
+TC_PADZ = 128        # zero entries in front of E in the tensor-core table (csrc/attn3.cuh: A3_PADZ)
+
+
+def tc_table_entries(L: int) -> int:
+    """Entries per copy of the tensor-core table (csrc/engine.cu: attn_tc_lz)."""
+    return (2 * L + 264 + 1) // 2 * 2
+
+
+def pack_pos_table_tc(e: torch.Tensor) -> torch.Tensor:
+    """E[h][r][d] fp32 (H, 2L-1, 4) -> the table of the tensor-core attention kernel (csrc/attn3.cuh), uint8 tensor:
+    [H][2][LZ] entries of 4 fp16: copy 0 holds log2e*E[h][r][0..3] at entry TC_PADZ + r and zeros elsewhere, copy 1 is
+    copy 0 shifted by one entry (so that a window starting at an odd entry is 16-byte aligned in one of the two);
+    followed by [H] fp32 max_r |log2e*E[h][r]|_2, the bound of the cheap softmax shift."""
+    H, R, D = e.shape
+    assert D == 4 and R % 2 == 1
+    L = (R + 1) // 2
+    LZ = tc_table_entries(L)
+    es = e.float() * 1.4426950408889634
+    emax = es.norm(dim=2).amax(dim=1).contiguous()
+    z = torch.zeros(H, 2, LZ + 1, 4, dtype=torch.float32, device=e.device)
+    z[:, 0, TC_PADZ:TC_PADZ + R] = es
+    z[:, 1, :LZ] = z[:, 0, 1:LZ + 1]
+    tab = z[:, :, :LZ].to(torch.float16).contiguous()
+    return torch.cat([tab.view(torch.uint8).reshape(-1), emax.view(torch.uint8).reshape(-1)]).contiguous()
+
+
 def rel_pos_embedding(L: int, pos_dim: int, device) -> torch.Tensor:
     """CompactRelPositionalEncoding rows for offsets -(L-1)..(L-1) (reference:
     modules/zipformer.py:995-1056), shape (2L-1, pos_dim) fp32."""
@@ -200,7 +226,7 @@ class PackedZipformer:
             tabs = _PosTables()
             for wp in self.linear_pos:
                 e = (pe @ wp.t()).reshape(2 * L - 1, c.num_heads, c.pos_head_dim).permute(1, 0, 2).contiguous()
-                tabs.append(pack_pos_table(e))
+                tabs.append((pack_pos_table(e), pack_pos_table_tc(e)))
             self._pos_cache[L] = tabs
         return tabs
 
@@ -226,7 +252,8 @@ class PackedZipformer:
             for j in range(st["nl"]):
                 ly, z = self.layers[li], arr[li]
                 z.attn_in = self._lin_struct(ly["attn_in"])
-                z.pos_table = tabs[li].data_ptr()
+                z.pos_table = tabs[li][0].data_ptr()
+                z.pos_table_tc = tabs[li][1].data_ptr()
                 for i in range(3):
                     z.ff_in[i] = self._lin_struct(ly["ff_in"][i])
                     z.ff_out[i] = self._lin_struct(ly["ff_out"][i])
