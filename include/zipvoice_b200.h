@@ -31,9 +31,10 @@
 extern "C" {
 #endif
 
-#define ZVB_ABI_VERSION 4
+#define ZVB_ABI_VERSION 5
 #define ZVB_MAX_STACKS 8
 #define ZVB_MAX_LAYERS 64
+#define ZVB_VOC_MAX_LAYERS 16
 
 typedef enum {
     ZVB_OK = 0,
@@ -185,8 +186,60 @@ int zvb_sample(zvb_plan* plan, float* x, const float* text, const float* speech,
                const float* guidance, const float* ts, const float* ts_host, int num_step, int mode,
                int B, int F, int Ft, float* vrec, void* stream);
 
+/* ---- the stages either side of the sampler ------------------------- */
+
+/* Prompt log-mel, the reference's VocosFbank (reference: zipvoice/utils/feature.py:47-116: torchaudio
+ * MelSpectrogram(sample_rate 24000, n_fft 1024, hop 256, n_mels 100, center=True (reflect), power=1) followed by
+ * clamp(min=1e-7).log(), trimmed to lhotse's compute_num_frames = (samples + hop/2) / hop frames).
+ *   wav      fp32 [B][s_pitch] (device), lens int32 [B] valid samples per row (device)
+ *   window   fp32 [1024] (torch.hann_window, periodic); fb fp32 [n_mels][513] mel filterbank; fb_range int32
+ *            [n_mels][2] = first / one-past-last non-zero bin of every filter
+ *   out      fp32 [B][T][n_mels]: scale * log-mel for t < (len + hop/2) / hop, zeros after
+ * n_fft is fixed at 1024 (the reference's VocosFbankConfig). */
+int zvb_fbank(const float* wav, const int32_t* lens, int B, int s_pitch, const float* window, const float* fb,
+              const int32_t* fb_range, int n_mels, int hop, float scale, float* out, int T, void* stream);
+
+/* Vocoder: `vocoder.decode(mel)` of the reference's call sites (zipvoice/bin/infer_zipvoice.py:301-312, 409, 594) =
+ * the external vocos 0.1.0 model (uv.lock:1239-1241) VocosBackbone + ISTFTHead(padding="center"):
+ *   Conv1d(n_mels, dim, 7, padding 3) -> LayerNorm(eps 1e-6) -> n_layers x ConvNeXtBlock [depthwise Conv1d(dim, 7) ->
+ *   LayerNorm -> Linear(dim, intermediate) -> GELU -> Linear(intermediate, dim) -> * gamma -> + residual] ->
+ *   LayerNorm -> Linear(dim, n_fft + 2) -> (mag, phase) -> exp, clip 1e2 -> mag*(cos p + i sin p) -> torch.istft.
+ * Every utterance of a batch is decoded as if alone (frames past its length are zero padding of the convolutions). */
+typedef struct {
+    const float* dw_w;        /* depthwise taps fp32 [7][dim] */
+    const float* dw_b;        /* fp32 [dim] */
+    const float* ln_w; const float* ln_b;
+    zvb_linear pw1;           /* Linear(dim, intermediate), GELU in the epilogue */
+    zvb_linear pw2;           /* Linear(intermediate, dim) with the block's layer scale gamma folded in */
+} zvb_voc_layer;
+
+typedef struct {
+    int32_t abi_version;
+    int32_t dim, intermediate, n_layers, n_mels, n_fft, hop, kernel;   /* 512, 1536, 8, 100, 1024, 256, 7 */
+    zvb_linear embed;         /* Conv1d as a linear over the 7-frame window: W[dim][k * n_mels + c] (k_pitch % 8 == 0) */
+    const float* norm_w; const float* norm_b;
+    zvb_voc_layer layers[ZVB_VOC_MAX_LAYERS];
+    const float* final_w; const float* final_b;
+    zvb_linear head;          /* Linear(dim, n_fft + 2): rows [0, n_fft/2] log-magnitude, the rest phase */
+    const float* window;      /* fp32 [n_fft] (head.istft.window) */
+} zvb_vocoder;
+
+typedef struct zvb_vocoder_plan zvb_vocoder_plan;
+int zvb_vocoder_workspace_bytes(const zvb_vocoder* voc, int N, int T, size_t* bytes);
+int zvb_vocoder_create(const zvb_vocoder* voc, int N, int T, void* workspace, size_t workspace_bytes,
+                       zvb_vocoder_plan** plan);
+void zvb_vocoder_destroy(zvb_vocoder_plan* plan);
+/* mel fp32 [N][T][n_mels] (device; multiplied by `scale`, the caller's 1 / feat_scale), lens int32 [N] frames per
+ * utterance (device, 1 <= len <= T); wav fp32 [N][hop * (T - 1)]: hop * (len - 1) samples per row, zeros after;
+ * clamp != 0 applies the caller's .clamp(-1, 1) (infer_zipvoice.py:409). */
+int zvb_vocoder_decode(zvb_vocoder_plan* plan, const float* mel, const int32_t* lens, float scale, int clamp, float* wav,
+                       void* stream);
+/* per-kernel timing of one decode over the resident buffers, as zvb_decoder_profile */
+int zvb_vocoder_profile(zvb_vocoder_plan* plan, void* stream, int max_ops, float* ms, int* category, double* work,
+                        double* bytes, int* num_ops);
+
 /* ---- single-kernel entry points used by the parity tests -------------------------------- */
-/* C = epilogue(A·Wᵀ): A fp16 [M][lda], W fp16 [n_out][k_pitch]; act 0 none/1 SwooshL/2 SwooshR;
+/* C = epilogue(A·Wᵀ): A fp16 [M][lda], W fp16 [n_out][k_pitch]; act 0 none/1 SwooshL/2 SwooshR/3 GELU (erf);
  * resid fp16 [M][ldc] nullable (added); orig fp16 [M][ldc] + bypass_scale fp32 [n_out] nullable:
  * C = orig + (C - orig)*scale (needs resid); out_mode 0: out fp16 / 1: out fp32. */
 int zvb_test_linear(const void* A, int M, int K, int lda, const void* W, const float* bias, int n_out,
@@ -210,6 +263,19 @@ int zvb_test_biasnorm_bypass(const void* src, const void* orig, void* out, void*
                              const float* bscale, long long rows, int C, void* stream);
 int zvb_test_dwconv(const void* x, void* out, const float* wt, const float* bias, int N, int L, int C, int K,
                     void* stream);
+/* the same depthwise convolution without the activation (vocoder ConvNeXt blocks) */
+int zvb_test_dwconv_linear(const void* x, void* out, const float* wt, const float* bias, int N, int L, int C, int K,
+                           void* stream);
+/* torch.nn.LayerNorm over C (fp16 in / out, C % 256 == 0, <= 1024); rows with mask != 0 (nullable) are zeroed */
+int zvb_test_layernorm(const void* x, void* out, const float* w, const float* b, const uint8_t* mask, long long rows, int C,
+                       float eps, void* stream);
+/* linear with a row mask: rows with mask != 0 are written as zeros (resid fp16 nullable, as zvb_test_linear) */
+int zvb_test_linear_masked(const void* A, int M, int K, int lda, const void* W, const float* bias, int n_out, int k_pitch,
+                           int act, const void* resid, const uint8_t* row_mask, void* out, int ldc, void* stream);
+/* inverse STFT of head outputs S fp32 [N*T][ld] = [log-mag 513 | phase 513]: frames scratch fp32 [N*T][1024],
+ * mask scratch u8 [N*T]; wav fp32 [N][hop * (T - 1)] */
+int zvb_test_istft(const float* S, int ld, const int32_t* lens, const float* window, float* frames, uint8_t* mask, float* wav,
+                   int N, int T, int hop, int clamp, void* stream);
 int zvb_test_cfg_euler(float* x, const float* v, const float* guidance, float gscale, const float* ts,
                        int step, int B, long long per_utt, int cfg, void* stream);
 /* linear with the transposed store of the value projections: out[(row / t_L)*t_batch_rows + drow(col)][row % t_L],

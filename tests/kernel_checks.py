@@ -408,6 +408,112 @@ def assert_ok(name, r):
         assert r["rel"] <= r["tol"], (name, r)
 
 
+
+# ------------------------------------------------------------------------------------------ vocoder pieces
+def check_layernorm(rows=301, C=512, masked=True, seed=0):
+    """tolerance: rel-L2 <= 8e-4 (fp16 output); masked rows exactly zero"""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = (torch.randn(rows, C, generator=g) * 2.0 + 0.5).to(H16).to(DEV)
+    w = (1.0 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    b = (0.3 * torch.randn(C, generator=g)).to(DEV)
+    m = (torch.rand(rows, generator=g) < 0.2).to(torch.uint8).to(DEV) if masked else None
+    out = torch.full((rows, C), float("nan"), dtype=H16, device=DEV)
+    _lib.check(lib.zvb_test_layernorm(x.data_ptr(), out.data_ptr(), w.data_ptr(), b.data_ptr(),
+                                      m.data_ptr() if masked else None, rows, C, 1e-6, _s()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), w, b, 1e-6)
+    if masked:
+        ref = ref * (m == 0).unsqueeze(1)
+        assert float(out[m != 0].float().abs().max()) == 0.0
+    return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=8e-4)
+
+
+def check_dwconv_linear(N=3, L=150, C=512, K=7, seed=0):
+    """depthwise convolution + bias without activation; tolerance: rel-L2 <= 8e-4 (fp16 output)"""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(N, L, C, generator=g).to(H16).to(DEV)
+    w = (torch.randn(C, 1, K, generator=g) / math.sqrt(K)).to(DEV)
+    b = (torch.randn(C, generator=g) * 0.2).to(DEV)
+    wt = w.reshape(C, K).t().contiguous()
+    out = torch.full((N, L, C), float("nan"), dtype=H16, device=DEV)
+    _lib.check(lib.zvb_test_dwconv_linear(x.data_ptr(), out.data_ptr(), wt.data_ptr(), b.data_ptr(), N, L, C, K, _s()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv1d(x.float().permute(0, 2, 1), w, b, padding=K // 2, groups=C).permute(0, 2, 1)
+    return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=8e-4)
+
+
+def check_linear_masked(M=700, K=1536, N=512, act=0, resid=True, seed=0):
+    """linear (+ exact GELU) + residual with a row mask: masked rows exactly zero; rel-L2 <= 8e-4"""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = torch.randn(M, K, generator=g).to(H16).to(DEV)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(H16).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    R = torch.randn(M, N, generator=g).to(H16).to(DEV) if resid else None
+    m = (torch.rand(M, generator=g) < 0.3).to(torch.uint8).to(DEV)
+    out = torch.full((M, N), float("nan"), dtype=H16, device=DEV)
+    _lib.check(lib.zvb_test_linear_masked(A.data_ptr(), M, K, K, W.data_ptr(), b.data_ptr(), N, K, act,
+                                          R.data_ptr() if resid else None, m.data_ptr(), out.data_ptr(), N, _s()))
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + b
+    if act == 3:
+        ref = torch.nn.functional.gelu(ref)
+    if resid:
+        ref = ref + R.float()
+    ref = ref * (m == 0).unsqueeze(1)
+    assert float(out[m != 0].float().abs().max()) == 0.0
+    return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=8e-4)
+
+
+def check_linear_gelu(M=1000, K=512, N=1536, seed=0):
+    """pwconv1 of a ConvNeXt block: linear + exact (erf) GELU on the lean epilogue; rel-L2 <= 8e-4"""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = torch.randn(M, K, generator=g).to(H16).to(DEV)
+    W = (torch.randn(N, K, generator=g) * 2.0 / math.sqrt(K)).to(H16).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    out = torch.full((M, N), float("nan"), dtype=H16, device=DEV)
+    _lib.check(lib.zvb_test_linear(A.data_ptr(), M, K, K, W.data_ptr(), b.data_ptr(), N, K, 0, 3, None, None, None,
+                                   out.data_ptr(), N, 0, _s()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.gelu(A.float() @ W.float().t() + b)
+    return dict(rel=_rel(out.float(), ref), nan=int(torch.isnan(out.float()).sum()), tol=8e-4)
+
+
+def check_istft(N=3, T=40, seed=0):
+    """inverse STFT head (exp / clip / cos / sin -> irfft -> window -> overlap-add / envelope) against torch.istft per
+    utterance, ragged lengths; fp32: max-abs <= 2e-5 of the signal peak"""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    lens = torch.tensor([T, max(2, T // 2 + 1), 2][:N], dtype=torch.int32)
+    ld = 1028
+    S = torch.zeros(N, T, ld)
+    S[..., :513] = torch.randn(N, T, 513, generator=g) * 1.5 + 1.0          # some log-magnitudes beyond the clip at log(100)
+    S[..., 513:1026] = torch.randn(N, T, 513, generator=g) * 3.0
+    win = torch.hann_window(1024)
+    Sd, ld_, wd = S.to(DEV), lens.to(DEV), win.to(DEV)
+    frames = torch.zeros(N * T, 1024, device=DEV)
+    mask = torch.zeros(N * T, dtype=torch.uint8, device=DEV)
+    wav = torch.full((N, 256 * (T - 1)), float("nan"), device=DEV)
+    _lib.check(lib.zvb_test_istft(Sd.data_ptr(), ld, ld_.data_ptr(), wd.data_ptr(), frames.data_ptr(), mask.data_ptr(),
+                                  wav.data_ptr(), N, T, 256, 0, _s()))
+    torch.cuda.synchronize()
+    err, peak = 0.0, 0.0
+    for n in range(N):
+        L = int(lens[n])
+        mag = torch.clip(torch.exp(S[n, :L, :513].double()), max=1e2)
+        p = S[n, :L, 513:1026].double()
+        spec = (mag * (torch.cos(p) + 1j * torch.sin(p))).t().unsqueeze(0)
+        ref = torch.istft(spec, 1024, 256, 1024, win.double(), center=True)[0]
+        got = wav[n].cpu().double()
+        err = max(err, float((got[: ref.numel()] - ref).abs().max()))
+        peak = max(peak, float(ref.abs().max()))
+        assert float(got[ref.numel():].abs().max() if got.numel() > ref.numel() else 0.0) == 0.0
+    return dict(rel=err / peak, nan=int(torch.isnan(wav).sum()), tol=2e-5)
+
+
 ALL = {
     "linear_basic": lambda: check_linear(M=300, K=512, N=272),
     "linear_k48": lambda: check_linear(M=257, K=48, N=512, resid=True),
@@ -437,7 +543,7 @@ ALL = {
     # sit far below it; weights must stay normal fp16 numbers thanks to the 2^12 head-room (looser
     # tolerance: the fp16 bias sum carries ~2^-6 absolute error at magnitudes of 16..32)
     "attn_strong_pos": lambda: check_attn(N=2, H=4, L=333, masked=True, pos_scale=2.5, tol=3e-2),
-    # the CUDA-core-bias kernel (attn.cuh, kept behind ZVB_ATTN_V2=1)
+    # the CUDA-core-bias kernel (attn.cuh, the default)
     "attn_v2_masked": lambda: check_attn(N=3, H=4, L=333, masked=True, tc=False),
     "attn_v2_strong_pos": lambda: check_attn(N=2, H=4, L=333, masked=True, pos_scale=2.5, tol=3e-2, tc=False),
     # tensor-core bias: odd / even L (window alignment in the two table copies), one tile, tile boundaries
@@ -472,6 +578,14 @@ ALL = {
     "masks_ds1": lambda: check_masks(ds=1),
     "masks_ds2": lambda: check_masks(ds=2),
     "masks_ds4": lambda: check_masks(N=2, T=1219, ds=4),
+    "layernorm": lambda: check_layernorm(),
+    "layernorm_c256": lambda: check_layernorm(rows=77, C=256, masked=False),
+    "dwconv7_linear": lambda: check_dwconv_linear(),
+    "linear_masked_resid": lambda: check_linear_masked(),
+    "linear_masked_gelu": lambda: check_linear_masked(M=300, K=512, N=768, act=3, resid=False),
+    "linear_gelu": lambda: check_linear_gelu(),
+    "istft": lambda: check_istft(),
+    "istft_long": lambda: check_istft(N=2, T=333, seed=1),
     "cfg_euler": lambda: check_cfg_euler(cfg=1),
     "euler_nocfg": lambda: check_cfg_euler(cfg=0),
 }

@@ -1,0 +1,120 @@
+"""-m gpu: the stages either side of the sampler through the C ABI:
+prompt log-mel (zvb_fbank) against the torchaudio-generated vectors and live torchaudio, the speaker cache, and the
+Vocos vocoder (zvb_vocoder_decode) against the CPU oracle (oracle/audio_oracle.py), ragged batches included."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import audio_oracle as ao
+from util import load_golden, rel_l2
+from zipvoice_b200.frontend import SpeakerCache, VocosFbank, num_frames_for, rms_norm
+from zipvoice_b200.vocoder import Vocos, synth_vocos_state_dict
+
+pytestmark = pytest.mark.gpu
+
+# fp32 FFT + fp32 filterbank on both sides: the log of a mel bin ~60 dB under the frame energy moves by ~1e-4
+LOGMEL_ATOL = 2e-3
+# 16-bit backbone (fp16 operands, fp32 accumulate), fp32 inverse STFT: thresholds on the waveform
+VOC_REL, VOC_MAXABS = 1.5e-2, 4e-2
+
+
+@pytest.mark.parametrize("name", ["fbank_mono", "fbank_stereo", "fbank_short"])
+def test_fbank_matches_reference_vectors(name):
+    g = load_golden(name)
+    wav, want = g["wav"], g["logmel"]
+    fe = VocosFbank(num_channels=wav.shape[0])
+    got = fe.extract(wav, 24000)
+    assert got.shape == want.shape and got.device.type == "cuda"
+    err = (got.cpu() - want).abs()
+    assert float(err.max()) < LOGMEL_ATOL, float(err.max())
+    # the numpy path of the reference's extractor returns numpy
+    assert isinstance(fe.extract(wav.numpy(), 24000), np.ndarray)
+
+
+def test_fbank_batch_ragged_vs_torchaudio_and_oracle():
+    ta = pytest.importorskip("torchaudio")
+    g = torch.Generator().manual_seed(7)
+    lens = torch.tensor([72000, 30017, 5000, 128])          # 3 s prompt, ragged, one-frame utterance
+    wavs = torch.zeros(4, int(lens.max()))
+    for i, n in enumerate(lens.tolist()):
+        wavs[i, :n] = torch.randn(n, generator=g) * (0.02 + 0.1 * i)
+    fe = VocosFbank()
+    feats, frames = fe.extract_batch(wavs, lens, scale=0.1)
+    assert frames.tolist() == [num_frames_for(n) for n in lens.tolist()] == [281, 117, 20, 1]
+    fb = ta.transforms.MelSpectrogram(sample_rate=24000, n_fft=1024, hop_length=256, n_mels=100, center=True, power=1)
+    for i, n in enumerate(lens.tolist()):
+        T = int(frames[i])
+        if n > 512:                                          # torch's reflect pad needs more samples than the pad
+            want = fb(wavs[i:i + 1, :n]).clamp(min=1e-7).log()[0].t()[:T] * 0.1
+            assert float((feats[i, :T].cpu() - want).abs().max()) < LOGMEL_ATOL * 0.1
+            assert np.abs(feats[i, :T].cpu().numpy() - 0.1 * ao.vocos_fbank(wavs[i, :n].numpy())).max() < LOGMEL_ATOL * 0.1
+        assert float(feats[i, T:].abs().max() if T < feats.shape[1] else 0.0) == 0.0
+
+
+def test_speaker_cache():
+    g = torch.Generator().manual_seed(9)
+    fe = VocosFbank()
+    cache = SpeakerCache(fe, max_speakers=2)
+    wav_a = torch.randn(24000, generator=g) * 0.01           # quieter than target_rms: scaled up
+    wav_b = torch.randn(2, 12000, generator=g) * 0.3         # stereo prompt: averaged
+    ta, fa, ra = cache.get("a", wav_a, [1, 2, 3])
+    want, _ = rms_norm(wav_a, 0.1)
+    ref = torch.from_numpy(ao.vocos_fbank(want.numpy())).float() * 0.1
+    assert fa.shape == ref.shape and float((fa.cpu() - ref).abs().max()) < LOGMEL_ATOL * 0.1
+    assert abs(ra - float(wav_a.square().mean().sqrt())) < 1e-7 and ta == [1, 2, 3]
+    cache.get("b", wav_b, [4])
+    assert cache.get("a")[1] is fa and cache.hits == 1       # served from the cache, no re-extraction
+    toks, feats, lens, rms = cache.batch(["a", "b"])
+    assert feats.shape[0] == 2 and lens.tolist() == [num_frames_for(24000), num_frames_for(12000)] and toks == [[1, 2, 3], [4]]
+    cache.get("c", wav_a, [5])
+    assert "b" not in cache and "a" in cache and len(cache) == 2     # least recently used entry dropped
+    with pytest.raises(KeyError):
+        cache.get("zzz")
+
+
+def _mel(B, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, 100, T, generator=g) * 2.0 - 4.0    # log-mel range of speech
+
+
+def test_vocoder_decode_matches_oracle():
+    sd = synth_vocos_state_dict(0)
+    voc = Vocos().load_state_dict(sd).to("cuda").eval()
+    mel = _mel(2, 150, 1)
+    got = voc.decode(mel.cuda())
+    want = ao.vocos_decode(sd, mel)
+    assert got.shape == want.shape == (2, 256 * 149)
+    r, m = rel_l2(got, want), float((got.cpu() - want).abs().max())
+    print(f"vocoder decode: rel-L2 {r:.2e}, max-abs {m:.2e} (rms {float(want.square().mean().sqrt()):.3f})")
+    assert r < VOC_REL and m < VOC_MAXABS * float(want.abs().max())
+
+
+def test_vocoder_ragged_batch_equals_single_utterance_decodes():
+    sd = synth_vocos_state_dict(1)
+    voc = Vocos(frame_bucket=64).load_state_dict(sd).to("cuda").eval()
+    lens = torch.tensor([333, 128, 47, 2])
+    melT = torch.zeros(4, 333, 100)
+    full = _mel(4, 333, 2).permute(0, 2, 1)
+    for i, n in enumerate(lens.tolist()):
+        melT[i, :n] = full[i, :n] * 0.1                       # feat-scaled, as model.sample returns it
+    wav, wl = voc.decode_batch(melT.cuda(), lens.cuda(), scale=10.0, clamp=True)
+    assert wl.tolist() == [(n - 1) * 256 for n in lens.tolist()]
+    for i, n in enumerate(lens.tolist()):
+        want = ao.vocos_decode(sd, (melT[i:i + 1, :n] * 10.0).permute(0, 2, 1))[0].clamp(-1, 1)
+        got = wav[i, : want.numel()].cpu()
+        assert rel_l2(got, want) < VOC_REL, (i, rel_l2(got, want))
+        assert float(wav[i, want.numel():].abs().max() if want.numel() < wav.shape[1] else 0.0) == 0.0
+    # the same utterance alone (another plan shape) gives the same samples as inside the batch
+    alone, _ = voc.decode_batch(melT[1:2, :128].cuda(), lens[1:2].cuda(), scale=10.0, clamp=True)
+    assert float((alone[0] - wav[1, : alone.shape[1]]).abs().max()) < 2e-3
+
+
+def test_vocoder_full_pipeline_shapes():
+    """wav -> fbank -> (identity sampler stand-in) -> vocoder: the glue a caller writes (infer_zipvoice.py:372-409)."""
+    fe = VocosFbank()
+    voc = Vocos().load_state_dict(synth_vocos_state_dict(2)).to("cuda")
+    g = torch.Generator().manual_seed(4)
+    wav = torch.randn(1, 24000, generator=g) * 0.05
+    feats = fe.extract(wav, 24000).unsqueeze(0) * 0.1          # (1, T, 100) feat-scaled
+    out = voc.decode((feats / 0.1).permute(0, 2, 1)).clamp(-1, 1)
+    assert out.shape == (1, 256 * (feats.shape[1] - 1)) and torch.isfinite(out).all()

@@ -10,8 +10,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # ZVB_LIB: an alternative in-tree build of the same sources (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("ZVB_LIB") or os.path.join(HERE, "libzipvoice_b200.so")
 
-ZVB_ABI_VERSION = 4
+ZVB_ABI_VERSION = 5
 ZVB_MAX_STACKS = 8
+ZVB_VOC_MAX_LAYERS = 16
 
 
 class ZvbError(RuntimeError):
@@ -52,6 +53,19 @@ class zvb_model(C.Structure):
                 ("stacks", zvb_stack * ZVB_MAX_STACKS), ("layers", C.POINTER(zvb_layer))]
 
 
+class zvb_voc_layer(C.Structure):
+    _fields_ = [("dw_w", C.c_void_p), ("dw_b", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
+                ("pw1", zvb_linear), ("pw2", zvb_linear)]
+
+
+class zvb_vocoder(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("dim", C.c_int32), ("intermediate", C.c_int32), ("n_layers", C.c_int32),
+                ("n_mels", C.c_int32), ("n_fft", C.c_int32), ("hop", C.c_int32), ("kernel", C.c_int32),
+                ("embed", zvb_linear), ("norm_w", C.c_void_p), ("norm_b", C.c_void_p),
+                ("layers", zvb_voc_layer * ZVB_VOC_MAX_LAYERS), ("final_w", C.c_void_p), ("final_b", C.c_void_p),
+                ("head", zvb_linear), ("window", C.c_void_p)]
+
+
 class zvb_io(C.Structure):
     _fields_ = [("xin", C.c_void_p), ("t", C.c_void_p), ("g", C.c_void_p), ("mask", C.c_void_p),
                 ("out", C.c_void_p), ("xin_pitch", C.c_int32)]
@@ -73,6 +87,20 @@ EXPORTS = {
                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "zvb_decoder_forward_f32": (C.c_int, [C.c_void_p] * 7),
     "zvb_sample": (C.c_int, [C.c_void_p] * 8 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    "zvb_fbank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                            C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
+    "zvb_vocoder_workspace_bytes": (C.c_int, [C.POINTER(zvb_vocoder), C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "zvb_vocoder_create": (C.c_int, [C.POINTER(zvb_vocoder), C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                     C.POINTER(C.c_void_p)]),
+    "zvb_vocoder_destroy": (None, [C.c_void_p]),
+    "zvb_vocoder_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
+    "zvb_vocoder_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.POINTER(C.c_int)]),
+    "zvb_test_dwconv_linear": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]),
+    "zvb_test_layernorm": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
+    "zvb_test_linear_masked": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "zvb_test_istft": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]),
     "zvb_test_linear": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_int, C.c_void_p]),

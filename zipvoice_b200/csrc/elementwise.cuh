@@ -237,7 +237,17 @@ upsample_combine_kernel(const __half* __restrict__ orig, const __half* __restric
 // 64-channel group's taps staged once.  Thread = one channel pair x 16 consecutive frames with the
 // 16+K-1 input window in registers as packed fp32x2: one FFMA2 advances both channels.
 constexpr int DW_TT = 128;     // frames per tile
-constexpr int DW_OT = 16;      // outputs per thread
+// Outputs per thread and threads per block by tap count.  The fp32x2 window (OT + K - 1 pairs) and the OT
+// accumulators must live in registers: at K = 31 that is 62 + 32 register pairs, so the block is 128 threads
+// (two blocks per SM, 255 registers each) with 32 outputs per thread -- 31 FFMA2 per output pair against
+// (32 + 30) / 32 window loads and conversions.  (Round 1 ran 16 outputs per thread under an 80-register cap:
+// ptxas re-loaded and re-converted the window inside the tap loop, FFMA2 was 52% of the issued instructions
+// and the kernel sat at 40% of the FMA pipe, 0.24 of HBM peak.)
+template <int K> struct DwShape {
+    static constexpr int OT = K > 15 ? 32 : 16;
+    static constexpr int THREADS = 32 * (DW_TT / OT);
+};
+template <int K> constexpr int dw_threads() { return DwShape<K>::THREADS; }
 template <int K> constexpr int dw_smem_bytes() { return 2 * (DW_TT + K - 1) * 128 + K * 32 * 8 + 128 /*align*/ + 16; }
 
 // SwooshR of a channel pair (see swoosh_direct): everything but the two MUFU ops runs as FFMA2 --
@@ -265,12 +275,13 @@ __device__ __forceinline__ void swoosh_r_pair(f32x2 acc, float& o0, float& o1) {
 
 // tma_x: x viewed as (C, L, N) fp16, box = 64 channels x (DW_TT + K - 1) frames, no swizzle.
 // grid = (blocks per channel group, channel groups); tiles = N * ceil(L / DW_TT) per channel group.
-template <int K>
-__global__ void __launch_bounds__(256, 3)
-dwconv_swooshr_kernel(const __grid_constant__ CUtensorMap tma_x, __half* __restrict__ out,
-                      const float* __restrict__ wt /*[K][C]*/, const float* __restrict__ bias, int L,
-                      int C, int N) {
-    constexpr int HALF = K / 2, WIN = DW_TT + K - 1, NW = DW_OT + K - 1;
+// ACT = 1: SwooshR (ConvolutionModule); ACT = 0: bias only (the vocoder's ConvNeXt blocks, vocoder.cuh).
+template <int K, int ACT>
+__global__ void __launch_bounds__(DwShape<K>::THREADS, 2)
+dwconv_kernel(const __grid_constant__ CUtensorMap tma_x, __half* __restrict__ out,
+              const float* __restrict__ wt /*[K][C]*/, const float* __restrict__ bias, int L,
+              int C, int N) {
+    constexpr int HALF = K / 2, WIN = DW_TT + K - 1, OT = DwShape<K>::OT, NW = OT + K - 1, THREADS = DwShape<K>::THREADS;
     extern __shared__ uint8_t dw_smem_raw[];
     const uint32_t raw = smem_u32(dw_smem_raw);
     uint8_t* smem = dw_smem_raw + (((raw + 127u) & ~127u) - raw);
@@ -282,7 +293,7 @@ dwconv_swooshr_kernel(const __grid_constant__ CUtensorMap tma_x, __half* __restr
     const int tg = threadIdx.x >> 5;
     const int n_tt = (L + DW_TT - 1) / DW_TT;
     const int total = N * n_tt;
-    for (int idx = threadIdx.x; idx < K * 32; idx += 256) {
+    for (int idx = threadIdx.x; idx < K * 32; idx += THREADS) {
         const int k = idx >> 5, q = idx & 31;
         const int c = c0 + 2 * q;
         wsm[idx] = c < C ? make_float2(__ldg(wt + k * C + c), __ldg(wt + k * C + c + 1)) : make_float2(0.f, 0.f);
@@ -313,30 +324,31 @@ dwconv_swooshr_kernel(const __grid_constant__ CUtensorMap tma_x, __half* __restr
                         nxt / n_tt);
         }
         mbar_wait(&bar[buf], (it >> 1) & 1u);
-        const uint32_t* tb = tile + buf * (WIN * 32) + (tg * DW_OT) * 32 + cp;
+        const uint32_t* tb = tile + buf * (WIN * 32) + (tg * OT) * 32 + cp;
         f32x2 win[NW];                          // the input window of the channel pair, fp32x2 packed
 #pragma unroll
         for (int q = 0; q < NW; ++q) {
             const uint32_t u = tb[q * 32];
             win[q] = pack2(h2_lo(u), h2_hi(u));
         }
-        f32x2 acc[DW_OT];
+        f32x2 acc[OT];
 #pragma unroll
-        for (int o = 0; o < DW_OT; ++o) acc[o] = b2;
+        for (int o = 0; o < OT; ++o) acc[o] = b2;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const f32x2 w = *reinterpret_cast<const f32x2*>(&wsm[k * 32 + cp]);
 #pragma unroll
-            for (int o = 0; o < DW_OT; ++o) acc[o] = fma2(w, win[o + k], acc[o]);     // one FFMA2 = both channels
+            for (int o = 0; o < OT; ++o) acc[o] = fma2(w, win[o + k], acc[o]);     // one FFMA2 = both channels
         }
         const int n = tl / n_tt;
-        const int t0 = (tl - n * n_tt) * DW_TT + tg * DW_OT;
+        const int t0 = (tl - n * n_tt) * DW_TT + tg * OT;
         __half* on = out + (static_cast<long long>(n) * L + t0) * C + c0 + 2 * cp;
         if (ch_ok) {
 #pragma unroll
-            for (int o = 0; o < DW_OT; ++o) {
+            for (int o = 0; o < OT; ++o) {
                 float a0, a1;
-                swoosh_r_pair(acc[o], a0, a1);
+                if (ACT) swoosh_r_pair(acc[o], a0, a1);
+                else unpack2(acc[o], a0, a1);
                 if (t0 + o < L) *reinterpret_cast<uint32_t*>(on + static_cast<long long>(o) * C) = pack_h2(a0, a1);
             }
         }

@@ -20,6 +20,7 @@
 #include "gemm.cuh"
 namespace zvb { constexpr int ACT_SWOOSH_R_ = 2; }
 #include "elementwise.cuh"
+#include "audio.cuh"
 
 using namespace zvb;
 typedef __half h16;
@@ -74,7 +75,7 @@ static int g_tma_store_ok = 1;
 static int g_wide_pref = 1;       // ZVB_WIDE_PREF=0: exact-fit tile widths first
 static int g_bn192 = 0;           // ZVB_BN192=1: 192-column tiles for short-K GEMMs (measured: no gain)
 static int g_layout_ok = 1;       // ZVB_NO_LAYOUT=1 keeps the default operand-ring / aux split everywhere
-static int g_attn_tc = 1;         // ZVB_ATTN_V2=1: attention weights with the CUDA-core rel-pos bias (attn.cuh)
+static int g_attn_tc = 0;         // ZVB_ATTN_TC=1: attention weights with the tensor-core rel-pos bias (attn3.cuh; measured slower)
 static int g_fast_epi = 1;        // ZVB_NO_FAST_EPI=1: generic epilogue everywhere
 static int g_resident_ok = 0;     // ZVB_RESIDENT=1: A-stationary tile order for the K = 512 GEMMs (measured 5-8% SLOWER, profiles/gemm_resident_ab_r2.txt)
 static int g_pair_min_kb = 8;     // ZVB_PAIR_MIN_KB: fewest k-blocks for which a CTA pair is used    // ZVB_NO_TMA_STORE=1 keeps the epilogue on per-thread stores
@@ -110,7 +111,7 @@ static int init_device() {
         if (const char* e = getenv("ZVB_NO_PDL")) g_pdl = atoi(e) == 0;
         if (const char* e = getenv("ZVB_RESIDENT")) g_resident_ok = atoi(e) != 0;
         if (const char* e = getenv("ZVB_NO_FAST_EPI")) g_fast_epi = atoi(e) == 0;
-        if (const char* e = getenv("ZVB_ATTN_V2")) g_attn_tc = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_ATTN_TC")) g_attn_tc = atoi(e) != 0;
         if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
         if (const char* e = getenv("ZVB_WIDE_PREF")) g_wide_pref = atoi(e) != 0;
         void* fn = nullptr;
@@ -125,13 +126,15 @@ static int init_device() {
     ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 1>)); ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 2>));
     ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 1>)); ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 2>));
     ZVB_SMEM_ATTR((gemm_kernel<EPI_GATED, ACT_NONE, 1>));      ZVB_SMEM_ATTR((gemm_kernel<EPI_GATED, ACT_NONE, 2>));
+    ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_GELU, 1>));     ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_GELU, 2>));
 #undef ZVB_SMEM_ATTR
     CUDA_TRY(cudaFuncSetAttribute(attn_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(attn_weights_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_swooshr_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_swooshr_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<9>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_swooshr_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<15>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_swooshr_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<31>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<9, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<9>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<15, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<15>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<31, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<31>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
     g_dev_sms[dev] = prop.multiProcessorCount;
     g_num_sms = prop.multiProcessorCount;
     return 0;
@@ -177,7 +180,8 @@ static int make_tmap_plain(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_
 }
 
 // ------------------------------------------------------------------------------------------ ops
-enum OpType { OP_GEMM, OP_ATTN, OP_ATTN_TC, OP_BIASNORM, OP_PREP, OP_DOWN, OP_UP, OP_DWCONV, OP_MASK, OP_MASKW, OP_TSEMB, OP_SMALL };
+enum OpType { OP_GEMM, OP_ATTN, OP_ATTN_TC, OP_BIASNORM, OP_PREP, OP_DOWN, OP_UP, OP_DWCONV, OP_MASK, OP_MASKW, OP_TSEMB, OP_SMALL,
+              OP_LAYERNORM, OP_VOC_MASK, OP_VOC_WINDOW, OP_ISTFT_FRAMES, OP_OLA };
 
 struct Op {
     OpType type;
@@ -270,6 +274,7 @@ struct LinearEpi {
     int out_mode = OUT_H16;
     int t_L = 0, t_pitch = 0, t_batch_rows = 0, t_hd = 1, t_hp = 1;   // OUT_T_H16
     int block_n = 0;                     // 0 = choose
+    const uint8_t* row_mask = nullptr;   // rows with mask != 0 are written as zeros (generic epilogue)
 };
 
 // Decides whether the op runs as 2-CTA clusters with a multicast B tile, and the persistent grid.
@@ -359,6 +364,7 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
     p.rowbias = e.rowbias; p.rows_per_group = e.rows_per_group; p.ld_rowbias = lin.out_features;
     p.bypass_scale = e.bypass_scale;
     p.act = e.act;
+    p.row_mask = e.row_mask;
     p.t_L = e.t_L; p.t_pitch = e.t_pitch; p.t_batch_rows = e.t_batch_rows; p.t_hd = e.t_hd; p.t_hp = e.t_hp;
     set_grid(op);
     TRY(make_tmap(&op.ma, A, K, M, 1, (uint64_t)lda * 2, (uint64_t)lda * 2 * M, GEMM_BLOCK_M));
@@ -539,10 +545,11 @@ static Op mask_words_op(const uint8_t* mask, uint32_t* out, int N, int L) {
     return op;
 }
 
-static int build_dwconv(Op& d, const h16* x, h16* out, const float* w, const float* b, int N, int L, int C, int K) {
+static int build_dwconv(Op& d, const h16* x, h16* out, const float* w, const float* b, int N, int L, int C, int K, int act = 1) {
     d = Op();
     d.type = OP_DWCONV; d.p0 = x; d.o0 = out; d.f0 = w; d.f1 = b;
-    d.i0 = N; d.i1 = L; d.i2 = C; d.i3 = K;
+    d.i0 = N; d.i1 = L; d.i2 = C; d.i3 = K; d.i4 = act;
+    if (act == 0 && K != 7) return fail(ZVB_ERR_INVALID, "dwconv without activation is built for 7 taps only");
     if (K != 7 && K != 9 && K != 15 && K != 31)
         return fail(ZVB_ERR_INVALID, "depthwise kernel size %d not built (7, 9, 15, 31)", K);
     if (C % 8 != 0) return fail(ZVB_ERR_INVALID, "dwconv: channels must be a multiple of 8");
@@ -555,16 +562,16 @@ static int build_dwconv(Op& d, const h16* x, h16* out, const float* w, const flo
     return 0;
 }
 
-template <int K>
+template <int K, int ACT = 1>
 static void launch_dwconv(const Op& op, cudaStream_t st) {
     const int N = op.i0, L = op.i1, C = op.i2;
     const int groups = (C + 63) / 64;
     const int tiles = N * ((L + DW_TT - 1) / DW_TT);
-    int per_group = (3 * g_num_sms) / groups;            // 3 resident blocks per SM
+    int per_group = (2 * g_num_sms) / groups;            // 2 resident blocks per SM
     if (per_group < 1) per_group = 1;
     if (per_group > tiles) per_group = tiles;
     dim3 grid(per_group, groups);
-    launch_k(dwconv_swooshr_kernel<K>, dim3(grid), dim3(256), dw_smem_bytes<K>(), st, op.ma, (h16*)op.o0, op.f0, op.f1, L, C, N);
+    launch_k(dwconv_kernel<K, ACT>, dim3(grid), dim3(dw_threads<K>()), dw_smem_bytes<K>(), st, op.ma, (h16*)op.o0, op.f0, op.f1, L, C, N);
 }
 
 static int launch_op(const Op& op, cudaStream_t st) {
@@ -585,7 +592,7 @@ static int launch_op(const Op& op, cudaStream_t st) {
             attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = g_pdl ? 2 : 1;
-            const int sel = (op.kind == EPI_GATED ? 3 : op.gp.act) * 2 + (op.cluster - 1);
+            const int sel = (op.kind == EPI_GATED ? 4 : op.gp.act) * 2 + (op.cluster - 1);
             cudaError_t e = cudaSuccess;
             switch (sel) {
                 case 0: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 1>, op.ma, op.mb, mx, ms, mo, op.gp); break;
@@ -594,7 +601,9 @@ static int launch_op(const Op& op, cudaStream_t st) {
                 case 3: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 2>, op.ma, op.mb, mx, ms, mo, op.gp); break;
                 case 4: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 1>, op.ma, op.mb, mx, ms, mo, op.gp); break;
                 case 5: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 2>, op.ma, op.mb, mx, ms, mo, op.gp); break;
-                case 6: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 1>, op.ma, op.mb, mx, ms, mo, op.gp); break;
+                case 6: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_GELU, 1>, op.ma, op.mb, mx, ms, mo, op.gp); break;
+                case 7: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_GELU, 2>, op.ma, op.mb, mx, ms, mo, op.gp); break;
+                case 8: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 1>, op.ma, op.mb, mx, ms, mo, op.gp); break;
                 default: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 2>, op.ma, op.mb, mx, ms, mo, op.gp); break;
             }
             if (e != cudaSuccess) return fail(ZVB_ERR_CUDA, "launch gemm: %s", cudaGetErrorString(e));
@@ -642,7 +651,8 @@ static int launch_op(const Op& op, cudaStream_t st) {
         }
         case OP_DWCONV: {
             const int K = op.i3;
-            if (K == 7) launch_dwconv<7>(op, st);
+            if (K == 7 && op.i4 == 0) launch_dwconv<7, 0>(op, st);
+            else if (K == 7) launch_dwconv<7>(op, st);
             else if (K == 9) launch_dwconv<9>(op, st);
             else if (K == 15) launch_dwconv<15>(op, st);
             else if (K == 31) launch_dwconv<31>(op, st);
@@ -670,6 +680,37 @@ static int launch_op(const Op& op, cudaStream_t st) {
             launch_k(small_linear_kernel, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, st, 
                 op.f0, op.f1, op.f2, op.f3, (float*)op.o0, op.i0, op.i1, op.i2, op.i3, op.i4);
             return check_launch("small_linear");
+        }
+        case OP_LAYERNORM: {
+            const int blocks = static_cast<int>((op.rows + 7) / 8);
+            launch_k(layernorm_kernel<4>, dim3(blocks), dim3(256), 0, st, (const h16*)op.p0, (h16*)op.o0, op.f0, op.f1,
+                     (const uint8_t*)op.p1, op.rows, op.i0, op.w[0]);
+            return check_launch("layernorm");
+        }
+        case OP_VOC_MASK: {
+            const int n = op.i0 * op.i1;
+            launch_k(voc_mask_kernel, dim3((n + 255) / 256), dim3(256), 0, st, (const int*)op.p0, (uint8_t*)op.o0, op.i0, op.i1);
+            return check_launch("voc_mask");
+        }
+        case OP_VOC_WINDOW: {
+            const long long n = (long long)op.i0 * op.i1 * op.i4;
+            launch_k(voc_window_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const float*)op.p0, (const int*)op.p1,
+                     (h16*)op.o0, op.i0, op.i1, op.i2, op.i3, op.i4, op.w[0]);
+            return check_launch("voc_window");
+        }
+        case OP_ISTFT_FRAMES: {
+            long long blocks = op.rows < 8LL * g_num_sms ? op.rows : 8LL * g_num_sms;
+            if (blocks < 1) blocks = 1;
+            launch_k(voc_istft_frames_kernel, dim3((unsigned)blocks), dim3(AUD_THREADS), (size_t)AUD_FFT_SMEM, st, (const float*)op.p0,
+                     op.i0, (const uint8_t*)op.p1, op.f0, (float*)op.o0, op.rows);
+            return check_launch("voc_istft_frames");
+        }
+        case OP_OLA: {
+            const long long n = (long long)op.i0 * op.i2 * (op.i1 - 1);
+            if (n <= 0) return 0;
+            launch_k(voc_overlap_add_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const float*)op.p0,
+                     (const int*)op.p1, op.f0, (float*)op.o0, op.i0, op.i1, op.i2, op.i5);
+            return check_launch("voc_overlap_add");
         }
     }
     return fail(ZVB_ERR_INVALID, "unknown op");
@@ -951,6 +992,99 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------ vocoder plan (§8 f1)
+struct zvb_vocoder_plan {
+    int N = 0, T = 0, n_mels = 0, hop = 0;
+    std::vector<Op> ops;
+    int i_mask = -1, i_window = -1, i_ola = -1;      // ops whose operands are the call's own buffers
+};
+
+// ops of one `vocoder.decode` over N utterances of <= T frames; with ws == nullptr only measures the workspace
+static int build_vocoder(const zvb_vocoder* v, int N, int T, void* ws, size_t* bytes_out, zvb_vocoder_plan* plan) {
+    if (v == nullptr || v->abi_version != ZVB_ABI_VERSION) return fail(ZVB_ERR_INVALID, "vocoder description: ABI version mismatch");
+    if (N <= 0 || T <= 1) return fail(ZVB_ERR_INVALID, "vocoder: N must be positive and T at least 2");
+    if (v->n_fft != AUD_NFFT || v->kernel != 7) return fail(ZVB_ERR_INVALID, "vocoder: built for n_fft 1024 and 7-tap convolutions");
+    if (v->dim % 256 != 0 || v->dim > 1024) return fail(ZVB_ERR_INVALID, "vocoder: dim %d unsupported (multiple of 256, <= 1024)", v->dim);
+    if (v->n_layers <= 0 || v->n_layers > ZVB_VOC_MAX_LAYERS) return fail(ZVB_ERR_INVALID, "vocoder: bad layer count");
+    if (v->hop <= 0 || AUD_NFFT % v->hop != 0) return fail(ZVB_ERR_INVALID, "vocoder: hop must divide n_fft");
+    if (v->head.out_features != AUD_NFFT + 2) return fail(ZVB_ERR_INVALID, "vocoder: head must have n_fft + 2 outputs");
+    const int D = v->dim, I = v->intermediate;
+    const long long M = (long long)N * T;
+    const int ldA = v->embed.k_pitch;
+    if (ldA < v->kernel * v->n_mels || ldA % 8 != 0) return fail(ZVB_ERR_INVALID, "vocoder: embed pitch %d too small", ldA);
+    const int ldS = (AUD_NFFT + 2 + 3) / 4 * 4;
+    Carver c(ws);
+    uint8_t* mask = c.take<uint8_t>(M);
+    h16* A0 = c.take<h16>(M * ldA);
+    h16* X[2] = {c.take<h16>(M * D), c.take<h16>(M * D)};
+    h16* Y = c.take<h16>(M * D);
+    h16* Y2 = c.take<h16>(M * D);
+    h16* Hd = c.take<h16>(M * I);
+    float* S = c.take<float>(M * ldS);
+    float* frames = c.take<float>(M * AUD_NFFT);
+    if (bytes_out) *bytes_out = (c.off + 255) & ~static_cast<size_t>(255);
+    if (ws == nullptr) return 0;
+    plan->N = N; plan->T = T; plan->n_mels = v->n_mels; plan->hop = v->hop;
+    std::vector<Op>& ops = plan->ops;
+    auto ln_op = [&](const h16* x, h16* out, const float* w, const float* b, const uint8_t* m) {
+        Op o; o.type = OP_LAYERNORM; o.p0 = x; o.o0 = out; o.f0 = w; o.f1 = b; o.p1 = m; o.rows = M; o.i0 = D; o.w[0] = 1e-6f;
+        o.cat = ZVB_CAT_BIASNORM; o.work = 2.0 * 2.0 * (double)M * D;
+        return o;
+    };
+    { Op o; o.type = OP_VOC_MASK; o.o0 = mask; o.i0 = N; o.i1 = T; plan->i_mask = (int)ops.size(); ops.push_back(o); }
+    { Op o; o.type = OP_VOC_WINDOW; o.o0 = A0; o.i0 = N; o.i1 = T; o.i2 = v->n_mels; o.i3 = v->kernel; o.i4 = ldA; o.w[0] = 1.0f;
+      o.cat = ZVB_CAT_ELEMENTWISE; o.work = (double)M * (v->n_mels * 4.0 + ldA * 2.0);
+      plan->i_window = (int)ops.size(); ops.push_back(o); }
+    { Op op; LinearEpi e; TRY(build_linear(op, A0, M, ldA, v->embed, Y, D, e)); ops.push_back(op); }
+    ops.push_back(ln_op(Y, X[0], v->norm_w, v->norm_b, mask));
+    int cur = 0;
+    for (int l = 0; l < v->n_layers; ++l) {
+        const zvb_voc_layer& ly = v->layers[l];
+        { Op d; TRY(build_dwconv(d, X[cur], Y, ly.dw_w, ly.dw_b, N, T, D, v->kernel, 0)); ops.push_back(d); }
+        ops.push_back(ln_op(Y, Y2, ly.ln_w, ly.ln_b, nullptr));
+        { Op op; LinearEpi e; e.act = ACT_GELU; TRY(build_linear(op, Y2, M, D, ly.pw1, Hd, I, e)); ops.push_back(op); }
+        { Op op; LinearEpi e; e.resid = X[cur]; e.row_mask = mask;
+          TRY(build_linear(op, Hd, M, I, ly.pw2, X[cur ^ 1], D, e)); ops.push_back(op); }
+        cur ^= 1;
+    }
+    ops.push_back(ln_op(X[cur], Y2, v->final_w, v->final_b, nullptr));
+    { Op op; LinearEpi e; e.out_mode = OUT_F32; TRY(build_linear(op, Y2, M, D, v->head, S, ldS, e)); ops.push_back(op); }
+    { Op o; o.type = OP_ISTFT_FRAMES; o.p0 = S; o.i0 = ldS; o.p1 = mask; o.f0 = v->window; o.o0 = frames; o.rows = M;
+      o.cat = ZVB_CAT_OTHER; o.work = (double)M * (ldS + AUD_NFFT) * 4.0; ops.push_back(o); }
+    { Op o; o.type = OP_OLA; o.p0 = frames; o.f0 = v->window; o.i0 = N; o.i1 = T; o.i2 = v->hop; o.i5 = 0;
+      o.cat = ZVB_CAT_OTHER; o.work = (double)M * AUD_NFFT * 4.0 + (double)N * v->hop * (T - 1) * 4.0;
+      plan->i_ola = (int)ops.size(); ops.push_back(o); }
+    return 0;
+}
+
+// one CUDA event pair per op (synchronises): shared by zvb_decoder_profile / zvb_vocoder_profile
+static int profile_ops(const std::vector<Op>& ops, cudaStream_t st, int max_ops, float* ms, int* category, double* work,
+                       double* bytes, int* shapes, int* num_ops) {
+    const int n = static_cast<int>(ops.size());
+    *num_ops = n;
+    if (n > max_ops) return fail(ZVB_ERR_INVALID, "profile buffers too small: %d ops", n);
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaEventRecord(ev[0], st));
+    int rc = 0;
+    for (int i = 0; i < n && rc == 0; ++i) {
+        rc = launch_op(ops[i], st);
+        if (rc == 0 && cudaEventRecord(ev[i + 1], st) != cudaSuccess) rc = fail(ZVB_ERR_CUDA, "event record");
+    }
+    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(ZVB_ERR_CUDA, "profile: stream sync failed");
+    for (int i = 0; i < n && rc == 0; ++i) {
+        cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+        category[i] = ops[i].cat;
+        work[i] = ops[i].work;
+        if (bytes != nullptr) bytes[i] = ops[i].bytes > 0.0 ? ops[i].bytes : ops[i].work;
+        if (shapes != nullptr)
+            for (int k = 0; k < 4; ++k) shapes[4 * i + k] = ops[i].shape[k];
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -1016,29 +1150,7 @@ int zvb_decoder_profile(zvb_plan* plan, void* stream, int max_ops, float* ms, in
                         double* bytes, int* shapes, int* num_ops) {
     if (plan == nullptr || ms == nullptr || category == nullptr || work == nullptr || num_ops == nullptr)
         return fail(ZVB_ERR_INVALID, "null argument");
-    const int n = static_cast<int>(plan->ops.size());
-    *num_ops = n;
-    if (n > max_ops) return fail(ZVB_ERR_INVALID, "profile buffers too small: %d ops", n);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    std::vector<cudaEvent_t> ev(n + 1);
-    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
-    CUDA_TRY(cudaEventRecord(ev[0], st));
-    int rc = 0;
-    for (int i = 0; i < n && rc == 0; ++i) {
-        rc = launch_op(plan->ops[i], st);
-        if (rc == 0 && cudaEventRecord(ev[i + 1], st) != cudaSuccess) rc = fail(ZVB_ERR_CUDA, "event record");
-    }
-    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(ZVB_ERR_CUDA, "profile: stream sync failed");
-    for (int i = 0; i < n && rc == 0; ++i) {
-        cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
-        category[i] = plan->ops[i].cat;
-        work[i] = plan->ops[i].work;
-        if (bytes != nullptr) bytes[i] = plan->ops[i].bytes > 0.0 ? plan->ops[i].bytes : plan->ops[i].work;
-        if (shapes != nullptr)
-            for (int k = 0; k < 4; ++k) shapes[4 * i + k] = plan->ops[i].shape[k];
-    }
-    for (auto& e : ev) cudaEventDestroy(e);
-    return rc;
+    return profile_ops(plan->ops, static_cast<cudaStream_t>(stream), max_ops, ms, category, work, bytes, shapes, num_ops);
 }
 
 int zvb_decoder_forward_f32(zvb_plan* plan, const float* x, const float* t, const uint8_t* mask, const float* g,
@@ -1264,6 +1376,99 @@ int zvb_test_cfg_euler(float* x, const float* v, const float* guidance, float gs
     launch_k(cfg_euler_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         x, v, guidance, gscale, ts, step, nullptr, B, per_utt, cfg);
     return check_launch("cfg_euler");
+}
+
+// ------------------------------------------------------------------------------------------ f3 / f1 entry points
+int zvb_fbank(const float* wav, const int32_t* lens, int B, int s_pitch, const float* window, const float* fb,
+              const int32_t* fb_range, int n_mels, int hop, float scale, float* out, int T, void* stream) {
+    TRY(init_device());
+    if (wav == nullptr || lens == nullptr || window == nullptr || fb == nullptr || fb_range == nullptr || out == nullptr)
+        return fail(ZVB_ERR_INVALID, "fbank: null argument");
+    if (B <= 0 || T <= 0 || n_mels <= 0 || hop <= 0 || s_pitch <= 0) return fail(ZVB_ERR_INVALID, "fbank: bad sizes");
+    const long long total = (long long)B * T;
+    long long blocks = total < 8LL * g_num_sms ? total : 8LL * g_num_sms;
+    launch_k(fbank_kernel, dim3((unsigned)blocks), dim3(AUD_THREADS), (size_t)AUD_FFT_SMEM, static_cast<cudaStream_t>(stream), wav,
+             (const int*)lens, B, s_pitch, window, fb, reinterpret_cast<const int2*>(fb_range), n_mels, hop, scale, out, T);
+    return check_launch("fbank");
+}
+
+int zvb_vocoder_workspace_bytes(const zvb_vocoder* voc, int N, int T, size_t* bytes) {
+    if (bytes == nullptr) return fail(ZVB_ERR_INVALID, "bytes is null");
+    return build_vocoder(voc, N, T, nullptr, bytes, nullptr);
+}
+
+int zvb_vocoder_create(const zvb_vocoder* voc, int N, int T, void* workspace, size_t workspace_bytes, zvb_vocoder_plan** plan) {
+    if (plan == nullptr || workspace == nullptr) return fail(ZVB_ERR_INVALID, "null argument");
+    TRY(init_device());
+    size_t need = 0;
+    TRY(build_vocoder(voc, N, T, nullptr, &need, nullptr));
+    if (workspace_bytes < need) return fail(ZVB_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes, need);
+    zvb_vocoder_plan* p = new zvb_vocoder_plan();
+    int r = build_vocoder(voc, N, T, workspace, nullptr, p);
+    if (r != 0) { delete p; return r; }
+    *plan = p;
+    return 0;
+}
+
+void zvb_vocoder_destroy(zvb_vocoder_plan* plan) { delete plan; }
+
+int zvb_vocoder_decode(zvb_vocoder_plan* plan, const float* mel, const int32_t* lens, float scale, int clamp, float* wav,
+                       void* stream) {
+    if (plan == nullptr || mel == nullptr || lens == nullptr || wav == nullptr) return fail(ZVB_ERR_INVALID, "null argument");
+    Op& m = plan->ops[plan->i_mask];
+    m.p0 = lens;
+    Op& w = plan->ops[plan->i_window];
+    w.p0 = mel; w.p1 = lens; w.w[0] = scale;
+    Op& o = plan->ops[plan->i_ola];
+    o.p1 = lens; o.o0 = wav; o.i5 = clamp;
+    for (const Op& op : plan->ops) TRY(launch_op(op, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int zvb_vocoder_profile(zvb_vocoder_plan* plan, void* stream, int max_ops, float* ms, int* category, double* work,
+                        double* bytes, int* num_ops) {
+    if (plan == nullptr || ms == nullptr || category == nullptr || work == nullptr || num_ops == nullptr)
+        return fail(ZVB_ERR_INVALID, "null argument");
+    if (plan->ops[plan->i_window].p0 == nullptr) return fail(ZVB_ERR_INVALID, "vocoder profile: call zvb_vocoder_decode once first");
+    return profile_ops(plan->ops, static_cast<cudaStream_t>(stream), max_ops, ms, category, work, bytes, nullptr, num_ops);
+}
+
+int zvb_test_dwconv_linear(const void* x, void* out, const float* wt, const float* bias, int N, int L, int C, int K,
+                           void* stream) {
+    TRY(init_device());
+    Op d;
+    TRY(build_dwconv(d, (const h16*)x, (h16*)out, wt, bias, N, L, C, K, 0));
+    return launch_op(d, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_layernorm(const void* x, void* out, const float* w, const float* b, const uint8_t* mask, long long rows, int C,
+                       float eps, void* stream) {
+    TRY(init_device());
+    if (C % 256 != 0 || C > 1024) return fail(ZVB_ERR_INVALID, "layernorm: C must be a multiple of 256, <= 1024");
+    Op o; o.type = OP_LAYERNORM; o.p0 = x; o.o0 = out; o.f0 = w; o.f1 = b; o.p1 = mask; o.rows = rows; o.i0 = C; o.w[0] = eps;
+    return launch_op(o, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_linear_masked(const void* A, int M, int K, int lda, const void* W, const float* bias, int n_out, int k_pitch,
+                           int act, const void* resid, const uint8_t* row_mask, void* out, int ldc, void* stream) {
+    TRY(init_device());
+    zvb_linear lin{W, bias, n_out, K, k_pitch, n_out};
+    Op op; LinearEpi e; e.act = act; e.resid = (const h16*)resid; e.row_mask = row_mask;
+    TRY(build_linear(op, (const h16*)A, M, lda, lin, out, ldc, e));
+    return launch_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int zvb_test_istft(const float* S, int ld, const int32_t* lens, const float* window, float* frames, uint8_t* mask, float* wav,
+                   int N, int T, int hop, int clamp, void* stream) {
+    TRY(init_device());
+    if (T < 2 || hop <= 0 || AUD_NFFT % hop != 0 || ld < AUD_NFFT + 2) return fail(ZVB_ERR_INVALID, "istft: bad sizes");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    { Op o; o.type = OP_VOC_MASK; o.p0 = lens; o.o0 = mask; o.i0 = N; o.i1 = T; TRY(launch_op(o, st)); }
+    { Op o; o.type = OP_ISTFT_FRAMES; o.p0 = S; o.i0 = ld; o.p1 = mask; o.f0 = window; o.o0 = frames; o.rows = (long long)N * T;
+      TRY(launch_op(o, st)); }
+    { Op o; o.type = OP_OLA; o.p0 = frames; o.p1 = lens; o.f0 = window; o.o0 = wav; o.i0 = N; o.i1 = T; o.i2 = hop; o.i5 = clamp;
+      TRY(launch_op(o, st)); }
+    return 0;
 }
 
 }  // extern "C"

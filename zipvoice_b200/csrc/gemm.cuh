@@ -53,7 +53,7 @@ constexpr int GEMM_EPI_WARPS = 16;
 constexpr int GEMM_TMEM_COLS = 512;
 
 enum { EPI_LINEAR = 0, EPI_GATED = 1 };
-enum { ACT_NONE = 0, ACT_SWOOSH_L = 1, ACT_SWOOSH_R = 2 };
+enum { ACT_NONE = 0, ACT_SWOOSH_L = 1, ACT_SWOOSH_R = 2, ACT_GELU = 3 };
 enum { GATE_TANH_SX = 1, GATE_GLU_XS = 2 };
 enum { AUX_NONE = 0, AUX_ADD_H16 = 1, AUX_MUL_H16 = 2 };      // tile operand: residual (added) / gate (multiplied)
 enum { OUT_H16 = 0, OUT_F32 = 1, OUT_T_H16 = 3 };
@@ -106,6 +106,7 @@ struct GemmParams {
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == ACT_SWOOSH_L) return swoosh_l(v);
     if (act == ACT_SWOOSH_R) return swoosh_r(v);
+    if (act == ACT_GELU) return gelu_erf(v);
     return v;
 }
 
@@ -646,6 +647,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         } else if (ACT == ACT_SWOOSH_R) {
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) swoosh_x2_group<4>(v2 + j, SWOOSH_R_C, SWOOSH_R_K0);
+                        } else if (ACT == ACT_GELU) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float g0, g1;
+                                unpack2(v2[j], g0, g1);
+                                v2[j] = pack2(gelu_erf(g0), gelu_erf(g1));
+                            }
                         }
                         if (kcount >= depth) {
                             const uint32_t kd = kcount - depth;
@@ -797,6 +805,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         } else if (ACT == ACT_SWOOSH_R) {
 #pragma unroll
                             for (int i = 0; i < 32; i += 2) swoosh_direct2(v[i], v[i + 1], SWOOSH_R_C, SWOOSH_R_K0);
+                        } else if (ACT == ACT_GELU) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
                         }
                         if (p.aux_mode == AUX_ADD_H16) {
 #pragma unroll
@@ -834,6 +845,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                 o = h2_lo(o4.w); v[8 * j + 6] = fmaf(v[8 * j + 6] - o, s1.z, o);
                                 o = h2_hi(o4.w); v[8 * j + 7] = fmaf(v[8 * j + 7] - o, s1.w, o);
                             }
+                        }
+                        if (masked) {                  // frames past the utterance: the row is zero (vocoder, audio.cuh)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
                         }
                         if (p.tma_store) {             // stage into the (swizzled) TMA box, own row only
                             wait_sfree();              // earlier stores no longer read what is overwritten

@@ -490,6 +490,8 @@ __device__ __forceinline__ void swoosh_x2_group(f32x2* v, float c, float k0) {
         v[i] = fma2_o(pack2(fabsf(z0), fabsf(z1)), pack2(0.5f / L2E, 0.5f / L2E), q[i]);
     }
 }
+// exact GELU, 0.5 x (1 + erf(x / sqrt 2)) (the vocoder's ConvNeXt blocks: torch.nn.GELU default)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 constexpr float SWOOSH_L_C = 4.0f, SWOOSH_L_K0 = -(0.08f * 4.0f + 0.035f);
 constexpr float SWOOSH_R_C = 1.0f, SWOOSH_R_K0 = -(0.08f * 1.0f + 0.313261687f);
 __device__ __forceinline__ float swoosh_l(float x) {
