@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 # fp32 FFT + fp32 filterbank on both sides: the log of a mel bin ~60 dB under the frame energy moves by ~1e-4
 LOGMEL_ATOL = 2e-3
 # 16-bit backbone (fp16 operands, fp32 accumulate), fp32 inverse STFT: thresholds on the waveform
-VOC_REL, VOC_MAXABS = 1.5e-2, 4e-2
+VOC_REL, VOC_MAXABS = 6e-3, 1e-2          # measured on B200: 1.9e-3 / 0.9e-2 of the peak -> see BASELINE.md
 
 
 @pytest.mark.parametrize("name", ["fbank_mono", "fbank_stereo", "fbank_short"])
@@ -66,6 +66,7 @@ def test_speaker_cache():
     assert cache.get("a")[1] is fa and cache.hits == 1       # served from the cache, no re-extraction
     toks, feats, lens, rms = cache.batch(["a", "b"])
     assert feats.shape[0] == 2 and lens.tolist() == [num_frames_for(24000), num_frames_for(12000)] and toks == [[1, 2, 3], [4]]
+    cache.get("a")                                           # "b" is now the least recently used entry
     cache.get("c", wav_a, [5])
     assert "b" not in cache and "a" in cache and len(cache) == 2     # least recently used entry dropped
     with pytest.raises(KeyError):
