@@ -20,6 +20,9 @@ call over the rank's batch.  Prints ONE JSON line (rank 0).  Extra keys of the s
   other_configs   C1 (one utterance), C2 (distill, 64 utterances, 4 steps), C4 (60 s dialog), C5 (stereo, 16
                   utterances) timed through `solver.sample` (N = 1 runs only)
   torch_gpu_baseline  the unmodified reference, eager PyTorch on cuda:0 (fp32 and bf16 autocast), informational
+  stages          the steps either side of the sampler at the same shape: prompt log-mel of 64 x 3 s
+                  host waveforms (zvb_fbank), vocoder decode of the 64 x 938 generated frames (zvb_vocoder_decode), and the
+                  whole chain waveform -> log-mel -> model.sample -> vocoder -> waveform on the host (N = 1 runs only)
 """
 from __future__ import annotations
 
@@ -298,6 +301,72 @@ def time_torch_gpu_baseline(dev):
     return res
 
 
+def time_audio_stages(dev):
+    """Prompt waveform -> log-mel (f3), generated mel -> waveform (f1), and the chain around `model.sample` with host
+    waveforms in and host waveforms out (pinned buffers, copies inside the timed region)."""
+    import torch
+    from zipvoice_b200.config import ZipVoiceConfig
+    from zipvoice_b200.frontend import VocosFbank
+    from zipvoice_b200.model import build_model
+    from zipvoice_b200.synth import synth_state_dict, synth_utterances
+    from zipvoice_b200.vocoder import Vocos, synth_vocos_state_dict
+    B, S = 64, PROMPT_FRAMES * 256
+    cfg = ZipVoiceConfig("zipvoice")
+    model = build_model(cfg, synth_state_dict(cfg, 0), dev, use_cuda_graph=True)
+    u = synth_utterances(cfg, batch=B, prompt_frames=PROMPT_FRAMES, target_frames=TARGET_FRAMES,
+                         prompt_tokens=PROMPT_TOKENS, tokens=TOKENS, seed=31)
+    gen = torch.Generator().manual_seed(32)
+    wav_host = (torch.randn(B, S, generator=gen) * 0.05).pin_memory()
+    wav_lens = torch.full((B,), S)
+    tl_host = u["target_lens"].pin_memory()
+    fe = VocosFbank(device=dev)
+    voc = Vocos(frame_bucket=1).load_state_dict(synth_vocos_state_dict(0)).to(dev)
+    out_host = torch.empty(B, 256 * (TARGET_FRAMES - 1)).pin_memory()
+    kw = dict(duration="real", num_step=NUM_STEP, guidance_scale=GUIDANCE, t_shift=T_SHIFT)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    marks = {}
+
+    def chain(record=False):
+        e = [ev() for _ in range(4)] if record else None
+        wav = wav_host.to(dev, non_blocking=True)
+        if record: e[0].record()
+        feats, frames = fe.extract_batch(wav, wav_lens, 0.1)
+        if record: e[1].record()
+        mel, lens, _, _ = model.sample(u["tokens"], u["prompt_tokens"], feats, frames, features_lens=tl_host.to(dev, non_blocking=True), **kw)
+        if record: e[2].record()
+        audio, alens = voc.decode_batch(mel, lens, scale=10.0, clamp=True)
+        if record: e[3].record()
+        out_host.copy_(audio, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if record:
+            marks.update(fbank_ms=e[0].elapsed_time(e[1]), sample_ms=e[1].elapsed_time(e[2]), vocoder_ms=e[2].elapsed_time(e[3]))
+        return frames, lens, alens
+
+    with torch.inference_mode():
+        for _ in range(2):
+            chain()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            frames, lens, alens = chain()
+        sec = (time.perf_counter() - t0) / reps
+        chain(record=True)
+    gen_frames = int(lens.sum())
+    audio_s = float(alens.sum()) / 24000.0
+    res = {"utterances": B, "prompt_seconds": S / 24000.0, "prompt_frames": int(frames[0]), "generated_frames": gen_frames,
+           "fbank_ms": marks["fbank_ms"], "sample_ms": marks["sample_ms"], "vocoder_ms": marks["vocoder_ms"],
+           "fbank_gbs": (B * S * 4 + B * int(frames[0]) * 400) / marks["fbank_ms"] / 1e6,
+           "vocoder_frames_per_s": gen_frames / marks["vocoder_ms"] * 1e3,
+           "chain_ms": sec * 1e3, "chain_frames_per_s": gen_frames / sec, "chain_rtf": sec / audio_s,
+           "h2d_bytes": wav_host.numel() * 4 + tl_host.numel() * 8, "d2h_bytes": out_host.numel() * 4,
+           "finite": bool(torch.isfinite(out_host).all()),
+           "note": "synthetic vocoder weights with the key set of vocos-mel-24khz (no checkpoint offline)"}
+    del model, voc, fe
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_strong(args, dev, rank, world, barrier, max_over_ranks):
     """Strong scaling: ONE ragged set of 512 utterances for the whole job (module docstring)."""
     import torch
@@ -527,9 +596,10 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return 0
-    other = torch_gpu = cpu_baseline = None
+    other = torch_gpu = cpu_baseline = stages = None
     if world == 1 and not args.quick:
         other = time_other_configs(dev, peaks)
+        stages = time_audio_stages(dev)
         torch_gpu = time_torch_gpu_baseline(dev)
     if world == 1 and not args.no_cpu_baseline:
         v, per, cores, kind = cpu_reference_samples(1, 0)
@@ -547,7 +617,7 @@ def run_b200(args):
                     "ms_per_step": e2e_s * 1e3 / args.steps, "rtf": e2e_s / args.steps / audio_sec},
             "gpu_launches": launches_per_sample * args.steps,
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "clocks": clock_info,
-            "finite": finite, "strong": strong, "other_configs": other, "torch_gpu_baseline": torch_gpu}
+            "finite": finite, "strong": strong, "other_configs": other, "stages": stages, "torch_gpu_baseline": torch_gpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -73,6 +73,13 @@ def main():
         print(f"  {cat:16s} n={n:4d}  {ms:8.2f} ms  {100 * ms / tot:5.1f}%   {rate / scale:9.1f} {unit}")
     if a.detail:
         det = plan.profile(shapes=True, with_bytes=True)
+        byk = collections.OrderedDict()
+        for cat, ms, work, nbytes, shp in det:
+            if cat == "dwconv_swooshr":
+                d = byk.setdefault(shp[2], [0, 0.0, 0.0])
+                d[0] += 1; d[1] += ms; d[2] += nbytes
+        for k, (n, ms, nb) in byk.items():
+            print(f"  dwconv K={k:2d}: n={n:3d} {ms:7.3f} ms  {nb / ms / 1e6:7.0f} GB/s")
         # first layer of the first stack: ops after the preamble up to the first biasnorm
         i0 = next(i for i, d in enumerate(det) if d[0] == "attn_weights") - 1
         i1 = next(i for i, d in enumerate(det) if d[0] == "biasnorm_bypass")

@@ -41,7 +41,7 @@ constexpr int A3_APRIME_BYTES = 128 * 128 * 2;      // A': 16 row groups x 16 ch
 constexpr int A3_EWIN_BYTES = 2048;                 // 128 chunks of 16 B per operand (127 used)
 constexpr int A3_ESTAGES = 2;
 constexpr int A3_PADZ = 128;                        // zero entries in front of E in the table (weights.py)
-constexpr int A3_STAGE_BYTES = 2 * 8 * 4096;        // [2 buffers][4 quarters x 2 unit pairs][32 rows x 128 B]
+constexpr int A3_STAGE_BYTES = 16 * 2 * 2048;       // [16 warps][2 buffers][32 rows x 64 B] (64-byte swizzle)
 constexpr float A3_BOUND_SLACK_L2 = 10.0f;
 constexpr int A3_SMEM_BYTES = (1 + A3_KSTAGES) * A3_TILE_BYTES + A3_APRIME_BYTES + A3_ESTAGES * 2 * A3_EWIN_BYTES +
                               A3_STAGE_BYTES + 4 * 128 * 4 + 64 + 256 + 1024 /*alignment*/;
@@ -59,6 +59,7 @@ struct Attn3Params {
     int mask_words;
     __half* P;                       // [N][H][L][Lk] (written through tma_p)
     float* inv_l;                    // [N][H][L]
+    int dbg;                         // timing ablations (ZVB_ATTN_DBG): 1 bias in both passes, 2 no bias MMAs, 4 no stores
 };
 
 // un-swizzled K-major shared-memory descriptor: LBO = byte offset between the two 16-byte K chunks of one MMA,
@@ -72,7 +73,8 @@ __device__ __forceinline__ uint64_t umma_desc_k_plain(uint32_t smem_addr, uint32
     return d;                        // layout type 0: no swizzle
 }
 
-// tma_qk: [q | k | p] rows, box 64 x 128 (128B swizzle); tma_p: P viewed as (Lk, L, N*H), box 64 columns x 32 rows.
+// tma_qk: [q | k | p] rows, box 64 x 128 (128B swizzle); tma_p: P viewed as (Lk, L, N*H), box 32 columns x 32 rows
+// (64B swizzle): every softmax warp stores its own 32 x 32 block, no barrier between warps.
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attn_weights_tc_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_constant__ CUtensorMap tma_p,
                        const Attn3Params p) {
@@ -167,8 +169,8 @@ attn_weights_tc_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_
         if (lane == 0) {
             float pmax = flag[0];
             for (int w = 1; w < A3_SM_WARPS; ++w) pmax = fmaxf(pmax, flag[w]);
-            const bool exact_max = 2.0f * pmax * emax_h > A3_BOUND_SLACK_L2;
-            const int e_first = exact_max ? 0 : num_jt;            // first iteration that needs the rel-pos window
+            const bool exact_max = 2.0f * pmax * emax_h > A3_BOUND_SLACK_L2 || (p.dbg & 1);
+            const int e_first = (p.dbg & 2) ? total_it : exact_max ? 0 : num_jt;            // first iteration that needs the rel-pos window
             const uint2* Zh = p.Z + static_cast<long long>(h) * 2 * p.LZ;
             for (int it = 0; it < total_it; ++it) {
                 const int jt = it >= num_jt ? it - num_jt : it;
@@ -194,8 +196,8 @@ attn_weights_tc_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_
         if (lane == 0) {
             float pmax = flag[0];
             for (int w = 1; w < A3_SM_WARPS; ++w) pmax = fmaxf(pmax, flag[w]);
-            const bool exact_max = 2.0f * pmax * emax_h > A3_BOUND_SLACK_L2;
-            const int e_first = exact_max ? 0 : num_jt;
+            const bool exact_max = 2.0f * pmax * emax_h > A3_BOUND_SLACK_L2 || (p.dbg & 1);
+            const int e_first = (p.dbg & 2) ? total_it : exact_max ? 0 : num_jt;
             const uint32_t idesc_s = umma_idesc_f16(A3_BN);
             const uint32_t idesc_d = umma_idesc_f16(A3_ND);
             mbar_wait(q_full, 0);
@@ -281,18 +283,18 @@ attn_weights_tc_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_
         float pmax_cta = flag[0];
 #pragma unroll
         for (int w = 1; w < A3_SM_WARPS; ++w) pmax_cta = fmaxf(pmax_cta, flag[w]);
-        const bool exact_max = 2.0f * pmax_cta * emax_h > A3_BOUND_SLACK_L2;
-        const int e_first = exact_max ? 0 : num_jt;
+        const bool exact_max = 2.0f * pmax_cta * emax_h > A3_BOUND_SLACK_L2 || (p.dbg & 1);
+        const int e_first = (p.dbg & 2) ? total_it : exact_max ? 0 : num_jt;
 
         const uint32_t* mwrow = p.maskw + static_cast<long long>(n) * p.mask_words + unit;
-        // staging: the two units of a pair (unit >> 1) fill the two 64-byte halves of the pair's 32 rows x 128 B box
-        const int pair = quarter * 2 + (unit >> 1);
-        const int bar_id = 3 + pair;                      // named barriers 3..10, 64 threads each
-        const bool issuer = (unit & 1) == 0 && lane == 0;
-        const uint32_t stage_row = smem_u32(stage_all) + static_cast<uint32_t>(pair * 4096 + lane * 128);
+        // staging: each warp owns two 2 KB buffers of 32 rows x 64 B; chunk j of row `lane` sits at j ^ ((lane >> 1) & 3)
+        // (the 64-byte swizzle of the store's tensor map: conflict-free 16-byte shared-memory writes)
+        const int qbar = 3 + quarter;                     // named barriers 3..6: the four unit warps of a quarter
+        const uint32_t stage_mine = smem_u32(stage_all) + static_cast<uint32_t>(warp * 4096);
+        uint8_t* stage_ptr = stage_all + warp * 4096;
         uint32_t chunk_off[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) chunk_off[j] = static_cast<uint32_t>(((4 * (unit & 1) + j) ^ (lane & 7)) << 4);
+        for (int j = 0; j < 4; ++j) chunk_off[j] = static_cast<uint32_t>(lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
         const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(32 * unit);
         const uint32_t dcol = static_cast<uint32_t>((32 * unit - 32 * quarter + 96) >> 1);     // multiple of 16
         const uint32_t t_de = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + A3_COL_DE + dcol;
@@ -307,7 +309,7 @@ attn_weights_tc_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_
             const bool with_bias = it >= e_first;
             if (it == num_jt) {                           // between the passes: m >= every score of the row (log2 units)
                 xch[unit * 128 + r] = m_run;
-                asm volatile("bar.sync 1, 512;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
                 const float mr = fmaxf(fmaxf(xch[r], xch[128 + r]), fmaxf(xch[256 + r], xch[384 + r]));
                 const float mb = mr == -INFINITY ? 0.f : mr;
                 m_l2 = (exact_max ? mb : mb + pn * emax_h) - 12.0f;       // weights are stored scaled by 2^12
@@ -355,14 +357,12 @@ attn_weights_tc_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_
             }
             // ---- second pass: weights of this warp's 32 columns
             const int jc = jt * A3_BN + 32 * unit;        // first key column of this warp
-            const int jpair = jt * A3_BN + 64 * (unit >> 1);
+            if (jc >= p.Lk || (p.dbg & 4)) continue;      // warp-uniform: past the padded width
             const uint32_t buf = tile2 & 1u;
-            if (jpair < p.Lk) {
-                if (issuer) bulk_wait_read<1>();          // the store that read this buffer two tiles ago is done
-                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-            }
+            if (lane == 0) bulk_wait_read<1>();           // the store that read this buffer two tiles ago is done
+            __syncwarp();
             uint32_t w[16];
-            if (jc < p.Lk) {
+            {
                 const f32x2 nm = pack2(-m_l2, -m_l2);
                 const f32x2 l2 = pack2(LOG2E, LOG2E);
 #pragma unroll
@@ -386,32 +386,26 @@ attn_weights_tc_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_
                 const uint32_t sb = hadd2(hadd2(hadd2(w[8], w[9]), hadd2(w[10], w[11])),
                                           hadd2(hadd2(w[12], w[13]), hadd2(w[14], w[15])));
                 l_run += (h2_lo(sa) + h2_hi(sa)) + (h2_lo(sb) + h2_hi(sb));
-                const uint32_t row_addr = stage_row + buf * (8u * 4096u);
+                const uint32_t row_addr = stage_mine + buf * 2048u;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     sts128_u32(row_addr + chunk_off[j], w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-            } else if (jpair < p.Lk) {          // partner unit is live, this one is past the padded width: zeros
-                const uint32_t row_addr = stage_row + buf * (8u * 4096u);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sts128_u32(row_addr + chunk_off[j], 0u, 0u, 0u, 0u);
             }
-            if (jpair < p.Lk) {
-                fence_proxy_async_smem();
-                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-                if (issuer) {
-                    tma_store_3d(&tma_p, stage_all + buf * (8 * 4096) + pair * 4096, jpair, i0 + quarter * 32, n * p.H + h);
-                    bulk_commit();
-                }
-                ++tile2;
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_3d(&tma_p, stage_ptr + buf * 2048, jc, i0 + quarter * 32, n * p.H + h);
+                bulk_commit();
             }
+            ++tile2;
         }
         xch[unit * 128 + r] = l_run;
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
         if (unit == 0 && row_ok) {
             const float l = (xch[r] + xch[128 + r]) + (xch[256 + r] + xch[384 + r]);
             p.inv_l[(static_cast<long long>(n) * p.H + h) * p.L + i] = l > 0.f ? 1.0f / l : 0.f;
         }
-        if (issuer) bulk_wait_read<0>();                  // staging must outlive the stores reading it
+        if (lane == 0) bulk_wait_read<0>();               // staging must outlive the stores reading it
     }
 
     tc_fence_before();

@@ -243,11 +243,17 @@ constexpr int DW_TT = 128;     // frames per tile
 // (32 + 30) / 32 window loads and conversions.  (Round 1 ran 16 outputs per thread under an 80-register cap:
 // ptxas re-loaded and re-converted the window inside the tap loop, FFMA2 was 52% of the issued instructions
 // and the kernel sat at 40% of the FMA pipe, 0.24 of HBM peak.)
-template <int K> struct DwShape {
-    static constexpr int OT = K > 15 ? 32 : 16;
+// MODE 0: the register-resident shape above (ZVB_DW_MODE=0); MODE 1 (default): 16 outputs per thread, 256 threads,
+// three blocks per SM under an 80-register cap.  A/B on one B200 (round 2, gpurun_out/r2b_dwab_*): K = 31 launches
+// 207-212 us (mode 0) against 197-212 us (mode 1) -- the ideal instruction mix buys nothing because both shapes
+// sit on the same limit: every FMA form issues at most 32 lanes x 1 FMA per clock and scheduler
+// (tools/microbench/fma_rates.cu: FFMA 1.05 clk, FFMA2 2.18 clk, HFMA2 2.0 clk per warp instruction), i.e.
+// 128 FMA/clk/SM, and 31 taps + SwooshR need 40 FMA per output: 0.47 of HBM peak at best for K = 31.
+template <int K, int MODE> struct DwShape {
+    static constexpr int OT = (MODE == 0 && K > 15) ? 32 : 16;
     static constexpr int THREADS = 32 * (DW_TT / OT);
+    static constexpr int MINB = MODE == 0 ? 2 : 3;
 };
-template <int K> constexpr int dw_threads() { return DwShape<K>::THREADS; }
 template <int K> constexpr int dw_smem_bytes() { return 2 * (DW_TT + K - 1) * 128 + K * 32 * 8 + 128 /*align*/ + 16; }
 
 // SwooshR of a channel pair (see swoosh_direct): everything but the two MUFU ops runs as FFMA2 --
@@ -276,12 +282,12 @@ __device__ __forceinline__ void swoosh_r_pair(f32x2 acc, float& o0, float& o1) {
 // tma_x: x viewed as (C, L, N) fp16, box = 64 channels x (DW_TT + K - 1) frames, no swizzle.
 // grid = (blocks per channel group, channel groups); tiles = N * ceil(L / DW_TT) per channel group.
 // ACT = 1: SwooshR (ConvolutionModule); ACT = 0: bias only (the vocoder's ConvNeXt blocks, vocoder.cuh).
-template <int K, int ACT>
-__global__ void __launch_bounds__(DwShape<K>::THREADS, 2)
+template <int K, int ACT, int MODE>
+__global__ void __launch_bounds__(DwShape<K, MODE>::THREADS, DwShape<K, MODE>::MINB)
 dwconv_kernel(const __grid_constant__ CUtensorMap tma_x, __half* __restrict__ out,
               const float* __restrict__ wt /*[K][C]*/, const float* __restrict__ bias, int L,
               int C, int N) {
-    constexpr int HALF = K / 2, WIN = DW_TT + K - 1, OT = DwShape<K>::OT, NW = OT + K - 1, THREADS = DwShape<K>::THREADS;
+    constexpr int HALF = K / 2, WIN = DW_TT + K - 1, OT = DwShape<K, MODE>::OT, NW = OT + K - 1, THREADS = DwShape<K, MODE>::THREADS;
     extern __shared__ uint8_t dw_smem_raw[];
     const uint32_t raw = smem_u32(dw_smem_raw);
     uint8_t* smem = dw_smem_raw + (((raw + 127u) & ~127u) - raw);

@@ -76,6 +76,7 @@ static int g_wide_pref = 1;       // ZVB_WIDE_PREF=0: exact-fit tile widths firs
 static int g_bn192 = 0;           // ZVB_BN192=1: 192-column tiles for short-K GEMMs (measured: no gain)
 static int g_layout_ok = 1;       // ZVB_NO_LAYOUT=1 keeps the default operand-ring / aux split everywhere
 static int g_attn_tc = 0;         // ZVB_ATTN_TC=1: attention weights with the tensor-core rel-pos bias (attn3.cuh; measured slower)
+static int g_dw_mode = 1;          // ZVB_DW_MODE=0: register-resident window (32 outputs / thread); measured equal, DESIGN.md §3
 static int g_fast_epi = 1;        // ZVB_NO_FAST_EPI=1: generic epilogue everywhere
 static int g_resident_ok = 0;     // ZVB_RESIDENT=1: A-stationary tile order for the K = 512 GEMMs (measured 5-8% SLOWER, profiles/gemm_resident_ab_r2.txt)
 static int g_pair_min_kb = 8;     // ZVB_PAIR_MIN_KB: fewest k-blocks for which a CTA pair is used    // ZVB_NO_TMA_STORE=1 keeps the epilogue on per-thread stores
@@ -113,6 +114,7 @@ static int init_device() {
         if (const char* e = getenv("ZVB_NO_FAST_EPI")) g_fast_epi = atoi(e) == 0;
         if (const char* e = getenv("ZVB_ATTN_TC")) g_attn_tc = atoi(e) != 0;
         if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
+        if (const char* e = getenv("ZVB_DW_MODE")) g_dw_mode = atoi(e) != 0 ? 1 : 0;
         if (const char* e = getenv("ZVB_WIDE_PREF")) g_wide_pref = atoi(e) != 0;
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -130,11 +132,16 @@ static int init_device() {
 #undef ZVB_SMEM_ATTR
     CUDA_TRY(cudaFuncSetAttribute(attn_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(attn_weights_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<9, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<9>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<15, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<15>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<31, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<31>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<9, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<9>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<9, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<9>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<15, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<15>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<15, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<15>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<31, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<31>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<31, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<31>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
     g_dev_sms[dev] = prop.multiProcessorCount;
     g_num_sms = prop.multiProcessorCount;
     return 0;
@@ -156,6 +163,22 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
     CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
                           const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ZVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+// h16 tensor, box = (32 elements = 64 bytes, box1, 1) with the 64-byte swizzle (attention-weight stores, attn3.cuh)
+static int make_tmap_sw64(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
+                          uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box1) {
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (stride1_bytes & 15) != 0 || (stride2_bytes & 15) != 0)
+        return fail(ZVB_ERR_INVALID, "tensor map: pointer/strides must be 16-byte aligned");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {32u, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ZVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
@@ -529,9 +552,10 @@ static int build_attn_tc(Op& op, const h16* qkp, int ld, const void* pos_table_t
     a.LZ = attn_tc_lz(L);
     a.emax = reinterpret_cast<const float*>(a.Z + static_cast<size_t>(H) * 2 * a.LZ);
     a.maskw = maskw; a.mask_words = attn_mask_words(L);
+    a.dbg = getenv("ZVB_ATTN_DBG") ? atoi(getenv("ZVB_ATTN_DBG")) : 0;
     if (ld % 8 != 0 || Lk % 8 != 0) return fail(ZVB_ERR_INVALID, "attn: pitches must be multiples of 8");
     TRY(make_tmap(&op.ma, qkp, ld, L, N, (uint64_t)ld * 2, (uint64_t)ld * 2 * L, A3_BM));
-    TRY(make_tmap(&op.ms, P, Lk, L, (uint64_t)N * H, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * L, 32));
+    TRY(make_tmap_sw64(&op.ms, P, Lk, L, (uint64_t)N * H, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * L, 32));
     op.has_ms = true;
     mark_out(op, 0, P, (long long)N * H * L * Lk);
     op.cat = ZVB_CAT_ATTN_WEIGHTS;
@@ -557,6 +581,7 @@ static int build_dwconv(Op& d, const h16* x, h16* out, const float* w, const flo
     TRY(make_tmap_plain(&d.ma, x, C, L, N, (uint64_t)C * 2, (uint64_t)C * 2 * L, 64, DW_TT + K - 1));
     mark_out(d, 0, out, (long long)N * L * C);
     d.cat = ZVB_CAT_DWCONV;
+    d.shape[0] = N * L; d.shape[1] = C; d.shape[2] = K; d.shape[3] = act;
     d.work = 2.0 * 2.0 * (double)N * L * C;
     d.bytes = d.work;
     return 0;
@@ -567,11 +592,15 @@ static void launch_dwconv(const Op& op, cudaStream_t st) {
     const int N = op.i0, L = op.i1, C = op.i2;
     const int groups = (C + 63) / 64;
     const int tiles = N * ((L + DW_TT - 1) / DW_TT);
-    int per_group = (2 * g_num_sms) / groups;            // 2 resident blocks per SM
+    const int minb = g_dw_mode == 0 ? DwShape<K, 0>::MINB : DwShape<K, 1>::MINB;
+    int per_group = (minb * g_num_sms) / groups;         // resident blocks per SM
     if (per_group < 1) per_group = 1;
     if (per_group > tiles) per_group = tiles;
     dim3 grid(per_group, groups);
-    launch_k(dwconv_kernel<K, ACT>, dim3(grid), dim3(dw_threads<K>()), dw_smem_bytes<K>(), st, op.ma, (h16*)op.o0, op.f0, op.f1, L, C, N);
+    if (g_dw_mode == 0)
+        launch_k(dwconv_kernel<K, ACT, 0>, dim3(grid), dim3(DwShape<K, 0>::THREADS), dw_smem_bytes<K>(), st, op.ma, (h16*)op.o0, op.f0, op.f1, L, C, N);
+    else
+        launch_k(dwconv_kernel<K, ACT, 1>, dim3(grid), dim3(DwShape<K, 1>::THREADS), dw_smem_bytes<K>(), st, op.ma, (h16*)op.o0, op.f0, op.f1, L, C, N);
 }
 
 static int launch_op(const Op& op, cudaStream_t st) {
