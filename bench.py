@@ -598,9 +598,15 @@ def run_b200(args):
         return 0
     other = torch_gpu = cpu_baseline = stages = None
     if world == 1 and not args.quick:
-        other = time_other_configs(dev, peaks)
-        stages = time_audio_stages(dev)
-        torch_gpu = time_torch_gpu_baseline(dev)
+        def guarded(fn, *a):                       # informational legs never take the headline line down with them
+            try:
+                return fn(*a)
+            except Exception as e:                  # noqa: BLE001
+                torch.cuda.empty_cache()
+                return {"error": f"{type(e).__name__}: {e}"[:300]}
+        other = guarded(time_other_configs, dev, peaks)
+        stages = guarded(time_audio_stages, dev)
+        torch_gpu = guarded(time_torch_gpu_baseline, dev)
     if world == 1 and not args.no_cpu_baseline:
         v, per, cores, kind = cpu_reference_samples(1, 0)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
