@@ -73,10 +73,12 @@ static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 static int g_cluster_ok = 1;      // ZVB_NO_CLUSTER=1 disables the CTA-pair (cta_group::2) GEMM variant
 static int g_tma_store_ok = 1;
 static int g_wide_pref = 1;       // ZVB_WIDE_PREF=0: exact-fit tile widths first
+static double g_wide_waste = 0.08; // ZVB_WIDE_WASTE: largest padding share accepted for a 256-column tile when K <= 512
 static int g_bn192 = 0;           // ZVB_BN192=1: 192-column tiles for short-K GEMMs (measured: no gain)
 static int g_layout_ok = 1;       // ZVB_NO_LAYOUT=1 keeps the default operand-ring / aux split everywhere
 static int g_attn_tc = 0;         // ZVB_ATTN_TC=1: attention weights with the tensor-core rel-pos bias (attn3.cuh; measured slower)
 static int g_dw_mode = 1;          // ZVB_DW_MODE=0: register-resident window (32 outputs / thread); measured equal, DESIGN.md §3
+static int g_fast_resid = 1;       // ZVB_NO_FAST_RESID=1: generic epilogue for the residual-stream GEMMs
 static int g_fast_epi = 1;        // ZVB_NO_FAST_EPI=1: generic epilogue everywhere
 static int g_resident_ok = 0;     // ZVB_RESIDENT=1: A-stationary tile order for the K = 512 GEMMs (measured 5-8% SLOWER, profiles/gemm_resident_ab_r2.txt)
 static int g_pair_min_kb = 8;     // ZVB_PAIR_MIN_KB: fewest k-blocks for which a CTA pair is used    // ZVB_NO_TMA_STORE=1 keeps the epilogue on per-thread stores
@@ -112,10 +114,12 @@ static int init_device() {
         if (const char* e = getenv("ZVB_NO_PDL")) g_pdl = atoi(e) == 0;
         if (const char* e = getenv("ZVB_RESIDENT")) g_resident_ok = atoi(e) != 0;
         if (const char* e = getenv("ZVB_NO_FAST_EPI")) g_fast_epi = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_NO_FAST_RESID")) g_fast_resid = atoi(e) == 0;
         if (const char* e = getenv("ZVB_ATTN_TC")) g_attn_tc = atoi(e) != 0;
         if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
         if (const char* e = getenv("ZVB_DW_MODE")) g_dw_mode = atoi(e) != 0 ? 1 : 0;
         if (const char* e = getenv("ZVB_WIDE_PREF")) g_wide_pref = atoi(e) != 0;
+        if (const char* e = getenv("ZVB_WIDE_WASTE")) g_wide_waste = atof(e);
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
         CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
@@ -250,7 +254,8 @@ static int pick_block_n(int n_out, long long m_tiles, int k_blocks) {
             const double waste = (double)tiles * bn / n_out - 1.0;
             // wider tiles move fewer operand bytes per output: a 256-column tile that wastes < 8% beats a
             // narrower exact fit (N = 1920: 8 x 256 at 962 TFLOP/s against 10 x 192 at 840)
-            if (bn == 256 && waste < 0.08 && g_wide_pref) return 256;
+            // (K <= 512, N = 1152 as 5 x 256 instead of 6 x 192 -- ZVB_WIDE_WASTE=0.12 -- measured equal within noise)
+            if (bn == 256 && waste < (k_blocks <= 8 ? g_wide_waste : 0.08) && g_wide_pref) return 256;
             if (waste < best_waste - 1e-9) { best_waste = waste; best = bn; }
         }
         if (best != 0 && best_waste < 0.08) return best;
@@ -414,6 +419,10 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
     p.fast_epi = (g_fast_epi && p.tma_store && p.aux_mode == AUX_NONE && p.out_mode == OUT_H16 && p.rowbias == nullptr &&
                   p.rowscale == nullptr && p.row_mask == nullptr && bn % 64 == 0 && lin.out_features % 32 == 0 &&
                   (reinterpret_cast<uintptr_t>(lin.b) & 15) == 0) ? 1 : 0;
+    p.fast_resid = (g_fast_resid && e.act == ACT_NONE && p.tma_store && p.aux_mode == AUX_ADD_H16 && !p.orig_tma &&
+                    p.out_mode == OUT_H16 && p.rowscale == nullptr && p.row_mask == nullptr && bn % 64 == 0 &&
+                    lin.out_features % bn == 0 && (reinterpret_cast<uintptr_t>(lin.b) & 15) == 0 &&
+                    (p.rowbias == nullptr || ((reinterpret_cast<uintptr_t>(p.rowbias) & 15) == 0 && p.ld_rowbias % 4 == 0))) ? 1 : 0;
     if (e.out_mode == OUT_H16) mark_out(op, 0, out, M * ldc);
     else if (e.out_mode == OUT_T_H16 && e.t_L > 0) mark_out(op, 0, out, (M / e.t_L) * (long long)e.t_batch_rows * e.t_pitch);
     op.shape[0] = (int)M; op.shape[1] = lin.out_features; op.shape[2] = lin.in_features; op.shape[3] = bn;
