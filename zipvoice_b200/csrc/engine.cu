@@ -422,7 +422,7 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
     p.fast_resid = (g_fast_resid && e.act == ACT_NONE && p.tma_store && p.aux_mode == AUX_ADD_H16 && !p.orig_tma &&
                     p.out_mode == OUT_H16 && p.rowscale == nullptr && p.row_mask == nullptr && bn % 64 == 0 &&
                     lin.out_features % bn == 0 && (reinterpret_cast<uintptr_t>(lin.b) & 15) == 0 &&
-                    (p.rowbias == nullptr || ((reinterpret_cast<uintptr_t>(p.rowbias) & 15) == 0 && p.ld_rowbias % 4 == 0))) ? 1 : 0;
+                    (p.rowbias == nullptr || p.rows_per_group >= GEMM_BLOCK_M)) ? 1 : 0;
     if (e.out_mode == OUT_H16) mark_out(op, 0, out, M * ldc);
     else if (e.out_mode == OUT_T_H16 && e.t_L > 0) mark_out(op, 0, out, (M / e.t_L) * (long long)e.t_batch_rows * e.t_pitch);
     op.shape[0] = (int)M; op.shape[1] = lin.out_features; op.shape[2] = lin.in_features; op.shape[3] = bn;

@@ -45,7 +45,10 @@ inline void gemm_ring(int block_n, int cluster, int ring_bytes, int* stages, int
     *stage_bytes = sb;
 }
 constexpr int GEMM_BIAS_BYTES = 16 * 64 * 4;               // per epilogue warp: bias of the unit in flight (32 columns, 2 x 32 gated)
-constexpr int GEMM_LAYOUT_BYTES = GEMM_SHARED_BUDGET + GEMM_BIAS_BYTES + 512 /*barriers*/;
+// Lean epilogues: bias (+ per-utterance row bias) of the tile in flight, [2 tile parities][2 utterances][256 columns] fp32.
+// The kernel leaves the L1 no capacity (227 KB of shared memory), so a global bias load costs an L2 round trip per unit.
+constexpr int GEMM_CBIAS_BYTES = 2 * 2 * 256 * 4;
+constexpr int GEMM_LAYOUT_BYTES = GEMM_SHARED_BUDGET + GEMM_BIAS_BYTES + GEMM_CBIAS_BYTES + 512 /*barriers*/;
 constexpr int GEMM_SMEM_BYTES = 232448;                    // all 227 KB; layout + alignment pad must fit (checked)
 static_assert(GEMM_LAYOUT_BYTES <= GEMM_SMEM_BYTES, "shared-memory layout too large");
 constexpr int GEMM_THREADS = 640;
@@ -248,7 +251,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     float* bias_smem = reinterpret_cast<float*>(aux_smem + p.aux_slots * GEMM_AUX_BYTES);      // [16 warps][64]
     const int AUX_SLOTS = p.aux_slots;
     const uint32_t dsh = static_cast<uint32_t>(p.stage_depth - 1);     // staging buffer of sub-tile k: k & dsh
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_smem) + GEMM_BIAS_BYTES);
+    float* cbias_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bias_smem) + GEMM_BIAS_BYTES);   // [2][2][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(cbias_smem) + GEMM_CBIAS_BYTES);
     if (threadIdx.x == 0 && ((smem - smem_raw) + GEMM_LAYOUT_BYTES > GEMM_SMEM_BYTES ||
                              p.ring_bytes + p.aux_slots * GEMM_AUX_BYTES > GEMM_SHARED_BUDGET)) {
         printf("zvb: gemm shared-memory layout does not fit (base misaligned by %d)\n", (int)(smem - smem_raw));
@@ -608,6 +612,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (p.rowscale != nullptr && row_ok)
                 rscale = __ldg(p.rowscale + static_cast<long long>(b * p.rs_zb + n_tile * p.rs_zn) * p.M + m);
 
+            // lean paths: the 512 epilogue threads fill this tile's bias cache (one L2 round trip per tile, requested
+            // before the accumulator wait), double buffered by tile parity; one named barrier per tile
+            uint32_t cb_addr = 0;
+            if (KIND == EPI_LINEAR && (p.fast_epi || p.fast_resid)) {
+                const int e = ew * 32 + lane;                     // 0..511
+                const int ccol = acc_base + (e & 255);
+                const long long row_first = static_cast<long long>(b) * p.M + m_tile * GEMM_BLOCK_M;
+                long long g0 = 0, g_last = 0;
+                if (p.rowbias != nullptr) {
+                    g0 = row_first / p.rows_per_group;
+                    g_last = (static_cast<long long>(b) * p.M + p.M - 1) / p.rows_per_group;
+                }
+                float cv = (p.bias != nullptr && ccol < p.n_out) ? __ldg(p.bias + ccol) : 0.0f;
+                if (p.rowbias != nullptr && ccol < p.n_out) {
+                    long long g = g0 + (e >> 8);
+                    g = g > g_last ? g_last : g;
+                    cv += __ldg(p.rowbias + g * p.ld_rowbias + ccol);
+                }
+                float* cb = cbias_smem + (tile_iter & 1u) * 512;
+                cb[e] = cv;
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                // rows of the tile's second utterance (a tile spans at most two when rows_per_group >= 128) read row 1
+                const uint32_t rsel = (p.rowbias != nullptr && row_ok && grp != g0) ? 1024u : 0u;
+                cb_addr = smem_u32(cb) + rsel;
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * 256u +
@@ -619,7 +648,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 // 51%), so everything that is not arithmetic is hoisted: shared-memory and barrier addresses are
                 // 32-bit window addresses computed once per kernel, the bias is read as warp-uniform 16-byte loads
                 // (no staging through shared memory, no warp barriers), no per-unit bounds beyond `live`.
-                const float4* bias4 = reinterpret_cast<const float4*>(p.bias);
                 for (int s = half; s < n_sub; s += 2) {
                     const int c0 = (2 * s + part) * 32;
                     const int gc = acc_base + c0;
@@ -629,16 +657,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         uint32_t acc_r[32];
                         tmem_ld32(taddr + c0, acc_r);
                         f32x2 v2[16];
-                        if (bias4 != nullptr) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 bq = __ldg(bias4 + (gc >> 2) + j);
-                                v2[2 * j] = pack2(bq.x, bq.y);
-                                v2[2 * j + 1] = pack2(bq.z, bq.w);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) v2[j] = pack2(0.f, 0.f);
+                        for (int j = 0; j < 8; ++j) {             // bias from the tile's shared-memory cache (broadcast reads)
+                            const uint4 bq = lds128_u32(cb_addr + static_cast<uint32_t>(c0 * 4 + j * 16));
+                            v2[2 * j] = pack2(__uint_as_float(bq.x), __uint_as_float(bq.y));
+                            v2[2 * j + 1] = pack2(__uint_as_float(bq.z), __uint_as_float(bq.w));
                         }
                         tmem_ld_wait();
 #pragma unroll
@@ -685,12 +708,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 // the generic path below executed ~620 warp instructions per 32 x 32 unit for ~6 per column pair of
                 // arithmetic (ncu round 2: issue slots 52-56% busy, tensor pipe 5-47%, 90 us against a 51-73 us HBM bound).
                 // Same hand-shakes (aux ring in, staging in place over the consumed residual rows, store thread out), but
-                // bias / row bias come as warp-uniform 16-byte loads, the residual as four 16-byte shared-memory reads on
+                // bias + row bias come from the tile's shared-memory cache, the residual as four 16-byte shared-memory reads on
                 // precomputed window addresses, and there are no per-unit bounds (every sub-tile is inside the output).
-                const float4* bias4 = reinterpret_cast<const float4*>(p.bias);
-                const float4* rb4 = p.rowbias != nullptr
-                                        ? reinterpret_cast<const float4*>(p.rowbias + grp * p.ld_rowbias + acc_base)
-                                        : nullptr;
                 const uint32_t aux_row0 = smem_u32(aux_smem) + static_cast<uint32_t>(r * 128);
                 for (int s = half; s < n_sub; s += 2) {
                     const uint32_t q = tile_iter * static_cast<uint32_t>(n_sub) + static_cast<uint32_t>(s);
@@ -699,24 +718,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     uint32_t acc_r[32];
                     tmem_ld32(taddr + c0, acc_r);
                     f32x2 v2[16];
-                    if (bias4 != nullptr) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 bq = __ldg(bias4 + ((acc_base + c0) >> 2) + j);
-                            v2[2 * j] = pack2(bq.x, bq.y);
-                            v2[2 * j + 1] = pack2(bq.z, bq.w);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v2[j] = pack2(0.f, 0.f);
-                    }
-                    if (rb4 != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 bq = __ldg(rb4 + (c0 >> 2) + j);
-                            v2[2 * j] = add2(v2[2 * j], pack2(bq.x, bq.y));
-                            v2[2 * j + 1] = add2(v2[2 * j + 1], pack2(bq.z, bq.w));
-                        }
+                    for (int j = 0; j < 8; ++j) {                 // bias + row bias from the tile's shared-memory cache
+                        const uint4 bq = lds128_u32(cb_addr + static_cast<uint32_t>(c0 * 4 + j * 16));
+                        v2[2 * j] = pack2(__uint_as_float(bq.x), __uint_as_float(bq.y));
+                        v2[2 * j + 1] = pack2(__uint_as_float(bq.z), __uint_as_float(bq.w));
                     }
                     mbar_wait(&aux_full[slot], (q / static_cast<uint32_t>(AUX_SLOTS)) & 1u);
                     const uint32_t arow = aux_row0 + slot * static_cast<uint32_t>(GEMM_AUX_BYTES);
