@@ -84,6 +84,26 @@ static int g_resident_ok = 0;     // ZVB_RESIDENT=1: A-stationary tile order for
 static int g_pair_min_kb = 8;     // ZVB_PAIR_MIN_KB: fewest k-blocks for which a CTA pair is used    // ZVB_NO_TMA_STORE=1 keeps the epilogue on per-thread stores
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
+
+// every instantiation of the GEMM kernel: [epilogue kind][activation][CTA pair][lean path] (nullptr = not built)
+typedef void (*gemm_fn_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                          const GemmParams);
+static gemm_fn_t gemm_fn(int kind, int act, int cluster, int lean) {
+#define ZVB_G(K, A, C, L) return gemm_kernel<K, A, C, L>
+    if (kind == EPI_GATED) { if (cluster == 1) ZVB_G(EPI_GATED, ACT_NONE, 1, 0); ZVB_G(EPI_GATED, ACT_NONE, 2, 0); }
+    if (lean == 2) {
+        if (act != ACT_NONE) return nullptr;
+        if (cluster == 1) ZVB_G(EPI_LINEAR, ACT_NONE, 1, 2);
+        ZVB_G(EPI_LINEAR, ACT_NONE, 2, 2);
+    }
+#define ZVB_G2(A, L) if (act == A && lean == L) { if (cluster == 1) ZVB_G(EPI_LINEAR, A, 1, L); ZVB_G(EPI_LINEAR, A, 2, L); }
+    ZVB_G2(ACT_NONE, 0) ZVB_G2(ACT_SWOOSH_L, 0) ZVB_G2(ACT_SWOOSH_R, 0) ZVB_G2(ACT_GELU, 0)
+    ZVB_G2(ACT_NONE, 1) ZVB_G2(ACT_SWOOSH_L, 1) ZVB_G2(ACT_SWOOSH_R, 1) ZVB_G2(ACT_GELU, 1)
+#undef ZVB_G2
+#undef ZVB_G
+    return nullptr;
+}
+
 // Per-device initialisation: the opt-in shared-memory sizes (cudaFuncSetAttribute) and the SM count belong to
 // the CURRENT device, so a process that builds plans on several GPUs initialises each of them once.
 #ifndef ZVB_SOURCE_HASH
@@ -128,11 +148,11 @@ static int init_device() {
         g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     }
 #define ZVB_SMEM_ATTR(k) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES))
-    ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_NONE, 1>));     ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_NONE, 2>));
-    ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 1>)); ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 2>));
-    ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 1>)); ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 2>));
-    ZVB_SMEM_ATTR((gemm_kernel<EPI_GATED, ACT_NONE, 1>));      ZVB_SMEM_ATTR((gemm_kernel<EPI_GATED, ACT_NONE, 2>));
-    ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_GELU, 1>));     ZVB_SMEM_ATTR((gemm_kernel<EPI_LINEAR, ACT_GELU, 2>));
+    for (int lean = 0; lean < 3; ++lean)
+        for (int act = 0; act < 4; ++act)
+            for (int cl = 1; cl <= 2; ++cl)
+                if (gemm_fn(EPI_LINEAR, act, cl, lean) != nullptr) ZVB_SMEM_ATTR(gemm_fn(EPI_LINEAR, act, cl, lean));
+    ZVB_SMEM_ATTR(gemm_fn(EPI_GATED, ACT_NONE, 1, 0)); ZVB_SMEM_ATTR(gemm_fn(EPI_GATED, ACT_NONE, 2, 0));
 #undef ZVB_SMEM_ATTR
     CUDA_TRY(cudaFuncSetAttribute(attn_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(attn_weights_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM_BYTES));
@@ -630,20 +650,10 @@ static int launch_op(const Op& op, cudaStream_t st) {
             attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = g_pdl ? 2 : 1;
-            const int sel = (op.kind == EPI_GATED ? 4 : op.gp.act) * 2 + (op.cluster - 1);
-            cudaError_t e = cudaSuccess;
-            switch (sel) {
-                case 0: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 1>, op.ma, op.mb, mx, ms, mo, op.gp); break;
-                case 1: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_NONE, 2>, op.ma, op.mb, mx, ms, mo, op.gp); break;
-                case 2: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 1>, op.ma, op.mb, mx, ms, mo, op.gp); break;
-                case 3: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_L, 2>, op.ma, op.mb, mx, ms, mo, op.gp); break;
-                case 4: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 1>, op.ma, op.mb, mx, ms, mo, op.gp); break;
-                case 5: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_SWOOSH_R, 2>, op.ma, op.mb, mx, ms, mo, op.gp); break;
-                case 6: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_GELU, 1>, op.ma, op.mb, mx, ms, mo, op.gp); break;
-                case 7: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_LINEAR, ACT_GELU, 2>, op.ma, op.mb, mx, ms, mo, op.gp); break;
-                case 8: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 1>, op.ma, op.mb, mx, ms, mo, op.gp); break;
-                default: e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI_GATED, ACT_NONE, 2>, op.ma, op.mb, mx, ms, mo, op.gp); break;
-            }
+            const int lean = op.kind == EPI_GATED ? 0 : (op.gp.fast_epi ? 1 : op.gp.fast_resid ? 2 : 0);
+            gemm_fn_t fn = gemm_fn(op.kind, op.gp.act, op.cluster, lean);
+            if (fn == nullptr) return fail(ZVB_ERR_INVALID, "gemm: no kernel for kind %d act %d lean %d", op.kind, op.gp.act, lean);
+            cudaError_t e = cudaLaunchKernelEx(&cfg, fn, op.ma, op.mb, mx, ms, mo, op.gp);
             if (e != cudaSuccess) return fail(ZVB_ERR_CUDA, "launch gemm: %s", cudaGetErrorString(e));
             return check_launch("gemm");
         }

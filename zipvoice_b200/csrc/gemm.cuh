@@ -236,7 +236,11 @@ __device__ __forceinline__ void store_unit(const GemmParams& p, uint8_t* stage, 
 // de-duplicates the two requests.)  Protocol: both producers wait on their LOCAL `empty` barrier and
 // complete bytes on the LEADER's `full` barrier; the leader commits with a multicast arrive to both
 // CTAs' `empty` / `tmem_full`; the peer's epilogue warps arrive remotely on the leader's `tmem_empty`.
-template <int KIND, int ACT, int CLUSTER>
+// LEAN selects the epilogue at COMPILE time: 0 = generic (every operand / store mode), 1 = lean plain epilogue
+// (GemmParams::fast_epi), 2 = lean residual-stream epilogue (GemmParams::fast_resid).  Separate instantiations, because
+// one kernel carrying all three paths costs the generic path registers (round 2: +20% on the N = 272 / N = 48 projections
+// when the lean paths were runtime branches of the same kernel).
+template <int KIND, int ACT, int CLUSTER, int LEAN = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_out,
@@ -615,7 +619,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             // lean paths: the 512 epilogue threads fill this tile's bias cache (one L2 round trip per tile, requested
             // before the accumulator wait), double buffered by tile parity; one named barrier per tile
             uint32_t cb_addr = 0;
-            if (KIND == EPI_LINEAR && (p.fast_epi || p.fast_resid)) {
+            if (KIND == EPI_LINEAR && LEAN != 0) {
                 const int e = ew * 32 + lane;                     // 0..511
                 const int ccol = acc_base + (e & 255);
                 const long long row_first = static_cast<long long>(b) * p.M + m_tile * GEMM_BLOCK_M;
@@ -642,7 +646,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * 256u +
                                    (static_cast<uint32_t>(quarter * 32) << 16);
 
-            if (KIND == EPI_LINEAR && p.fast_epi) {
+            if (KIND == EPI_LINEAR && LEAN == 1) {
                 // Lean path of the feed-forward input GEMMs.  These kernels are bound by the epilogue's issue slots
                 // (ncu, round 2: 415 executed instructions per 32 x 32 unit of which 176 are FFMA2 / MUFU; tensor pipe
                 // 51%), so everything that is not arithmetic is hoisted: shared-memory and barrier addresses are
@@ -703,7 +707,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     if (lane == 0) mbar_arrive_u32(fast_staged + 8u * buf);
                     ++kcount;
                 }
-            } else if (KIND == EPI_LINEAR && ACT == ACT_NONE && p.fast_resid) {
+            } else if (KIND == EPI_LINEAR && ACT == ACT_NONE && LEAN == 2) {
                 // Lean path of the residual-stream GEMMs (out = resid + A.W^T + b [+ time embedding of the row's utterance]):
                 // the generic path below executed ~620 warp instructions per 32 x 32 unit for ~6 per column pair of
                 // arithmetic (ncu round 2: issue slots 52-56% busy, tensor pipe 5-47%, 90 us against a 51-73 us HBM bound).
