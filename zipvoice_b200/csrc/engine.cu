@@ -78,6 +78,7 @@ static int g_bn192 = 0;           // ZVB_BN192=1: 192-column tiles for short-K G
 static int g_layout_ok = 1;       // ZVB_NO_LAYOUT=1 keeps the default operand-ring / aux split everywhere
 static int g_attn_tc = 0;         // ZVB_ATTN_TC=1: attention weights with the tensor-core rel-pos bias (attn3.cuh; measured slower)
 static int g_dw_mode = 1;          // ZVB_DW_MODE=0: register-resident window (32 outputs / thread); measured equal, DESIGN.md §3
+static int g_lean_pad = 1;         // ZVB_NO_LEAN_PAD=1: exact-fit tile widths for projections that are no multiple of 64 wide
 static int g_fast_resid = 1;       // ZVB_NO_FAST_RESID=1: generic epilogue for the residual-stream GEMMs
 static int g_fast_epi = 1;        // ZVB_NO_FAST_EPI=1: generic epilogue everywhere
 static int g_resident_ok = 0;     // ZVB_RESIDENT=1: A-stationary tile order for the K = 512 GEMMs (measured 5-8% SLOWER, profiles/gemm_resident_ab_r2.txt)
@@ -135,6 +136,7 @@ static int init_device() {
         if (const char* e = getenv("ZVB_RESIDENT")) g_resident_ok = atoi(e) != 0;
         if (const char* e = getenv("ZVB_NO_FAST_EPI")) g_fast_epi = atoi(e) == 0;
         if (const char* e = getenv("ZVB_NO_FAST_RESID")) g_fast_resid = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_NO_LEAN_PAD")) g_lean_pad = atoi(e) == 0;
         if (const char* e = getenv("ZVB_ATTN_TC")) g_attn_tc = atoi(e) != 0;
         if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
         if (const char* e = getenv("ZVB_DW_MODE")) g_dw_mode = atoi(e) != 0 ? 1 : 0;
@@ -396,7 +398,15 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
     if (lin.k_pitch % 8 != 0 || lda % 8 != 0) return fail(ZVB_ERR_INVALID, "linear: pitches must be multiples of 8");
     const int K = lin.k_pitch < lda ? lin.k_pitch : lda;    // both zero padded beyond in_features
     const long long m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
-    const int bn = e.block_n ? e.block_n : pick_block_n(lin.out_features, m_tiles, (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K);
+    int bn = e.block_n ? e.block_n : pick_block_n(lin.out_features, m_tiles, (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K);
+    // plain fp16 projections whose width is no multiple of 64 (attention in_proj: 272 columns): tiles of a multiple of 64
+    // columns keep them on the lean epilogue (whole 64-column store boxes per tile; columns past n_out are clipped by the
+    // store's tensor map and their weight rows are TMA zero fill) -- 2 x 192 instead of 2 x 144
+    if (e.block_n == 0 && g_fast_epi && g_lean_pad && bn % 64 != 0 && lin.out_features > 128 && e.out_mode == OUT_H16 &&
+        e.resid == nullptr && e.rowbias == nullptr && e.row_mask == nullptr && lin.out_features % 8 == 0) {
+        const int tiles = (lin.out_features + 255) / 256;
+        bn = (((lin.out_features + tiles - 1) / tiles) + 63) / 64 * 64;
+    }
     GemmParams& p = op.gp;
     gp_defaults(p);
     p.M = static_cast<int>(M);
@@ -437,7 +447,7 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
     }
     gemm_layout(op);
     p.fast_epi = (g_fast_epi && p.tma_store && p.aux_mode == AUX_NONE && p.out_mode == OUT_H16 && p.rowbias == nullptr &&
-                  p.rowscale == nullptr && p.row_mask == nullptr && bn % 64 == 0 && lin.out_features % 32 == 0 &&
+                  p.rowscale == nullptr && p.row_mask == nullptr && bn % 64 == 0 && lin.out_features % 8 == 0 &&
                   (reinterpret_cast<uintptr_t>(lin.b) & 15) == 0) ? 1 : 0;
     p.fast_resid = (g_fast_resid && e.act == ACT_NONE && p.tma_store && p.aux_mode == AUX_ADD_H16 && !p.orig_tma &&
                     p.out_mode == OUT_H16 && p.rowscale == nullptr && p.row_mask == nullptr && bn % 64 == 0 &&
