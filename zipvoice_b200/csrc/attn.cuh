@@ -225,6 +225,9 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
         const int sw = lane & 7;
         constexpr float LOG2E = 1.4426950408889634f;
         float m_run = -INFINITY, m_l2 = 0.f, l_run = 0.f;
+        // excluded-key words one tile ahead: two CTAs of ~106 KB leave the L1 almost no capacity, so every global load
+        // here is an L2 round trip; requested a whole tile before it is needed
+        uint32_t mw0n = __ldg(mwrow), mw1n = __ldg(mwrow + 1);
         for (int it = 0; it < total_it; ++it) {
             const int pass = it >= num_jt ? 1 : 0;
             const int jt = pass ? it - num_jt : it;
@@ -245,7 +248,12 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
                 }
             }
             const uint4* ew = ewin + acc * ATT_EWIN;
-            const uint32_t mw0 = __ldg(mwrow + 4 * jt), mw1 = __ldg(mwrow + 4 * jt + 1);
+            const uint32_t mw0 = mw0n, mw1 = mw1n;
+            if (it + 1 < total_it) {
+                const int jn = it + 1 >= num_jt ? it + 1 - num_jt : it + 1;
+                mw0n = __ldg(mwrow + 4 * jn);
+                mw1n = __ldg(mwrow + 4 * jn + 1);
+            }
             if (it >= e_first) mbar_wait(&e_full[acc], static_cast<uint32_t>((it - e_first) >> 1) & 1u);
             mbar_wait(&s_full[acc], acc_phase);
             tc_fence_after();
