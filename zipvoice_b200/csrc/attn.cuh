@@ -308,6 +308,40 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
                 const int jh = j0 + 64 * half;            // first key column of this warp
                 if (lane == 0) bulk_wait_read<0>();       // the previous box store has read the staging rows
                 __syncwarp();
+                if (jh + 64 <= p.Lk && (mw0 | mw1) == 0u) {
+                    // interior tile (the common case): all 64 columns inside the padded width, no excluded key --
+                    // straight-line code, no per-group bounds or mask selects
+                    const f32x2 l2e2 = pack2(LOG2E, LOG2E), nm2 = pack2(-m_l2, -m_l2);
+#pragma unroll 1
+                    for (int gg = 0; gg < 2; ++gg) {
+                        uint32_t sr32[32];
+                        tmem_ld32(taddr + 32 * gg, sr32);
+                        tmem_ld_wait();
+                        const uint4* ep = ew + (64 * half + 32 * gg - r + 127);
+                        uint32_t w[16];
+#pragma unroll
+                        for (int c = 0; c < 32; c += 2) {
+                            const uint4 e4 = ep[c];
+                            float a, b;                   // (q.k) log2e - m for the column pair: one packed FFMA2
+                            unpack2(fma2(pack2(__uint_as_float(sr32[c]), __uint_as_float(sr32[c + 1])), l2e2, nm2), a, b);
+                            uint32_t bias = hmul2(ph0, e4.x);
+                            bias = hfma2(ph1, e4.y, bias);
+                            bias = hfma2(ph2, e4.z, bias);
+                            bias = hfma2(ph3, e4.w, bias);
+                            w[c >> 1] = ex2_h2(hadd2(bias, pack_h2(a, b)));
+                        }
+                        // half2 partial row sums per 16 columns (<= 8 x 2^12 per half), then fp32
+                        const uint32_t sa = hadd2(hadd2(hadd2(w[0], w[1]), hadd2(w[2], w[3])),
+                                                  hadd2(hadd2(w[4], w[5]), hadd2(w[6], w[7])));
+                        const uint32_t sb = hadd2(hadd2(hadd2(w[8], w[9]), hadd2(w[10], w[11])),
+                                                  hadd2(hadd2(w[12], w[13]), hadd2(w[14], w[15])));
+                        l_run += (h2_lo(sa) + h2_hi(sa)) + (h2_lo(sb) + h2_hi(sb));
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4)
+                            *reinterpret_cast<uint4*>(my + (((4 * gg + q4) ^ sw) << 4)) =
+                                make_uint4(w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
+                    }
+                } else {
 #pragma unroll 1
                 for (int gg = 0; gg < 2; ++gg) {
                     if (jh + 32 * gg >= p.Lk) break;
@@ -349,6 +383,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
                     l_run += h2_lo(sum2) + h2_hi(sum2);
                     *reinterpret_cast<uint4*>(my + (((2 * g) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                     *reinterpret_cast<uint4*>(my + (((2 * g + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+                }
                 }
                 }
                 if (jh < p.Lk) {
