@@ -2,7 +2,7 @@
 # GPU box: launch list of one sampler step, full ncu captures of the two dominant kernels, and the DRAM
 # traffic of every gemm_kernel launch of one decoder forward.  Usage: bash tools/ncu_capture.sh <tag>
 TAG=${1:-r1}
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --quick --no-strong"
 QP="python tools/quick_perf.py --batch 64 --reps 0 --no-graph"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&

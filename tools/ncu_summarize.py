@@ -65,5 +65,5 @@ if os.path.exists(tcsv):
            "dram_read_bytes_total": rd, "dram_write_bytes_total": wr, "serialized_time_ms_total": ms,
            "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:gemm_kernel: every gemm_kernel "
                      f"launch of one decoder forward (N=128, T=1219), tools/ncu_capture.sh {tag}"}
-    json.dump(out, open(f"{out_dir}/traffic_r1.json", "w"), indent=1)
+    json.dump(out, open(f"{out_dir}/traffic_r2.json", "w"), indent=1)
     print(json.dumps(out, indent=1))
