@@ -535,6 +535,13 @@ ALL = {
     "gated_tanh96": lambda: check_gated(M=81, K=128, n_out=96, mode=1),
     "gated_glu_masked": lambda: check_gated(M=1000, n_out=512, mode=2, masked=True),
     "linear_bn64": lambda: check_linear(M=128, K=64, N=64, block_n=64),
+    # tile widths the wave model picks for single-utterance shapes (no multiple of 64: per-thread store path)
+    "linear_bn80_resid": lambda: check_linear(M=2438, K=1920, N=512, block_n=80, resid=True),
+    "linear_bn112_bypass": lambda: check_linear(M=2438, K=1536, N=512, block_n=112, resid=True, bypass=True),
+    "linear_bn224_swoosh": lambda: check_linear(M=2438, K=512, N=1536, block_n=224, act=1),
+    "linear_bn160_swoosh": lambda: check_linear(M=2438, K=512, N=1920, block_n=160, act=1),
+    "linear_bn48_f32": lambda: check_linear(M=2438, K=512, N=100, block_n=48, out_mode=1),
+    "linear_small_auto": lambda: check_linear(M=2438, K=1152, N=512, resid=True),
     "linear_tail": lambda: check_linear(M=77, K=192, N=640, act=2),
     "attn_small": lambda: check_attn(N=2, H=4, L=100, masked=False),
     "attn_masked": lambda: check_attn(N=3, H=4, L=333, masked=True),

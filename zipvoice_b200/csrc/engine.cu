@@ -78,6 +78,7 @@ static int g_bn192 = 0;           // ZVB_BN192=1: 192-column tiles for short-K G
 static int g_layout_ok = 1;       // ZVB_NO_LAYOUT=1 keeps the default operand-ring / aux split everywhere
 static int g_attn_tc = 0;         // ZVB_ATTN_TC=1: attention weights with the tensor-core rel-pos bias (attn3.cuh; measured slower)
 static int g_dw_mode = 1;          // ZVB_DW_MODE=0: register-resident window (32 outputs / thread); measured equal, DESIGN.md §3
+static int g_small_model = 1;      // ZVB_NO_SMALL_MODEL=1: round 1's tile-width choice for small problems
 static int g_lean_pad = 1;         // ZVB_NO_LEAN_PAD=1: exact-fit tile widths for projections that are no multiple of 64 wide
 static int g_fast_resid = 1;       // ZVB_NO_FAST_RESID=1: generic epilogue for the residual-stream GEMMs
 static int g_fast_epi = 1;        // ZVB_NO_FAST_EPI=1: generic epilogue everywhere
@@ -137,6 +138,7 @@ static int init_device() {
         if (const char* e = getenv("ZVB_NO_FAST_EPI")) g_fast_epi = atoi(e) == 0;
         if (const char* e = getenv("ZVB_NO_FAST_RESID")) g_fast_resid = atoi(e) == 0;
         if (const char* e = getenv("ZVB_NO_LEAN_PAD")) g_lean_pad = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_NO_SMALL_MODEL")) g_small_model = atoi(e) == 0;
         if (const char* e = getenv("ZVB_ATTN_TC")) g_attn_tc = atoi(e) != 0;
         if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
         if (const char* e = getenv("ZVB_DW_MODE")) g_dw_mode = atoi(e) != 0 ? 1 : 0;
@@ -261,7 +263,31 @@ struct Op {
 };
 static inline void mark_out(Op& op, int i, const void* p, long long n) { op.scan_ptr[i] = p; op.scan_n[i] = n; }
 
+// Small problems (single utterances: 20 m-tiles at T = 1219, 103 at T = 6563): a tile's time is the operand bytes its SM
+// streams (measured at N = 2: 5.2 us fixed + 128 B x (128 + tile columns) per k-block at ~62 GB/s per SM), and the kernel's
+// time is that times the number of WAVES the tiles need on 148 SMs / 74 CTA pairs.  Round 1 picked multiples of 64 only:
+// N = 512 at 20 m-tiles became 160 tiles of 64 columns = 2 waves where 140 tiles of 80 columns run in one.
+static int pick_block_n_small(int n_out, long long m_tiles, int k_blocks) {
+    int best = 0;
+    double best_cost = 1e30;
+    for (int bn = 16; bn <= 256; bn += 16) {
+        const long long n_tiles = (n_out + bn - 1) / bn;
+        if (bn > 16 && (n_tiles - 1) * bn >= n_out) continue;
+        const long long slots2 = ((m_tiles + 1) / 2) * n_tiles;
+        const bool pair = g_cluster_ok && bn >= 64 && m_tiles >= 2 && slots2 >= g_num_sms / 4 && k_blocks >= g_pair_min_kb;
+        const long long units = pair ? slots2 : m_tiles * n_tiles;
+        const long long lanes = pair ? g_num_sms / 2 : g_num_sms;
+        const long long waves = (units + lanes - 1) / lanes;
+        const double tile_us = 5.2 + k_blocks * 128.0 * (128 + (pair ? bn / 2 : bn)) / 62000.0 + 0.004 * bn;
+        double cost = waves * tile_us;
+        if (bn % 64 != 0) cost *= 1.03;              // multiples of 64 keep the TMA-store / lean epilogues: prefer them on a tie
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
 static int pick_block_n(int n_out, long long m_tiles, int k_blocks) {
+    if (g_small_model && n_out >= 64 && m_tiles * ((n_out + 255) / 256) < 2LL * g_num_sms) return pick_block_n_small(n_out, m_tiles, k_blocks);
     // short K (<= 8 k-blocks): the mainloop is bound by operand bytes in flight, and a 40 KB stage (192
     // columns) fits four times into the wide ring where a 48 KB stage (256 columns) fits three times
     if (g_bn192 && k_blocks <= 8 && n_out >= 768 && n_out % 192 == 0 && m_tiles * (n_out / 192) >= g_num_sms) return 192;
@@ -404,6 +430,7 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
     // columns keep them on the lean epilogue (whole 64-column store boxes per tile; columns past n_out are clipped by the
     // store's tensor map and their weight rows are TMA zero fill) -- 2 x 192 instead of 2 x 144
     if (e.block_n == 0 && g_fast_epi && g_lean_pad && bn % 64 != 0 && lin.out_features > 128 && e.out_mode == OUT_H16 &&
+        m_tiles * ((lin.out_features + 255) / 256) >= 2LL * g_num_sms &&
         e.resid == nullptr && e.rowbias == nullptr && e.row_mask == nullptr && lin.out_features % 8 == 0) {
         const int tiles = (lin.out_features + 255) / 256;
         bn = (((lin.out_features + tiles - 1) / tiles) + 63) / 64 * 64;
