@@ -250,11 +250,14 @@ constexpr int DW_TT = 128;     // frames per tile
 // (tools/microbench/fma_rates.cu: FFMA 1.05 clk, FFMA2 2.18 clk, HFMA2 2.0 clk per warp instruction), i.e.
 // 128 FMA/clk/SM, and 31 taps + SwooshR need 40 FMA per output: 0.47 of HBM peak at best for K = 31.
 template <int K, int MODE> struct DwShape {
-    static constexpr int OT = (MODE == 0 && K > 15) ? 32 : 16;
-    static constexpr int THREADS = 32 * (DW_TT / OT);
+    // MODE 2 (K > 15): 20 outputs per thread, four warps, three blocks per SM at <= 168 registers -- three warps per scheduler
+    static constexpr int OT = (K > 15) ? (MODE == 0 ? 32 : MODE == 2 ? 20 : 16) : 16;
+    static constexpr int WARPS = (K > 15 && MODE == 2) ? 4 : DW_TT / OT;
+    static constexpr int TT = OT * WARPS;                      // frames per tile
+    static constexpr int THREADS = 32 * WARPS;
     static constexpr int MINB = MODE == 0 ? 2 : 3;
 };
-template <int K> constexpr int dw_smem_bytes() { return 2 * (DW_TT + K - 1) * 128 + K * 32 * 8 + 128 /*align*/ + 16; }
+template <int K, int MODE> constexpr int dw_smem_bytes() { return 2 * (DwShape<K, MODE>::TT + K - 1) * 128 + K * 32 * 8 + 128 /*align*/ + 16; }
 
 // SwooshR of a channel pair (see swoosh_direct): everything but the two MUFU ops runs as FFMA2 --
 // 8 packed FMAs per pair; |z| is two ALU-pipe LOP3s, the negation rides on the MUFU operand.
@@ -287,7 +290,8 @@ __global__ void __launch_bounds__(DwShape<K, MODE>::THREADS, DwShape<K, MODE>::M
 dwconv_kernel(const __grid_constant__ CUtensorMap tma_x, __half* __restrict__ out,
               const float* __restrict__ wt /*[K][C]*/, const float* __restrict__ bias, int L,
               int C, int N) {
-    constexpr int HALF = K / 2, WIN = DW_TT + K - 1, OT = DwShape<K, MODE>::OT, NW = OT + K - 1, THREADS = DwShape<K, MODE>::THREADS;
+    constexpr int HALF = K / 2, TT = DwShape<K, MODE>::TT, WIN = TT + K - 1, OT = DwShape<K, MODE>::OT, NW = OT + K - 1,
+                  THREADS = DwShape<K, MODE>::THREADS;
     extern __shared__ uint8_t dw_smem_raw[];
     const uint32_t raw = smem_u32(dw_smem_raw);
     uint8_t* smem = dw_smem_raw + (((raw + 127u) & ~127u) - raw);
@@ -297,7 +301,7 @@ dwconv_kernel(const __grid_constant__ CUtensorMap tma_x, __half* __restrict__ ou
     const int c0 = blockIdx.y * 64;
     const int cp = threadIdx.x & 31;
     const int tg = threadIdx.x >> 5;
-    const int n_tt = (L + DW_TT - 1) / DW_TT;
+    const int n_tt = (L + TT - 1) / TT;
     const int total = N * n_tt;
     for (int idx = threadIdx.x; idx < K * 32; idx += THREADS) {
         const int k = idx >> 5, q = idx & 31;
@@ -316,7 +320,7 @@ dwconv_kernel(const __grid_constant__ CUtensorMap tma_x, __half* __restrict__ ou
     int tl = blockIdx.x;
     if (threadIdx.x == 0 && tl < total) {
         mbar_arrive_expect_tx(&bar[0], WIN * 128);
-        tma_load_3d(tile, &tma_x, &bar[0], c0, (tl % n_tt) * DW_TT - HALF, tl / n_tt);
+        tma_load_3d(tile, &tma_x, &bar[0], c0, (tl % n_tt) * TT - HALF, tl / n_tt);
     }
     const bool ch_ok = c0 + 2 * cp < C;
     f32x2 b2 = pack2(0.f, 0.f);
@@ -326,7 +330,7 @@ dwconv_kernel(const __grid_constant__ CUtensorMap tma_x, __half* __restrict__ ou
         const int nxt = tl + gridDim.x;
         if (threadIdx.x == 0 && nxt < total) {        // buffer buf^1 was drained before the last __syncthreads
             mbar_arrive_expect_tx(&bar[buf ^ 1u], WIN * 128);
-            tma_load_3d(tile + (buf ^ 1u) * (WIN * 32), &tma_x, &bar[buf ^ 1u], c0, (nxt % n_tt) * DW_TT - HALF,
+            tma_load_3d(tile + (buf ^ 1u) * (WIN * 32), &tma_x, &bar[buf ^ 1u], c0, (nxt % n_tt) * TT - HALF,
                         nxt / n_tt);
         }
         mbar_wait(&bar[buf], (it >> 1) & 1u);
@@ -347,7 +351,7 @@ dwconv_kernel(const __grid_constant__ CUtensorMap tma_x, __half* __restrict__ ou
             for (int o = 0; o < OT; ++o) acc[o] = fma2(w, win[o + k], acc[o]);     // one FFMA2 = both channels
         }
         const int n = tl / n_tt;
-        const int t0 = (tl - n * n_tt) * DW_TT + tg * OT;
+        const int t0 = (tl - n * n_tt) * TT + tg * OT;
         __half* on = out + (static_cast<long long>(n) * L + t0) * C + c0 + 2 * cp;
         if (ch_ok) {
 #pragma unroll

@@ -141,7 +141,7 @@ static int init_device() {
         if (const char* e = getenv("ZVB_NO_SMALL_MODEL")) g_small_model = atoi(e) == 0;
         if (const char* e = getenv("ZVB_ATTN_TC")) g_attn_tc = atoi(e) != 0;
         if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
-        if (const char* e = getenv("ZVB_DW_MODE")) g_dw_mode = atoi(e) != 0 ? 1 : 0;
+        if (const char* e = getenv("ZVB_DW_MODE")) g_dw_mode = atoi(e);
         if (const char* e = getenv("ZVB_WIDE_PREF")) g_wide_pref = atoi(e) != 0;
         if (const char* e = getenv("ZVB_WIDE_WASTE")) g_wide_waste = atof(e);
         void* fn = nullptr;
@@ -160,16 +160,21 @@ static int init_device() {
 #undef ZVB_SMEM_ATTR
     CUDA_TRY(cudaFuncSetAttribute(attn_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(attn_weights_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<9, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<9>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<9, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<9>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<15, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<15>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<15, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<15>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<31, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<31>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<31, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<31>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
-    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7, 0>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7, 1>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7, 2>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<9, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<9, 0>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<9, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<9, 1>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<9, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<9, 2>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<15, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<15, 0>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<15, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<15, 1>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<15, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<15, 2>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<31, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<31, 0>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<31, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<31, 1>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<31, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<31, 2>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7, 0>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7, 1>()));
+    CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7, 2>()));
     g_dev_sms[dev] = prop.multiProcessorCount;
     g_num_sms = prop.multiProcessorCount;
     return 0;
@@ -636,6 +641,11 @@ static Op mask_words_op(const uint8_t* mask, uint32_t* out, int N, int L) {
     return op;
 }
 
+static int dw_tile_frames(int K, int mode) {
+    if (K > 15 && mode == 2) return DwShape<31, 2>::TT;
+    return DW_TT;
+}
+
 static int build_dwconv(Op& d, const h16* x, h16* out, const float* w, const float* b, int N, int L, int C, int K, int act = 1) {
     d = Op();
     d.type = OP_DWCONV; d.p0 = x; d.o0 = out; d.f0 = w; d.f1 = b;
@@ -645,7 +655,8 @@ static int build_dwconv(Op& d, const h16* x, h16* out, const float* w, const flo
         return fail(ZVB_ERR_INVALID, "depthwise kernel size %d not built (7, 9, 15, 31)", K);
     if (C % 8 != 0) return fail(ZVB_ERR_INVALID, "dwconv: channels must be a multiple of 8");
     // x as (C, L, N); a box = 64 channels x (128 + K - 1) frames, rows outside [0, L) are zero-filled
-    TRY(make_tmap_plain(&d.ma, x, C, L, N, (uint64_t)C * 2, (uint64_t)C * 2 * L, 64, DW_TT + K - 1));
+    d.i5 = g_dw_mode;                  // the tile height is part of the tensor map: the shape is fixed at plan creation
+    TRY(make_tmap_plain(&d.ma, x, C, L, N, (uint64_t)C * 2, (uint64_t)C * 2 * L, 64, dw_tile_frames(K, g_dw_mode) + K - 1));
     mark_out(d, 0, out, (long long)N * L * C);
     d.cat = ZVB_CAT_DWCONV;
     d.shape[0] = N * L; d.shape[1] = C; d.shape[2] = K; d.shape[3] = act;
@@ -654,20 +665,22 @@ static int build_dwconv(Op& d, const h16* x, h16* out, const float* w, const flo
     return 0;
 }
 
-template <int K, int ACT = 1>
-static void launch_dwconv(const Op& op, cudaStream_t st) {
+template <int K, int ACT, int MODE>
+static void launch_dwconv_mode(const Op& op, cudaStream_t st) {
     const int N = op.i0, L = op.i1, C = op.i2;
     const int groups = (C + 63) / 64;
-    const int tiles = N * ((L + DW_TT - 1) / DW_TT);
-    const int minb = g_dw_mode == 0 ? DwShape<K, 0>::MINB : DwShape<K, 1>::MINB;
-    int per_group = (minb * g_num_sms) / groups;         // resident blocks per SM
+    const int tiles = N * ((L + DwShape<K, MODE>::TT - 1) / DwShape<K, MODE>::TT);
+    int per_group = (DwShape<K, MODE>::MINB * g_num_sms) / groups;         // resident blocks per SM
     if (per_group < 1) per_group = 1;
     if (per_group > tiles) per_group = tiles;
-    dim3 grid(per_group, groups);
-    if (g_dw_mode == 0)
-        launch_k(dwconv_kernel<K, ACT, 0>, dim3(grid), dim3(DwShape<K, 0>::THREADS), dw_smem_bytes<K>(), st, op.ma, (h16*)op.o0, op.f0, op.f1, L, C, N);
-    else
-        launch_k(dwconv_kernel<K, ACT, 1>, dim3(grid), dim3(DwShape<K, 1>::THREADS), dw_smem_bytes<K>(), st, op.ma, (h16*)op.o0, op.f0, op.f1, L, C, N);
+    launch_k(dwconv_kernel<K, ACT, MODE>, dim3(per_group, groups), dim3(DwShape<K, MODE>::THREADS), dw_smem_bytes<K, MODE>(), st,
+             op.ma, (h16*)op.o0, op.f0, op.f1, L, C, N);
+}
+template <int K, int ACT = 1>
+static void launch_dwconv(const Op& op, cudaStream_t st) {
+    if (op.i5 == 0) launch_dwconv_mode<K, ACT, 0>(op, st);
+    else if (op.i5 == 2) launch_dwconv_mode<K, ACT, 2>(op, st);
+    else launch_dwconv_mode<K, ACT, 1>(op, st);
 }
 
 static int launch_op(const Op& op, cudaStream_t st) {
