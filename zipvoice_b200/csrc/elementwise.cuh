@@ -243,19 +243,22 @@ constexpr int DW_TT = 128;     // frames per tile
 // (32 + 30) / 32 window loads and conversions.  (Round 1 ran 16 outputs per thread under an 80-register cap:
 // ptxas re-loaded and re-converted the window inside the tap loop, FFMA2 was 52% of the issued instructions
 // and the kernel sat at 40% of the FMA pipe, 0.24 of HBM peak.)
-// MODE 0: the register-resident shape above (ZVB_DW_MODE=0); MODE 1 (default): 16 outputs per thread, 256 threads,
-// three blocks per SM under an 80-register cap.  A/B on one B200 (round 2, gpurun_out/r2b_dwab_*): K = 31 launches
-// 207-212 us (mode 0) against 197-212 us (mode 1) -- the ideal instruction mix buys nothing because both shapes
-// sit on the same limit: every FMA form issues at most 32 lanes x 1 FMA per clock and scheduler
+// MODE 0 (default): the register-resident shape above for K > 15, round 1's shape (16 outputs per thread, 256 threads, three
+// blocks per SM under an 80-register cap) for the short kernels; MODE 1: round 1's shape everywhere; MODE 2: 20 outputs per
+// thread, three warps per scheduler (ZVB_DW_MODE).  History (round 2, one B200, K = 31 launches of the forward): with the
+// activation and the stores of an output inside one `if (t < L)` block, ALL shapes measured 205 us -- ptxas could not
+// interleave the MUFU -> Horner chains of different outputs, they ran back to back whatever the block shape; with the
+// activation straight-line for all outputs and the stores behind one tile-uniform branch: 184 us (round-1 shape) and
+// 175 us (register-resident).  Ceiling: every FMA form issues at most 32 lanes x 1 FMA per clock and scheduler
 // (tools/microbench/fma_rates.cu: FFMA 1.05 clk, FFMA2 2.18 clk, HFMA2 2.0 clk per warp instruction), i.e.
-// 128 FMA/clk/SM, and 31 taps + SwooshR need 40 FMA per output: 0.47 of HBM peak at best for K = 31.
+// 128 FMA/clk/SM, and 31 taps + SwooshR need 40 FMA per output: 121 us at 1.55 GHz, 0.40 of HBM peak.
 template <int K, int MODE> struct DwShape {
     // MODE 2 (K > 15): 20 outputs per thread, four warps, three blocks per SM at <= 168 registers -- three warps per scheduler
     static constexpr int OT = (K > 15) ? (MODE == 0 ? 32 : MODE == 2 ? 20 : 16) : 16;
     static constexpr int WARPS = (K > 15 && MODE == 2) ? 4 : DW_TT / OT;
     static constexpr int TT = OT * WARPS;                      // frames per tile
     static constexpr int THREADS = 32 * WARPS;
-    static constexpr int MINB = MODE == 0 ? 2 : 3;
+    static constexpr int MINB = (MODE == 0 && K > 15) ? 2 : 3;
 };
 template <int K, int MODE> constexpr int dw_smem_bytes() { return 2 * (DwShape<K, MODE>::TT + K - 1) * 128 + K * 32 * 8 + 128 /*align*/ + 16; }
 
@@ -354,12 +357,26 @@ dwconv_kernel(const __grid_constant__ CUtensorMap tma_x, __half* __restrict__ ou
         const int t0 = (tl - n * n_tt) * TT + tg * OT;
         __half* on = out + (static_cast<long long>(n) * L + t0) * C + c0 + 2 * cp;
         if (ch_ok) {
+            // activation for all outputs first, straight-line (a store inside its own `if (t < L)` block per output kept
+            // ptxas from interleaving the MUFU -> Horner chains of different outputs: they ran back to back), then the
+            // stores: unpredicated for tiles inside the utterance, per-row bounds only in its last tile
+            uint32_t res[OT];
 #pragma unroll
             for (int o = 0; o < OT; ++o) {
                 float a0, a1;
                 if (ACT) swoosh_r_pair(acc[o], a0, a1);
                 else unpack2(acc[o], a0, a1);
-                if (t0 + o < L) *reinterpret_cast<uint32_t*>(on + static_cast<long long>(o) * C) = pack_h2(a0, a1);
+                res[o] = pack_h2(a0, a1);
+            }
+            const long long rowb = static_cast<long long>(C) * 2;          // bytes per frame
+            uint8_t* ob = reinterpret_cast<uint8_t*>(on);
+            if (t0 + OT <= L) {
+#pragma unroll
+                for (int o = 0; o < OT; ++o) *reinterpret_cast<uint32_t*>(ob + o * rowb) = res[o];
+            } else {
+#pragma unroll
+                for (int o = 0; o < OT; ++o)
+                    if (t0 + o < L) *reinterpret_cast<uint32_t*>(ob + o * rowb) = res[o];
             }
         }
         __syncthreads();                        // the window reads of this buffer are done: it may be refilled

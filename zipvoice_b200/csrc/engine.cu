@@ -77,7 +77,7 @@ static double g_wide_waste = 0.12; // ZVB_WIDE_WASTE: largest padding share acce
 static int g_bn192 = 0;           // ZVB_BN192=1: 192-column tiles for short-K GEMMs (measured: no gain)
 static int g_layout_ok = 1;       // ZVB_NO_LAYOUT=1 keeps the default operand-ring / aux split everywhere
 static int g_attn_tc = 0;         // ZVB_ATTN_TC=1: attention weights with the tensor-core rel-pos bias (attn3.cuh; measured slower)
-static int g_dw_mode = 1;          // ZVB_DW_MODE=0: register-resident window (32 outputs / thread); measured equal, DESIGN.md §3
+static int g_dw_mode = 0;          // ZVB_DW_MODE: depthwise-convolution block shapes (elementwise.cuh: DwShape), 0 = measured best
 static int g_small_model = 1;      // ZVB_NO_SMALL_MODEL=1: round 1's tile-width choice for small problems
 static int g_lean_pad = 1;         // ZVB_NO_LEAN_PAD=1: exact-fit tile widths for projections that are no multiple of 64 wide
 static int g_fast_resid = 1;       // ZVB_NO_FAST_RESID=1: generic epilogue for the residual-stream GEMMs
