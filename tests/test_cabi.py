@@ -69,3 +69,39 @@ def test_no_cpu_fallback(lib):
     model = build_model(cfg, synth_state_dict(cfg), "cpu")
     with pytest.raises(_lib.ZvbError):
         model.sample([[1, 2]], [[3]], torch.zeros(1, 4, 100), torch.tensor([4]), num_step=1)
+
+
+def test_vocoder_workspace_sizing_and_errors_are_host_only(lib):
+    """zvb_vocoder_workspace_bytes needs no device; bad descriptions are rejected with a message."""
+    from zipvoice_b200.vocoder import PackedVocos, synth_vocos_state_dict
+    pk = PackedVocos(synth_vocos_state_dict(0, dim=256, intermediate=512, n_layers=2), "cpu")
+    n = C.c_size_t()
+    assert lib.zvb_vocoder_workspace_bytes(C.byref(pk.struct), 2, 100, C.byref(n)) == 0
+    small = n.value
+    assert lib.zvb_vocoder_workspace_bytes(C.byref(pk.struct), 4, 100, C.byref(n)) == 0
+    assert n.value > small > 2 * 100 * 1024 * 4                       # at least the windowed time frames
+    assert lib.zvb_vocoder_workspace_bytes(C.byref(pk.struct), 2, 1, C.byref(n)) == -1
+    assert b"T at least 2" in lib.zvb_last_error()
+    bad = _lib.zvb_vocoder.from_buffer_copy(pk.struct)
+    bad.hop = 300                                                     # does not divide n_fft
+    assert lib.zvb_vocoder_workspace_bytes(C.byref(bad), 2, 100, C.byref(n)) == -1
+    assert b"hop" in lib.zvb_last_error()
+    bad = _lib.zvb_vocoder.from_buffer_copy(pk.struct)
+    bad.abi_version = 1
+    assert lib.zvb_vocoder_workspace_bytes(C.byref(bad), 2, 100, C.byref(n)) == -1
+    assert b"ABI" in lib.zvb_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_audio_stages_have_no_cpu_fallback(lib):
+    from zipvoice_b200.frontend import VocosFbank
+    from zipvoice_b200.vocoder import Vocos, synth_vocos_state_dict
+    with pytest.raises(_lib.ZvbError):
+        VocosFbank(device="cpu")
+    voc = Vocos().load_state_dict(synth_vocos_state_dict(0, dim=256, intermediate=512, n_layers=1))
+    with pytest.raises(_lib.ZvbError):
+        voc.decode(torch.zeros(1, 100, 10))
+    w = torch.zeros(1, 2048)
+    out = torch.zeros(1, 8, 100)
+    rc = lib.zvb_fbank(w.data_ptr(), None, 1, 2048, None, None, None, 100, 256, 1.0, out.data_ptr(), 8, None)
+    assert rc in (-4, -1)                                             # no device (or null argument): never computed on the host
