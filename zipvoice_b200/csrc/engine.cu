@@ -80,6 +80,7 @@ static int g_attn_tc = 0;         // ZVB_ATTN_TC=1: attention weights with the t
 static int g_dw_mode = 0;          // ZVB_DW_MODE: depthwise-convolution block shapes (elementwise.cuh: DwShape), 0 = measured best
 static int g_small_model = 1;      // ZVB_NO_SMALL_MODEL=1: round 1's tile-width choice for small problems
 static int g_lean_pad = 1;         // ZVB_NO_LEAN_PAD=1: exact-fit tile widths for projections that are no multiple of 64 wide
+static int g_fast_bypass = 1;      // ZVB_NO_FAST_BYPASS=1: generic epilogue for the bypass GEMM (feed_forward2)
 static int g_fast_resid = 1;       // ZVB_NO_FAST_RESID=1: generic epilogue for the residual-stream GEMMs
 static int g_fast_epi = 1;        // ZVB_NO_FAST_EPI=1: generic epilogue everywhere
 static int g_resident_ok = 0;     // ZVB_RESIDENT=1: A-stationary tile order for the K = 512 GEMMs (measured 5-8% SLOWER, profiles/gemm_resident_ab_r2.txt)
@@ -97,6 +98,11 @@ static gemm_fn_t gemm_fn(int kind, int act, int cluster, int lean) {
         if (act != ACT_NONE) return nullptr;
         if (cluster == 1) ZVB_G(EPI_LINEAR, ACT_NONE, 1, 2);
         ZVB_G(EPI_LINEAR, ACT_NONE, 2, 2);
+    }
+    if (lean == 3) {
+        if (act != ACT_NONE) return nullptr;
+        if (cluster == 1) ZVB_G(EPI_LINEAR, ACT_NONE, 1, 3);
+        ZVB_G(EPI_LINEAR, ACT_NONE, 2, 3);
     }
 #define ZVB_G2(A, L) if (act == A && lean == L) { if (cluster == 1) ZVB_G(EPI_LINEAR, A, 1, L); ZVB_G(EPI_LINEAR, A, 2, L); }
     ZVB_G2(ACT_NONE, 0) ZVB_G2(ACT_SWOOSH_L, 0) ZVB_G2(ACT_SWOOSH_R, 0) ZVB_G2(ACT_GELU, 0)
@@ -137,6 +143,7 @@ static int init_device() {
         if (const char* e = getenv("ZVB_RESIDENT")) g_resident_ok = atoi(e) != 0;
         if (const char* e = getenv("ZVB_NO_FAST_EPI")) g_fast_epi = atoi(e) == 0;
         if (const char* e = getenv("ZVB_NO_FAST_RESID")) g_fast_resid = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_NO_FAST_BYPASS")) g_fast_bypass = atoi(e) == 0;
         if (const char* e = getenv("ZVB_NO_LEAN_PAD")) g_lean_pad = atoi(e) == 0;
         if (const char* e = getenv("ZVB_NO_SMALL_MODEL")) g_small_model = atoi(e) == 0;
         if (const char* e = getenv("ZVB_ATTN_TC")) g_attn_tc = atoi(e) != 0;
@@ -152,7 +159,7 @@ static int init_device() {
         g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     }
 #define ZVB_SMEM_ATTR(k) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES))
-    for (int lean = 0; lean < 3; ++lean)
+    for (int lean = 0; lean < 4; ++lean)
         for (int act = 0; act < 4; ++act)
             for (int cl = 1; cl <= 2; ++cl)
                 if (gemm_fn(EPI_LINEAR, act, cl, lean) != nullptr) ZVB_SMEM_ATTR(gemm_fn(EPI_LINEAR, act, cl, lean));
@@ -482,10 +489,13 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
     p.fast_epi = (g_fast_epi && p.tma_store && p.aux_mode == AUX_NONE && p.out_mode == OUT_H16 && p.rowbias == nullptr &&
                   p.rowscale == nullptr && p.row_mask == nullptr && bn % 64 == 0 && lin.out_features % 8 == 0 &&
                   (reinterpret_cast<uintptr_t>(lin.b) & 15) == 0) ? 1 : 0;
-    p.fast_resid = (g_fast_resid && e.act == ACT_NONE && p.tma_store && p.aux_mode == AUX_ADD_H16 && !p.orig_tma &&
-                    p.out_mode == OUT_H16 && p.rowscale == nullptr && p.row_mask == nullptr && bn % 64 == 0 &&
-                    lin.out_features % bn == 0 && (reinterpret_cast<uintptr_t>(lin.b) & 15) == 0 &&
-                    (p.rowbias == nullptr || p.rows_per_group >= GEMM_BLOCK_M)) ? 1 : 0;
+    {
+        const bool base = g_fast_resid && e.act == ACT_NONE && p.tma_store && p.aux_mode == AUX_ADD_H16 && p.out_mode == OUT_H16 &&
+                          p.rowscale == nullptr && p.row_mask == nullptr && bn % 64 == 0 && lin.out_features % bn == 0;
+        p.fast_resid = 0;
+        if (base && !p.orig_tma && (p.rowbias == nullptr || p.rows_per_group >= GEMM_BLOCK_M)) p.fast_resid = 1;
+        else if (base && p.orig_tma && p.rowbias == nullptr && g_fast_bypass) p.fast_resid = 2;      // + bypass (LEAN 3)
+    }
     if (e.out_mode == OUT_H16) mark_out(op, 0, out, M * ldc);
     else if (e.out_mode == OUT_T_H16 && e.t_L > 0) mark_out(op, 0, out, (M / e.t_L) * (long long)e.t_batch_rows * e.t_pitch);
     op.shape[0] = (int)M; op.shape[1] = lin.out_features; op.shape[2] = lin.in_features; op.shape[3] = bn;
@@ -701,7 +711,7 @@ static int launch_op(const Op& op, cudaStream_t st) {
             attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = g_pdl ? 2 : 1;
-            const int lean = op.kind == EPI_GATED ? 0 : (op.gp.fast_epi ? 1 : op.gp.fast_resid ? 2 : 0);
+            const int lean = op.kind == EPI_GATED ? 0 : (op.gp.fast_epi ? 1 : op.gp.fast_resid == 2 ? 3 : op.gp.fast_resid ? 2 : 0);
             gemm_fn_t fn = gemm_fn(op.kind, op.gp.act, op.cluster, lean);
             if (fn == nullptr) return fail(ZVB_ERR_INVALID, "gemm: no kernel for kind %d act %d lean %d", op.kind, op.gp.act, lean);
             cudaError_t e = cudaLaunchKernelEx(&cfg, fn, op.ma, op.mb, mx, ms, mo, op.gp);

@@ -238,7 +238,7 @@ __device__ __forceinline__ void store_unit(const GemmParams& p, uint8_t* stage, 
 // CTAs' `empty` / `tmem_full`; the peer's epilogue warps arrive remotely on the leader's `tmem_empty`.
 // LEAN selects the epilogue at COMPILE time: 0 = generic (every operand / store mode), 1 = lean plain epilogue
 // (GemmParams::fast_epi), 2 = lean residual-stream epilogue (GemmParams::fast_resid).  Separate instantiations, because
-// one kernel carrying all three paths costs the generic path registers (round 2: +20% on the N = 272 / N = 48 projections
+// 3 = lean residual epilogue with the bypass (fast_resid == 2); one kernel carrying all paths costs the generic path registers (round 2: +20% on the N = 272 / N = 48 projections
 // when the lean paths were runtime branches of the same kernel).
 template <int KIND, int ACT, int CLUSTER, int LEAN = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -634,6 +634,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     g = g > g_last ? g_last : g;
                     cv += __ldg(p.rowbias + g * p.ld_rowbias + ccol);
                 }
+                if (LEAN == 3 && (e >> 8) != 0) cv = ccol < p.n_out ? __ldg(p.bypass_scale + ccol) : 0.0f;   // row 1: bypass scale
                 float* cb = cbias_smem + (tile_iter & 1u) * 512;
                 cb[e] = cv;
                 asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -751,6 +752,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         unpack2(v2[4 * j], a0, a1); unpack2(v2[4 * j + 1], a2, a3);
                         unpack2(v2[4 * j + 2], a4f, a5); unpack2(v2[4 * j + 3], a6, a7);
                         sts128_u32(arow + fast_chunk[j], pack_h2(a0, a1), pack_h2(a2, a3), pack_h2(a4f, a5), pack_h2(a6, a7));
+                    }
+                    signal_staged();
+                }
+            } else if (KIND == EPI_LINEAR && ACT == ACT_NONE && LEAN == 3) {
+                // Lean residual epilogue with the bypass (feed_forward2 + bypass_mid, reference: zipformer.py:584-590):
+                //   v = resid + A.W^T + b;  out = orig + (v - orig) * scale[col]
+                // `orig` rides the aux ring next to the residual sub-tile (two slots per sub-tile); the scale comes from row 1
+                // of the tile's bias cache.  Chunk by chunk (8 columns) to stay inside the register budget.
+                const uint32_t aux_row0 = smem_u32(aux_smem) + static_cast<uint32_t>(r * 128);
+                for (int s = half; s < n_sub; s += 2) {
+                    const uint32_t q = (tile_iter * static_cast<uint32_t>(n_sub) + static_cast<uint32_t>(s)) * 2u;
+                    const uint32_t slot = q % static_cast<uint32_t>(AUX_SLOTS);
+                    const uint32_t slot2 = (q + 1u) % static_cast<uint32_t>(AUX_SLOTS);
+                    const int c0 = (2 * s + part) * 32;
+                    uint32_t acc_r[32];
+                    tmem_ld32(taddr + c0, acc_r);
+                    mbar_wait(&aux_full[slot], (q / static_cast<uint32_t>(AUX_SLOTS)) & 1u);
+                    mbar_wait(&aux_full[slot2], ((q + 1u) / static_cast<uint32_t>(AUX_SLOTS)) & 1u);
+                    const uint32_t arow = aux_row0 + slot * static_cast<uint32_t>(GEMM_AUX_BYTES);
+                    const uint32_t orow = aux_row0 + slot2 * static_cast<uint32_t>(GEMM_AUX_BYTES);
+                    tmem_ld_wait();
+                    wait_sfree();                      // earlier stores no longer read what is overwritten
+                    const uint32_t cbb = cb_addr + static_cast<uint32_t>(c0 * 4);     // row 0: bias, row 1 (+1024 B): scale (no row bias here)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 a4 = lds128_u32(arow + fast_chunk[j]);
+                        const uint4 o4 = lds128_u32(orow + fast_chunk[j]);
+                        const uint32_t av[4] = {a4.x, a4.y, a4.z, a4.w}, ov[4] = {o4.x, o4.y, o4.z, o4.w};
+                        uint32_t hv[4];
+#pragma unroll
+                        for (int h2i = 0; h2i < 2; ++h2i) {
+                            const uint4 bq = lds128_u32(cbb + static_cast<uint32_t>(j * 32 + h2i * 16));
+                            const uint4 sq = lds128_u32(cbb + 1024u + static_cast<uint32_t>(j * 32 + h2i * 16));
+                            const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w}, sw4[4] = {sq.x, sq.y, sq.z, sq.w};
+#pragma unroll
+                            for (int e2 = 0; e2 < 2; ++e2) {
+                                const int pi = 2 * h2i + e2;                    // pair inside the chunk
+                                const int ci = 8 * j + 2 * pi;                  // first column of the pair inside the unit
+                                f32x2 v = add2(pack2(__uint_as_float(acc_r[ci]), __uint_as_float(acc_r[ci + 1])),
+                                               pack2(__uint_as_float(bw[2 * e2]), __uint_as_float(bw[2 * e2 + 1])));
+                                v = add2(v, pack2(h2_lo(av[pi]), h2_hi(av[pi])));
+                                const f32x2 o2 = pack2(h2_lo(ov[pi]), h2_hi(ov[pi]));
+                                const f32x2 d = fma2(o2, pack2(-1.0f, -1.0f), v);
+                                const f32x2 y = fma2(d, pack2(__uint_as_float(sw4[2 * e2]), __uint_as_float(sw4[2 * e2 + 1])), o2);
+                                float y0, y1;
+                                unpack2(y, y0, y1);
+                                hv[pi] = pack_h2(y0, y1);
+                            }
+                        }
+                        sts128_u32(arow + fast_chunk[j], hv[0], hv[1], hv[2], hv[3]);   // in place over the residual bytes
                     }
                     signal_staged();
                 }
