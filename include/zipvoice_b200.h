@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ZVB_ABI_VERSION 5
+#define ZVB_ABI_VERSION 6
 #define ZVB_MAX_STACKS 8
 #define ZVB_MAX_LAYERS 64
 #define ZVB_VOC_MAX_LAYERS 16
@@ -69,6 +69,9 @@ typedef struct {
                                * one entry, LZ = even(2L + 264); followed by [H] fp32 max_r |log2e*E[h][r]|_2
                                * (zipvoice_b200/weights.py: pack_pos_table_tc).  null: the CUDA-core kernel is used */
     zvb_linear ff_in[3], ff_out[3];
+    zvb_linear ff1_attn;      /* rows [feed_forward1.in_proj ; self_attn_weights.in_proj] in ONE weight (both read the layer input;
+                               * the time embedding of feed_forward1's input becomes a per-utterance row bias W1*temb).
+                               * w == null: the two projections run as separate GEMMs (attn_in, ff_in[0]) */
     zvb_linear na_sx;         /* nonlin_attention.in_proj rows (s,x), gated-packed          */
     zvb_linear na_y;          /* nonlin_attention.in_proj rows y                            */
     zvb_linear na_out;

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # ZVB_LIB: an alternative in-tree build of the same sources (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("ZVB_LIB") or os.path.join(HERE, "libzipvoice_b200.so")
 
-ZVB_ABI_VERSION = 5
+ZVB_ABI_VERSION = 6
 ZVB_MAX_STACKS = 8
 ZVB_VOC_MAX_LAYERS = 16
 
@@ -26,7 +26,7 @@ class zvb_linear(C.Structure):
 
 class zvb_layer(C.Structure):
     _fields_ = [("attn_in", zvb_linear), ("pos_table", C.c_void_p), ("pos_table_tc", C.c_void_p),
-                ("ff_in", zvb_linear * 3), ("ff_out", zvb_linear * 3),
+                ("ff_in", zvb_linear * 3), ("ff_out", zvb_linear * 3), ("ff1_attn", zvb_linear),
                 ("na_sx", zvb_linear), ("na_y", zvb_linear), ("na_out", zvb_linear),
                 ("sa_in", zvb_linear * 2), ("sa_out", zvb_linear * 2),
                 ("conv_in", zvb_linear * 2), ("dw_w", C.c_void_p * 2), ("dw_b", C.c_void_p * 2),

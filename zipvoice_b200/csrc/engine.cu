@@ -78,6 +78,7 @@ static int g_bn192 = 0;           // ZVB_BN192=1: 192-column tiles for short-K G
 static int g_layout_ok = 1;       // ZVB_NO_LAYOUT=1 keeps the default operand-ring / aux split everywhere
 static int g_attn_tc = 0;         // ZVB_ATTN_TC=1: attention weights with the tensor-core rel-pos bias (attn3.cuh; measured slower)
 static int g_dw_mode = 0;          // ZVB_DW_MODE: depthwise-convolution block shapes (elementwise.cuh: DwShape), 0 = measured best
+static int g_merge_ff1 = 1;        // ZVB_NO_MERGE=1: feed_forward1 / attention in-projections as separate GEMMs
 static int g_small_model = 1;      // ZVB_NO_SMALL_MODEL=1: round 1's tile-width choice for small problems
 static int g_lean_pad = 1;         // ZVB_NO_LEAN_PAD=1: exact-fit tile widths for projections that are no multiple of 64 wide
 static int g_fast_bypass = 1;      // ZVB_NO_FAST_BYPASS=1: generic epilogue for the bypass GEMM (feed_forward2)
@@ -122,6 +123,31 @@ constexpr int ZVB_MAX_DEVICES = 64;
 static std::mutex g_init_mutex;
 static int g_dev_sms[ZVB_MAX_DEVICES] = {};
 
+// Measurement switches (environment), read once per process -- before any host-only sizing call, so that
+// zvb_plan_workspace_bytes and zvb_plan_create always agree on the plan's shape.
+static std::once_flag g_switch_once;
+static void load_switches() {
+    std::call_once(g_switch_once, [] {
+        if (const char* e = getenv("ZVB_NO_CLUSTER")) g_cluster_ok = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_NO_TMA_STORE")) g_tma_store_ok = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
+        if (const char* e = getenv("ZVB_NO_LAYOUT")) g_layout_ok = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_NO_PDL")) g_pdl = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_RESIDENT")) g_resident_ok = atoi(e) != 0;
+        if (const char* e = getenv("ZVB_NO_FAST_EPI")) g_fast_epi = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_NO_FAST_RESID")) g_fast_resid = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_NO_FAST_BYPASS")) g_fast_bypass = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_NO_LEAN_PAD")) g_lean_pad = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_NO_SMALL_MODEL")) g_small_model = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_NO_MERGE")) g_merge_ff1 = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_ATTN_TC")) g_attn_tc = atoi(e) != 0;
+        if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
+        if (const char* e = getenv("ZVB_DW_MODE")) g_dw_mode = atoi(e);
+        if (const char* e = getenv("ZVB_WIDE_PREF")) g_wide_pref = atoi(e) != 0;
+        if (const char* e = getenv("ZVB_WIDE_WASTE")) g_wide_waste = atof(e);
+    });
+}
+
 static int init_device() {
     std::lock_guard<std::mutex> lock(g_init_mutex);
     int dev = 0, count = 0;
@@ -134,23 +160,8 @@ static int init_device() {
     CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10)
         return fail(ZVB_ERR_NO_DEVICE, "device sm_%d%d is not sm_100 (B200)", prop.major, prop.minor);
+    load_switches();
     if (g_encode == nullptr) {
-        if (const char* e = getenv("ZVB_NO_CLUSTER")) g_cluster_ok = atoi(e) == 0;
-        if (const char* e = getenv("ZVB_NO_TMA_STORE")) g_tma_store_ok = atoi(e) == 0;
-        if (const char* e = getenv("ZVB_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
-        if (const char* e = getenv("ZVB_NO_LAYOUT")) g_layout_ok = atoi(e) == 0;
-        if (const char* e = getenv("ZVB_NO_PDL")) g_pdl = atoi(e) == 0;
-        if (const char* e = getenv("ZVB_RESIDENT")) g_resident_ok = atoi(e) != 0;
-        if (const char* e = getenv("ZVB_NO_FAST_EPI")) g_fast_epi = atoi(e) == 0;
-        if (const char* e = getenv("ZVB_NO_FAST_RESID")) g_fast_resid = atoi(e) == 0;
-        if (const char* e = getenv("ZVB_NO_FAST_BYPASS")) g_fast_bypass = atoi(e) == 0;
-        if (const char* e = getenv("ZVB_NO_LEAN_PAD")) g_lean_pad = atoi(e) == 0;
-        if (const char* e = getenv("ZVB_NO_SMALL_MODEL")) g_small_model = atoi(e) == 0;
-        if (const char* e = getenv("ZVB_ATTN_TC")) g_attn_tc = atoi(e) != 0;
-        if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
-        if (const char* e = getenv("ZVB_DW_MODE")) g_dw_mode = atoi(e);
-        if (const char* e = getenv("ZVB_WIDE_PREF")) g_wide_pref = atoi(e) != 0;
-        if (const char* e = getenv("ZVB_WIDE_WASTE")) g_wide_waste = atof(e);
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
         CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
@@ -243,7 +254,7 @@ static int make_tmap_plain(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_
 }
 
 // ------------------------------------------------------------------------------------------ ops
-enum OpType { OP_GEMM, OP_ATTN, OP_ATTN_TC, OP_BIASNORM, OP_PREP, OP_DOWN, OP_UP, OP_DWCONV, OP_MASK, OP_MASKW, OP_TSEMB, OP_SMALL,
+enum OpType { OP_CAST, OP_GEMM, OP_ATTN, OP_ATTN_TC, OP_BIASNORM, OP_PREP, OP_DOWN, OP_UP, OP_DWCONV, OP_MASK, OP_MASKW, OP_TSEMB, OP_SMALL,
               OP_LAYERNORM, OP_VOC_MASK, OP_VOC_WINDOW, OP_ISTFT_FRAMES, OP_OLA };
 
 struct Op {
@@ -364,6 +375,7 @@ struct LinearEpi {
     int t_L = 0, t_pitch = 0, t_batch_rows = 0, t_hd = 1, t_hp = 1;   // OUT_T_H16
     int block_n = 0;                     // 0 = choose
     const uint8_t* row_mask = nullptr;   // rows with mask != 0 are written as zeros (generic epilogue)
+    int act_cols = 0;                    // > 0: activation on output columns < act_cols only
 };
 
 // Decides whether the op runs as 2-CTA clusters with a multicast B tile, and the persistent grid.
@@ -462,6 +474,7 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
     p.rowbias = e.rowbias; p.rows_per_group = e.rows_per_group; p.ld_rowbias = lin.out_features;
     p.bypass_scale = e.bypass_scale;
     p.act = e.act;
+    p.act_cols = e.act_cols;
     p.row_mask = e.row_mask;
     p.t_L = e.t_L; p.t_pitch = e.t_pitch; p.t_batch_rows = e.t_batch_rows; p.t_hd = e.t_hd; p.t_hp = e.t_hp;
     set_grid(op);
@@ -486,7 +499,8 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
         p.orig_tma = 1;
     }
     gemm_layout(op);
-    p.fast_epi = (g_fast_epi && p.tma_store && p.aux_mode == AUX_NONE && p.out_mode == OUT_H16 && p.rowbias == nullptr &&
+    p.fast_epi = (g_fast_epi && p.tma_store && p.aux_mode == AUX_NONE && p.out_mode == OUT_H16 &&
+                  (p.rowbias == nullptr || p.rows_per_group >= GEMM_BLOCK_M) && p.act_cols % 32 == 0 &&
                   p.rowscale == nullptr && p.row_mask == nullptr && bn % 64 == 0 && lin.out_features % 8 == 0 &&
                   (reinterpret_cast<uintptr_t>(lin.b) & 15) == 0) ? 1 : 0;
     {
@@ -790,6 +804,12 @@ static int launch_op(const Op& op, cudaStream_t st) {
                 op.f0, op.f1, op.f2, op.f3, (float*)op.o0, op.i0, op.i1, op.i2, op.i3, op.i4);
             return check_launch("small_linear");
         }
+        case OP_CAST: {
+            const long long n = op.rows * op.i1;
+            launch_k(cast_pad_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const float*)op.p0, (h16*)op.o0, op.rows,
+                     op.i0, op.i1);
+            return check_launch("cast_pad");
+        }
         case OP_LAYERNORM: {
             const int blocks = static_cast<int>((op.rows + 7) / 8);
             launch_k(layernorm_kernel<4>, dim3(blocks), dim3(256), 0, st, (const h16*)op.p0, (h16*)op.o0, op.f0, op.f1,
@@ -872,7 +892,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
     const int hp = (dv + 15) / 16 * 16;
     const int attn_w = H * (2 * 32 + 4);
     const int nah = m->na_hidden;
-    const int ffmax = std::max(m->ff_dims[0], std::max(m->ff_dims[1], m->ff_dims[2]));
+    const int ffmax = std::max(std::max(m->ff_dims[0] + H * (2 * 32 + 4), m->ff_dims[1]), m->ff_dims[2]);
     const int xin_pitch = round8(m->in_dim);
     const long long M = (long long)N * T;
 
@@ -899,9 +919,20 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
     h16* cur0 = c.take<h16>(M * D);             // full-rate stream (ping-pong)
     h16* cur1 = c.take<h16>(M * D);
     h16* S[2] = {c.take<h16>(M * D), c.take<h16>(M * D)};        // layer inputs inside a stack
-    h16* St[2] = {c.take<h16>(M * D), c.take<h16>(M * D)};       // src + temb
+    const bool merged = g_merge_ff1 && m->layers[0].ff1_attn.w != nullptr;
+    h16* St[2] = {nullptr, nullptr};                             // src + temb (only when the projections are not merged)
+    if (!merged) { St[0] = c.take<h16>(M * D); St[1] = c.take<h16>(M * D); }
     h16* R[2] = {c.take<h16>(M * D), c.take<h16>(M * D)};        // stream inside a layer
     h16* qkp = c.take<h16>(M * attn_w);
+    // merged feed_forward1 / attention in-projection (zvb_layer::ff1_attn): fp16 time embedding per stack and the
+    // per-utterance row bias W1 * temb (fp32, pitch = merged width; the attention columns stay zero)
+    const int mw = m->ff_dims[0] + attn_w;
+    h16* tembh[ZVB_MAX_STACKS] = {};
+    float* rb1 = nullptr;
+    if (merged && td > 0) {
+        for (int s = 0; s < m->num_stacks; ++s) tembh[s] = c.take<h16>((size_t)N * D);
+        rb1 = c.take<float>((size_t)N * mw);
+    }
     h16* hid = c.take<h16>(M * ffmax);
     h16* nay = c.take<h16>(M * nah);
     h16* pvna = c.take<h16>(M * nah);
@@ -960,6 +991,11 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
         for (int s = 0; s < m->num_stacks; ++s)
             ops.push_back(small_op(te3, m->stacks[s].time_w, m->stacks[s].time_b, nullptr, temb[s], N, td, D,
                                    ACT_SWOOSH_R_, 0));
+        if (merged)
+            for (int s = 0; s < m->num_stacks; ++s) {
+                Op cst; cst.type = OP_CAST; cst.p0 = temb[s]; cst.o0 = tembh[s]; cst.rows = N; cst.i0 = D; cst.i1 = D;
+                ops.push_back(cst);
+            }
     }
     // in_proj (reference: modules/zipformer.py:264-265) -> stream
     {
@@ -988,14 +1024,14 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             ops.push_back(op);
         }
         const h16* src = ds == 1 ? cur : S[0];
-        if (tb != nullptr) {   // time-embedded copy of the stack input: St[0] = src + temb
+        if (tb != nullptr && !merged) {   // time-embedded copy of the stack input: St[0] = src + temb
             Op op; op.type = OP_PREP; op.p0 = src; op.o0 = St[0];
             op.f0 = tb; op.i0 = D; op.i1 = L; op.rows = Ms;
             op.cat = ZVB_CAT_ELEMENTWISE; op.work = (double)Ms * D * (2.0 + 2.0);
             mark_out(op, 0, St[0], Ms * D);
             ops.push_back(op);
         }
-        const h16* srct = tb != nullptr ? St[0] : src;
+        const h16* srct = (tb != nullptr && !merged) ? St[0] : src;
         for (int j = 0; j < stk.num_layers; ++j) {
             const zvb_layer& ly = m->layers[stk.first_layer + j];
             const bool last = j == stk.num_layers - 1;
@@ -1010,19 +1046,39 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
                 x.t_hd = hd_; x.t_hp = hp_;
                 return x;
             };
-            // 1. attention projections + weights (on the un-time-embedded input)
-            e = LinearEpi();
-            TRY(build_linear(op, src, Ms, D, ly.attn_in, qkp, attn_w, e)); ops.push_back(op);
+            const h16* qkp_l = qkp;
+            int qkp_ld = attn_w, hid_ld = m->ff_dims[0];
+            if (merged) {
+                // 1+2. ONE GEMM over the layer input for feed_forward1.in_proj (SwooshL) and the attention projections (no
+                // activation): hid = [SwooshL(W1 src + W1 temb + b1) | q k p].  feed_forward1 runs on src + temb
+                // (reference: zipformer.py:532-536): the time embedding enters as the per-utterance row bias W1 temb.
+                if (tb != nullptr) {
+                    zvb_linear w1 = ly.ff1_attn;
+                    w1.b = nullptr; w1.out_features = m->ff_dims[0]; w1.rows = m->ff_dims[0];
+                    e = LinearEpi(); e.out_mode = OUT_F32;
+                    TRY(build_linear(op, tembh[s], N, D, w1, rb1, mw, e)); op.cat = ZVB_CAT_OTHER; ops.push_back(op);
+                }
+                e = LinearEpi(); e.act = ACT_SWOOSH_L; e.act_cols = m->ff_dims[0];
+                if (tb != nullptr) { e.rowbias = rb1; e.rows_per_group = L; }
+                TRY(build_linear(op, src, Ms, D, ly.ff1_attn, hid, mw, e)); ops.push_back(op);
+                qkp_l = hid + m->ff_dims[0]; qkp_ld = mw; hid_ld = mw;
+            } else {
+                // 1. attention projections (on the un-time-embedded input)
+                e = LinearEpi();
+                TRY(build_linear(op, src, Ms, D, ly.attn_in, qkp, attn_w, e)); ops.push_back(op);
+            }
             if (g_attn_tc && ly.pos_table_tc != nullptr)
-                TRY(build_attn_tc(op, qkp, attn_w, ly.pos_table_tc, maskw_ds[ds], P, invl, N, H, L, Lk));
+                TRY(build_attn_tc(op, qkp_l, qkp_ld, ly.pos_table_tc, maskw_ds[ds], P, invl, N, H, L, Lk));
             else
-                TRY(build_attn(op, qkp, attn_w, ly.pos_table, maskw_ds[ds], P, invl, N, H, L, Lk));
+                TRY(build_attn(op, qkp_l, qkp_ld, ly.pos_table, maskw_ds[ds], P, invl, N, H, L, Lk));
             ops.push_back(op);
             // 2. feed_forward1 on src + temb:  R0 = src + temb + FF1(src + temb)
-            e = LinearEpi(); e.act = ACT_SWOOSH_L;
-            TRY(build_linear(op, srct, Ms, D, ly.ff_in[0], hid, m->ff_dims[0], e)); ops.push_back(op);
+            if (!merged) {
+                e = LinearEpi(); e.act = ACT_SWOOSH_L;
+                TRY(build_linear(op, srct, Ms, D, ly.ff_in[0], hid, m->ff_dims[0], e)); ops.push_back(op);
+            }
             e = stream_epi(src); e.rowbias = tb; e.rows_per_group = L;
-            TRY(build_linear(op, hid, Ms, m->ff_dims[0], ly.ff_out[0], R[0], D, e)); ops.push_back(op);
+            TRY(build_linear(op, hid, Ms, hid_ld, ly.ff_out[0], R[0], D, e)); ops.push_back(op);
             // 3. nonlin attention
             e = t_epi(nah, 1, 1);
             TRY(build_gated(op, R[0], Ms, D, ly.na_sx, nah, GATE_TANH_SX, vtna[ds], 0, nullptr, e)); ops.push_back(op);
@@ -1067,7 +1123,7 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
             TRY(build_linear(op, hid, Ms, m->ff_dims[2], ly.ff_out[2], R[1], D, e)); ops.push_back(op);
             // 10. BiasNorm + bypass -> next layer input and its time-embedded copy
             h16* nsrc = (last && ds == 1) ? cur_alt : S[si ^ 1];     // never aliases `src`
-            h16* nsrct = (!last && tb != nullptr) ? St[si ^ 1] : nullptr;
+            h16* nsrct = (!last && tb != nullptr && !merged) ? St[si ^ 1] : nullptr;
             { Op b; b.type = OP_BIASNORM; b.p0 = R[1]; b.p1 = src; b.o0 = nsrc; b.o1 = nsrct;
               b.f0 = ly.norm_bias; b.f1 = ly.norm_log_scale; b.f2 = ly.bypass_scale; b.f3 = tb;
               b.i0 = D; b.i1 = L; b.rows = Ms;
@@ -1202,6 +1258,7 @@ int zvb_abi_version(void) { return ZVB_ABI_VERSION; }
 long long zvb_launch_count(void) { return g_launches; }
 
 int zvb_plan_workspace_bytes(const zvb_model* model, int N, int T, size_t* bytes) {
+    load_switches();
     if (bytes == nullptr) return fail(ZVB_ERR_INVALID, "bytes is null");
     return build_plan(model, N, T, nullptr, bytes, nullptr);
 }
@@ -1502,6 +1559,7 @@ int zvb_fbank(const float* wav, const int32_t* lens, int B, int s_pitch, const f
 }
 
 int zvb_vocoder_workspace_bytes(const zvb_vocoder* voc, int N, int T, size_t* bytes) {
+    load_switches();
     if (bytes == nullptr) return fail(ZVB_ERR_INVALID, "bytes is null");
     return build_vocoder(voc, N, T, nullptr, bytes, nullptr);
 }

@@ -102,6 +102,7 @@ struct GemmParams {
     int orig_tma;          // bypass: orig + (v - orig)*scale[col]; `orig` (fp16) rides through the aux ring
     const float* bypass_scale;
     int act;
+    int act_cols;          // > 0: the activation applies to output columns < act_cols only (merged projections)
     int gate_mode;
     const uint8_t* row_mask;        // [rows] non-zero -> output row is zero
     // OUT_T_H16: dst[(row / t_L)*t_batch_rows + drow(col)][row % t_L], pitch t_pitch,
@@ -672,7 +673,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             v2[j] = add2(pack2(__uint_as_float(acc_r[2 * j]), __uint_as_float(acc_r[2 * j + 1])), v2[j]);
-                        if (ACT == ACT_SWOOSH_L) {
+                        if (ACT != ACT_NONE && p.act_cols > 0 && gc >= p.act_cols) {
+                            // columns past act_cols (the attention projections of a merged GEMM): no activation
+                        } else if (ACT == ACT_SWOOSH_L) {
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) swoosh_x2_group<4>(v2 + j, SWOOSH_L_C, SWOOSH_L_K0);
                         } else if (ACT == ACT_SWOOSH_R) {
@@ -927,7 +930,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                     if (i < ncols) v[i] += __ldg(rbp + i);
                             }
                         }
-                        if (ACT == ACT_SWOOSH_L) {
+                        if (ACT != ACT_NONE && p.act_cols > 0 && oc + 32 > p.act_cols) {
+                            // unit at or across the activation boundary of a merged GEMM: per column
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (oc + i < p.act_cols) v[i] = apply_act(v[i], ACT);
+                        } else if (ACT == ACT_SWOOSH_L) {
 #pragma unroll
                             for (int i = 0; i < 32; i += 2) swoosh_direct2(v[i], v[i + 1], SWOOSH_L_C, SWOOSH_L_K0);
                         } else if (ACT == ACT_SWOOSH_R) {

@@ -175,6 +175,12 @@ class PackedZipformer:
         bd = self._dev(b.detach().float()) if b is not None else None
         return self._mk(self._pack_w(w), bd, w.shape[0], w.shape[1])
 
+    def _stacked(self, ps: List[str]):
+        """Several nn.Linear with the same input as ONE weight: rows (and biases) concatenated in the given order."""
+        w = torch.cat([self._sd[q + ".weight"].detach().float().cpu() for q in ps], dim=0)
+        b = torch.cat([self._sd[q + ".bias"].detach().float().cpu() for q in ps], dim=0)
+        return self._mk(self._pack_w(w), self._dev(b), w.shape[0], w.shape[1])
+
     def _gated(self, p: str, a: slice, b: slice):
         w = self._sd[p + ".weight"].detach().float().cpu()
         bias = self._sd[p + ".bias"].detach().float().cpu()
@@ -198,6 +204,7 @@ class PackedZipformer:
             attn_in=self._linear(p + "self_attn_weights.in_proj"),
             ff_in=[self._linear(p + f"feed_forward{i}.in_proj") for i in (1, 2, 3)],
             ff_out=[self._linear(p + f"feed_forward{i}.out_proj") for i in (1, 2, 3)],
+            ff1_attn=self._stacked([p + "feed_forward1.in_proj", p + "self_attn_weights.in_proj"]),
             na_sx=self._gated(p + "nonlin_attention.in_proj", slice(0, nah), slice(nah, 2 * nah)),
             na_y=self._linear(p + "nonlin_attention.in_proj", slice(2 * nah, 3 * nah)),
             na_out=self._linear(p + "nonlin_attention.out_proj"),
@@ -257,6 +264,7 @@ class PackedZipformer:
                 for i in range(3):
                     z.ff_in[i] = self._lin_struct(ly["ff_in"][i])
                     z.ff_out[i] = self._lin_struct(ly["ff_out"][i])
+                z.ff1_attn = self._lin_struct(ly["ff1_attn"])
                 z.na_sx = self._lin_struct(ly["na_sx"])
                 z.na_y = self._lin_struct(ly["na_y"])
                 z.na_out = self._lin_struct(ly["na_out"])
