@@ -78,6 +78,7 @@ static int g_bn192 = 0;           // ZVB_BN192=1: 192-column tiles for short-K G
 static int g_layout_ok = 1;       // ZVB_NO_LAYOUT=1 keeps the default operand-ring / aux split everywhere
 static int g_attn_tc = 0;         // ZVB_ATTN_TC=1: attention weights with the tensor-core rel-pos bias (attn3.cuh; measured slower)
 static int g_dw_mode = 0;          // ZVB_DW_MODE: depthwise-convolution block shapes (elementwise.cuh: DwShape), 0 = measured best
+static int g_pv_bn = 0;            // ZVB_PV_BN=<columns>: tile width of the NonlinAttention P.V GEMM (0 = two equal tiles)
 static int g_merge_ff1 = 1;        // ZVB_NO_MERGE=1: feed_forward1 / attention in-projections as separate GEMMs
 static int g_small_model = 1;      // ZVB_NO_SMALL_MODEL=1: round 1's tile-width choice for small problems
 static int g_lean_pad = 1;         // ZVB_NO_LEAN_PAD=1: exact-fit tile widths for projections that are no multiple of 64 wide
@@ -140,6 +141,7 @@ static void load_switches() {
         if (const char* e = getenv("ZVB_NO_LEAN_PAD")) g_lean_pad = atoi(e) == 0;
         if (const char* e = getenv("ZVB_NO_SMALL_MODEL")) g_small_model = atoi(e) == 0;
         if (const char* e = getenv("ZVB_NO_MERGE")) g_merge_ff1 = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_PV_BN")) g_pv_bn = atoi(e);
         if (const char* e = getenv("ZVB_ATTN_TC")) g_attn_tc = atoi(e) != 0;
         if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
         if (const char* e = getenv("ZVB_DW_MODE")) g_dw_mode = atoi(e);
@@ -583,6 +585,7 @@ static int build_pv(Op& op, const h16* P, const float* inv_l, const h16* Vt, voi
     } else {
         const int tiles = (hd + 255) / 256;
         p.block_n = (((hd + tiles - 1) / tiles) + 15) / 16 * 16;
+        if (g_pv_bn > 0 && g_pv_bn % 16 == 0 && g_pv_bn <= 256) p.block_n = g_pv_bn;      // ZVB_PV_BN: measurement override
         p.num_n_tiles = (hd + p.block_n - 1) / p.block_n; p.a_zn = 0;
         p.n_out = hd; p.out_col_stride = p.block_n; p.n_valid = p.block_n;
         vt_rows = hd;
