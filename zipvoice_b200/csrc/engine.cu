@@ -632,7 +632,7 @@ static int build_attn(Op& op, const h16* qkp, int ld, const void* pos_table, con
     op.cat = ZVB_CAT_ATTN_WEIGHTS;
     // q.k (K = 32) + rel-pos (4-dim dot against 2L-1 offsets), reference FLOP model SURVEY.md §8d
     op.work = (double)N * H * (2.0 * L * L * 32 + 2.0 * L * (2.0 * L - 1) * 4);
-    op.bytes = 2.0 * ((double)N * L * ld + (double)N * H * L * Lk) + 4.0 * N * H * L;
+    op.bytes = 2.0 * ((double)N * L * (H * 68) + (double)N * H * L * Lk) + 4.0 * N * H * L;     // q, k, p read once (not the row pitch)
     return 0;
 }
 
@@ -659,7 +659,7 @@ static int build_attn_tc(Op& op, const h16* qkp, int ld, const void* pos_table_t
     mark_out(op, 0, P, (long long)N * H * L * Lk);
     op.cat = ZVB_CAT_ATTN_WEIGHTS;
     op.work = (double)N * H * (2.0 * L * L * 32 + 2.0 * L * (2.0 * L - 1) * 4);
-    op.bytes = 2.0 * ((double)N * L * ld + (double)N * H * L * Lk) + 4.0 * N * H * L;
+    op.bytes = 2.0 * ((double)N * L * (H * 68) + (double)N * H * L * Lk) + 4.0 * N * H * L;     // q, k, p read once (not the row pitch)
     return 0;
 }
 
