@@ -228,6 +228,46 @@ __device__ __forceinline__ void store_unit(const GemmParams& p, uint8_t* stage, 
     }
 }
 
+
+// One 32-column unit of a gated projection: v = (a + ba) gate (g + bg), bias from the warp's staging (bs[0..31] first
+// operand, bs[32..63] second).  TANH: x * tanh(s) with a = s, g = x (NonlinAttention); else GLU x * sigmoid(s) with a = x,
+// g = s (ConvolutionModule).  Straight-line over the 16 column pairs.
+template <bool TANH>
+__device__ __forceinline__ void gated_unit(const uint32_t* ra, const uint32_t* rb, const float* bs, bool masked, float* v) {
+    constexpr float NL2E = -1.4426950408889634f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {           // two columns per packed fp32x2 instruction
+        const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * j);
+        const float4 g4 = *reinterpret_cast<const float4*>(bs + 32 + 4 * j);
+        const float abv[4] = {b4.x, b4.y, b4.z, b4.w};
+        const float gbv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+            const f32x2 a2 = add2(pack2(__uint_as_float(ra[4 * j + e]), __uint_as_float(ra[4 * j + e + 1])),
+                                  pack2(abv[e], abv[e + 1]));
+            const f32x2 g2 = add2(pack2(__uint_as_float(rb[4 * j + e]), __uint_as_float(rb[4 * j + e + 1])),
+                                  pack2(gbv[e], gbv[e + 1]));
+            f32x2 o2;
+            if (TANH) {
+                float a0, a1;
+                unpack2(a2, a0, a1);
+                o2 = mul2(g2, pack2(fast_tanh(a0), fast_tanh(a1)));
+            } else {
+                float z0, z1;
+                unpack2(mul2(g2, pack2(NL2E, NL2E)), z0, z1);
+                const f32x2 d2 = add2(pack2(fast_exp2(z0), fast_exp2(z1)), pack2(1.0f, 1.0f));
+                float d0, d1;
+                unpack2(d2, d0, d1);
+                o2 = mul2(a2, pack2(fast_rcp(d0), fast_rcp(d1)));
+            }
+            float o0, o1;
+            unpack2(o2, o0, o1);
+            v[4 * j + e] = masked ? 0.0f : o0;
+            v[4 * j + e + 1] = masked ? 0.0f : o1;
+        }
+    }
+}
+
 // CLUSTER == 2: a CTA pair computes a 256 x BN tile with `tcgen05.mma.cta_group::2` (UMMA_M = 256):
 // each CTA stages its own 128 rows of A and HALF of the B tile, the leader's MMA thread consumes both
 // CTAs' shared memory, and each CTA's TMEM receives its 128 accumulator rows.  Per SM and k-block
@@ -830,39 +870,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     tmem_ld32(taddr + hcols + c0, rb);
                     tmem_ld_wait();
                     float v[32];
-                    const bool tanh_gate = p.gate_mode == GATE_TANH_SX;
-                    constexpr float NL2E = -1.4426950408889634f;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {           // two columns per packed fp32x2 instruction
-                        const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * j);
-                        const float4 g4 = *reinterpret_cast<const float4*>(bs + 32 + 4 * j);
-                        const float abv[4] = {b4.x, b4.y, b4.z, b4.w};
-                        const float gbv[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-                        for (int e = 0; e < 4; e += 2) {
-                            const f32x2 a2 = add2(pack2(__uint_as_float(ra[4 * j + e]), __uint_as_float(ra[4 * j + e + 1])),
-                                                  pack2(abv[e], abv[e + 1]));
-                            const f32x2 g2 = add2(pack2(__uint_as_float(rb[4 * j + e]), __uint_as_float(rb[4 * j + e + 1])),
-                                                  pack2(gbv[e], gbv[e + 1]));
-                            f32x2 o2;
-                            if (tanh_gate) {                 // x * tanh(s): a = s, g = x
-                                float a0, a1;
-                                unpack2(a2, a0, a1);
-                                o2 = mul2(g2, pack2(fast_tanh(a0), fast_tanh(a1)));
-                            } else {                         // GLU x * sigmoid(s): a = x, g = s
-                                float z0, z1;
-                                unpack2(mul2(g2, pack2(NL2E, NL2E)), z0, z1);
-                                const f32x2 d2 = add2(pack2(fast_exp2(z0), fast_exp2(z1)), pack2(1.0f, 1.0f));
-                                float d0, d1;
-                                unpack2(d2, d0, d1);
-                                o2 = mul2(a2, pack2(fast_rcp(d0), fast_rcp(d1)));
-                            }
-                            float o0, o1;
-                            unpack2(o2, o0, o1);
-                            v[4 * j + e] = masked ? 0.0f : o0;
-                            v[4 * j + e + 1] = masked ? 0.0f : o1;
-                        }
-                    }
+                    // the gate is chosen OUTSIDE the column loop: with the branch inside it every pair was its own basic
+                    // block and ptxas ran the MUFU chains (ex2 -> add -> rcp -> mul) of the 16 pairs back to back
+                    if (p.gate_mode == GATE_TANH_SX) gated_unit<true>(ra, rb, bs, masked, v);
+                    else gated_unit<false>(ra, rb, bs, masked, v);
                     if (g_tma) stage_h16_unit(tbuf, lane, v, 4 * part);
                     else store_unit(p, private_stage, lane, row_ok, row, row0, rows_ok, oc, ncols, v, 0);
                 }
