@@ -144,3 +144,46 @@ def test_generate_long_end_to_end():
     lens = [int(torch.ceil(torch.tensor(24 / 6 * len(c))).item()) for c in chunks]
     parts = [torch.zeros(1, 256 * (n - 1)) for n in lens]
     assert wav.shape[1] == cross_fade_concat(parts, 0.1, 24000).shape[1]
+
+
+def test_fbank_properties():
+    """Size-independent properties at the bench shape: silence clamps to log(1e-7) exactly, scaling the waveform by c adds
+    log(c) to every unclamped log-mel, and an utterance's features do not depend on its batch neighbours."""
+    import math
+    fe = VocosFbank()
+    g = torch.Generator().manual_seed(21)
+    S = 281 * 256
+    wav = torch.randn(8, S, generator=g) * 0.05
+    lens = torch.full((8,), S)
+    f1, fr = fe.extract_batch(wav, lens)
+    assert fr.tolist() == [281] * 8
+    sil, _ = fe.extract_batch(torch.zeros(2, S), torch.full((2,), S), scale=0.1)
+    assert torch.equal(sil, torch.full_like(sil, 0.1 * math.log(1e-7)))
+    f2, _ = fe.extract_batch(wav * 4.0, lens)
+    assert float((f2 - f1 - math.log(4.0)).abs().max()) < 1e-4
+    perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4])
+    fp, _ = fe.extract_batch(wav[perm], lens)
+    assert torch.equal(fp, f1[perm.to(f1.device)])
+
+
+def test_vocoder_properties_fullsize():
+    """64 x 938 frames (the bench shape): finite, deterministic, and every utterance independent of its neighbours
+    (a permuted batch gives the permuted waveforms bit for bit); frames past an utterance's length change nothing."""
+    voc = Vocos(frame_bucket=1).load_state_dict(synth_vocos_state_dict(4)).to("cuda")
+    g = torch.Generator().manual_seed(22)
+    B, T = 64, 938
+    mel = (torch.randn(B, T, 100, generator=g) * 0.2 - 0.4).cuda()
+    lens = torch.randint(600, T + 1, (B,), generator=g).cuda()
+    w1, l1 = voc.decode_batch(mel, lens, scale=10.0, clamp=True)
+    w2, _ = voc.decode_batch(mel, lens, scale=10.0, clamp=True)
+    assert torch.isfinite(w1).all() and torch.equal(w1, w2)
+    perm = torch.randperm(B, generator=g).cuda()
+    wp, lp = voc.decode_batch(mel[perm], lens[perm], scale=10.0, clamp=True)
+    assert torch.equal(lp, l1[perm]) and torch.equal(wp, w1[perm])
+    junk = mel.clone()
+    for i in range(B):
+        junk[i, int(lens[i]):] = 7.0                          # garbage past the end of every utterance
+    wj, _ = voc.decode_batch(junk, lens, scale=10.0, clamp=True)
+    assert torch.equal(wj, w1)
+    for i in (0, 17, 63):
+        assert float(w1[i, int(l1[i]):].abs().max() if int(l1[i]) < w1.shape[1] else 0.0) == 0.0
