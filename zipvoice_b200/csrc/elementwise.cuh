@@ -520,6 +520,111 @@ __global__ void mask_words_kernel(const uint8_t* __restrict__ mask, uint32_t* __
     out[idx] = bits;
 }
 
+// ---------------------------------------------------------------------------------------
+// Per-forward prologue in three launches instead of twenty-six (single utterances pay ~8.5 us per launch):
+//   * prologue_masks_kernel: the strided key-padding masks mask[:, ::ds] (bytes) AND the attention kernel's excluded-key
+//     bit words of every resolution in one launch;
+//   * multi_small_linear_kernel: the per-stack time-embedding projections (reference: zipformer.py:676-680) in one launch;
+//   * rowbias_all_kernel: for EVERY layer the row bias W1 * temb of the merged feed_forward1 / attention projection.
+struct MaskJob {
+    uint8_t* strided;      // [N][Ld] bytes (null for ds == 1: the input mask itself)
+    uint32_t* words;       // [N][nwords]
+    int ds, Ld, nwords;
+};
+struct MaskJobs { MaskJob j[3]; int n; };
+
+__global__ void prologue_masks_kernel(const uint8_t* __restrict__ mask, const MaskJobs jobs, int N, int T) {
+    pdl_wait();
+    pdl_launch();
+    if (static_cast<int>(blockIdx.y) >= jobs.n) return;
+    const MaskJob jb = jobs.j[blockIdx.y];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * jb.nwords) return;
+    const int n = idx / jb.nwords, w = idx - n * jb.nwords;
+    const uint8_t* mrow = mask + static_cast<long long>(n) * T;
+    uint32_t bits = 0u;
+    for (int b = 0; b < 32; ++b) {
+        const int j = w * 32 + b;
+        bool ex = true;
+        if (j < jb.Ld) {
+            const uint8_t v = mrow[j * jb.ds];
+            ex = v != 0;
+            if (jb.strided != nullptr) jb.strided[static_cast<long long>(n) * jb.Ld + j] = v;
+        }
+        bits |= (ex ? 1u : 0u) << b;
+    }
+    jb.words[idx] = bits;
+}
+
+struct SmallJob { const float* W; const float* b; float* out; };
+struct SmallJobs { SmallJob j[8]; int n; };
+
+// out_s[n,o] = b_s[o] + sum_k W_s[o,k] * swoosh_r(in[n,k]) for every job s (one warp per output element)
+__global__ void __launch_bounds__(256)
+multi_small_linear_kernel(const float* __restrict__ in, const SmallJobs jobs, int N, int K, int O) {
+    pdl_wait();
+    pdl_launch();
+    if (static_cast<int>(blockIdx.y) >= jobs.n) return;
+    const SmallJob jb = jobs.j[blockIdx.y];
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= N * O) return;
+    const int n = gw / O, o = gw - n * O;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32)
+        acc = fmaf(__ldg(jb.W + static_cast<long long>(o) * K + k), swoosh_r(in[n * K + k]), acc);
+#pragma unroll
+    for (int q = 16; q > 0; q >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, q);
+    if (lane == 0) jb.out[n * O + o] = acc + (jb.b != nullptr ? jb.b[o] : 0.f);
+}
+
+struct RowBiasJob { const __half* W; const float* temb; float* out; };     // W [rows][kp] fp16, temb [N][D], out [N][ld]
+constexpr int RB_MAX_JOBS = 64;
+struct RowBiasJobs { RowBiasJob j[RB_MAX_JOBS]; int n; };
+constexpr int RB_NCHUNK = 16;
+
+// out_l[n][c] = sum_k W_l[c][k] * temb_l[n][k], c < cols: one warp per (layer, column, chunk of 16 utterances); the lanes
+// stride over k (16-byte weight loads), the time embeddings of the chunk sit in shared memory.  D <= 512, D % 8 == 0.
+__global__ void __launch_bounds__(256)
+rowbias_all_kernel(const RowBiasJobs jobs, int N, int D, int kp, int cols, int ld) {
+    __shared__ __align__(16) float te[RB_NCHUNK][512];
+    pdl_wait();
+    pdl_launch();
+    const RowBiasJob jb = jobs.j[blockIdx.y];
+    const int n0 = blockIdx.z * RB_NCHUNK;
+    const int nn = N - n0 < RB_NCHUNK ? N - n0 : RB_NCHUNK;
+    for (int i = threadIdx.x; i < nn * D; i += blockDim.x) te[i / D][i % D] = jb.temb[static_cast<long long>(n0 + i / D) * D + i % D];
+    __syncthreads();
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= cols) return;
+    float acc[RB_NCHUNK];
+#pragma unroll
+    for (int n = 0; n < RB_NCHUNK; ++n) acc[n] = 0.f;
+    for (int k0 = lane * 8; k0 < D; k0 += 256) {
+        float w[8];
+        unpack8(*reinterpret_cast<const uint4*>(jb.W + static_cast<long long>(c) * kp + k0), w);
+#pragma unroll
+        for (int n = 0; n < RB_NCHUNK; ++n) {
+            if (n < nn) {
+                const float4 t0 = *reinterpret_cast<const float4*>(&te[n][k0]);
+                const float4 t1 = *reinterpret_cast<const float4*>(&te[n][k0 + 4]);
+                acc[n] = fmaf(w[0], t0.x, acc[n]); acc[n] = fmaf(w[1], t0.y, acc[n]);
+                acc[n] = fmaf(w[2], t0.z, acc[n]); acc[n] = fmaf(w[3], t0.w, acc[n]);
+                acc[n] = fmaf(w[4], t1.x, acc[n]); acc[n] = fmaf(w[5], t1.y, acc[n]);
+                acc[n] = fmaf(w[6], t1.z, acc[n]); acc[n] = fmaf(w[7], t1.w, acc[n]);
+            }
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < RB_NCHUNK; ++n) {
+        float a = acc[n];
+#pragma unroll
+        for (int q = 16; q > 0; q >>= 1) a += __shfl_xor_sync(0xffffffffu, a, q);
+        if (lane == 0 && n < nn) jb.out[static_cast<long long>(n0 + n) * ld + c] = a;
+    }
+}
+
 // Debug / parity aid: counts fp16 elements whose magnitude is the largest finite value or above (what the
 // saturating conversions `cvt.rn.satfinite.f16x2.f32` of the path produce on overflow, plus inf / NaN).
 __global__ void __launch_bounds__(256)

@@ -78,6 +78,7 @@ static int g_bn192 = 0;           // ZVB_BN192=1: 192-column tiles for short-K G
 static int g_layout_ok = 1;       // ZVB_NO_LAYOUT=1 keeps the default operand-ring / aux split everywhere
 static int g_attn_tc = 0;         // ZVB_ATTN_TC=1: attention weights with the tensor-core rel-pos bias (attn3.cuh; measured slower)
 static int g_dw_mode = 0;          // ZVB_DW_MODE: depthwise-convolution block shapes (elementwise.cuh: DwShape), 0 = measured best
+static int g_fuse_prologue = 1;    // ZVB_NO_FUSED_PROLOGUE=1: masks, per-stack time projections and row biases as separate launches
 static int g_pv_bn = 0;            // ZVB_PV_BN=<columns>: tile width of the NonlinAttention P.V GEMM (0 = two equal tiles)
 static int g_merge_ff1 = 1;        // ZVB_NO_MERGE=1: feed_forward1 / attention in-projections as separate GEMMs
 static int g_small_model = 1;      // ZVB_NO_SMALL_MODEL=1: round 1's tile-width choice for small problems
@@ -142,6 +143,7 @@ static void load_switches() {
         if (const char* e = getenv("ZVB_NO_SMALL_MODEL")) g_small_model = atoi(e) == 0;
         if (const char* e = getenv("ZVB_NO_MERGE")) g_merge_ff1 = atoi(e) == 0;
         if (const char* e = getenv("ZVB_PV_BN")) g_pv_bn = atoi(e);
+        if (const char* e = getenv("ZVB_NO_FUSED_PROLOGUE")) g_fuse_prologue = atoi(e) == 0;
         if (const char* e = getenv("ZVB_ATTN_TC")) g_attn_tc = atoi(e) != 0;
         if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
         if (const char* e = getenv("ZVB_DW_MODE")) g_dw_mode = atoi(e);
@@ -256,7 +258,7 @@ static int make_tmap_plain(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_
 }
 
 // ------------------------------------------------------------------------------------------ ops
-enum OpType { OP_CAST, OP_GEMM, OP_ATTN, OP_ATTN_TC, OP_BIASNORM, OP_PREP, OP_DOWN, OP_UP, OP_DWCONV, OP_MASK, OP_MASKW, OP_TSEMB, OP_SMALL,
+enum OpType { OP_PMASKS, OP_MSMALL, OP_ROWBIAS, OP_CAST, OP_GEMM, OP_ATTN, OP_ATTN_TC, OP_BIASNORM, OP_PREP, OP_DOWN, OP_UP, OP_DWCONV, OP_MASK, OP_MASKW, OP_TSEMB, OP_SMALL,
               OP_LAYERNORM, OP_VOC_MASK, OP_VOC_WINDOW, OP_ISTFT_FRAMES, OP_OLA };
 
 struct Op {
@@ -807,6 +809,25 @@ static int launch_op(const Op& op, cudaStream_t st) {
                 op.f0, op.f1, op.f2, op.f3, (float*)op.o0, op.i0, op.i1, op.i2, op.i3, op.i4);
             return check_launch("small_linear");
         }
+        case OP_PMASKS: {
+            const MaskJobs& mj = *static_cast<const MaskJobs*>(op.p1);
+            int maxw = 1;
+            for (int i = 0; i < mj.n; ++i) maxw = mj.j[i].nwords > maxw ? mj.j[i].nwords : maxw;
+            launch_k(prologue_masks_kernel, dim3((op.i0 * maxw + 255) / 256, mj.n), dim3(256), 0, st, (const uint8_t*)op.p0, mj, op.i0, op.i1);
+            return check_launch("prologue_masks");
+        }
+        case OP_MSMALL: {
+            const SmallJobs& sj = *static_cast<const SmallJobs*>(op.p1);
+            const long long warps = (long long)op.i0 * op.i2;
+            launch_k(multi_small_linear_kernel, dim3((unsigned)((warps * 32 + 255) / 256), sj.n), dim3(256), 0, st, op.f0, sj, op.i0, op.i1, op.i2);
+            return check_launch("multi_small_linear");
+        }
+        case OP_ROWBIAS: {
+            const RowBiasJobs& rj = *static_cast<const RowBiasJobs*>(op.p1);
+            launch_k(rowbias_all_kernel, dim3((op.i2 + 7) / 8, rj.n, (op.i0 + RB_NCHUNK - 1) / RB_NCHUNK), dim3(256), 0, st, rj, op.i0, op.i1,
+                     op.i3, op.i2, op.i4);
+            return check_launch("rowbias_all");
+        }
         case OP_CAST: {
             const long long n = op.rows * op.i1;
             launch_k(cast_pad_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const float*)op.p0, (h16*)op.o0, op.rows,
@@ -855,6 +876,10 @@ struct zvb_plan {
     zvb_io io{};
     std::vector<Op> ops;
     unsigned long long* sat_counter = nullptr;      // device counter (caller owned), see zvb_plan_set_saturation_counter
+    // argument blocks of the fused prologue kernels (ops point at them: the plan lives on the heap and is never moved)
+    MaskJobs mjobs{};
+    SmallJobs sjobs{};
+    RowBiasJobs rjobs{};
 };
 
 struct Carver {
@@ -930,11 +955,19 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
     // merged feed_forward1 / attention in-projection (zvb_layer::ff1_attn): fp16 time embedding per stack and the
     // per-utterance row bias W1 * temb (fp32, pitch = merged width; the attention columns stay zero)
     const int mw = m->ff_dims[0] + attn_w;
+    // fused prologue (g_fuse_prologue): every layer's row bias is computed up front by ONE kernel into its own buffer;
+    // otherwise per layer by a 128-row GEMM over the fp16 time embedding into one shared buffer
+    const bool fused_rb = merged && td > 0 && g_fuse_prologue && D <= 512 && D % 8 == 0 && m->num_layers <= RB_MAX_JOBS;
     h16* tembh[ZVB_MAX_STACKS] = {};
     float* rb1 = nullptr;
+    std::vector<float*> rbl(m->num_layers > 0 ? m->num_layers : 1, nullptr);
     if (merged && td > 0) {
-        for (int s = 0; s < m->num_stacks; ++s) tembh[s] = c.take<h16>((size_t)N * D);
-        rb1 = c.take<float>((size_t)N * mw);
+        if (fused_rb) {
+            for (int l = 0; l < m->num_layers; ++l) rbl[l] = c.take<float>((size_t)N * mw);
+        } else {
+            for (int s = 0; s < m->num_stacks; ++s) tembh[s] = c.take<h16>((size_t)N * D);
+            rb1 = c.take<float>((size_t)N * mw);
+        }
     }
     h16* hid = c.take<h16>(M * ffmax);
     h16* nay = c.take<h16>(M * nah);
@@ -968,15 +1001,29 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
     plan->io.xin_pitch = xin_pitch;
     std::vector<Op>& ops = plan->ops;
 
-    // strided masks
-    for (int ds = 2; ds <= 4; ds *= 2) {
-        if (mask_ds[ds] == nullptr) continue;
-        Op op; op.type = OP_MASK; op.p0 = mask; op.o0 = mask_ds[ds];
-        op.i0 = N; op.i1 = T; op.i2 = (T + ds - 1) / ds; op.i3 = ds;
+    // strided masks + excluded-key bit words
+    if (g_fuse_prologue) {
+        MaskJobs& mj = plan->mjobs;
+        mj.n = 0;
+        for (int ds = 1; ds <= 4; ds *= 2) {
+            if (maskw_ds[ds] == nullptr) continue;
+            MaskJob& jb = mj.j[mj.n++];
+            jb.ds = ds; jb.Ld = (T + ds - 1) / ds; jb.nwords = attn_mask_words(jb.Ld);
+            jb.strided = ds == 1 ? nullptr : mask_ds[ds];
+            jb.words = maskw_ds[ds];
+        }
+        Op op; op.type = OP_PMASKS; op.p0 = mask; op.p1 = &plan->mjobs; op.i0 = N; op.i1 = T;
         ops.push_back(op);
+    } else {
+        for (int ds = 2; ds <= 4; ds *= 2) {
+            if (mask_ds[ds] == nullptr) continue;
+            Op op; op.type = OP_MASK; op.p0 = mask; op.o0 = mask_ds[ds];
+            op.i0 = N; op.i1 = T; op.i2 = (T + ds - 1) / ds; op.i3 = ds;
+            ops.push_back(op);
+        }
+        for (int ds = 1; ds <= 4; ds *= 2)
+            if (maskw_ds[ds] != nullptr) ops.push_back(mask_words_op(mask_ds[ds], maskw_ds[ds], N, (T + ds - 1) / ds));
     }
-    for (int ds = 1; ds <= 4; ds *= 2)
-        if (maskw_ds[ds] != nullptr) ops.push_back(mask_words_op(mask_ds[ds], maskw_ds[ds], N, (T + ds - 1) / ds));
     // time embedding chain (reference: modules/zipformer.py:267-278, 676-680, 727-729)
     if (td > 0) {
         Op e; e.type = OP_TSEMB; e.f0 = tbuf; e.o0 = te0; e.i0 = N; e.i1 = td;
@@ -991,14 +1038,34 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
         }
         ops.push_back(small_op(t_in, m->time0_w, m->time0_b, nullptr, te1, N, td, 2 * td, 0, ACT_SWOOSH_R_));
         ops.push_back(small_op(te1, m->time2_w, m->time2_b, nullptr, te3, N, 2 * td, td, 0, 0));
-        for (int s = 0; s < m->num_stacks; ++s)
-            ops.push_back(small_op(te3, m->stacks[s].time_w, m->stacks[s].time_b, nullptr, temb[s], N, td, D,
-                                   ACT_SWOOSH_R_, 0));
-        if (merged)
+        if (g_fuse_prologue && m->num_stacks <= 8) {       // the per-stack projections in one launch
+            SmallJobs& sj = plan->sjobs;
+            sj.n = m->num_stacks;
+            for (int s = 0; s < m->num_stacks; ++s) sj.j[s] = SmallJob{m->stacks[s].time_w, m->stacks[s].time_b, temb[s]};
+            Op op; op.type = OP_MSMALL; op.f0 = te3; op.p1 = &plan->sjobs; op.i0 = N; op.i1 = td; op.i2 = D;
+            ops.push_back(op);
+        } else {
+            for (int s = 0; s < m->num_stacks; ++s)
+                ops.push_back(small_op(te3, m->stacks[s].time_w, m->stacks[s].time_b, nullptr, temb[s], N, td, D,
+                                       ACT_SWOOSH_R_, 0));
+        }
+        if (fused_rb) {                                     // W1 * temb of every layer in one launch
+            RowBiasJobs& rj = plan->rjobs;
+            rj.n = 0;
+            for (int s = 0; s < m->num_stacks; ++s)
+                for (int j = 0; j < m->stacks[s].num_layers; ++j) {
+                    const int l = m->stacks[s].first_layer + j;
+                    rj.j[rj.n++] = RowBiasJob{static_cast<const h16*>(m->layers[l].ff1_attn.w), temb[s], rbl[l]};
+                }
+            Op op; op.type = OP_ROWBIAS; op.p1 = &plan->rjobs; op.i0 = N; op.i1 = D; op.i2 = m->ff_dims[0];
+            op.i3 = m->layers[0].ff1_attn.k_pitch; op.i4 = mw;
+            ops.push_back(op);
+        } else if (merged) {
             for (int s = 0; s < m->num_stacks; ++s) {
                 Op cst; cst.type = OP_CAST; cst.p0 = temb[s]; cst.o0 = tembh[s]; cst.rows = N; cst.i0 = D; cst.i1 = D;
                 ops.push_back(cst);
             }
+        }
     }
     // in_proj (reference: modules/zipformer.py:264-265) -> stream
     {
@@ -1055,14 +1122,15 @@ static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_
                 // 1+2. ONE GEMM over the layer input for feed_forward1.in_proj (SwooshL) and the attention projections (no
                 // activation): hid = [SwooshL(W1 src + W1 temb + b1) | q k p].  feed_forward1 runs on src + temb
                 // (reference: zipformer.py:532-536): the time embedding enters as the per-utterance row bias W1 temb.
-                if (tb != nullptr) {
+                const float* rb_l = fused_rb ? rbl[stk.first_layer + j] : rb1;
+                if (tb != nullptr && !fused_rb) {
                     zvb_linear w1 = ly.ff1_attn;
                     w1.b = nullptr; w1.out_features = m->ff_dims[0]; w1.rows = m->ff_dims[0];
                     e = LinearEpi(); e.out_mode = OUT_F32;
                     TRY(build_linear(op, tembh[s], N, D, w1, rb1, mw, e)); op.cat = ZVB_CAT_OTHER; ops.push_back(op);
                 }
                 e = LinearEpi(); e.act = ACT_SWOOSH_L; e.act_cols = m->ff_dims[0];
-                if (tb != nullptr) { e.rowbias = rb1; e.rows_per_group = L; }
+                if (tb != nullptr) { e.rowbias = rb_l; e.rows_per_group = L; }
                 TRY(build_linear(op, src, Ms, D, ly.ff1_attn, hid, mw, e)); ops.push_back(op);
                 qkp_l = hid + m->ff_dims[0]; qkp_ld = mw; hid_ld = mw;
             } else {
