@@ -13,8 +13,9 @@ utterances, no collective on the data path (the output mels are gathered at the 
 call over the rank's batch.  Prints ONE JSON line (rank 0).  Extra keys of the same line:
 
   strong          one fixed ragged set of 512 utterances (targets U[600,938] frames) partitioned over the N ranks
-                  by `sharding.partition_utterances`, each shard sampled through the length-sorted batcher
-                  (`batcher.sample_batched`, 64-frame buckets) with host inputs, then `sharding.gather_mels`
+                  by `sharding.choose_partition` (length-sorted runs per rank, cuts balancing the padded cost; the
+                  valid-frame balance of `partition_utterances` with ZVB_STRONG_LPT=1), each shard sampled through the
+                  length-sorted batcher (`batcher.sample_batched`, 64-frame buckets) with host inputs, then `sharding.gather_mels`
                   (NCCL) and the device->host copy of the gathered mels on rank 0: strong scaling, wall = slowest
                   rank + gather
   other_configs   C1 (one utterance), C2 (distill, 64 utterances, 4 steps), C4 (60 s dialog), C5 (stereo, 16
@@ -373,7 +374,7 @@ def run_strong(args, dev, rank, world, barrier, max_over_ranks):
     from zipvoice_b200.batcher import padding_waste, plan_batches, sample_batched
     from zipvoice_b200.config import ZipVoiceConfig
     from zipvoice_b200.model import build_model
-    from zipvoice_b200.sharding import gather_mels, partition_utterances
+    from zipvoice_b200.sharding import choose_partition, gather_mels, partition_utterances
     from zipvoice_b200.synth import synth_state_dict, synth_utterances
     cfg = ZipVoiceConfig("zipvoice")
     gen = torch.Generator().manual_seed(4242)
@@ -381,10 +382,13 @@ def run_strong(args, dev, rank, world, barrier, max_over_ranks):
     u = synth_utterances(cfg, batch=STRONG_UTTS, prompt_frames=PROMPT_FRAMES, target_frames=tgt.tolist(),
                          prompt_tokens=PROMPT_TOKENS, tokens=TOKENS, seed=4243)
     total = u["features_lens"].tolist()
-    shards = partition_utterances(total, world)
+    bucket = 64
+    if os.environ.get("ZVB_STRONG_LPT", "0") == "1":     # round-2a policy: valid frames balanced, full length range per rank
+        shards, max_rows = partition_utterances(total, world), 64
+    else:                                                # length-sorted runs per rank, cuts balance the padded cost
+        shards, max_rows = choose_partition(total, world, frame_bucket=bucket)
     shard = shards[rank]
     per_rank = max(len(s) for s in shards)
-    bucket = 64
     model = build_model(cfg, synth_state_dict(cfg, 0), dev, use_cuda_graph=True, frame_bucket=bucket)
     toks = [u["tokens"][i] for i in shard]
     ptoks = [u["prompt_tokens"][i] for i in shard]
@@ -400,7 +404,7 @@ def run_strong(args, dev, rank, world, barrier, max_over_ranks):
         pf = pf_host.to(dev, non_blocking=True)
         pfl = pfl_host.to(dev, non_blocking=True)
         tl = tl_host.to(dev, non_blocking=True)
-        mel, lens, _, _ = sample_batched(model, toks, ptoks, pf, pfl, features_lens=tl, max_rows=64, **kw)
+        mel, lens, _, _ = sample_batched(model, toks, ptoks, pf, pfl, features_lens=tl, max_rows=max_rows, **kw)
         full, full_lens = gather_mels(mel, lens, shard, STRONG_UTTS, max_frames, per_rank=per_rank)
         if rank == 0:
             out_host.copy_(full, non_blocking=True)
@@ -417,13 +421,15 @@ def run_strong(args, dev, rank, world, barrier, max_over_ranks):
         barrier()
         sec = max_over_ranks(time.perf_counter() - t0) / reps
     ok = bool(torch.equal(lens.cpu(), u["target_lens"]))
-    my_batches = plan_batches([total[i] for i in shard], max_rows=64, frame_bucket=bucket)
+    my_batches = plan_batches([total[i] for i in shard], max_rows=max_rows, frame_bucket=bucket)
     waste = padding_waste([total[i] for i in shard], my_batches, bucket)
     rank_frames = [sum(total[i] for i in s) for s in shards]
     plans = model.solver.decoders[cfg.feat_dim].plans
     res = {"utterances": STRONG_UTTS, "target_frames": f"U[{STRONG_LO},{STRONG_HI}]", "generated_frames": int(u["target_lens"].sum()),
            "seconds": sec, "frames_per_s": int(u["target_lens"].sum()) / sec, "rtf": sec / (int(u["target_lens"].sum()) * FRAME_SEC),
            "batches_on_rank0": len(my_batches), "padding_waste_rank0": waste, "frame_bucket": bucket,
+           "partition": "lpt" if os.environ.get("ZVB_STRONG_LPT", "0") == "1" else "sorted runs, padded-cost balanced",
+           "max_rows": max_rows, "utterances_per_rank": [len(s) for s in shards],
            "plans_built_rank0": plans.created, "frames_per_rank_max_over_mean": max(rank_frames) / (sum(rank_frames) / world),
            "h2d_bytes": pf_host.numel() * 4 + pfl_host.numel() * 8 + tl_host.numel() * 8,
            "d2h_bytes_rank0": STRONG_UTTS * max_frames * cfg.feat_dim * 4, "lengths_ok": ok,

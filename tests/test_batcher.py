@@ -61,6 +61,8 @@ def test_plan_batches_invariants():
     assert all(total[b[0]] == max(total[i] for i in b) for b in batches)
     assert padding_waste(total, batches, 64) < 0.08
     assert padding_waste(total, [list(range(512))], 0) > 0.1      # one batch of everything pads far more
+    assert [len(b) for b in plan_batches(total[:70], max_rows=64)] == [35, 35]        # no 6-row tail batch
+    assert [len(b) for b in plan_batches(total[:130], max_rows=64)] == [44, 43, 43] and plan_batches([], max_rows=4) == []
     capped = plan_batches(total, max_rows=64, frame_bucket=64, max_batch_frames=20000)
     assert all(len(b) * ((max(total[i] for i in b) + 63) // 64 * 64) <= 20000 or len(b) == 1 for b in capped)
 
@@ -93,7 +95,7 @@ def test_sample_batched_restores_order_and_padding():
     pf = torch.zeros(U, 7, 4)
     m = _FakeModel()
     x1, l1, xp, lp = sample_batched(m, tokens, ptoks, pf, pfl, features_lens=fl, max_rows=4, num_step=2)
-    assert m.calls == [4, 4, 2]
+    assert m.calls == [4, 3, 3]                          # equal row counts, not 4 + 4 + 2
     assert torch.equal(l1, fl) and torch.equal(lp, pfl) and x1.shape == (U, 50, 4) and xp.shape == (U, 7, 4)
     for i in range(U):
         assert float(x1[i, : fl[i]].min()) == 100 + i and float(x1[i, fl[i]:].abs().sum()) == 0

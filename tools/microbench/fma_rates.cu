@@ -50,6 +50,14 @@ __global__ void bench(float* out, long long* cyc, const float* in) {
                 if (MODE == 5) ah[i] = hfma2(xh[(i + k) & 15], wh, ah[i]);            // half2, 3 registers
                 if (MODE == 6) ah[i] = hfma2(xh[(i + k) & 15], chw[k], ah[i]);        // half2, constant-bank
                 if (MODE == 7) a[i] = ffma(x[(i + k) & 15], x[(i + k + 1) & 15], a[i]);  // 3 distinct vector registers, no reuse
+                if (MODE == 8) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(a[i]) : "f"(a[i]));            // MUFU.EX2
+                if (MODE == 9) asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(ah[i]) : "r"(ah[i]));            // 2 x MUFU.EX2.F16 ?
+                if (MODE == 10) { asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(ah[i]) : "r"(ah[i]));          // MUFU pair + 3 HFMA2
+                                  xh[i] = hfma2(xh[i], wh, ah[i]); xh[(i + 5) & 15] = hfma2(xh[(i + 5) & 15], wh, xh[i]);
+                                  xh[(i + 9) & 15] = hfma2(xh[(i + 9) & 15], wh, xh[i]); }
+                if (MODE == 11) { asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(a[i]) : "f"(a[i]));          // MUFU + 3 FFMA
+                                  x[i] = ffma(x[i], w, a[i]); x[(i + 5) & 15] = ffma(x[(i + 5) & 15], w, x[i]);
+                                  x[(i + 9) & 15] = ffma(x[(i + 9) & 15], w, x[i]); }
             }
         }
     }
@@ -94,6 +102,10 @@ int main() {
     run<4>("FFMA2 x2, c[bank].64, acc2", out, cyc, in);
     run<5>("HFMA2 xh, wh(reg), acch", out, cyc, in);
     run<6>("HFMA2 xh, c[bank], acch", out, cyc, in);
+    run<8>("MUFU.EX2 f32 (per ex2 instruction)", out, cyc, in);
+    run<9>("ex2.approx.f16x2 (per PTX instruction)", out, cyc, in);
+    run<10>("ex2.f16x2 + 3 HFMA2 (per group of 4)", out, cyc, in);
+    run<11>("MUFU.EX2 f32 + 3 FFMA (per group of 4)", out, cyc, in);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }

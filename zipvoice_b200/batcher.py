@@ -43,18 +43,39 @@ def batchify_tokens(tokens_list: List[List[int]], max_duration: float, prompt_du
     return batches, order
 
 
+def batch_cost(rows: int, frames: int) -> float:
+    """Relative time of one sampler batch of `rows` utterances padded to `frames`, fitted to B200 measurements
+    (profiles/batch_sweep_r2.txt: 59.6 / 71.5 / 77.3 / 81 / 82.2 k frames/s at 8 / 16 / 32 / 64 / 96 rows of 1219 frames =
+    85.4 k x rows / (rows + 3.5)): every batch costs 3.5 rows of fixed work, and the attention share (26 % of a
+    1219-frame forward: bench.py's per-kernel table) is quadratic in the frames, i.e. T / 3500 of the linear term."""
+    return (rows + 3.5) * frames * (1.0 + frames / 3500.0)
+
+
 def plan_batches(total_frames: Sequence[int], max_rows: int = 64, frame_bucket: int = 64,
                  max_batch_frames: Optional[int] = None) -> List[List[int]]:
     """Utterance indices per batch.  Longest first, so a batch's padded length is its first utterance's length
-    rounded up to `frame_bucket`; a batch closes when it holds `max_rows` utterances or one more row would push
-    rows x padded frames over `max_batch_frames`.  Deterministic (ties broken by index)."""
+    rounded up to `frame_bucket`.  Without a frame budget the sorted list is cut into ceil(n / max_rows) batches of
+    (nearly) equal row counts -- 70 utterances become 35 + 35, not 64 + 6: a small tail batch runs the GPU at a fraction
+    of its rate.  With `max_batch_frames` a batch closes when it holds `max_rows` utterances or one more row would push
+    rows x padded frames over the budget.  Deterministic (ties broken by index)."""
     order = sorted(range(len(total_frames)), key=lambda i: (-int(total_frames[i]), i))
+    if max_batch_frames is None:
+        n = len(order)
+        if n == 0:
+            return []
+        nb = -(-n // max_rows)
+        base, extra = divmod(n, nb)
+        batches, a = [], 0
+        for k in range(nb):
+            b = a + base + (1 if k < extra else 0)
+            batches.append(order[a:b])
+            a = b
+        return batches
     batches: List[List[int]] = []
     cur: List[int] = []
     cur_T = 0
     for i in order:
-        if cur and (len(cur) >= max_rows or
-                    (max_batch_frames is not None and (len(cur) + 1) * cur_T > max_batch_frames)):
+        if cur and (len(cur) >= max_rows or (len(cur) + 1) * cur_T > max_batch_frames):
             batches.append(cur)
             cur = []
         if not cur:
@@ -63,6 +84,11 @@ def plan_batches(total_frames: Sequence[int], max_rows: int = 64, frame_bucket: 
     if cur:
         batches.append(cur)
     return batches
+
+
+def batches_cost(total_frames: Sequence[int], batches: Sequence[Sequence[int]], frame_bucket: int = 0) -> float:
+    """Sum of `batch_cost` over the batches (each padded to its longest utterance, rounded up to the bucket)."""
+    return sum(batch_cost(len(b), round_up(max(int(total_frames[i]) for i in b), frame_bucket)) for b in batches if b)
 
 
 def padding_waste(total_frames: Sequence[int], batches: Sequence[Sequence[int]], frame_bucket: int = 0) -> float:
