@@ -582,10 +582,12 @@ struct RowBiasJob { const __half* W; const float* temb; float* out; };     // W 
 constexpr int RB_MAX_JOBS = 64;
 struct RowBiasJobs { RowBiasJob j[RB_MAX_JOBS]; int n; };
 constexpr int RB_NCHUNK = 16;
+constexpr int RB_COLS = 128;
 
-// out_l[n][c] = sum_k W_l[c][k] * temb_l[n][k], c < cols: one warp per (layer, column, chunk of 16 utterances); the lanes
-// stride over k (16-byte weight loads), the time embeddings of the chunk sit in shared memory.  D <= 512, D % 8 == 0.
-__global__ void __launch_bounds__(256)
+// out_l[n][c] = sum_k W_l[c][k] * temb_l[n][k], c < cols.  One block per (128 columns, layer, chunk of 16 utterances): a
+// thread owns ONE column (its 16 sums need no reduction; its weight row streams through L1 16 bytes at a time), the chunk's
+// time embeddings sit in shared memory and are read as warp-wide broadcasts.  D <= 512, D % 8 == 0.
+__global__ void __launch_bounds__(RB_COLS)
 rowbias_all_kernel(const RowBiasJobs jobs, int N, int D, int kp, int cols, int ld) {
     __shared__ __align__(16) float te[RB_NCHUNK][512];
     pdl_wait();
@@ -593,17 +595,61 @@ rowbias_all_kernel(const RowBiasJobs jobs, int N, int D, int kp, int cols, int l
     const RowBiasJob jb = jobs.j[blockIdx.y];
     const int n0 = blockIdx.z * RB_NCHUNK;
     const int nn = N - n0 < RB_NCHUNK ? N - n0 : RB_NCHUNK;
-    for (int i = threadIdx.x; i < nn * D; i += blockDim.x) te[i / D][i % D] = jb.temb[static_cast<long long>(n0 + i / D) * D + i % D];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int n = warp; n < nn; n += RB_COLS / 32)
+        for (int k = lane * 4; k < D; k += 128)
+            *reinterpret_cast<float4*>(&te[n][k]) = *reinterpret_cast<const float4*>(jb.temb + static_cast<long long>(n0 + n) * D + k);
     __syncthreads();
-    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * RB_COLS + threadIdx.x;
+    if (c >= cols) return;
+    float acc[RB_NCHUNK];
+#pragma unroll
+    for (int n = 0; n < RB_NCHUNK; ++n) acc[n] = 0.f;
+    const __half* wrow = jb.W + static_cast<long long>(c) * kp;
+#pragma unroll 2
+    for (int k0 = 0; k0 < D; k0 += 8) {
+        float w[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(wrow + k0)), w);
+#pragma unroll
+        for (int n = 0; n < RB_NCHUNK; ++n) {
+            if (n < nn) {
+                const float4 t0 = *reinterpret_cast<const float4*>(&te[n][k0]);
+                const float4 t1 = *reinterpret_cast<const float4*>(&te[n][k0 + 4]);
+                acc[n] = fmaf(w[0], t0.x, acc[n]); acc[n] = fmaf(w[1], t0.y, acc[n]);
+                acc[n] = fmaf(w[2], t0.z, acc[n]); acc[n] = fmaf(w[3], t0.w, acc[n]);
+                acc[n] = fmaf(w[4], t1.x, acc[n]); acc[n] = fmaf(w[5], t1.y, acc[n]);
+                acc[n] = fmaf(w[6], t1.z, acc[n]); acc[n] = fmaf(w[7], t1.w, acc[n]);
+            }
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < RB_NCHUNK; ++n)
+        if (n < nn) jb.out[static_cast<long long>(n0 + n) * ld + c] = acc[n];
+}
+
+// The same for N <= 16 utterances (single samples: latency, not throughput): one WARP per (layer, column), the lanes stride
+// over k with coalesced 16-byte weight loads -- 18 k warps keep every SM's load pipes full where one thread per column would
+// walk its row 16 bytes at a time (32 us against ~10 at N = 2).
+__global__ void __launch_bounds__(256)
+rowbias_small_kernel(const RowBiasJobs jobs, int N, int D, int kp, int cols, int ld) {
+    __shared__ __align__(16) float te[RB_NCHUNK][512];
+    pdl_wait();
+    pdl_launch();
+    const RowBiasJob jb = jobs.j[blockIdx.y];
+    const int nn = N < RB_NCHUNK ? N : RB_NCHUNK;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int n = warp; n < nn; n += 8)
+        for (int k = lane * 4; k < D; k += 128)
+            *reinterpret_cast<float4*>(&te[n][k]) = *reinterpret_cast<const float4*>(jb.temb + static_cast<long long>(n) * D + k);
+    __syncthreads();
+    const int c = blockIdx.x * 8 + warp;
     if (c >= cols) return;
     float acc[RB_NCHUNK];
 #pragma unroll
     for (int n = 0; n < RB_NCHUNK; ++n) acc[n] = 0.f;
     for (int k0 = lane * 8; k0 < D; k0 += 256) {
         float w[8];
-        unpack8(*reinterpret_cast<const uint4*>(jb.W + static_cast<long long>(c) * kp + k0), w);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(jb.W + static_cast<long long>(c) * kp + k0)), w);
 #pragma unroll
         for (int n = 0; n < RB_NCHUNK; ++n) {
             if (n < nn) {
@@ -618,10 +664,12 @@ rowbias_all_kernel(const RowBiasJobs jobs, int N, int D, int kp, int cols, int l
     }
 #pragma unroll
     for (int n = 0; n < RB_NCHUNK; ++n) {
-        float a = acc[n];
+        if (n < nn) {                                  // warp-uniform
+            float a = acc[n];
 #pragma unroll
-        for (int q = 16; q > 0; q >>= 1) a += __shfl_xor_sync(0xffffffffu, a, q);
-        if (lane == 0 && n < nn) jb.out[static_cast<long long>(n0 + n) * ld + c] = a;
+            for (int q = 16; q > 0; q >>= 1) a += __shfl_xor_sync(0xffffffffu, a, q);
+            if (lane == 0) jb.out[static_cast<long long>(n) * ld + c] = a;
+        }
     }
 }
 

@@ -824,8 +824,11 @@ static int launch_op(const Op& op, cudaStream_t st) {
         }
         case OP_ROWBIAS: {
             const RowBiasJobs& rj = *static_cast<const RowBiasJobs*>(op.p1);
-            launch_k(rowbias_all_kernel, dim3((op.i2 + 7) / 8, rj.n, (op.i0 + RB_NCHUNK - 1) / RB_NCHUNK), dim3(256), 0, st, rj, op.i0, op.i1,
-                     op.i3, op.i2, op.i4);
+            if (op.i0 <= RB_NCHUNK)
+                launch_k(rowbias_small_kernel, dim3((op.i2 + 7) / 8, rj.n), dim3(256), 0, st, rj, op.i0, op.i1, op.i3, op.i2, op.i4);
+            else
+                launch_k(rowbias_all_kernel, dim3((op.i2 + RB_COLS - 1) / RB_COLS, rj.n, (op.i0 + RB_NCHUNK - 1) / RB_NCHUNK), dim3(RB_COLS), 0, st,
+                         rj, op.i0, op.i1, op.i3, op.i2, op.i4);
             return check_launch("rowbias_all");
         }
         case OP_CAST: {
