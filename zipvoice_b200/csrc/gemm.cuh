@@ -11,6 +11,7 @@
 // Serves every dense contraction of the TTSZipformer forward (reference:
 // modules/zipformer.py:1172,1377,1393,1434-1437,1511,1534,1542,1655,1678, 265, 291).
 #pragma once
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace zvb {
@@ -694,7 +695,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 // 51%), so everything that is not arithmetic is hoisted: shared-memory and barrier addresses are
                 // 32-bit window addresses computed once per kernel, the bias is read as warp-uniform 16-byte loads
                 // (no staging through shared memory, no warp barriers), no per-unit bounds beyond `live`.
-                for (int s = half; s < n_sub; s += 2) {
+                // Units whose columns lie past `act_cols` (the attention projections of a merged GEMM) take no activation.  The
+                // two kinds run in two loops over the same body, not behind a branch inside one: with the branch ptxas
+                // reconciled the two paths' register assignments with ~40 moves per unit ahead of it (ncu r2f: IMAD.MOV the most
+                // executed opcode of the merged GEMM).
+                auto unit = [&](const int s, auto with_act) {
+                    constexpr bool kAct = decltype(with_act)::value;
                     const int c0 = (2 * s + part) * 32;
                     const int gc = acc_base + c0;
                     const bool live = gc < p.n_out;               // whole unit inside the output (n_out % 32 == 0)
@@ -713,8 +719,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             v2[j] = add2(pack2(__uint_as_float(acc_r[2 * j]), __uint_as_float(acc_r[2 * j + 1])), v2[j]);
-                        if (ACT != ACT_NONE && p.act_cols > 0 && gc >= p.act_cols) {
-                            // columns past act_cols (the attention projections of a merged GEMM): no activation
+                        if (!kAct) {
                         } else if (ACT == ACT_SWOOSH_L) {
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) swoosh_x2_group<4>(v2 + j, SWOOSH_L_C, SWOOSH_L_K0);
@@ -750,7 +755,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     __syncwarp();
                     if (lane == 0) mbar_arrive_u32(fast_staged + 8u * buf);
                     ++kcount;
+                };
+                int s_act = n_sub;                                // units s < s_act of this warp carry the activation
+                if (ACT != ACT_NONE && p.act_cols > 0) {
+                    const int units = (p.act_cols - acc_base) / 32 - part;          // act_cols % 32 == 0
+                    s_act = units <= 0 ? 0 : (units + 1) >> 1;
+                    s_act = s_act < n_sub ? s_act : n_sub;
                 }
+                int s = half;
+                for (; s < s_act; s += 2) unit(s, std::true_type());
+                if (ACT != ACT_NONE)
+                    for (; s < n_sub; s += 2) unit(s, std::false_type());
             } else if (KIND == EPI_LINEAR && ACT == ACT_NONE && LEAN == 2) {
                 // Lean path of the residual-stream GEMMs (out = resid + A.W^T + b [+ time embedding of the row's utterance]):
                 // the generic path below executed ~620 warp instructions per 32 x 32 unit for ~6 per column pair of
