@@ -12,6 +12,6 @@ $QP > gpurun_out/plain2_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"gemm_kernel|attn_weights" -s 1 -c 4 \
     -o gpurun_out/prof_top_$TAG -f $QP > gpurun_out/ncu_full_$TAG.log 2>&1
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-    -k regex:gemm_kernel -s 0 -c ${GEMMS:-306} --csv --log-file gpurun_out/gemm_traffic_$TAG.csv $QP > gpurun_out/ncu_traffic_$TAG.log 2>&1
+    -k regex:gemm_kernel -s 0 -c ${GEMMS:-322} --csv --log-file gpurun_out/gemm_traffic_$TAG.csv $QP > gpurun_out/ncu_traffic_$TAG.log 2>&1
 ls -la gpurun_out/ | tail -8
 tail -n 2 gpurun_out/ncu_list_$TAG.log gpurun_out/ncu_full_$TAG.log gpurun_out/ncu_traffic_$TAG.log
