@@ -19,7 +19,8 @@ call over the rank's batch.  Prints ONE JSON line (rank 0).  Extra keys of the s
                   (NCCL) and the device->host copy of the gathered mels on rank 0: strong scaling, wall = slowest
                   rank + gather
   other_configs   C1 (one utterance), C2 (distill, 64 utterances, 4 steps), C4 (60 s dialog), C5 (stereo, 16
-                  utterances) timed through `solver.sample` (N = 1 runs only)
+                  utterances) timed through `solver.sample` (N = 1 runs only); C1 also end to end through `model.sample`
+                  with host inputs and outputs (`e2e`: p50 / p90 latency of 20 calls)
   torch_gpu_baseline  the unmodified reference, eager PyTorch on cuda:0 (fp32 and bf16 autocast), informational
   stages          the steps either side of the sampler at the same shape: prompt log-mel of 64 x 3 s
                   host waveforms (zvb_fbank), vocoder decode of the 64 x 938 generated frames (zvb_vocoder_decode), and the
@@ -253,9 +254,42 @@ def time_other_configs(dev, peaks):
         out[name] = {"model": variant, "utterances": B, "frames": f"{Pf}+{Tg}", "steps": steps, "guidance": g,
                      "ms_per_sample": med, "frames_per_s": B * Tg / (med * 1e-3), "rtf": med * 1e-3 / (B * Tg * FRAME_SEC),
                      "ideal_ms_tensor_peak": ideal_ms, "frac_of_ideal": ideal_ms / med, "finite": bool(torch.isfinite(x1).all())}
+        if name == "C1_single_utterance":
+            out[name]["e2e"] = time_single_utterance_e2e(model, cfg, dev, Pf, Tg, kw)
         del model, x0, text, speech, mask, x1
         torch.cuda.empty_cache()
     return out
+
+
+def time_single_utterance_e2e(model, cfg, dev, Pf, Tg, kw, calls=20):
+    """Latency of ONE utterance through the public API: host tokens + pinned prompt mel in, `model.sample` (text prelude and
+    encoder, duration rule, CUDA-graph sampler), host mel out; wall clock per call with a stream synchronize, p50 / p90."""
+    import torch
+    from zipvoice_b200.synth import synth_utterances
+    u = synth_utterances(cfg, batch=1, prompt_frames=Pf, target_frames=Tg, prompt_tokens=PROMPT_TOKENS, tokens=TOKENS, seed=5)
+    pf_host, pfl_host, tl_host = u["prompt_features"].pin_memory(), u["prompt_features_lens"].pin_memory(), u["target_lens"].pin_memory()
+    out_host = torch.empty(1, Tg, cfg.feat_dim).pin_memory()
+
+    def call():
+        mel, _, _, _ = model.sample(u["tokens"], u["prompt_tokens"], pf_host.to(dev, non_blocking=True),
+                                    pfl_host.to(dev, non_blocking=True), features_lens=tl_host.to(dev, non_blocking=True),
+                                    duration="real", **kw)
+        out_host.copy_(mel, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    with torch.inference_mode():
+        for _ in range(3):
+            call()
+        ms = []
+        for _ in range(calls):
+            t0 = time.perf_counter()
+            call()
+            ms.append((time.perf_counter() - t0) * 1e3)
+    ms.sort()
+    p50, p90 = ms[len(ms) // 2], ms[int(len(ms) * 0.9)]
+    return {"calls": calls, "ms_p50": p50, "ms_p90": p90, "rtf_p50": p50 * 1e-3 / (Tg * FRAME_SEC),
+            "h2d_bytes": pf_host.numel() * 4 + 16, "d2h_bytes": out_host.numel() * 4,
+            "finite": bool(torch.isfinite(out_host).all())}
 
 
 def time_torch_gpu_baseline(dev):
