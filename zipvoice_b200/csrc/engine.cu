@@ -82,6 +82,7 @@ static int g_fuse_prologue = 1;    // ZVB_NO_FUSED_PROLOGUE=1: masks, per-stack 
 static int g_pv_bn = 0;            // ZVB_PV_BN=<columns>: tile width of the NonlinAttention P.V GEMM (0 = two equal tiles)
 static int g_merge_ff1 = 1;        // ZVB_NO_MERGE=1: feed_forward1 / attention in-projections as separate GEMMs
 static int g_small_model = 1;      // ZVB_NO_SMALL_MODEL=1: round 1's tile-width choice for small problems
+static int g_small_lean = 1;       // ZVB_SMALL_LEAN=0: the small-problem cost model without the measured epilogue costs
 static int g_lean_pad = 1;         // ZVB_NO_LEAN_PAD=1: exact-fit tile widths for projections that are no multiple of 64 wide
 static int g_fast_bypass = 1;      // ZVB_NO_FAST_BYPASS=1: generic epilogue for the bypass GEMM (feed_forward2)
 static int g_fast_resid = 1;       // ZVB_NO_FAST_RESID=1: generic epilogue for the residual-stream GEMMs
@@ -141,6 +142,7 @@ static void load_switches() {
         if (const char* e = getenv("ZVB_NO_FAST_BYPASS")) g_fast_bypass = atoi(e) == 0;
         if (const char* e = getenv("ZVB_NO_LEAN_PAD")) g_lean_pad = atoi(e) == 0;
         if (const char* e = getenv("ZVB_NO_SMALL_MODEL")) g_small_model = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_SMALL_LEAN")) g_small_lean = atoi(e) != 0;
         if (const char* e = getenv("ZVB_NO_MERGE")) g_merge_ff1 = atoi(e) == 0;
         if (const char* e = getenv("ZVB_PV_BN")) g_pv_bn = atoi(e);
         if (const char* e = getenv("ZVB_NO_FUSED_PROLOGUE")) g_fuse_prologue = atoi(e) == 0;
@@ -291,10 +293,16 @@ struct Op {
 static inline void mark_out(Op& op, int i, const void* p, long long n) { op.scan_ptr[i] = p; op.scan_n[i] = n; }
 
 // Small problems (single utterances: 20 m-tiles at T = 1219, 103 at T = 6563): a tile's time is the operand bytes its SM
-// streams (measured at N = 2: 5.2 us fixed + 128 B x (128 + tile columns) per k-block at ~62 GB/s per SM), and the kernel's
-// time is that times the number of WAVES the tiles need on 148 SMs / 74 CTA pairs.  Round 1 picked multiples of 64 only:
-// N = 512 at 20 m-tiles became 160 tiles of 64 columns = 2 waves where 140 tiles of 80 columns run in one.
-static int pick_block_n_small(int n_out, long long m_tiles, int k_blocks) {
+// streams plus its epilogue, and the kernel's time is that times the number of WAVES the tiles need on 148 SMs / 74 CTA pairs.
+// Round 1 picked multiples of 64 only: N = 512 at 20 m-tiles became 160 tiles of 64 columns = 2 waves where 140 tiles of 80
+// columns run in one.  The constants are read off the per-launch critical path of a single-utterance sample (tools/timeline_c1.py,
+// a -DZVB_TIMELINE build; gpurun_out/r2d_timeline.log): ~1.5 us until the first operands land + ~1.2 us of hand-offs and drain,
+// 128 B x (128 + tile columns) per k-block at ~62 GB/s per SM, and an epilogue that costs 0.5-0.9 us per 64 columns on the lean
+// paths (tile width a multiple of 64; the residual form also needs n_out % width == 0) but 2.5 us at <= 80 columns and 5-6 us at
+// 144-224 columns on the generic path -- which an earlier version of this model ignored (it put every single-utterance GEMM on
+// widths like 80 / 144 / 208 / 224 and hence on the generic epilogue).
+// lean_kind: 0 = the op can only use the generic epilogue, 1 = lean plain epilogue possible, 2 = lean residual epilogue possible.
+static int pick_block_n_small(int n_out, long long m_tiles, int k_blocks, int lean_kind) {
     int best = 0;
     double best_cost = 1e30;
     for (int bn = 16; bn <= 256; bn += 16) {
@@ -305,16 +313,25 @@ static int pick_block_n_small(int n_out, long long m_tiles, int k_blocks) {
         const long long units = pair ? slots2 : m_tiles * n_tiles;
         const long long lanes = pair ? g_num_sms / 2 : g_num_sms;
         const long long waves = (units + lanes - 1) / lanes;
-        const double tile_us = 5.2 + k_blocks * 128.0 * (128 + (pair ? bn / 2 : bn)) / 62000.0 + 0.004 * bn;
-        double cost = waves * tile_us;
-        if (bn % 64 != 0) cost *= 1.03;              // multiples of 64 keep the TMA-store / lean epilogues: prefer them on a tie
+        const bool lean = g_small_lean && bn % 64 == 0 && (lean_kind == 1 || (lean_kind == 2 && n_out % bn == 0));
+        double tile_us, cost;
+        if (g_small_lean) {
+            const double epi_us = lean ? 0.3 + 0.0065 * bn : 2.0 + 0.02 * bn;
+            tile_us = 2.7 + k_blocks * 128.0 * (128 + (pair ? bn / 2 : bn)) / 62000.0 + epi_us;
+            cost = waves * tile_us;
+        } else {                                       // the round-2 model before the timeline measurement (ZVB_SMALL_LEAN=0)
+            tile_us = 5.2 + k_blocks * 128.0 * (128 + (pair ? bn / 2 : bn)) / 62000.0 + 0.004 * bn;
+            cost = waves * tile_us;
+            if (bn % 64 != 0) cost *= 1.03;
+        }
         if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
     }
     return best;
 }
 
-static int pick_block_n(int n_out, long long m_tiles, int k_blocks) {
-    if (g_small_model && n_out >= 64 && m_tiles * ((n_out + 255) / 256) < 2LL * g_num_sms) return pick_block_n_small(n_out, m_tiles, k_blocks);
+static int pick_block_n(int n_out, long long m_tiles, int k_blocks, int lean_kind = 0) {
+    if (g_small_model && n_out >= 64 && m_tiles * ((n_out + 255) / 256) < 2LL * g_num_sms)
+        return pick_block_n_small(n_out, m_tiles, k_blocks, lean_kind);
     // short K (<= 8 k-blocks): the mainloop is bound by operand bytes in flight, and a 40 KB stage (192
     // columns) fits four times into the wide ring where a 48 KB stage (256 columns) fits three times
     if (g_bn192 && k_blocks <= 8 && n_out >= 768 && n_out % 192 == 0 && m_tiles * (n_out / 192) >= g_num_sms) return 192;
@@ -453,7 +470,17 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
     if (lin.k_pitch % 8 != 0 || lda % 8 != 0) return fail(ZVB_ERR_INVALID, "linear: pitches must be multiples of 8");
     const int K = lin.k_pitch < lda ? lin.k_pitch : lda;    // both zero padded beyond in_features
     const long long m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
-    int bn = e.block_n ? e.block_n : pick_block_n(lin.out_features, m_tiles, (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K);
+    // which lean epilogue the op could take if its tile width allows (the conditions of fast_epi / fast_resid below)
+    int lean_kind = 0;
+    if (e.out_mode == OUT_H16 && e.row_mask == nullptr && lin.out_features % 8 == 0 && ldc % 8 == 0 &&
+        (e.rowbias == nullptr || e.rows_per_group >= GEMM_BLOCK_M)) {
+        if (e.resid == nullptr && e.act_cols % 32 == 0 && (reinterpret_cast<uintptr_t>(lin.b) & 15) == 0) lean_kind = g_fast_epi ? 1 : 0;
+        else if (e.resid != nullptr && e.act == ACT_NONE && g_fast_resid &&
+                 (e.orig == nullptr || (g_fast_bypass && e.rowbias == nullptr)))
+            lean_kind = 2;
+    }
+    int bn = e.block_n ? e.block_n
+                       : pick_block_n(lin.out_features, m_tiles, (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K, lean_kind);
     // plain fp16 projections whose width is no multiple of 64 (attention in_proj: 272 columns): tiles of a multiple of 64
     // columns keep them on the lean epilogue (whole 64-column store boxes per tile; columns past n_out are clipped by the
     // store's tensor map and their weight rows are TMA zero fill) -- 2 x 192 instead of 2 x 144
@@ -1711,5 +1738,20 @@ int zvb_test_istft(const float* S, int ld, const int32_t* lens, const float* win
       TRY(launch_op(o, st)); }
     return 0;
 }
+
+#ifdef ZVB_TIMELINE
+// Debug build only (tools/timeline_c1.py): copies the per-launch stamps of CTA 0 of every GEMM launch and resets the counter.
+int zvb_debug_timeline(unsigned long long* out, int max_rows) {
+    unsigned int n = 0;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(&n, g_tl_n, sizeof n));
+    int rows = static_cast<int>(n < (unsigned)TL_MAX ? n : (unsigned)TL_MAX);
+    rows = rows < max_rows ? rows : max_rows;
+    if (rows > 0) CUDA_TRY(cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 12 * rows));
+    n = 0;
+    CUDA_TRY(cudaMemcpyToSymbol(g_tl_n, &n, sizeof n));
+    return rows;
+}
+#endif
 
 }  // extern "C"

@@ -282,6 +282,15 @@ __device__ __forceinline__ void gated_unit(const uint32_t* ra, const uint32_t* r
 // (GemmParams::fast_epi), 2 = lean residual-stream epilogue (GemmParams::fast_resid).  Separate instantiations, because
 // 3 = lean residual epilogue with the bypass (fast_resid == 2); one kernel carrying all paths costs the generic path registers (round 2: +20% on the N = 272 / N = 48 projections
 // when the lean paths were runtime branches of the same kernel).
+#ifdef ZVB_TIMELINE
+// Debug build only (tools/timeline_c1.py): CTA 0 of every GEMM launch stamps clock64 at the points of its critical path.
+constexpr int TL_MAX = 1 << 15;
+__device__ unsigned long long g_tl[TL_MAX][12];
+__device__ unsigned int g_tl_n;
+#define TL_STAMP(k) do { if (blockIdx.x == 0 && tl_slot < TL_MAX) g_tl[tl_slot][k] = clock64(); } while (0)
+#else
+#define TL_STAMP(k) do { } while (0)
+#endif
 template <int KIND, int ACT, int CLUSTER, int LEAN = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -289,6 +298,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const __grid_constant__ CUtensorMap tma_orig,
             const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
+#ifdef ZVB_TIMELINE
+    const unsigned long long tl_c0 = clock64(), tl_g0 = globaltimer_ns();
+#endif
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     const int STAGES = p.stages;
@@ -315,6 +327,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint64_t* a_full = sfree + 4;                               // [8] resident A k-block landed (TMA -> MMA)
     uint64_t* a_empty = a_full + 8;                             // [8] resident A k-block released (MMA -> TMA)
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_empty + 8);
+#ifdef ZVB_TIMELINE
+    volatile unsigned int* tl_slot_p = tmem_holder + 1;         // inside the 512 bytes reserved for the barriers
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const unsigned int sl = atomicAdd(&g_tl_n, 1u);
+        *tl_slot_p = sl;
+        if (sl < TL_MAX) {
+            g_tl[sl][0] = tl_c0;
+            g_tl[sl][8] = tl_g0;
+            g_tl[sl][10] = (static_cast<unsigned long long>(p.M) << 32) | static_cast<unsigned>(p.n_out);
+            g_tl[sl][11] = (static_cast<unsigned long long>(p.num_k_blocks) << 32) | (static_cast<unsigned>(p.block_n) << 8) |
+                           (static_cast<unsigned>(CLUSTER) << 4) | static_cast<unsigned>(LEAN);
+        }
+    }
+#endif
 
     // Roles: warps 0..15 = epilogue, 16 = TMA producer (A/B), 17 = MMA issuer (+TMEM alloc), 18 = TMA producer
     // (aux), 19 = TMA store thread.  The single-thread roles sit in the HIGHEST warp ids because the
@@ -382,8 +408,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (CLUSTER > 1) cluster_sync_all();        // peers' barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+#ifdef ZVB_TIMELINE
+    const unsigned int tl_slot = blockIdx.x == 0 ? *tl_slot_p : TL_MAX;
+    if (threadIdx.x == 0) TL_STAMP(1);
+#endif
     pdl_wait();                 // set-up above overlaps the previous kernel's tail
     pdl_launch();
+    if (threadIdx.x == 0) TL_STAMP(2);
 
     if (warp == W_TMA) {
         // ------------------------------------------------------------------ TMA producer (A, B)
@@ -458,6 +489,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     if (new_mg) mbar_wait(&a_full[kb], mg & 1u);
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+                    if (tile == t_first && kb == 0) TL_STAMP(3);
                     const uint32_t sa = smem_u32(ring + stage * STAGE_BYTES);
                     const uint64_t da = umma_desc_k_sw128(resident ? smem_u32(smem + kb * GEMM_A_BYTES) : sa);
                     const uint64_t db = umma_desc_k_sw128(resident ? sa : sa + GEMM_A_BYTES);
@@ -484,6 +516,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 }
                 if (last_of_mg) ++mg;
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                if (tile == t_first) TL_STAMP(4);
             }
         }
     } else if (warp == W_AUX) {
@@ -686,6 +719,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
+            if (threadIdx.x == 0 && tile == t_first) TL_STAMP(5);
             const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * 256u +
                                    (static_cast<uint32_t>(quarter * 32) << 16);
 
@@ -1050,6 +1084,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
             tc_fence_before();
             __syncwarp();
+            if (threadIdx.x == 0 && tile == t_first) TL_STAMP(6);
             if (lane == 0) {                          // the leader's MMA thread owns the accumulator hand-shake
                 if (CLUSTER == 2 && crank != 0) mbar_arrive_remote(&tmem_empty[acc], 0);
                 else mbar_arrive(&tmem_empty[acc]);
@@ -1061,6 +1096,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
     tc_fence_before();
     __syncthreads();
+#ifdef ZVB_TIMELINE
+    if (threadIdx.x == 0 && blockIdx.x == 0 && tl_slot < TL_MAX) { g_tl[tl_slot][7] = clock64(); g_tl[tl_slot][9] = globaltimer_ns(); }
+#endif
     if (CLUSTER > 1) cluster_sync_all();        // no CTA exits while a peer may still write to it
     if (warp == W_MMA) {
         __syncwarp();
