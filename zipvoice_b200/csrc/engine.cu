@@ -82,6 +82,9 @@ static int g_fuse_prologue = 1;    // ZVB_NO_FUSED_PROLOGUE=1: masks, per-stack 
 static int g_pv_bn = 0;            // ZVB_PV_BN=<columns>: tile width of the NonlinAttention P.V GEMM (0 = two equal tiles)
 static int g_merge_ff1 = 1;        // ZVB_NO_MERGE=1: feed_forward1 / attention in-projections as separate GEMMs
 static int g_small_model = 1;      // ZVB_NO_SMALL_MODEL=1: round 1's tile-width choice for small problems
+static int g_pre_b = 1;            // ZVB_NO_PRE_B=1: weight tiles are requested after the dependency wait like the activations
+static thread_local bool g_plan_build = false;  // set while a plan is being built: B operands of build_linear / build_gated are model weights
+struct PlanBuildScope { PlanBuildScope() { g_plan_build = true; } ~PlanBuildScope() { g_plan_build = false; } };
 static int g_small_lean = 1;       // ZVB_SMALL_LEAN=0: the small-problem cost model without the measured epilogue costs
 static int g_lean_pad = 1;         // ZVB_NO_LEAN_PAD=1: exact-fit tile widths for projections that are no multiple of 64 wide
 static int g_fast_bypass = 1;      // ZVB_NO_FAST_BYPASS=1: generic epilogue for the bypass GEMM (feed_forward2)
@@ -143,6 +146,7 @@ static void load_switches() {
         if (const char* e = getenv("ZVB_NO_LEAN_PAD")) g_lean_pad = atoi(e) == 0;
         if (const char* e = getenv("ZVB_NO_SMALL_MODEL")) g_small_model = atoi(e) == 0;
         if (const char* e = getenv("ZVB_SMALL_LEAN")) g_small_lean = atoi(e) != 0;
+        if (const char* e = getenv("ZVB_NO_PRE_B")) g_pre_b = atoi(e) == 0;
         if (const char* e = getenv("ZVB_NO_MERGE")) g_merge_ff1 = atoi(e) == 0;
         if (const char* e = getenv("ZVB_PV_BN")) g_pv_bn = atoi(e);
         if (const char* e = getenv("ZVB_NO_FUSED_PROLOGUE")) g_fuse_prologue = atoi(e) == 0;
@@ -530,6 +534,7 @@ static int build_linear(Op& op, const h16* A, long long M, int lda, const zvb_li
         p.orig_tma = 1;
     }
     gemm_layout(op);
+    p.pre_b = (g_pre_b && g_plan_build) ? 1 : 0;        // B = model weights: requested before the dependency wait
     p.fast_epi = (g_fast_epi && p.tma_store && p.aux_mode == AUX_NONE && p.out_mode == OUT_H16 &&
                   (p.rowbias == nullptr || p.rows_per_group >= GEMM_BLOCK_M) && p.act_cols % 32 == 0 &&
                   p.rowscale == nullptr && p.row_mask == nullptr && bn % 64 == 0 && lin.out_features % 8 == 0 &&
@@ -579,6 +584,7 @@ static int build_gated(Op& op, const h16* A, long long M, int lda, const zvb_lin
                   b_box_rows(op)));
     TRY(setup_tma_store(op, (int)M, 1));
     gemm_layout(op);
+    p.pre_b = (g_pre_b && g_plan_build) ? 1 : 0;        // B = model weights: requested before the dependency wait
     if (e.out_mode == OUT_H16) mark_out(op, 0, out, M * ldc);
     else if (e.out_mode == OUT_T_H16 && e.t_L > 0) mark_out(op, 0, out, (M / e.t_L) * (long long)e.t_batch_rows * e.t_pitch);
     op.shape[0] = (int)M; op.shape[1] = 2 * n_out; op.shape[2] = lin.in_features; op.shape[3] = 256;
@@ -941,6 +947,7 @@ static Op small_op(const float* in, const float* W, const float* b, const float*
 // by the next residual-adding epilogue through the TMA aux ring (4 bytes of HBM traffic per element and
 // update, against 10 for an fp32 stream with a 16-bit operand shadow).
 static int build_plan(const zvb_model* m, int N, int T, void* ws, size_t* bytes_out, zvb_plan* plan) {
+    PlanBuildScope weights_are_b;
     if (m == nullptr || m->abi_version != ZVB_ABI_VERSION) return fail(ZVB_ERR_INVALID, "model description: ABI version mismatch");
     if (N <= 0 || T <= 0) return fail(ZVB_ERR_INVALID, "N and T must be positive");
     const int D = m->dim, H = m->num_heads, dv = m->value_head_dim;
@@ -1268,6 +1275,7 @@ struct zvb_vocoder_plan {
 
 // ops of one `vocoder.decode` over N utterances of <= T frames; with ws == nullptr only measures the workspace
 static int build_vocoder(const zvb_vocoder* v, int N, int T, void* ws, size_t* bytes_out, zvb_vocoder_plan* plan) {
+    PlanBuildScope weights_are_b;
     if (v == nullptr || v->abi_version != ZVB_ABI_VERSION) return fail(ZVB_ERR_INVALID, "vocoder description: ABI version mismatch");
     if (N <= 0 || T <= 1) return fail(ZVB_ERR_INVALID, "vocoder: N must be positive and T at least 2");
     if (v->n_fft != AUD_NFFT || v->kernel != 7) return fail(ZVB_ERR_INVALID, "vocoder: built for n_fft 1024 and 7-tap convolutions");
@@ -1747,7 +1755,7 @@ int zvb_debug_timeline(unsigned long long* out, int max_rows) {
     CUDA_TRY(cudaMemcpyFromSymbol(&n, g_tl_n, sizeof n));
     int rows = static_cast<int>(n < (unsigned)TL_MAX ? n : (unsigned)TL_MAX);
     rows = rows < max_rows ? rows : max_rows;
-    if (rows > 0) CUDA_TRY(cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 12 * rows));
+    if (rows > 0) CUDA_TRY(cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 16 * rows));
     n = 0;
     CUDA_TRY(cudaMemcpyToSymbol(g_tl_n, &n, sizeof n));
     return rows;

@@ -70,6 +70,8 @@ struct GemmParams {
     int block_n;           // UMMA N: multiple of 16, <= 256 (256 for EPI_GATED)
     int stages, stage_bytes;   // operand ring (gemm_ring)
     int ring_bytes;            // shared memory given to the operands (resident A + ring); the aux slots follow it
+    int pre_b;                 // B is a model weight (written long before the launch): the producer requests the B halves of its
+                               // first tile's stages BEFORE the dependency wait (griddepcontrol.wait); host: plan builders only
     int a_resident;            // A-stationary mode (CTA pairs, K <= 512): the pair walks a CONTIGUOUS range of tiles,
                                // n-tile fastest, keeps the 128 x K A tile of its m-group in shared memory and streams
                                // only B; `a_bytes` = num_k_blocks x 16 KB in front of the (B-only) ring
@@ -285,7 +287,7 @@ __device__ __forceinline__ void gated_unit(const uint32_t* ra, const uint32_t* r
 #ifdef ZVB_TIMELINE
 // Debug build only (tools/timeline_c1.py): CTA 0 of every GEMM launch stamps clock64 at the points of its critical path.
 constexpr int TL_MAX = 1 << 15;
-__device__ unsigned long long g_tl[TL_MAX][12];
+__device__ unsigned long long g_tl[TL_MAX][16];
 __device__ unsigned int g_tl_n;
 #define TL_STAMP(k) do { if (blockIdx.x == 0 && tl_slot < TL_MAX) g_tl[tl_slot][k] = clock64(); } while (0)
 #else
@@ -412,6 +414,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const unsigned int tl_slot = blockIdx.x == 0 ? *tl_slot_p : TL_MAX;
     if (threadIdx.x == 0) TL_STAMP(1);
 #endif
+    // Weights do not depend on the predecessor: the B halves of the first tile's stages are requested before the dependency
+    // wait, so that only the activations' L2 round trip remains after it (single-utterance critical path, tools/timeline_c1.py).
+    int npre = 0;
+    if (warp == W_TMA && lane == 0 && p.pre_b != 0 && !resident && t_first < t_end) {
+        const uint32_t stage_tx = CLUSTER * GEMM_A_BYTES + static_cast<uint32_t>(p.block_n) * GEMM_BLOCK_K * 2;
+        const int b_rows = p.block_n / CLUSTER;
+        const int n_tile = t_first % p.num_n_tiles;
+        const int bz = ((t_first / p.num_n_tiles) / m_groups) * p.b_zb;
+        npre = STAGES < p.num_k_blocks ? STAGES : p.num_k_blocks;
+        for (int kb = 0; kb < npre; ++kb) {
+            uint8_t* sb = ring + kb * STAGE_BYTES + GEMM_A_BYTES;
+            if (CLUSTER == 2) {
+                if (crank == 0) mbar_arrive_expect_tx(&full_bar[kb], stage_tx);
+                tma_load_3d_2sm(sb, &tma_b, &full_bar[kb], kb * GEMM_BLOCK_K, n_tile * p.block_n + crank * b_rows, bz);
+            } else {
+                mbar_arrive_expect_tx(&full_bar[kb], stage_tx);
+                tma_load_3d(sb, &tma_b, &full_bar[kb], kb * GEMM_BLOCK_K, n_tile * p.block_n, bz);
+            }
+        }
+    }
     pdl_wait();                 // set-up above overlaps the previous kernel's tail
     pdl_launch();
     if (threadIdx.x == 0) TL_STAMP(2);
@@ -452,8 +474,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     continue;
                 }
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
                     uint8_t* sa = ring + stage * STAGE_BYTES;
+                    if (tile == t_first && kb < npre) {        // barrier armed and B requested before the dependency wait
+                        if (CLUSTER == 2) tma_load_3d_2sm(sa, &tma_a, &full_bar[stage], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M, az);
+                        else tma_load_3d(sa, &tma_a, &full_bar[stage], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M, az);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
                     if (CLUSTER == 2) {
                         if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
                         tma_load_3d_2sm(sa, &tma_a, &full_bar[stage], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M, az);
@@ -960,9 +988,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     if (p.n_out - oc < ncols) ncols = p.n_out - oc;
                     ncols = ncols > 32 ? 32 : ncols;
                     if (c0 < p.block_n && (ncols > 0 || p.tma_store)) {
+                        if (threadIdx.x == 0 && tile == t_first && s == s_first) TL_STAMP(12);
                         uint32_t acc_r[32];
                         tmem_ld32(taddr + c0, acc_r);
                         tmem_ld_wait();
+                        if (threadIdx.x == 0 && tile == t_first && s == s_first) TL_STAMP(13);
                         float v[32];
                         const f32x2 rs2 = pack2(rscale, rscale);
 #pragma unroll
@@ -1046,6 +1076,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = 0.0f;
                         }
+                        if (threadIdx.x == 0 && tile == t_first && s == s_first) TL_STAMP(14);
                         if (p.tma_store) {             // stage into the (swizzled) TMA box, own row only
                             wait_sfree();              // earlier stores no longer read what is overwritten
                             if (out_f32) {
@@ -1069,6 +1100,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     } else if (p.tma_store) {
                         wait_sfree();                  // keeps the buffer hand-shake in step (no columns to stage)
                     }
+                    if (threadIdx.x == 0 && tile == t_first && s == s_first) TL_STAMP(15);
                     if (p.tma_store) {
                         signal_staged();
                         continue;
