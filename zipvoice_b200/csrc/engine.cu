@@ -620,6 +620,10 @@ static int build_pv(Op& op, const h16* P, const float* inv_l, const h16* Vt, voi
     } else {
         const int tiles = (hd + 255) / 256;
         p.block_n = (((hd + tiles - 1) / tiles) + 15) / 16 * 16;
+        // single utterances: 2 x 10 m-tiles x 2 n-tiles = 40 CTAs streamed 20 k-blocks of 40 KB each (9.2 us of the launch's
+        // 14 us, tools/timeline_c1.py); narrower tiles put the same bytes on three times as many SMs
+        if (g_small_model && g_small_lean && (long long)N * p.num_m_tiles * tiles < g_num_sms)
+            p.block_n = pick_block_n_small(hd, (long long)N * p.num_m_tiles, p.num_k_blocks, 0);
         if (g_pv_bn > 0 && g_pv_bn % 16 == 0 && g_pv_bn <= 256) p.block_n = g_pv_bn;      // ZVB_PV_BN: measurement override
         p.num_n_tiles = (hd + p.block_n - 1) / p.block_n; p.a_zn = 0;
         p.n_out = hd; p.out_col_stride = p.block_n; p.n_valid = p.block_n;
@@ -636,6 +640,10 @@ static int build_pv(Op& op, const h16* P, const float* inv_l, const h16* Vt, voi
     TRY(make_tmap(&op.mb, Vt, Lk, vt_rows, N, (uint64_t)Lk * 2, (uint64_t)Lk * 2 * vt_rows, b_box_rows(op)));
     if (!per_head) TRY(setup_tma_store(op, L, N));
     gemm_layout(op);
+    // inside a plan the weights P were written by the attention kernel at least two launches earlier (a launch starts
+    // only after its predecessor passed its own dependency wait), so their tiles may be requested before the wait; V^T is
+    // the predecessor's output and is not
+    p.pre_b = (g_pre_b && g_plan_build) ? 2 : 0;
     mark_out(op, 0, out, (long long)N * L * ldc);
     op.shape[0] = N * L; op.shape[1] = per_head ? H * hd : hd; op.shape[2] = L; op.shape[3] = p.block_n;
     op.cat = ZVB_CAT_GEMM_PV;

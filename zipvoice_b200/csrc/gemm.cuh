@@ -70,8 +70,9 @@ struct GemmParams {
     int block_n;           // UMMA N: multiple of 16, <= 256 (256 for EPI_GATED)
     int stages, stage_bytes;   // operand ring (gemm_ring)
     int ring_bytes;            // shared memory given to the operands (resident A + ring); the aux slots follow it
-    int pre_b;                 // B is a model weight (written long before the launch): the producer requests the B halves of its
-                               // first tile's stages BEFORE the dependency wait (griddepcontrol.wait); host: plan builders only
+    int pre_b;                 // 1: B is a model weight (written long before the launch): the producer requests the B halves of
+                               // its first tile's stages BEFORE the dependency wait (griddepcontrol.wait); 2: the same for A
+                               // (P.V: the attention weights are at least two launches old).  Host: plan builders only
     int a_resident;            // A-stationary mode (CTA pairs, K <= 512): the pair walks a CONTIGUOUS range of tiles,
                                // n-tile fastest, keeps the 128 x K A tile of its m-group in shared memory and streams
                                // only B; `a_bytes` = num_k_blocks x 16 KB in front of the (B-only) ring
@@ -421,16 +422,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const uint32_t stage_tx = CLUSTER * GEMM_A_BYTES + static_cast<uint32_t>(p.block_n) * GEMM_BLOCK_K * 2;
         const int b_rows = p.block_n / CLUSTER;
         const int n_tile = t_first % p.num_n_tiles;
-        const int bz = ((t_first / p.num_n_tiles) / m_groups) * p.b_zb;
+        const int rest = t_first / p.num_n_tiles;
+        const int b = rest / m_groups;
+        const int bz = b * p.b_zb;
+        const int az = b * p.a_zb + n_tile * p.a_zn;
+        const int m_tile = (rest % m_groups) * CLUSTER + crank;
         npre = STAGES < p.num_k_blocks ? STAGES : p.num_k_blocks;
         for (int kb = 0; kb < npre; ++kb) {
-            uint8_t* sb = ring + kb * STAGE_BYTES + GEMM_A_BYTES;
+            uint8_t* sa = ring + kb * STAGE_BYTES;
             if (CLUSTER == 2) {
                 if (crank == 0) mbar_arrive_expect_tx(&full_bar[kb], stage_tx);
-                tma_load_3d_2sm(sb, &tma_b, &full_bar[kb], kb * GEMM_BLOCK_K, n_tile * p.block_n + crank * b_rows, bz);
+                if (p.pre_b == 2) tma_load_3d_2sm(sa, &tma_a, &full_bar[kb], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M, az);
+                else tma_load_3d_2sm(sa + GEMM_A_BYTES, &tma_b, &full_bar[kb], kb * GEMM_BLOCK_K, n_tile * p.block_n + crank * b_rows, bz);
             } else {
                 mbar_arrive_expect_tx(&full_bar[kb], stage_tx);
-                tma_load_3d(sb, &tma_b, &full_bar[kb], kb * GEMM_BLOCK_K, n_tile * p.block_n, bz);
+                if (p.pre_b == 2) tma_load_3d(sa, &tma_a, &full_bar[kb], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M, az);
+                else tma_load_3d(sa + GEMM_A_BYTES, &tma_b, &full_bar[kb], kb * GEMM_BLOCK_K, n_tile * p.block_n, bz);
             }
         }
     }
@@ -475,9 +482,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 }
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     uint8_t* sa = ring + stage * STAGE_BYTES;
-                    if (tile == t_first && kb < npre) {        // barrier armed and B requested before the dependency wait
-                        if (CLUSTER == 2) tma_load_3d_2sm(sa, &tma_a, &full_bar[stage], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M, az);
-                        else tma_load_3d(sa, &tma_a, &full_bar[stage], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M, az);
+                    if (tile == t_first && kb < npre) {        // barrier armed and one operand requested before the dependency wait
+                        if (p.pre_b == 2) {
+                            if (CLUSTER == 2)
+                                tma_load_3d_2sm(sa + GEMM_A_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BLOCK_K,
+                                                n_tile * p.block_n + crank * b_rows, bz);
+                            else
+                                tma_load_3d(sa + GEMM_A_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BLOCK_K, n_tile * p.block_n, bz);
+                        } else if (CLUSTER == 2) {
+                            tma_load_3d_2sm(sa, &tma_a, &full_bar[stage], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M, az);
+                        } else {
+                            tma_load_3d(sa, &tma_a, &full_bar[stage], kb * GEMM_BLOCK_K, m_tile * GEMM_BLOCK_M, az);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                         continue;
                     }
