@@ -553,6 +553,13 @@ ALL = {
     # the CUDA-core-bias kernel (attn.cuh, the default)
     "attn_v2_masked": lambda: check_attn(N=3, H=4, L=333, masked=True, tc=False),
     "attn_v2_strong_pos": lambda: check_attn(N=2, H=4, L=333, masked=True, pos_scale=2.5, tol=3e-2, tc=False),
+    # small grids split the key tiles of a query tile over a cluster (attn.cuh, CS = 2 / 4; the two cases above already run
+    # as pairs with an uneven 1 + 2 split): four CTAs with 2 + 3 + 2 + 3 key tiles, the exact-maximum path over four CTAs,
+    # and a grid large enough to stay on one CTA per query tile
+    "attn_v2_split4_long": lambda: check_attn(N=1, H=4, L=1219, masked=True, tc=False),
+    "attn_v2_split4_strong": lambda: check_attn(N=1, H=4, L=610, masked=True, pos_scale=2.5, tol=3e-2, tc=False),
+    "attn_v2_split2_long": lambda: check_attn(N=2, H=4, L=1219, masked=True, tc=False),
+    "attn_v2_nosplit": lambda: check_attn(N=16, H=4, L=333, masked=True, tc=False),
     # tensor-core bias: odd / even L (window alignment in the two table copies), one tile, tile boundaries
     "attn_tc_L128": lambda: check_attn(N=2, H=4, L=128, masked=False),
     "attn_tc_L129": lambda: check_attn(N=2, H=4, L=129, masked=True),

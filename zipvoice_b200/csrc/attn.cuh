@@ -38,8 +38,9 @@ constexpr int ATT_POS_PAD = 128;     // zero entries on both sides of the rel-po
 constexpr int ATT_EWIN_BYTES = 255 * 16;
 constexpr float ATT_BOUND_SLACK_L2 = 10.0f;  // log2 units of slack the cheap softmax shift may have (weights >= 2^2)
 constexpr int ATT_STAGE_BYTES = ATT_SM_WARPS * 4096; // per softmax warp: 32 rows x 128 B TMA-store staging
-constexpr int ATT_SMEM_BYTES = (1 + ATT_KSTAGES) * ATT_TILE_BYTES + ATT_STAGE_BYTES + 2 * ATT_EWIN * 16 +
-                               2 * 128 * 4 + 1024 + 256;
+constexpr int ATT_MAX_SPLIT = 4;      // key tiles of one (query tile, head, utterance) over up to 4 CTAs of a cluster
+constexpr int ATT_XPEER_OFF = (1 + ATT_KSTAGES) * ATT_TILE_BYTES + ATT_STAGE_BYTES + 2 * ATT_EWIN * 16 + 2 * 128 * 4 + 256;
+constexpr int ATT_SMEM_BYTES = ATT_XPEER_OFF + 2 * ATT_MAX_SPLIT * 128 * 4 + 1024;   // two CTAs per SM: <= 113 KB each
 
 struct AttnParams {
     int L, Lk, H, N;
@@ -55,6 +56,12 @@ struct AttnParams {
 };
 
 // tma_qk: [q | k | p] rows, box 64 x 128; tma_p: P viewed as (Lk, L, N*H), box 64 columns x 32 rows.
+// CS > 1 (small grids: single utterances leave half of the SMs idle and every CTA walks 2 x num_jt tile iterations of ~1.2 us):
+// a cluster of CS CTAs shares one (query tile, head, utterance), CTA `rank` takes key tiles [rank num_jt / CS, (rank + 1) num_jt /
+// CS); the row maxima are exchanged between the passes and the row sums at the end through distributed shared memory
+// (st.shared::cluster + a release arrive on the peer's mbarrier), so all CTAs of the cluster use the same shift m and
+// rank 0 writes 1 / l.  Host: launch_op picks CS from the grid size and num_jt >= CS.
+template <int CS>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_constant__ CUtensorMap tma_p,
                     const AttnParams p) {
@@ -76,14 +83,19 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
     uint64_t* s_empty = s_full + 2;                   // [2]
     uint64_t* e_full = s_empty + 2;                   // [2] rel-pos window landed
     uint64_t* e_empty = e_full + 2;                   // [2] rel-pos window consumed (second pass only)
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(e_empty + 2);
+    uint64_t* x_bar = e_empty + 2;                    // [2] peers' row maxima / row sums landed (CS > 1)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(x_bar + 2);
+    float* xpeer = reinterpret_cast<float*>(smem + ATT_XPEER_OFF);     // [2][ATT_MAX_SPLIT][128] written by the peers
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int i0 = blockIdx.x * ATT_BM;
+    const int i0 = (blockIdx.x / CS) * ATT_BM;
     const int h = blockIdx.y;
     const int n = blockIdx.z;
-    const int num_jt = (p.L + ATT_BN - 1) / ATT_BN;
+    const uint32_t rank = CS > 1 ? cluster_ctarank() : 0u;
+    const int all_jt = (p.L + ATT_BN - 1) / ATT_BN;
+    const int jt_lo = CS > 1 ? static_cast<int>(rank) * all_jt / CS : 0;             // this CTA's key tiles
+    const int num_jt = CS > 1 ? (static_cast<int>(rank) + 1) * all_jt / CS - jt_lo : all_jt;
     const int total_it = 2 * num_jt;
 
     if (warp == ATT_SM_WARPS && lane == 0) {
@@ -99,6 +111,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
             mbar_init(&s_empty[s], ATT_SM_WARPS);
             mbar_init(&e_full[s], 1);
             mbar_init(&e_empty[s], ATT_SM_WARPS);
+            mbar_init(&x_bar[s], CS > 1 ? 128 * (CS - 1) : 1);
         }
         fence_barrier_init();
     }
@@ -108,6 +121,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();     // the peers' barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     pdl_wait();                 // set-up above overlaps the previous kernel's tail
@@ -127,7 +141,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
         int stage = 0;
         uint32_t phase = 0;
         auto load_k = [&](int it) {
-            const int jt = it >= num_jt ? it - num_jt : it;
+            const int jt = jt_lo + (it >= num_jt ? it - num_jt : it);
             mbar_wait(&k_empty[stage], phase ^ 1u);
             mbar_arrive_expect_tx(&k_full[stage], ATT_TILE_BYTES);
             tma_load_3d(k_tiles + stage * ATT_TILE_BYTES, &tma_qk, &k_full[stage], p.qd + h * 32,
@@ -149,7 +163,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
             const int e_first = exact_max ? 0 : num_jt;            // first iteration that needs the rel-pos window
             const uint4* Eh = p.Epair + static_cast<long long>(h) * (2 * p.L - 1 + 2 * ATT_POS_PAD);
             for (int it = 0; it < total_it; ++it) {
-                const int jt = it >= num_jt ? it - num_jt : it;
+                const int jt = jt_lo + (it >= num_jt ? it - num_jt : it);
                 if (it >= prefill) load_k(it);
                 if (it >= e_first) {
                     // rel-pos window of this (i-tile, j-tile): 255 consecutive pair entries, first offset
@@ -227,17 +241,31 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
         float m_run = -INFINITY, m_l2 = 0.f, l_run = 0.f;
         // excluded-key words one tile ahead: two CTAs of ~106 KB leave the L1 almost no capacity, so every global load
         // here is an L2 round trip; requested a whole tile before it is needed
-        uint32_t mw0n = __ldg(mwrow), mw1n = __ldg(mwrow + 1);
+        uint32_t mw0n = __ldg(mwrow + 4 * jt_lo), mw1n = __ldg(mwrow + 4 * jt_lo + 1);
         for (int it = 0; it < total_it; ++it) {
             const int pass = it >= num_jt ? 1 : 0;
-            const int jt = pass ? it - num_jt : it;
+            const int jt = jt_lo + (pass ? it - num_jt : it);
             const int j0 = jt * ATT_BN;
             const int acc = it & 1;
             const uint32_t acc_phase = static_cast<uint32_t>(it >> 1) & 1u;
             if (it == num_jt) {                           // between the passes: m >= every score of the row
                 xch[half * 128 + r] = m_run;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                const float mr = fmaxf(xch[r], xch[128 + r]);
+                float mr = fmaxf(xch[r], xch[128 + r]);
+                if (CS > 1) {                             // the row maximum over ALL key tiles: every CTA of the cluster must shift alike
+                    if (half == 0) {
+#pragma unroll
+                        for (uint32_t pr = 0; pr < static_cast<uint32_t>(CS); ++pr)
+                            if (pr != rank) {
+                                st_f32_remote(xpeer + rank * 128 + r, pr, mr);
+                                mbar_arrive_remote_release(&x_bar[0], pr);
+                            }
+                    }
+                    mbar_wait_acquire_cluster(&x_bar[0], 0u);
+#pragma unroll
+                    for (uint32_t pr = 0; pr < static_cast<uint32_t>(CS); ++pr)
+                        if (pr != rank) mr = fmaxf(mr, xpeer[pr * 128 + r]);
+                }
                 if (exact_max) {                          // exact (fp16) row maximum of the biased scores, log2 units
                     m_l2 = (mr == -INFINITY ? 0.f : mr) - 12.0f;
                 } else {
@@ -250,7 +278,7 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
             const uint4* ew = ewin + acc * ATT_EWIN;
             const uint32_t mw0 = mw0n, mw1 = mw1n;
             if (it + 1 < total_it) {
-                const int jn = it + 1 >= num_jt ? it + 1 - num_jt : it + 1;
+                const int jn = jt_lo + (it + 1 >= num_jt ? it + 1 - num_jt : it + 1);
                 mw0n = __ldg(mwrow + 4 * jn);
                 mw1n = __ldg(mwrow + 4 * jn + 1);
             }
@@ -404,9 +432,21 @@ attn_weights_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_con
         }
         xch[half * 128 + r] = l_run;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 0 && row_ok)
+        if (CS > 1 && half == 0) {                        // row sums of the other key ranges -> rank 0
+            if (rank != 0u) {
+                st_f32_remote(xpeer + (ATT_MAX_SPLIT + rank) * 128 + r, 0u, xch[r] + xch[128 + r]);
+                mbar_arrive_remote_release(&x_bar[1], 0u);
+            } else {
+                mbar_wait_acquire_cluster(&x_bar[1], 0u);
+            }
+        }
+        if (half == 0 && row_ok && rank == 0u)
         {
-            const float l = xch[r] + xch[128 + r];
+            float l = xch[r] + xch[128 + r];
+            if (CS > 1) {
+#pragma unroll
+                for (int pr = 1; pr < CS; ++pr) l += xpeer[(ATT_MAX_SPLIT + pr) * 128 + r];
+            }
             p.inv_l[(static_cast<long long>(n) * p.H + h) * p.L + i] = l > 0.f ? 1.0f / l : 0.f;
         }
         if (lane == 0) bulk_wait_read<0>();               // staging must outlive the stores reading it

@@ -76,6 +76,7 @@ static int g_wide_pref = 1;       // ZVB_WIDE_PREF=0: exact-fit tile widths firs
 static double g_wide_waste = 0.12; // ZVB_WIDE_WASTE: largest padding share accepted for a 256-column tile when K <= 512
 static int g_bn192 = 0;           // ZVB_BN192=1: 192-column tiles for short-K GEMMs (measured: no gain)
 static int g_layout_ok = 1;       // ZVB_NO_LAYOUT=1 keeps the default operand-ring / aux split everywhere
+static int g_attn_split = 1;      // ZVB_ATTN_SPLIT=0: no key split of the attention weights over a cluster; 3 / 4: force 2 / 4 CTAs (tests)
 static int g_attn_tc = 0;         // ZVB_ATTN_TC=1: attention weights with the tensor-core rel-pos bias (attn3.cuh; measured slower)
 static int g_dw_mode = 0;          // ZVB_DW_MODE: depthwise-convolution block shapes (elementwise.cuh: DwShape), 0 = measured best
 static int g_fuse_prologue = 1;    // ZVB_NO_FUSED_PROLOGUE=1: masks, per-stack time projections and row biases as separate launches
@@ -147,6 +148,7 @@ static void load_switches() {
         if (const char* e = getenv("ZVB_NO_SMALL_MODEL")) g_small_model = atoi(e) == 0;
         if (const char* e = getenv("ZVB_SMALL_LEAN")) g_small_lean = atoi(e) != 0;
         if (const char* e = getenv("ZVB_NO_PRE_B")) g_pre_b = atoi(e) == 0;
+        if (const char* e = getenv("ZVB_ATTN_SPLIT")) g_attn_split = atoi(e);
         if (const char* e = getenv("ZVB_NO_MERGE")) g_merge_ff1 = atoi(e) == 0;
         if (const char* e = getenv("ZVB_PV_BN")) g_pv_bn = atoi(e);
         if (const char* e = getenv("ZVB_NO_FUSED_PROLOGUE")) g_fuse_prologue = atoi(e) == 0;
@@ -186,7 +188,9 @@ static int init_device() {
                 if (gemm_fn(EPI_LINEAR, act, cl, lean) != nullptr) ZVB_SMEM_ATTR(gemm_fn(EPI_LINEAR, act, cl, lean));
     ZVB_SMEM_ATTR(gemm_fn(EPI_GATED, ACT_NONE, 1, 0)); ZVB_SMEM_ATTR(gemm_fn(EPI_GATED, ACT_NONE, 2, 0));
 #undef ZVB_SMEM_ATTR
-    CUDA_TRY(cudaFuncSetAttribute(attn_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(attn_weights_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(attn_weights_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(attn_weights_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(attn_weights_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7, 0>()));
     CUDA_TRY(cudaFuncSetAttribute(dwconv_kernel<7, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes<7, 1>()));
@@ -779,8 +783,30 @@ static int launch_op(const Op& op, cudaStream_t st) {
             return check_launch("gemm");
         }
         case OP_ATTN: {
-            dim3 grid((op.ap.L + ATT_BM - 1) / ATT_BM, op.ap.H, op.ap.N);
-            launch_k(attn_weights_kernel, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, st, op.ma, op.ms, op.ap);
+            const int q_tiles = (op.ap.L + ATT_BM - 1) / ATT_BM;          // also the number of key tiles
+            // small grids (single utterances): the key tiles of a query tile are split over a cluster of 2 or 4 CTAs while the
+            // grid still fits the SMs about once (attn.cuh; ZVB_ATTN_SPLIT=0 keeps one CTA per query tile)
+            int cs = 1;
+            const long long base = (long long)q_tiles * op.ap.H * op.ap.N;
+            if (g_attn_split) {
+                if (q_tiles >= 4 && base * 4 <= g_num_sms + g_num_sms / 8) cs = 4;
+                else if (q_tiles >= 2 && base * 2 <= g_num_sms + g_num_sms / 8) cs = 2;
+                if (g_attn_split > 1 && q_tiles >= g_attn_split) cs = g_attn_split == 3 ? 2 : g_attn_split;   // tests: force 2 (=3) or 4
+            }
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(q_tiles * cs, op.ap.H, op.ap.N);
+            cfg.blockDim = dim3(ATT_THREADS);
+            cfg.dynamicSmemBytes = ATT_SMEM_BYTES;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[2];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = g_pdl ? 2 : 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, cs == 4 ? attn_weights_kernel<4> : cs == 2 ? attn_weights_kernel<2> : attn_weights_kernel<1>,
+                                               op.ma, op.ms, op.ap);
+            if (e != cudaSuccess) return fail(ZVB_ERR_CUDA, "launch attn_weights: %s", cudaGetErrorString(e));
             return check_launch("attn_weights");
         }
         case OP_ATTN_TC: {

@@ -190,6 +190,44 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Distributed shared memory hand-off between the CTAs of a cluster (attention weights, key split): a float stored into
+// the peer's shared memory, published by a release arrive (cluster scope) on the peer's mbarrier; the waiter acquires at
+// cluster scope before it reads.
+__device__ __forceinline__ void st_f32_remote(const float* local_addr, uint32_t rank, float v) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "st.shared::cluster.f32 [ra], %2;\n\t}"
+        ::"r"(smem_u32(local_addr)), "r"(rank), "f"(v)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0, ok = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+            : "memory");
+        if (ok) return;
+        if ((++spins & 63u) == 0u && globaltimer_ns() - t0 > ZVB_WAIT_TIMEOUT_NS) {
+            printf("zvb: cluster mbarrier wait timeout block=(%d,%d,%d) thread=%d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
 // CTA-pair (cta_group::2) variants.  A shared::cluster address carries the CTA rank of the pair in
 // bit 24; clearing it addresses the same offset in the leader CTA (rank 0).
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
