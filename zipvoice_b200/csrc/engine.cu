@@ -791,6 +791,14 @@ static int launch_op(const Op& op, cudaStream_t st) {
             if (g_attn_split) {
                 if (q_tiles >= 4 && base * 4 <= g_num_sms + g_num_sms / 8) cs = 4;
                 else if (q_tiles >= 2 && base * 2 <= g_num_sms + g_num_sms / 8) cs = 2;
+                else if (q_tiles >= 8) {
+                    // tail of the last wave: two CTAs per SM = 296 slots; a 60 s dialog has 416 CTAs of 104 tile iterations each
+                    // (two waves for 1.4 waves of work), as pairs 832 half-length CTAs in three (measured: 2.41 -> 2.16 ms per
+                    // forward; on grids of many waves the split only adds its hand-offs: C5 +16%, C3 +31% when forced)
+                    const long long slots = 2LL * g_num_sms;
+                    const long long w1 = (base + slots - 1) / slots, w2 = (2 * base + slots - 1) / slots;
+                    if (10 * w2 <= 16 * w1) cs = 2;           // <= 0.8 of the unsplit wave count
+                }
                 if (g_attn_split > 1 && q_tiles >= g_attn_split) cs = g_attn_split == 3 ? 2 : g_attn_split;   // tests: force 2 (=3) or 4
             }
             cudaLaunchConfig_t cfg{};
