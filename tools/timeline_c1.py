@@ -49,7 +49,7 @@ def main():
     for _ in range(3):
         model.solver.sample(x=x0, text_condition=text, speech_condition=speech, padding_mask=mask, **kw)
     torch.cuda.synchronize()
-    buf = np.zeros((1 << 15, 16), dtype=np.uint64)
+    buf = np.zeros((1 << 15, 20), dtype=np.uint64)
     lib.zvb_debug_timeline(buf.ctypes.data, buf.shape[0])              # reset
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -83,6 +83,8 @@ def main():
         # stamps 3/4 come from the MMA thread, 5/6 from epilogue thread 0: keep them as differences along the chain
         line = " ".join(f"{v:6.2f}" for v in d.mean(axis=0))
         tot = (rr[:, 7] - rr[:, 0]).mean() / ghz / 1e3
+        su = np.stack([rr[:, 16] - rr[:, 0], rr[:, 17] - rr[:, 0], rr[:, 18] - rr[:, 0], rr[:, 19] - rr[:, 0]], axis=1).astype(np.float64) / ghz / 1e3
+        line += "   set-up (entry -> barriers initialised / TMEM allocated / block barrier / cluster barrier): " + " ".join(f"{v:5.2f}" for v in su.mean(axis=0))
         if key[5] == 0 and (rr[:, 12] > 0).all():      # generic linear epilogue: accumulator ready -> unit start -> TMEM read -> math -> stored
             g = np.stack([rr[:, 12] - rr[:, 5], rr[:, 13] - rr[:, 12], rr[:, 14] - rr[:, 13], rr[:, 15] - rr[:, 14],
                           rr[:, 6] - rr[:, 15]], axis=1).astype(np.float64) / ghz / 1e3

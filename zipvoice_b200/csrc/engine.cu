@@ -1797,7 +1797,7 @@ int zvb_debug_timeline(unsigned long long* out, int max_rows) {
     CUDA_TRY(cudaMemcpyFromSymbol(&n, g_tl_n, sizeof n));
     int rows = static_cast<int>(n < (unsigned)TL_MAX ? n : (unsigned)TL_MAX);
     rows = rows < max_rows ? rows : max_rows;
-    if (rows > 0) CUDA_TRY(cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 16 * rows));
+    if (rows > 0) CUDA_TRY(cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 20 * rows));
     n = 0;
     CUDA_TRY(cudaMemcpyToSymbol(g_tl_n, &n, sizeof n));
     return rows;

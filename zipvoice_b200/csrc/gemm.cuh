@@ -288,8 +288,9 @@ __device__ __forceinline__ void gated_unit(const uint32_t* ra, const uint32_t* r
 #ifdef ZVB_TIMELINE
 // Debug build only (tools/timeline_c1.py): CTA 0 of every GEMM launch stamps clock64 at the points of its critical path.
 constexpr int TL_MAX = 1 << 15;
-__device__ unsigned long long g_tl[TL_MAX][16];
+__device__ unsigned long long g_tl[TL_MAX][20];
 __device__ unsigned int g_tl_n;
+__device__ volatile unsigned long long g_tl_setup[4];       // set-up stamps of the CTA 0 in flight (one launch at a time writes them)
 #define TL_STAMP(k) do { if (blockIdx.x == 0 && tl_slot < TL_MAX) g_tl[tl_slot][k] = clock64(); } while (0)
 #else
 #define TL_STAMP(k) do { } while (0)
@@ -374,41 +375,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int aux_parts = p.orig_tma ? 2 : 1;          // ring entries per sub-tile: operand (+ bypass `orig`)
     const int n_sub = (n_units + units_per_sub - 1) / units_per_sub;
 
-    if (warp == W_TMA && lane == 0) {
-        tma_prefetch_desc(&tma_a);
-        tma_prefetch_desc(&tma_b);
-        if (p.aux_mode != AUX_NONE) tma_prefetch_desc(&tma_aux);
-        if (p.tma_store) tma_prefetch_desc(&tma_out);
-        if (p.orig_tma) tma_prefetch_desc(&tma_orig);
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+    if (warp == W_TMA) {
+        // the 60 barriers are initialised by the 32 lanes of the producer warp (set-up is ~0.8 us from kernel entry to the block
+        // barrier and +0.8 us for a pair's cluster barrier, tools/timeline_c1.py; one thread initialising them all measured the
+        // same sample time -- the set-up is dominated by the launch's cold start and the TMEM allocation, not by this loop)
+        if (lane == 0) {
+            tma_prefetch_desc(&tma_a);
+            tma_prefetch_desc(&tma_b);
+            if (p.aux_mode != AUX_NONE) tma_prefetch_desc(&tma_aux);
+            if (p.tma_store) tma_prefetch_desc(&tma_out);
+            if (p.orig_tma) tma_prefetch_desc(&tma_orig);
         }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], GEMM_EPI_WARPS * CLUSTER);
-        }
-        for (int s = 0; s < GEMM_AUX_SLOTS_MAX; ++s) {
-            mbar_init(&aux_full[s], 1);
-            mbar_init(&aux_empty[s], p.tma_store ? 1 : (units_per_sub == 2 ? 8 : 4));
-        }
-        for (int s = 0; s < 4; ++s) {
-            mbar_init(&staged[s], units_per_sub == 2 ? 8 : 4);
-            mbar_init(&sfree[s], 1);
-        }
-        for (int s = 0; s < 8; ++s) {
-            mbar_init(&a_full[s], 1);
-            mbar_init(&a_empty[s], 1);
+        constexpr int I_TMEM_FULL = 2 * GEMM_MAX_STAGES, I_TMEM_EMPTY = I_TMEM_FULL + 2, I_AUX_FULL = I_TMEM_EMPTY + 2,
+                      I_AUX_EMPTY = I_AUX_FULL + GEMM_AUX_SLOTS_MAX, I_STAGED = I_AUX_EMPTY + GEMM_AUX_SLOTS_MAX,
+                      I_SFREE = I_STAGED + 4, I_END = I_SFREE + 4 + 16;
+        for (int i = lane; i < I_END; i += 32) {
+            uint32_t cnt = 1;
+            if (i >= I_TMEM_EMPTY && i < I_AUX_FULL) cnt = GEMM_EPI_WARPS * CLUSTER;
+            else if (i >= I_AUX_EMPTY && i < I_STAGED) cnt = p.tma_store ? 1 : (units_per_sub == 2 ? 8 : 4);
+            else if (i >= I_STAGED && i < I_SFREE) cnt = units_per_sub == 2 ? 8 : 4;
+            mbar_init(&bars[i], cnt);
         }
         fence_barrier_init();
+#ifdef ZVB_TIMELINE
+        if (blockIdx.x == 0) g_tl_setup[0] = clock64();
+#endif
     }
     if (warp == W_MMA) {
         if (CLUSTER == 2) { tmem_alloc_2sm(tmem_holder, GEMM_TMEM_COLS); tmem_relinquish_2sm(); }
         else { tmem_alloc(tmem_holder, GEMM_TMEM_COLS); tmem_relinquish(); }
+#ifdef ZVB_TIMELINE
+        if (blockIdx.x == 0 && lane == 0) g_tl_setup[1] = clock64();
+#endif
     }
     tc_fence_before();
     __syncthreads();
+#ifdef ZVB_TIMELINE
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_tl_setup[2] = clock64();
+#endif
     if (CLUSTER > 1) cluster_sync_all();        // peers' barriers are initialised before any remote arrive
+#ifdef ZVB_TIMELINE
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned int sl = *tl_slot_p;
+        if (sl < TL_MAX) { g_tl[sl][16] = g_tl_setup[0]; g_tl[sl][17] = g_tl_setup[1]; g_tl[sl][18] = g_tl_setup[2]; g_tl[sl][19] = clock64(); }
+    }
+#endif
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 #ifdef ZVB_TIMELINE
