@@ -531,6 +531,13 @@ ALL = {
     "linear_resident_swoosh_n1152": lambda: check_linear(M=9000, K=512, N=1152, act=1),
     "linear_resident_n1536": lambda: check_linear(M=40000, K=512, N=1536, act=1),
     "gated_glu_resident": lambda: check_gated(M=6001, n_out=512, mode=2, masked=True),
+    # CTA pairs are only used from 2 x 148 m-tiles on (engine.cu: set_grid): the residual, bypass, gated and row-scaled
+    # (P.V) epilogues as pairs, with a last pair whose second m-tile is all padding
+    "linear_pair_resid": lambda: check_linear(M=38100, K=1536, N=512, resid=True),
+    "linear_pair_bypass": lambda: check_linear(M=38100, K=1536, N=512, resid=True, bypass=True),
+    "linear_pair_k48": lambda: check_linear(M=38100, K=48, N=512, resid=True),
+    "gated_glu_pair": lambda: check_gated(M=38100, n_out=512, mode=2, masked=True),
+    "pv_wide_mul_pair": lambda: check_pv(N=30, H=4, L=1219, hd=384, hp=384, per_head=False, mul=True),
     "gated_tanh": lambda: check_gated(M=300, n_out=384, mode=1),
     "gated_tanh96": lambda: check_gated(M=81, K=128, n_out=96, mode=1),
     "gated_glu_masked": lambda: check_gated(M=1000, n_out=512, mode=2, masked=True),

@@ -71,6 +71,7 @@ static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 static int g_cluster_ok = 1;      // ZVB_NO_CLUSTER=1 disables the CTA-pair (cta_group::2) GEMM variant
+static long long g_pair_min_mtiles = -1;    // ZVB_PAIR_MIN_MTILES: fewest 128-row tiles (all batches) for CTA pairs; default 2 x SMs
 static int g_tma_store_ok = 1;
 static int g_wide_pref = 1;       // ZVB_WIDE_PREF=0: exact-fit tile widths first
 static double g_wide_waste = 0.12; // ZVB_WIDE_WASTE: largest padding share accepted for a 256-column tile when K <= 512
@@ -149,6 +150,7 @@ static void load_switches() {
         if (const char* e = getenv("ZVB_SMALL_LEAN")) g_small_lean = atoi(e) != 0;
         if (const char* e = getenv("ZVB_NO_PRE_B")) g_pre_b = atoi(e) == 0;
         if (const char* e = getenv("ZVB_ATTN_SPLIT")) g_attn_split = atoi(e);
+        if (const char* e = getenv("ZVB_PAIR_MIN_MTILES")) g_pair_min_mtiles = atoll(e);
         if (const char* e = getenv("ZVB_NO_MERGE")) g_merge_ff1 = atoi(e) == 0;
         if (const char* e = getenv("ZVB_PV_BN")) g_pv_bn = atoi(e);
         if (const char* e = getenv("ZVB_NO_FUSED_PROLOGUE")) g_fuse_prologue = atoi(e) == 0;
@@ -300,6 +302,8 @@ struct Op {
 };
 static inline void mark_out(Op& op, int i, const void* p, long long n) { op.scan_ptr[i] = p; op.scan_n[i] = n; }
 
+static inline long long pair_min_mtiles() { return g_pair_min_mtiles >= 0 ? g_pair_min_mtiles : 2LL * g_num_sms; }
+
 // Small problems (single utterances: 20 m-tiles at T = 1219, 103 at T = 6563): a tile's time is the operand bytes its SM
 // streams plus its epilogue, and the kernel's time is that times the number of WAVES the tiles need on 148 SMs / 74 CTA pairs.
 // Round 1 picked multiples of 64 only: N = 512 at 20 m-tiles became 160 tiles of 64 columns = 2 waves where 140 tiles of 80
@@ -317,7 +321,8 @@ static int pick_block_n_small(int n_out, long long m_tiles, int k_blocks, int le
         const long long n_tiles = (n_out + bn - 1) / bn;
         if (bn > 16 && (n_tiles - 1) * bn >= n_out) continue;
         const long long slots2 = ((m_tiles + 1) / 2) * n_tiles;
-        const bool pair = g_cluster_ok && bn >= 64 && m_tiles >= 2 && slots2 >= g_num_sms / 4 && k_blocks >= g_pair_min_kb;
+        const bool pair = g_cluster_ok && bn >= 64 && m_tiles >= 2 && slots2 >= g_num_sms / 4 && k_blocks >= g_pair_min_kb &&
+                          m_tiles >= pair_min_mtiles();
         const long long units = pair ? slots2 : m_tiles * n_tiles;
         const long long lanes = pair ? g_num_sms / 2 : g_num_sms;
         const long long waves = (units + lanes - 1) / lanes;
@@ -415,8 +420,12 @@ static void set_grid(Op& op) {
     // P.V 222 -> 195 us).  For K = 512 they were a loss until the peer's accumulator hand-off stopped fencing
     // (relaxed remote arrive) and the epilogue arithmetic was packed; since then 8 k-blocks are worth it
     // (-30% L2->SM operand bytes; 790 -> 770 ms per sample, A/B on one box), fewer make no difference
+    // ... and only on large problems: a pair pays a cluster launch, a cluster barrier in its set-up (+0.8 us, tools/timeline_c1.py)
+    // and one at its exit, which a GEMM of a few tiles per SM never earns back -- without pairs a single utterance samples in
+    // 47.8 ms instead of 51.5, two in 57.7 instead of 61.9, a 60 s dialog in 144-146 ms instead of 147; 16 utterances are even,
+    // from 24 on (and the 16 x 2344-frame stereo batch) the pairs' smaller L2 -> SM traffic wins by 2 % (profiles/pair_threshold_r2.txt)
     op.cluster = (g_cluster_ok && p.block_n >= 64 && p.num_m_tiles >= 2 && slots2 >= g_num_sms / 4 &&
-                  p.num_k_blocks >= g_pair_min_kb) ? 2 : 1;
+                  p.num_k_blocks >= g_pair_min_kb && (long long)p.batches * p.num_m_tiles >= pair_min_mtiles()) ? 2 : 1;
     if (op.cluster == 2) {
         const long long clusters = slots2 < g_num_sms / 2 ? slots2 : g_num_sms / 2;
         op.grid = static_cast<int>(clusters * 2);
