@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -330,7 +331,10 @@ static int pick_block_n_small(int n_out, long long m_tiles, int k_blocks, int le
         double tile_us, cost;
         if (g_small_lean) {
             const double epi_us = lean ? 0.3 + 0.0065 * bn : 2.0 + 0.02 * bn;
-            tile_us = 2.7 + k_blocks * 128.0 * (128 + (pair ? bn / 2 : bn)) / 62000.0 + epi_us;
+            // a k-block of a single-CTA tile takes ~0.285 us whatever its width up to 128 columns (85-110 GB/s per SM: ring depth
+            // over load latency), a pair's 0.35-0.38 us (62 GB/s per SM): gpurun_out/r2d_timeline6.log / r2d_timeline4.log
+            const double kb_us = pair ? 128.0 * (128 + bn / 2) / 62000.0 : std::max(0.285, 128.0 * (128 + bn) / 110000.0);
+            tile_us = 2.7 + k_blocks * kb_us + epi_us;
             cost = waves * tile_us;
         } else {                                       // the round-2 model before the timeline measurement (ZVB_SMALL_LEAN=0)
             tile_us = 5.2 + k_blocks * 128.0 * (128 + (pair ? bn / 2 : bn)) / 62000.0 + 0.004 * bn;
