@@ -302,6 +302,13 @@ int zvb_test_timestep_embedding(const float* t, float* out, int N, int dim, void
 /* strided key mask mask[:, ::ds] and the attention kernel's excluded-key bit words (either output nullable) */
 int zvb_test_masks(const uint8_t* mask, int N, int T, int ds, uint8_t* strided, uint32_t* words, void* stream);
 
+/* Host only (no device needed): the launch shape the engine picks for a linear layer of `rows` x `n_out` outputs over `k`
+ * inputs on a device with `num_sms` SMs -- tile width, CTA pair (cta_group::2) or single CTA, and the attention kernel's
+ * key-split cluster size for `attn_ctas` = query tiles x heads x utterances with `q_tiles` key tiles.  lean_kind: 0 generic
+ * epilogue only, 1 plain lean epilogue possible, 2 residual lean epilogue possible.  Any output pointer may be null. */
+int zvb_debug_launch_shape(long long rows, int n_out, int k, int lean_kind, int num_sms, long long attn_ctas, int q_tiles,
+                           int* block_n, int* pair, int* attn_split);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,3 +105,42 @@ def test_audio_stages_have_no_cpu_fallback(lib):
     out = torch.zeros(1, 8, 100)
     rc = lib.zvb_fbank(w.data_ptr(), None, 1, 2048, None, None, None, 100, 256, 1.0, out.data_ptr(), 8, None)
     assert rc in (-4, -1)                                             # no device (or null argument): never computed on the host
+
+
+def _shape(lib, rows, n_out, k, lean_kind, attn_ctas=1, q_tiles=1, num_sms=148):
+    bn, pair, cs = C.c_int(), C.c_int(), C.c_int()
+    assert lib.zvb_debug_launch_shape(rows, n_out, k, lean_kind, num_sms, attn_ctas, q_tiles, C.byref(bn), C.byref(pair),
+                                      C.byref(cs)) == 0
+    return bn.value, pair.value, cs.value
+
+
+def test_launch_shapes_are_host_only_and_follow_the_measured_rules(lib):
+    """The launch-shape rules of DESIGN.md §3 (tile widths of small problems on the lean epilogues, CTA pairs only from
+    2 x SMs m-tiles on, key split of the attention weights on small grids and wave tails), queried without a device."""
+    one = 2 * 1218                                   # a single utterance: two CFG rows
+    # residual-stream GEMMs (N = 512): 128-column lean tiles in one wave, no pairs; K = 1920 likewise
+    assert _shape(lib, one, 512, 512, 2)[:2] == (128, 0)
+    assert _shape(lib, one, 512, 1920, 2)[:2] == (128, 0)
+    # feed-forward input GEMMs: multiples of 64 (lean plain epilogue), no pairs
+    for n_out in (1424, 1536, 1920):
+        bn, pair, _ = _shape(lib, one, n_out, 512, 1)
+        assert bn % 64 == 0 and pair == 0, (n_out, bn, pair)
+    # an op that can only take the generic epilogue may use any multiple of 16
+    assert _shape(lib, one, 512, 512, 0)[0] % 16 == 0
+    # the batch-64 workload: 256-column tiles as CTA pairs
+    big = 128 * 1219
+    assert _shape(lib, big, 512, 1536, 2)[:2] == (256, 1)
+    assert _shape(lib, big, 1536, 512, 1)[:2] == (256, 1)
+    # pairs start at 2 x SMs m-tiles (8 utterances: 153 m-tiles, 16: 305)
+    assert _shape(lib, 16 * 1219, 512, 1536, 2)[1] == 0
+    assert _shape(lib, 32 * 1219, 512, 1536, 2)[1] == 1
+    # attention key split: 80 CTAs of 10 key tiles -> pairs; 40 of 5 -> four CTAs; a 60 s dialog (416 CTAs of 52) -> pairs
+    # (tail of the last wave); batch 64 (5120 CTAs) and the stereo batch (2432) -> none
+    assert _shape(lib, one, 512, 512, 2, attn_ctas=80, q_tiles=10)[2] == 2
+    assert _shape(lib, one, 512, 512, 2, attn_ctas=40, q_tiles=5)[2] == 4
+    assert _shape(lib, one, 512, 512, 2, attn_ctas=416, q_tiles=52)[2] == 2
+    assert _shape(lib, one, 512, 512, 2, attn_ctas=5120, q_tiles=10)[2] == 1
+    assert _shape(lib, one, 512, 512, 2, attn_ctas=2432, q_tiles=19)[2] == 1
+    # errors are reported without a device as well
+    assert lib.zvb_debug_launch_shape(0, 512, 512, 0, 148, 1, 1, None, None, None) == -1
+    assert b"positive" in lib.zvb_last_error()

@@ -770,6 +770,25 @@ static void launch_dwconv(const Op& op, cudaStream_t st) {
     else launch_dwconv_mode<K, ACT, 1>(op, st);
 }
 
+// Cluster size of the attention-weights kernel's key split (attn.cuh) for `base` = query tiles x heads x utterances CTAs
+// with `q_tiles` key tiles each.
+static int attn_split_choice(long long base, int q_tiles) {
+    int cs = 1;
+    if (!g_attn_split) return cs;
+    if (q_tiles >= 4 && base * 4 <= g_num_sms + g_num_sms / 8) cs = 4;
+    else if (q_tiles >= 2 && base * 2 <= g_num_sms + g_num_sms / 8) cs = 2;
+    else if (q_tiles >= 8) {
+        // tail of the last wave: two CTAs per SM = 296 slots; a 60 s dialog has 416 CTAs of 104 tile iterations each
+        // (two waves for 1.4 waves of work), as pairs 832 half-length CTAs in three (measured: 2.41 -> 2.16 ms per
+        // forward; on grids of many waves the split only adds its hand-offs: C5 +16%, C3 +31% when forced)
+        const long long slots = 2LL * g_num_sms;
+        const long long w1 = (base + slots - 1) / slots, w2 = (2 * base + slots - 1) / slots;
+        if (10 * w2 <= 16 * w1) cs = 2;           // <= 0.8 of the unsplit wave count
+    }
+    if (g_attn_split > 1 && q_tiles >= g_attn_split) cs = g_attn_split == 3 ? 2 : g_attn_split;   // tests: force 2 (=3) or 4
+    return cs;
+}
+
 static int launch_op(const Op& op, cudaStream_t st) {
     switch (op.type) {
         case OP_GEMM: {
@@ -799,21 +818,7 @@ static int launch_op(const Op& op, cudaStream_t st) {
             const int q_tiles = (op.ap.L + ATT_BM - 1) / ATT_BM;          // also the number of key tiles
             // small grids (single utterances): the key tiles of a query tile are split over a cluster of 2 or 4 CTAs while the
             // grid still fits the SMs about once (attn.cuh; ZVB_ATTN_SPLIT=0 keeps one CTA per query tile)
-            int cs = 1;
-            const long long base = (long long)q_tiles * op.ap.H * op.ap.N;
-            if (g_attn_split) {
-                if (q_tiles >= 4 && base * 4 <= g_num_sms + g_num_sms / 8) cs = 4;
-                else if (q_tiles >= 2 && base * 2 <= g_num_sms + g_num_sms / 8) cs = 2;
-                else if (q_tiles >= 8) {
-                    // tail of the last wave: two CTAs per SM = 296 slots; a 60 s dialog has 416 CTAs of 104 tile iterations each
-                    // (two waves for 1.4 waves of work), as pairs 832 half-length CTAs in three (measured: 2.41 -> 2.16 ms per
-                    // forward; on grids of many waves the split only adds its hand-offs: C5 +16%, C3 +31% when forced)
-                    const long long slots = 2LL * g_num_sms;
-                    const long long w1 = (base + slots - 1) / slots, w2 = (2 * base + slots - 1) / slots;
-                    if (10 * w2 <= 16 * w1) cs = 2;           // <= 0.8 of the unsplit wave count
-                }
-                if (g_attn_split > 1 && q_tiles >= g_attn_split) cs = g_attn_split == 3 ? 2 : g_attn_split;   // tests: force 2 (=3) or 4
-            }
+            const int cs = attn_split_choice((long long)q_tiles * op.ap.H * op.ap.N, q_tiles);
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(q_tiles * cs, op.ap.H, op.ap.N);
             cfg.blockDim = dim3(ATT_THREADS);
@@ -1799,6 +1804,27 @@ int zvb_test_istft(const float* S, int ld, const int32_t* lens, const float* win
       TRY(launch_op(o, st)); }
     { Op o; o.type = OP_OLA; o.p0 = frames; o.p1 = lens; o.f0 = window; o.o0 = wav; o.i0 = N; o.i1 = T; o.i2 = hop; o.i5 = clamp;
       TRY(launch_op(o, st)); }
+    return 0;
+}
+
+int zvb_debug_launch_shape(long long rows, int n_out, int k, int lean_kind, int num_sms, long long attn_ctas, int q_tiles,
+                           int* block_n, int* pair, int* attn_split) {
+    if (rows <= 0 || n_out <= 0 || k <= 0 || num_sms <= 0) return fail(ZVB_ERR_INVALID, "launch shape: sizes must be positive");
+    std::lock_guard<std::mutex> lock(g_init_mutex);
+    load_switches();
+    const int saved = g_num_sms;
+    g_num_sms = num_sms;
+    const long long m_tiles = (rows + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+    const int k_blocks = (k + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+    const int bn = pick_block_n(n_out, m_tiles, k_blocks, lean_kind);
+    const long long n_tiles = (n_out + bn - 1) / bn;
+    const long long slots2 = ((m_tiles + 1) / 2) * n_tiles;
+    if (block_n != nullptr) *block_n = bn;
+    if (pair != nullptr)      // the conditions of set_grid
+        *pair = (g_cluster_ok && bn >= 64 && m_tiles >= 2 && slots2 >= g_num_sms / 4 && k_blocks >= g_pair_min_kb &&
+                 m_tiles >= pair_min_mtiles()) ? 1 : 0;
+    if (attn_split != nullptr) *attn_split = attn_split_choice(attn_ctas, q_tiles);
+    g_num_sms = saved;
     return 0;
 }
 
