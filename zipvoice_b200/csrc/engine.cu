@@ -82,6 +82,7 @@ static int g_attn_split = 1;      // ZVB_ATTN_SPLIT=0: no key split of the atten
 static int g_attn_tc = 0;         // ZVB_ATTN_TC=1: attention weights with the tensor-core rel-pos bias (attn3.cuh; measured slower)
 static int g_dw_mode = 0;          // ZVB_DW_MODE: depthwise-convolution block shapes (elementwise.cuh: DwShape), 0 = measured best
 static int g_fuse_prologue = 1;    // ZVB_NO_FUSED_PROLOGUE=1: masks, per-stack time projections and row biases as separate launches
+static int g_pv_deep = 0;          // ZVB_PV_DEEP=1: SelfAttention P.V with a 10-stage operand ring over the unused staging area
 static int g_pv_bn = 0;            // ZVB_PV_BN=<columns>: tile width of the NonlinAttention P.V GEMM (0 = two equal tiles)
 static int g_merge_ff1 = 1;        // ZVB_NO_MERGE=1: feed_forward1 / attention in-projections as separate GEMMs
 static int g_small_model = 1;      // ZVB_NO_SMALL_MODEL=1: round 1's tile-width choice for small problems
@@ -154,6 +155,7 @@ static void load_switches() {
         if (const char* e = getenv("ZVB_PAIR_MIN_MTILES")) g_pair_min_mtiles = atoll(e);
         if (const char* e = getenv("ZVB_NO_MERGE")) g_merge_ff1 = atoi(e) == 0;
         if (const char* e = getenv("ZVB_PV_BN")) g_pv_bn = atoi(e);
+        if (const char* e = getenv("ZVB_PV_DEEP")) g_pv_deep = atoi(e) != 0;
         if (const char* e = getenv("ZVB_NO_FUSED_PROLOGUE")) g_fuse_prologue = atoi(e) == 0;
         if (const char* e = getenv("ZVB_ATTN_TC")) g_attn_tc = atoi(e) != 0;
         if (const char* e = getenv("ZVB_BN192")) g_bn192 = atoi(e) != 0;
@@ -661,6 +663,15 @@ static int build_pv(Op& op, const h16* P, const float* inv_l, const h16* Vt, voi
     // only after its predecessor passed its own dependency wait), so their tiles may be requested before the wait; V^T is
     // the predecessor's output and is not
     p.pre_b = (g_pre_b && g_plan_build) ? 2 : 0;
+    // SelfAttention: the kernel only streams P (one 18 KB stage per k-block, ring-depth bound) and its 12-column head outputs
+    // always leave through the direct per-thread stores (never a multiple of 8 columns: store_unit's staged path is not taken),
+    // so the staging area is unused and the ring may take all of it but one slot: 10 stages instead of 8
+    if (g_pv_deep && per_head && (hd & 7) != 0 && p.aux_mode == AUX_NONE && !p.tma_store && op.cluster == 1) {
+        const int ring = GEMM_SHARED_BUDGET - GEMM_AUX_BYTES;
+        int st, sb;
+        gemm_ring(p.block_n, op.cluster, ring, &st, &sb);
+        if (st > p.stages) { p.ring_bytes = ring; p.aux_slots = 1; p.stage_depth = 1; p.stages = st; p.stage_bytes = sb; }
+    }
     mark_out(op, 0, out, (long long)N * L * ldc);
     op.shape[0] = N * L; op.shape[1] = per_head ? H * hd : hd; op.shape[2] = L; op.shape[3] = p.block_n;
     op.cat = ZVB_CAT_GEMM_PV;

@@ -26,7 +26,7 @@ constexpr int GEMM_B_BYTES = 256 * GEMM_BLOCK_K * 2;            // 32 KB (block_
 // pair, up to 8 for the 16..48-column tiles that only stream A (more bytes in flight per SM -- those
 // kernels are HBM-latency bound).  Host: gemm_ring() fills GemmParams::stages / stage_bytes.
 constexpr int GEMM_OPERAND_BYTES = 3 * (GEMM_A_BYTES + GEMM_B_BYTES);        // default operand ring (144 KB)
-constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_MAX_STAGES = 10;     // 10 only for the SelfAttention P.V ring over the unused staging area (engine.cu: build_pv)
 constexpr int GEMM_AUX_SLOTS = 4;                               // default aux / staging slots
 constexpr int GEMM_AUX_SLOTS_MAX = 8;
 constexpr int GEMM_AUX_BYTES = 128 * 128;                       // 128 rows x 128 B
@@ -49,7 +49,7 @@ constexpr int GEMM_BIAS_BYTES = 16 * 64 * 4;               // per epilogue warp:
 // Lean epilogues: bias (+ per-utterance row bias) of the tile in flight, [2 tile parities][2 utterances][256 columns] fp32.
 // The kernel leaves the L1 no capacity (227 KB of shared memory), so a global bias load costs an L2 round trip per unit.
 constexpr int GEMM_CBIAS_BYTES = 2 * 2 * 256 * 4;
-constexpr int GEMM_LAYOUT_BYTES = GEMM_SHARED_BUDGET + GEMM_BIAS_BYTES + GEMM_CBIAS_BYTES + 512 /*barriers*/;
+constexpr int GEMM_LAYOUT_BYTES = GEMM_SHARED_BUDGET + GEMM_BIAS_BYTES + GEMM_CBIAS_BYTES + 640 /*barriers: 64 x 8 B + TMEM holder*/;
 constexpr int GEMM_SMEM_BYTES = 232448;                    // all 227 KB; layout + alignment pad must fit (checked)
 static_assert(GEMM_LAYOUT_BYTES <= GEMM_SMEM_BYTES, "shared-memory layout too large");
 constexpr int GEMM_THREADS = 640;
