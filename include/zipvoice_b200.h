@@ -305,7 +305,9 @@ int zvb_test_masks(const uint8_t* mask, int N, int T, int ds, uint8_t* strided, 
 /* Host only (no device needed): the launch shape the engine picks for a linear layer of `rows` x `n_out` outputs over `k`
  * inputs on a device with `num_sms` SMs -- tile width, CTA pair (cta_group::2) or single CTA, and the attention kernel's
  * key-split cluster size for `attn_ctas` = query tiles x heads x utterances with `q_tiles` key tiles.  lean_kind: 0 generic
- * epilogue only, 1 plain lean epilogue possible, 2 residual lean epilogue possible.  Any output pointer may be null. */
+ * epilogue only, 1 plain lean epilogue possible, 2 residual lean epilogue possible.  Any output pointer may be null.
+ * Diagnostic: it evaluates the rules for `num_sms` under the library's init lock; do not call it while another thread
+ * creates plans. */
 int zvb_debug_launch_shape(long long rows, int n_out, int k, int lean_kind, int num_sms, long long attn_ctas, int q_tiles,
                            int* block_n, int* pair, int* attn_split);
 
